@@ -1,0 +1,589 @@
+// nbx_fkjac.cu -- fused forward kinematics + geometric Jacobian for sm_100a.
+//
+// Replaces reference numbotics/robots/helpers.py:33-187 (nb_joint_transform,
+// nb_compute_transformation, nb_compute_jacobian) and the arithmetic around them in
+// numbotics/robots/arm.py:394-406, 451-457.
+//
+// Design:
+//   * one thread per configuration, one CTA per tile of TILE consecutive configurations;
+//   * the path descriptor (pre-folded Rodrigues constants A, Bm, Cm, t per joint) is a
+//     __grid_constant__ kernel parameter: it sits in constant bank 0, so every joint constant
+//     is a direct FFMA operand -- no loads on the arithmetic path;
+//   * q is read with 128-bit coalesced loads into shared memory and re-read per thread;
+//   * the transform is accumulated in registers as a 3x4 rigid product; the Jacobian column of
+//     joint i needs the end point p_e that is only known after the last joint, so the walk keeps
+//     w_i = R_i a_i and the moment m_i = w_i x p_i and finishes with  v_i = w_i x p_e - m_i.
+//     No (B, I, 4, 4) `T_mats` intermediate (reference helpers.py:138-158) ever exists;
+//   * outputs (B,4,4) and (B,6,dof) are AoS with 64 / 24*dof byte rows: each thread writes its row
+//     into a shared-memory tile laid out exactly like global memory and one elected thread hands
+//     the whole tile to the TMA engine (cp.async.bulk shared -> global), so HBM sees full-line
+//     writes and the SM spends no issue slots on global stores.
+//
+// HBM-bound: 4*dof + 64 + 24*dof bytes per configuration (fp32), see DESIGN.md.
+#include "nbx_common.cuh"
+#include <algorithm>
+#include <mutex>
+
+namespace {
+
+constexpr int kSmallMax = 8;   // dense fully-unrolled kernels cover paths of 1..8 joints
+
+template <typename T> __device__ __forceinline__ void sincos_t(T x, T* s, T* c);
+template <> __device__ __forceinline__ void sincos_t<float>(float x, float* s, float* c) { sincosf(x, s, c); }
+template <> __device__ __forceinline__ void sincos_t<double>(double x, double* s, double* c) { sincos(x, s, c); }
+
+template <typename T> __device__ __forceinline__ T fma_t(T a, T b, T c);
+template <> __device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
+template <> __device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return fma(a, b, c); }
+
+// R (3x3 row-major) and p: world pose of the current joint frame.
+template <typename T>
+struct Pose {
+    T R[9];
+    T p[3];
+};
+
+// One joint of the walk: pose <- pose * X(q); returns the post-joint pose in place.
+template <typename T>
+__device__ __forceinline__ void joint_step(Pose<T>& X, const JointK<T>& jk, T qv) {
+    T M[9];
+    T tt[3];
+    if (jk.type == NBX_JOINT_REVOLUTE) {
+        T s, c;
+        sincos_t<T>(qv, &s, &c);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) M[k] = fma_t<T>(s, jk.Cm[k], fma_t<T>(-c, jk.Bm[k], jk.A[k]));
+        tt[0] = jk.t[0]; tt[1] = jk.t[1]; tt[2] = jk.t[2];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) M[k] = jk.A[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) tt[k] = fma_t<T>(qv, jk.d[k], jk.t[k]);
+    }
+    T Rn[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        X.p[r] = fma_t<T>(X.R[r * 3 + 0], tt[0], fma_t<T>(X.R[r * 3 + 1], tt[1], fma_t<T>(X.R[r * 3 + 2], tt[2], X.p[r])));
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            Rn[r * 3 + c] = fma_t<T>(X.R[r * 3 + 0], M[c], fma_t<T>(X.R[r * 3 + 1], M[3 + c], X.R[r * 3 + 2] * M[6 + c]));
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) X.R[k] = Rn[k];
+}
+
+// world axis w = R a and moment m = w x p of the joint frame just reached.  Prismatic joints are
+// stored as (w_store, m_store) = (0, -w) so the common finish  v = w_store x p_e - m_store,
+// omega = w_store  yields [w; 0] without a branch (reference helpers.py:181-185).
+template <typename T>
+__device__ __forceinline__ void joint_screw(const Pose<T>& X, const JointK<T>& jk, T* w, T* m) {
+    T a[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+        a[r] = fma_t<T>(X.R[r * 3 + 0], jk.ax[0], fma_t<T>(X.R[r * 3 + 1], jk.ax[1], X.R[r * 3 + 2] * jk.ax[2]));
+    if (jk.type == NBX_JOINT_REVOLUTE) {
+        w[0] = a[0]; w[1] = a[1]; w[2] = a[2];
+        m[0] = fma_t<T>(a[1], X.p[2], -a[2] * X.p[1]);
+        m[1] = fma_t<T>(a[2], X.p[0], -a[0] * X.p[2]);
+        m[2] = fma_t<T>(a[0], X.p[1], -a[1] * X.p[0]);
+    } else {
+        w[0] = w[1] = w[2] = T(0);
+        m[0] = -a[0]; m[1] = -a[1]; m[2] = -a[2];
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void pose_mul_const(Pose<T>& X, const T* c12) {
+    // X <- X * [C | t] with a constant pose12
+    T Rn[9], pn[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        pn[r] = fma_t<T>(X.R[r * 3 + 0], c12[3], fma_t<T>(X.R[r * 3 + 1], c12[7], fma_t<T>(X.R[r * 3 + 2], c12[11], X.p[r])));
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            Rn[r * 3 + c] = fma_t<T>(X.R[r * 3 + 0], c12[c], fma_t<T>(X.R[r * 3 + 1], c12[4 + c], X.R[r * 3 + 2] * c12[8 + c]));
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) X.R[k] = Rn[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) X.p[k] = pn[k];
+}
+
+template <typename T>
+__device__ __forceinline__ void pose_mul_global(Pose<T>& X, const T* __restrict__ g16) {
+    // X <- X * G, G a row-major 4x4 in global memory (per-configuration local_pose)
+    T c12[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) c12[k] = g16[k];
+    pose_mul_const<T>(X, c12);
+}
+
+// ---- TMA bulk copy shared -> global --------------------------------------------------------
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(ssrc));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// 16-byte streaming load (q is read exactly once)
+__device__ __forceinline__ int4 ld_stream16(const void* p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+template <typename T> struct Vec2;
+template <> struct Vec2<float> { using type = float2; };
+template <> struct Vec2<double> { using type = double2; };
+
+template <typename T>
+__device__ __forceinline__ void store_pose16(T* dst, const Pose<T>& X) {
+    // row-major 4x4, vectorised as 4 x 16 bytes (float) / 8 x 16 bytes (double)
+    using V2 = typename Vec2<T>::type;
+    V2* d = reinterpret_cast<V2*>(dst);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        V2 a, b;
+        a.x = X.R[r * 3 + 0]; a.y = X.R[r * 3 + 1];
+        b.x = X.R[r * 3 + 2]; b.y = X.p[r];
+        d[r * 2 + 0] = a;
+        d[r * 2 + 1] = b;
+    }
+    V2 z0, z1;
+    z0.x = T(0); z0.y = T(0); z1.x = T(0); z1.y = T(1);
+    d[6] = z0;
+    d[7] = z1;
+}
+
+// Stage this CTA's q tile in shared memory.
+template <typename T, int TILE>
+__device__ __forceinline__ void load_q_tile(T* sq, const T* __restrict__ q, int64_t tile0, int nvalid, int dof, bool vec_ok) {
+    const int n = nvalid * dof;
+    const T* src = q + tile0 * dof;
+    if (vec_ok && nvalid == TILE) {
+        const int n16 = (TILE * dof * (int)sizeof(T)) / 16;   // TILE*dof*sizeof(T) is a multiple of 16 for TILE % 4 == 0
+        const int4* s16 = reinterpret_cast<const int4*>(src);
+        int4* d16 = reinterpret_cast<int4*>(sq);
+        for (int i = threadIdx.x; i < n16; i += TILE) d16[i] = ld_stream16(s16 + i);
+    } else {
+        for (int i = threadIdx.x; i < n; i += TILE) sq[i] = src[i];
+    }
+}
+
+// =============================================================================================
+// dense kernel: path covers q columns 0..NJ-1 exactly (serial arms: Kinova tool_frame), NJ <= 8.
+// Fully unrolled; screws live in registers.
+// =============================================================================================
+template <typename T, int NJ, int TILE>
+__global__ void __launch_bounds__(TILE)
+fkjac_dense_kernel(const __grid_constant__ PathK<T, kSmallMax> P, const T* __restrict__ q, int64_t B,
+                   const T* __restrict__ lp, int64_t lps, const T* __restrict__ gp, int64_t gps,
+                   T* __restrict__ T_out, T* __restrict__ J_out, int vec_ok) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // layout: [J tile][T tile][q tile]; J and T tiles are 128-byte aligned for the bulk copies
+    T* sJ = reinterpret_cast<T*>(smem_raw);
+    T* sT = sJ + TILE * 6 * NJ;
+    T* sq = sT + TILE * 16;
+
+    const int64_t tile0 = (int64_t)blockIdx.x * TILE;
+    const int nvalid = (int)min((int64_t)TILE, B - tile0);
+    const int tid = threadIdx.x;
+
+    load_q_tile<T, TILE>(sq, q, tile0, nvalid, NJ, vec_ok != 0);
+    __syncthreads();
+
+    Pose<T> X;
+    T W[NJ][3], Mo[NJ][3];
+    const bool active = tid < nvalid;
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            X.R[k * 3 + 0] = P.base[k * 4 + 0]; X.R[k * 3 + 1] = P.base[k * 4 + 1]; X.R[k * 3 + 2] = P.base[k * 4 + 2];
+            X.p[k] = P.base[k * 4 + 3];
+        }
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) {
+            const T qv = sq[tid * NJ + i];
+            joint_step<T>(X, P.j[i], qv);
+            joint_screw<T>(X, P.j[i], W[i], Mo[i]);
+        }
+        pose_mul_const<T>(X, P.tail);
+        const int64_t b = tile0 + tid;
+        if (lp != nullptr) pose_mul_global<T>(X, lp + b * lps);
+        T pe[3] = {X.p[0], X.p[1], X.p[2]};
+        if (gp != nullptr) {
+            const T* g = gp + b * gps;
+            pe[0] = g[3]; pe[1] = g[7]; pe[2] = g[11];
+        }
+        if (T_out != nullptr) store_pose16<T>(sT + tid * 16, X);
+        if (J_out != nullptr) {
+            T row[6 * NJ];
+#pragma unroll
+            for (int i = 0; i < NJ; ++i) {
+                row[0 * NJ + i] = fma_t<T>(W[i][1], pe[2], fma_t<T>(-W[i][2], pe[1], -Mo[i][0]));
+                row[1 * NJ + i] = fma_t<T>(W[i][2], pe[0], fma_t<T>(-W[i][0], pe[2], -Mo[i][1]));
+                row[2 * NJ + i] = fma_t<T>(W[i][0], pe[1], fma_t<T>(-W[i][1], pe[0], -Mo[i][2]));
+                row[3 * NJ + i] = W[i][0];
+                row[4 * NJ + i] = W[i][1];
+                row[5 * NJ + i] = W[i][2];
+            }
+            using V2 = typename Vec2<T>::type;
+            V2* d = reinterpret_cast<V2*>(sJ + tid * 6 * NJ);
+#pragma unroll
+            for (int k = 0; k < 3 * NJ; ++k) {
+                V2 v;
+                v.x = row[2 * k]; v.y = row[2 * k + 1];
+                d[k] = v;
+            }
+        }
+    }
+
+    if (nvalid == TILE && vec_ok) {
+        // full tile: hand both output tiles to the TMA engine
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            if (T_out != nullptr) bulk_store(T_out + tile0 * 16, sT, TILE * 16 * sizeof(T));
+            if (J_out != nullptr) bulk_store(J_out + tile0 * 6 * NJ, sJ, TILE * 6 * NJ * sizeof(T));
+            bulk_commit();
+            bulk_wait_read_all();
+        }
+    } else {
+        // ragged last tile (or unaligned user pointers): cooperative coalesced copy-out
+        __syncthreads();
+        if (T_out != nullptr)
+            for (int i = tid; i < nvalid * 16; i += TILE) T_out[tile0 * 16 + i] = sT[i];
+        if (J_out != nullptr)
+            for (int i = tid; i < nvalid * 6 * NJ; i += TILE) J_out[tile0 * 6 * NJ + i] = sJ[i];
+    }
+}
+
+// =============================================================================================
+// generic kernel: any path length <= NBX_MAX_PATH, any dof, sparse columns.
+// Screws are parked in the Jacobian's own shared-memory tile (w in rows 3..5, m in rows 0..2
+// of the joint's column) and fixed up in place once p_e is known: registers stay O(1) in the
+// chain depth (BASELINE config 5, 30-DoF).
+// =============================================================================================
+template <typename T, int TILE>
+__global__ void __launch_bounds__(TILE)
+fkjac_generic_kernel(const __grid_constant__ PathK<T, NBX_MAX_PATH> P, const T* __restrict__ q, int64_t B,
+                     const T* __restrict__ lp, int64_t lps, const T* __restrict__ gp, int64_t gps,
+                     T* __restrict__ T_out, T* __restrict__ J_out, int vec_ok) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int dof = P.dof;
+    const int jrow = 6 * dof;
+    T* sJ = reinterpret_cast<T*>(smem_raw);
+    T* sT = sJ + TILE * jrow;
+    T* sq = sT + TILE * 16;
+
+    const int64_t tile0 = (int64_t)blockIdx.x * TILE;
+    const int nvalid = (int)min((int64_t)TILE, B - tile0);
+    const int tid = threadIdx.x;
+
+    load_q_tile<T, TILE>(sq, q, tile0, nvalid, dof, vec_ok != 0);
+    if (J_out != nullptr && !P.dense)
+        for (int i = tid; i < TILE * jrow; i += TILE) sJ[i] = T(0);
+    __syncthreads();
+
+    if (tid < nvalid) {
+        Pose<T> X;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            X.R[k * 3 + 0] = P.base[k * 4 + 0]; X.R[k * 3 + 1] = P.base[k * 4 + 1]; X.R[k * 3 + 2] = P.base[k * 4 + 2];
+            X.p[k] = P.base[k * 4 + 3];
+        }
+        T* myJ = sJ + tid * jrow;
+        const T* myq = sq + tid * dof;
+#pragma unroll 1
+        for (int i = 0; i < P.n; ++i) {
+            const JointK<T>& jk = P.j[i];
+            const int col = jk.qidx;
+            joint_step<T>(X, jk, myq[col]);
+            if (J_out != nullptr) {
+                T w[3], m[3];
+                joint_screw<T>(X, jk, w, m);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    myJ[k * dof + col] = m[k];
+                    myJ[(3 + k) * dof + col] = w[k];
+                }
+            }
+        }
+        pose_mul_const<T>(X, P.tail);
+        const int64_t b = tile0 + tid;
+        if (lp != nullptr) pose_mul_global<T>(X, lp + b * lps);
+        T pe[3] = {X.p[0], X.p[1], X.p[2]};
+        if (gp != nullptr) {
+            const T* g = gp + b * gps;
+            pe[0] = g[3]; pe[1] = g[7]; pe[2] = g[11];
+        }
+        if (T_out != nullptr) store_pose16<T>(sT + tid * 16, X);
+        if (J_out != nullptr) {
+#pragma unroll 2
+            for (int i = 0; i < P.n; ++i) {
+                const int col = P.j[i].qidx;
+                const T w0 = myJ[3 * dof + col], w1 = myJ[4 * dof + col], w2 = myJ[5 * dof + col];
+                const T m0 = myJ[0 * dof + col], m1 = myJ[1 * dof + col], m2 = myJ[2 * dof + col];
+                myJ[0 * dof + col] = fma_t<T>(w1, pe[2], fma_t<T>(-w2, pe[1], -m0));
+                myJ[1 * dof + col] = fma_t<T>(w2, pe[0], fma_t<T>(-w0, pe[2], -m1));
+                myJ[2 * dof + col] = fma_t<T>(w0, pe[1], fma_t<T>(-w1, pe[0], -m2));
+            }
+        }
+    }
+
+    if (nvalid == TILE && vec_ok) {
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            if (T_out != nullptr) bulk_store(T_out + tile0 * 16, sT, TILE * 16 * sizeof(T));
+            if (J_out != nullptr) bulk_store(J_out + tile0 * jrow, sJ, (uint32_t)(TILE * jrow * sizeof(T)));
+            bulk_commit();
+            bulk_wait_read_all();
+        }
+    } else {
+        __syncthreads();
+        if (T_out != nullptr)
+            for (int i = tid; i < nvalid * 16; i += TILE) T_out[tile0 * 16 + i] = sT[i];
+        if (J_out != nullptr)
+            for (int i = tid; i < nvalid * jrow; i += TILE) J_out[tile0 * jrow + i] = sJ[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <typename T, int MAXJ>
+int build_path(const nbx_chain* ch, int frame, const double* base_pose16, int use_com, PathK<T, MAXJ>& P) {
+    const std::vector<int>& path = ch->frame_path[frame];
+    NBX_REQUIRE((int)path.size() <= MAXJ, "path of frame %d has %d movable joints (max %d)", frame, (int)path.size(), MAXJ);
+    P.n = (int)path.size();
+    P.dof = ch->dof;
+    P.use_com = use_com;
+    bool dense = (P.n == ch->dof);
+    for (int i = 0; i < P.n; ++i) {
+        const int j = path[i];
+        nbx_fill_joint<T>(P.j[i], &ch->mov_offset[12 * j], &ch->mov_axis[3 * j], ch->mov_type[j], ch->mov_qidx[j]);
+        dense = dense && (ch->mov_qidx[j] == i);
+    }
+    P.dense = dense ? 1 : 0;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 4; ++c) P.base[r * 4 + c] = (T)base_pose16[r * 4 + c];
+    double tail[12];
+    for (int k = 0; k < 12; ++k) tail[k] = ch->frame_tail[12 * frame + k];
+    if (use_com) pose12_mul(tail, &ch->frame_com[12 * frame], tail);
+    for (int k = 0; k < 12; ++k) P.tail[k] = (T)tail[k];
+    return NBX_OK;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <typename T, int NJ, int TILE>
+int launch_dense(const PathK<T, kSmallMax>& P, const T* q, int64_t B, const T* lp, int64_t lps, const T* gp, int64_t gps,
+                 T* T_out, T* J_out, int vec_ok, cudaStream_t stream) {
+    const size_t smem = sizeof(T) * (size_t)TILE * (6 * NJ + 16 + NJ);
+    auto kern = fkjac_dense_kernel<T, NJ, TILE>;
+    NBX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t grid = (B + TILE - 1) / TILE;
+    NBX_REQUIRE(grid <= 0x7fffffffLL, "batch too large for one launch");
+    kern<<<(unsigned)grid, TILE, smem, stream>>>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok);
+    nbx_count_launch();
+    NBX_CUDA_OK(cudaGetLastError());
+    return NBX_OK;
+}
+
+template <typename T, int TILE>
+int launch_generic(const PathK<T, NBX_MAX_PATH>& P, const T* q, int64_t B, const T* lp, int64_t lps, const T* gp, int64_t gps,
+                   T* T_out, T* J_out, int vec_ok, size_t smem, cudaStream_t stream) {
+    auto kern = fkjac_generic_kernel<T, TILE>;
+    NBX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t grid = (B + TILE - 1) / TILE;
+    NBX_REQUIRE(grid <= 0x7fffffffLL, "batch too large for one launch");
+    kern<<<(unsigned)grid, TILE, smem, stream>>>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok);
+    nbx_count_launch();
+    NBX_CUDA_OK(cudaGetLastError());
+    return NBX_OK;
+}
+
+template <typename T>
+int launch_fkjac(const nbx_chain* ch, int frame, const T* q, int64_t B, const double* base_pose, int use_com,
+                 const T* lp, int64_t lps, const T* gp, int64_t gps, T* T_out, T* J_out, cudaStream_t stream) {
+    NBX_REQUIRE(ch != nullptr, "chain handle is NULL");
+    NBX_REQUIRE(frame >= 0 && frame < ch->n_frames, "frame id %d out of range [0, %d)", frame, ch->n_frames);
+    NBX_REQUIRE(B >= 0, "negative batch size");
+    NBX_REQUIRE(base_pose != nullptr, "base_pose is NULL");
+    NBX_REQUIRE(lp == nullptr || lps == 0 || lps == 16, "local_pose_stride must be 0 or 16");
+    NBX_REQUIRE(gp == nullptr || gps == 0 || gps == 16, "global_pose_stride must be 0 or 16");
+    NBX_REQUIRE(!(lp != nullptr && gp != nullptr), "local_pose and global_pose cannot both be provided");
+    if (B == 0 || (T_out == nullptr && J_out == nullptr)) return NBX_OK;
+    NBX_REQUIRE(q != nullptr, "q is NULL");
+    NBX_CUDA_OK(cudaSetDevice(ch->device));
+    const int vec_ok = aligned16(q) && (T_out == nullptr || aligned16(T_out)) && (J_out == nullptr || aligned16(J_out));
+    const int n = (int)ch->frame_path[frame].size();
+
+    constexpr int TILE = 128;
+    if (n >= 1 && n <= kSmallMax) {
+        PathK<T, kSmallMax> P;
+        int rc = build_path<T, kSmallMax>(ch, frame, base_pose, use_com, P);
+        if (rc != NBX_OK) return rc;
+        if (P.dense) {
+            switch (n) {
+#define NBX_CASE(N) case N: return launch_dense<T, N, TILE>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, stream);
+                NBX_CASE(1) NBX_CASE(2) NBX_CASE(3) NBX_CASE(4) NBX_CASE(5) NBX_CASE(6) NBX_CASE(7) NBX_CASE(8)
+#undef NBX_CASE
+            }
+        }
+    }
+    PathK<T, NBX_MAX_PATH> P;
+    int rc = build_path<T, NBX_MAX_PATH>(ch, frame, base_pose, use_com, P);
+    if (rc != NBX_OK) return rc;
+    // tile size: keep >= 2 CTAs per SM when the per-thread tile row allows it
+    const size_t per_thread = sizeof(T) * (size_t)(6 * ch->dof + 16 + ch->dof);
+    const size_t budget = 100 * 1024;
+    if (per_thread * 128 <= budget) return launch_generic<T, 128>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, per_thread * 128, stream);
+    if (per_thread * 64 <= budget) return launch_generic<T, 64>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, per_thread * 64, stream);
+    NBX_REQUIRE(per_thread * 32 <= 220 * 1024, "dof %d too large for the shared-memory staged Jacobian", ch->dof);
+    return launch_generic<T, 32>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, per_thread * 32, stream);
+}
+
+// ---- host-buffer pipeline ------------------------------------------------------------------
+struct HostPipe {
+    static constexpr int kSlots = 3;
+    int device = -1;
+    size_t cap[kSlots] = {0, 0, 0};
+    void* buf[kSlots] = {nullptr, nullptr, nullptr};
+    cudaStream_t st[kSlots] = {nullptr, nullptr, nullptr};
+    std::mutex mu;
+};
+HostPipe g_pipe[16];
+
+int pipe_prepare(HostPipe& hp, int device, size_t bytes_per_slot) {
+    NBX_CUDA_OK(cudaSetDevice(device));
+    for (int s = 0; s < HostPipe::kSlots; ++s) {
+        if (hp.st[s] == nullptr) NBX_CUDA_OK(cudaStreamCreateWithFlags(&hp.st[s], cudaStreamNonBlocking));
+        if (hp.cap[s] < bytes_per_slot) {
+            if (hp.buf[s]) NBX_CUDA_OK(cudaFree(hp.buf[s]));
+            hp.buf[s] = nullptr;
+            hp.cap[s] = 0;
+            NBX_CUDA_OK(cudaMalloc(&hp.buf[s], bytes_per_slot));
+            hp.cap[s] = bytes_per_slot;
+        }
+    }
+    hp.device = device;
+    return NBX_OK;
+}
+
+template <typename T>
+int fkjac_host(const nbx_chain* ch, int frame, const T* q, int64_t B, const double* base_pose, int use_com, T* T_out, T* J_out) {
+    NBX_REQUIRE(ch != nullptr, "chain handle is NULL");
+    NBX_REQUIRE(B >= 0, "negative batch size");
+    if (B == 0 || (T_out == nullptr && J_out == nullptr)) return NBX_OK;
+    NBX_REQUIRE(ch->device >= 0 && ch->device < 16, "device index out of range");
+    const int dof = ch->dof;
+    // chunk so that three slots stay well inside HBM and the copies are long enough to saturate PCIe
+    const int64_t chunk = 1 << 19;
+    const size_t q_bytes = sizeof(T) * (size_t)chunk * dof;
+    const size_t t_bytes = T_out ? sizeof(T) * (size_t)chunk * 16 : 0;
+    const size_t j_bytes = J_out ? sizeof(T) * (size_t)chunk * 6 * dof : 0;
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t slot_bytes = up(q_bytes) + up(t_bytes) + up(j_bytes);
+    HostPipe& hp = g_pipe[ch->device];
+    std::lock_guard<std::mutex> lock(hp.mu);
+    int rc = pipe_prepare(hp, ch->device, slot_bytes);
+    if (rc != NBX_OK) return rc;
+    int slot = 0;
+    for (int64_t off = 0; off < B; off += chunk, slot = (slot + 1) % HostPipe::kSlots) {
+        const int64_t n = std::min(chunk, B - off);
+        cudaStream_t st = hp.st[slot];
+        unsigned char* base = static_cast<unsigned char*>(hp.buf[slot]);
+        T* dq = reinterpret_cast<T*>(base);
+        T* dT = T_out ? reinterpret_cast<T*>(base + up(q_bytes)) : nullptr;
+        T* dJ = J_out ? reinterpret_cast<T*>(base + up(q_bytes) + up(t_bytes)) : nullptr;
+        // stream order guarantees the slot's previous D2H finished before this H2D overwrites it
+        NBX_CUDA_OK(cudaMemcpyAsync(dq, q + off * dof, sizeof(T) * (size_t)n * dof, cudaMemcpyHostToDevice, st));
+        rc = launch_fkjac<T>(ch, frame, dq, n, base_pose, use_com, nullptr, 0, nullptr, 0, dT, dJ, st);
+        if (rc != NBX_OK) return rc;
+        if (T_out) NBX_CUDA_OK(cudaMemcpyAsync(T_out + off * 16, dT, sizeof(T) * (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+        if (J_out) NBX_CUDA_OK(cudaMemcpyAsync(J_out + off * 6 * dof, dJ, sizeof(T) * (size_t)n * 6 * dof, cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < HostPipe::kSlots; ++s) NBX_CUDA_OK(cudaStreamSynchronize(hp.st[s]));
+    return NBX_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+void nbx_fill_joint(JointK<T>& jk, const double* off12, const double* axis, int type, int qidx) {
+    // R, t of the folded offset
+    double R[9], t[3];
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) R[r * 3 + c] = off12[r * 4 + c];
+        t[r] = off12[r * 4 + 3];
+    }
+    const double a[3] = {axis[0], axis[1], axis[2]};
+    double K[9], Ke[9], Ks[9] = {0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0};
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+            K[r * 3 + c] = a[r] * a[c];
+            Ke[r * 3 + c] = K[r * 3 + c] - (r == c ? 1.0 : 0.0);
+        }
+    auto mm = [&](const double* X, const double* Y, T* out) {
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c)
+                out[r * 3 + c] = (T)(X[r * 3 + 0] * Y[0 * 3 + c] + X[r * 3 + 1] * Y[1 * 3 + c] + X[r * 3 + 2] * Y[2 * 3 + c]);
+    };
+    if (type == NBX_JOINT_REVOLUTE) {
+        mm(R, K, jk.A);
+        mm(R, Ke, jk.Bm);
+        mm(R, Ks, jk.Cm);
+        for (int k = 0; k < 3; ++k) jk.d[k] = (T)0;
+    } else {
+        for (int k = 0; k < 9; ++k) { jk.A[k] = (T)R[k]; jk.Bm[k] = (T)0; jk.Cm[k] = (T)0; }
+        for (int r = 0; r < 3; ++r) jk.d[r] = (T)(R[r * 3 + 0] * a[0] + R[r * 3 + 1] * a[1] + R[r * 3 + 2] * a[2]);
+    }
+    for (int k = 0; k < 3; ++k) { jk.t[k] = (T)t[k]; jk.ax[k] = (T)a[k]; }
+    jk.type = type;
+    jk.qidx = qidx;
+}
+template void nbx_fill_joint<float>(JointK<float>&, const double*, const double*, int, int);
+template void nbx_fill_joint<double>(JointK<double>&, const double*, const double*, int, int);
+
+int nbx_launch_fkjac_f32(const nbx_chain* chain, int frame, const float* q, int64_t B, const double* base_pose, int use_com,
+                         const float* lp, int64_t lps, const float* gp, int64_t gps, float* T_out, float* J_out, cudaStream_t stream) {
+    return launch_fkjac<float>(chain, frame, q, B, base_pose, use_com, lp, lps, gp, gps, T_out, J_out, stream);
+}
+int nbx_launch_fkjac_f64(const nbx_chain* chain, int frame, const double* q, int64_t B, const double* base_pose, int use_com,
+                         const double* lp, int64_t lps, const double* gp, int64_t gps, double* T_out, double* J_out, cudaStream_t stream) {
+    return launch_fkjac<double>(chain, frame, q, B, base_pose, use_com, lp, lps, gp, gps, T_out, J_out, stream);
+}
+
+extern "C" {
+
+int nbx_fk_jac_f32(const nbx_chain* chain, int frame, const float* q, int64_t B, const double* base_pose, int use_com,
+                   const float* local_pose, int64_t local_pose_stride, const float* global_pose, int64_t global_pose_stride,
+                   float* T_out, float* J_out, void* stream) {
+    return launch_fkjac<float>(chain, frame, q, B, base_pose, use_com, local_pose, local_pose_stride, global_pose,
+                               global_pose_stride, T_out, J_out, static_cast<cudaStream_t>(stream));
+}
+
+int nbx_fk_jac_f64(const nbx_chain* chain, int frame, const double* q, int64_t B, const double* base_pose, int use_com,
+                   const double* local_pose, int64_t local_pose_stride, const double* global_pose, int64_t global_pose_stride,
+                   double* T_out, double* J_out, void* stream) {
+    return launch_fkjac<double>(chain, frame, q, B, base_pose, use_com, local_pose, local_pose_stride, global_pose,
+                                global_pose_stride, T_out, J_out, static_cast<cudaStream_t>(stream));
+}
+
+int nbx_fk_jac_host_f32(const nbx_chain* chain, int frame, const float* q, int64_t B, const double* base_pose, int use_com,
+                        float* T_out, float* J_out) {
+    return fkjac_host<float>(chain, frame, q, B, base_pose, use_com, T_out, J_out);
+}
+
+int nbx_fk_jac_host_f64(const nbx_chain* chain, int frame, const double* q, int64_t B, const double* base_pose, int use_com,
+                        double* T_out, double* J_out) {
+    return fkjac_host<double>(chain, frame, q, B, base_pose, use_com, T_out, J_out);
+}
+
+}  // extern "C"

@@ -1,0 +1,198 @@
+// nbx_gjk.cuh -- register-resident GJK distance between rounded convex primitives (fp32).
+//
+// Replaces, for the verdict `min distance < threshold`, the Bullet narrow phase that the
+// reference reaches through pybullet.getClosestPoints (numbotics/physics/chain.py:944-951).
+// Geometry model: every primitive is a sharp *core* (point / box /
+// z-cylinder) swept by a sphere of radius `margin`;  d(A,B) = d(coreA, coreB) - mA - mB.
+//
+// Everything is statically indexed so the simplex stays in registers.
+#pragma once
+#include <cuda_runtime.h>
+#include <float.h>
+#include "nbx.h"
+
+namespace nbxg {
+
+struct V3 {
+    float x, y, z;
+};
+__device__ __forceinline__ V3 mk(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator-(V3 a) { return mk(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ V3 operator*(float s, V3 a) { return mk(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) {
+    return mk(fmaf(a.y, b.z, -a.z * b.y), fmaf(a.z, b.x, -a.x * b.z), fmaf(a.x, b.y, -a.y * b.x));
+}
+__device__ __forceinline__ V3 madd(V3 a, float s, V3 b) { return mk(fmaf(s, b.x, a.x), fmaf(s, b.y, a.y), fmaf(s, b.z, a.z)); }
+
+// World-space core of a primitive.  `ax` holds the box axes as columns of a row-major 3x3
+// (axis k = (ax[k], ax[3+k], ax[6+k])); for a cylinder only the z axis is stored in ax[0..2].
+struct ShapeW {
+    V3 c;
+    float ax[9];
+    float d[3];   // core dims: box half extents / cylinder {radius, half height} / sphere: unused
+    int type;
+};
+
+__device__ __forceinline__ V3 support(const ShapeW& S, V3 dir) {
+    if (S.type == NBX_PRIM_SPHERE) return S.c;
+    if (S.type == NBX_PRIM_BOX) {
+        V3 p = S.c;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const V3 a = mk(S.ax[k], S.ax[3 + k], S.ax[6 + k]);
+            const float s = dot(dir, a);
+            p = madd(p, copysignf(S.d[k], s), a);
+        }
+        return p;
+    }
+    // cylinder: segment along u plus a disc of radius r orthogonal to u
+    const V3 u = mk(S.ax[0], S.ax[1], S.ax[2]);
+    const float du = dot(dir, u);
+    const V3 perp = madd(dir, -du, u);
+    const float l2 = dot(perp, perp);
+    V3 p = madd(S.c, copysignf(S.d[1], du), u);
+    if (l2 > 1e-30f) p = madd(p, S.d[0] * rsqrtf(l2), perp);
+    return p;
+}
+
+// Closest point to the origin on triangle (a,b,c); returns it and the bitmask (bit0=a, bit1=b, bit2=c)
+// of the vertices that support it (Ericson, Real-Time Collision Detection, 5.1.5).
+__device__ __forceinline__ V3 closest_tri(V3 a, V3 b, V3 c, int* mask) {
+    const V3 ab = b - a, ac = c - a;
+    const float d1 = -dot(ab, a), d2 = -dot(ac, a);
+    if (d1 <= 0.f && d2 <= 0.f) { *mask = 1; return a; }
+    const float d3 = -dot(ab, b), d4 = -dot(ac, b);
+    if (d3 >= 0.f && d4 <= d3) { *mask = 2; return b; }
+    const float vc = d1 * d4 - d3 * d2;
+    if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) {
+        *mask = 3;
+        return madd(a, d1 / (d1 - d3), ab);
+    }
+    const float d5 = -dot(ab, c), d6 = -dot(ac, c);
+    if (d6 >= 0.f && d5 <= d6) { *mask = 4; return c; }
+    const float vb = d5 * d2 - d1 * d6;
+    if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) {
+        *mask = 5;
+        return madd(a, d2 / (d2 - d6), ac);
+    }
+    const float va = d3 * d6 - d5 * d4;
+    if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) {
+        *mask = 6;
+        return madd(b, (d4 - d3) / ((d4 - d3) + (d5 - d6)), c - b);
+    }
+    *mask = 7;
+    // interior: project the origin on the plane (numerically better than the barycentric sum)
+    const V3 n = cross(ab, ac);
+    const float nn = dot(n, n);
+    if (nn <= 0.f) { *mask = 3; return a; }
+    return (dot(n, a) / nn) * n;
+}
+
+// Result of one GJK query on the cores.
+//   d    : distance estimate.  If `pruned` it is a LOWER bound that already exceeds stop_above;
+//          otherwise an UPPER bound (|v| of a point of the Minkowski difference) that is either
+//          below stop_below or converged.  Overlapping cores report d = 0 and overlap = true.
+struct GjkOut {
+    float d;
+    bool overlap;
+    bool pruned;
+};
+
+template <int MAX_ITER>
+__device__ GjkOut gjk_distance(const ShapeW& A, const ShapeW& B, float stop_above, float stop_below) {
+    GjkOut out;
+    out.overlap = false;
+    out.pruned = false;
+    V3 v = A.c - B.c;
+    float vv = dot(v, v);
+    if (vv < 1e-20f) { v = mk(1.f, 0.f, 0.f); vv = 1.f; }
+    V3 s0 = mk(0, 0, 0), s1 = s0, s2 = s0;
+    int n = 0;
+    bool have_ub = false;   // v is a point of the difference only after the first support call
+    float ub = FLT_MAX;
+#pragma unroll 1
+    for (int it = 0; it < MAX_ITER; ++it) {
+        const V3 w = support(A, -v) - support(B, v);
+        const float vw = dot(v, w);
+        // separating-plane lower bound: the difference lies in the half space {x : x.v >= v.w}
+        if (vw > 0.f) {
+            const float lb = vw * rsqrtf(vv);
+            if (lb > stop_above) { out.d = lb; out.pruned = true; return out; }
+            if (have_ub && ub - lb <= 1e-6f + 1e-5f * ub) break;   // converged
+        }
+        if (have_ub && vv - vw <= 1e-7f * vv) break;               // no progress possible
+        // closest point of conv(simplex + w) to the origin
+        V3 nv;
+        if (n == 0) {
+            s0 = w; n = 1; nv = w;
+        } else if (n == 1) {
+            const V3 ab = s0 - w;              // a = w (newest), b = s0
+            const float t = -dot(w, ab);
+            const float den = dot(ab, ab);
+            if (t <= 0.f || den <= 0.f) { s0 = w; n = 1; nv = w; }
+            else if (t >= den) { nv = s0; }
+            else { nv = madd(w, t / den, ab); s1 = w; n = 2; }
+        } else if (n == 2) {
+            int m;
+            nv = closest_tri(w, s0, s1, &m);
+            // compact: bit0 = w, bit1 = s0, bit2 = s1
+            V3 q0 = s0, q1 = s1;
+            int k = 0;
+            if (m & 2) { q0 = s0; k = 1; }
+            if (m & 4) { if (k == 0) q0 = s1; else q1 = s1; ++k; }
+            if (m & 1) { if (k == 0) q0 = w; else if (k == 1) q1 = w; else s2 = w; ++k; }
+            s0 = q0; s1 = q1; n = k;
+        } else {
+            // tetrahedron (w, s0, s1, s2): test the three faces that contain the new vertex and the old face
+            const V3 a = w, b = s0, c = s1, d = s2;
+            float best = FLT_MAX;
+            int bm = 0;
+            V3 bp = mk(0, 0, 0);
+            bool outside_any = false;
+#define NBX_FACE(P0, P1, P2, OPP, B0, B1, B2)                                         \
+            {                                                                          \
+                const V3 nrm = cross(P1 - P0, P2 - P0);                                \
+                const float sp = -dot(P0, nrm);                                        \
+                const float sd = dot(OPP - P0, nrm);                                   \
+                if (sp * sd < 0.f || sd == 0.f) {                                      \
+                    outside_any = true;                                                \
+                    int m3;                                                            \
+                    const V3 cp = closest_tri(P0, P1, P2, &m3);                        \
+                    const float dd = dot(cp, cp);                                      \
+                    if (dd < best) {                                                   \
+                        best = dd; bp = cp;                                            \
+                        bm = ((m3 & 1) ? B0 : 0) | ((m3 & 2) ? B1 : 0) | ((m3 & 4) ? B2 : 0); \
+                    }                                                                  \
+                }                                                                      \
+            }
+            NBX_FACE(a, b, c, d, 1, 2, 4)
+            NBX_FACE(a, c, d, b, 1, 4, 8)
+            NBX_FACE(a, d, b, c, 1, 8, 2)
+            NBX_FACE(b, d, c, a, 2, 8, 4)
+#undef NBX_FACE
+            if (!outside_any) { out.d = 0.f; out.overlap = true; return out; }
+            nv = bp;
+            V3 q0 = s0, q1 = s1, q2 = s2;
+            int k = 0;
+            if (bm & 2) { q0 = b; k = 1; }
+            if (bm & 4) { if (k == 0) q0 = c; else q1 = c; ++k; }
+            if (bm & 8) { if (k == 0) q0 = d; else if (k == 1) q1 = d; else q2 = d; ++k; }
+            if (bm & 1) { if (k == 0) q0 = a; else if (k == 1) q1 = a; else q2 = a; ++k; }
+            s0 = q0; s1 = q1; s2 = q2; n = k;
+            if (n == 4) { out.d = 0.f; out.overlap = true; return out; }
+        }
+        const float nvv = dot(nv, nv);
+        if (have_ub && nvv >= vv) break;   // numerical stall: keep the previous (better) estimate
+        v = nv; vv = nvv; have_ub = true;
+        ub = sqrtf(vv);
+        if (vv <= 1e-14f) { out.d = 0.f; out.overlap = true; return out; }
+        if (ub < stop_below) { out.d = ub; return out; }
+    }
+    out.d = have_ub ? ub : sqrtf(vv);
+    return out;
+}
+
+}  // namespace nbxg

@@ -1,0 +1,467 @@
+"""`Arm`: the reference's batched-kinematics / collision call surface over the sm_100a kernels.
+
+Mirror of the hot-path half of reference numbotics/robots/arm.py:
+
+* `__init__` cache build (`_link_joint_sequence`)                  arm.py:17-71
+* `forward_kinematics(q, frame, use_com=False, local_pose=None)`   arm.py:369-410
+* `jacobian(q, frame, use_com, local_pose, global_pose)`           arm.py:413-461
+* `self_collision_pairs` / `collision_pairs` / add / remove        arm.py:190-366
+* `in_collision(q, threshold=0.0)`                                 arm.py:603-604
+
+Same names, argument order, defaults, shapes and error texts.  Differences, all
+deliberate and documented in DESIGN.md:
+
+* every call is batched: `in_collision` accepts `(..., dof)` and returns a bool
+  array (the reference accepts one configuration only, arm.py:555-557);
+* dtype rule "same in, same out": float64/float32 NumPy in -> same dtype NumPy out,
+  torch tensors in -> torch tensors out on the same device;
+* frames whose path ends in a movable joint get the *correct* link frame (the
+  reference drops the last joint's rotation there);
+* `global_pose=False` (the reference's default, which crashes on `.shape`) is
+  treated as `None`;
+* there is no CPU fallback: without a CUDA device every compute call raises.
+"""
+import ctypes as C
+
+import numpy as np
+import networkx as nx
+
+from ..physics import GraphChain, Constraint, PhysicsObject, Chain, Link, Shape
+from .. import _cabi
+from . import descriptor
+
+try:  # torch is plumbing (device memory, streams); the package still imports without it
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _is_torch(x):
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def _cuda_stream_ptr(device_index: int) -> int:
+    return int(torch.cuda.current_stream(device_index).cuda_stream)
+
+
+class Arm:
+
+    def __init__(self, chain: GraphChain, device: int | None = None, margin_model: str = "bullet"):
+        if not isinstance(chain, GraphChain):
+            raise ValueError("Arm needs a GraphChain (it reads the chain's tree)")
+        self._chain = chain
+        G = chain._G
+        order = list(nx.topological_sort(G))
+        root_node = order[0]
+
+        # --- the reference's per-frame cache, reproduced verbatim in structure (arm.py:23-62) ---
+        self._link_joint_sequence = {root_node: tuple()}
+        self._links_from_nodes = {root_node: G.nodes[root_node]["link"]}
+        for node in order[1:]:
+            path = nx.shortest_path(G, root_node, node)
+            fixed_run, axes, offsets, types, idxs = [], [], [], [], []
+            for (u, v) in zip(path[:-1], path[1:]):
+                joint = G.edges[(u, v)]["joint"]
+                if joint.type == Constraint.FIXED:
+                    fixed_run.append(joint)
+                    continue
+                axes.append(joint.axis)
+                types.append(joint.type.value)
+                idxs.append(chain._joint_to_index.get(joint))
+                T = np.eye(4)
+                for fj in fixed_run:
+                    T = T @ fj.offset
+                fixed_run = []
+                offsets.append(T @ joint.offset)
+            if fixed_run:
+                T = np.eye(4)
+                for fj in fixed_run:
+                    T = T @ fj.offset
+                offsets.append(T)
+            self._link_joint_sequence[node] = (
+                np.array(offsets).reshape(-1, 4, 4), np.array(axes).reshape(-1, 3),
+                np.array(types, dtype=np.int64), np.array(idxs, dtype=np.int64))
+            self._links_from_nodes[node] = G.nodes[node]["link"]
+
+        self._additional_self_collision_pairs = set()
+        self._void_self_collision_pairs = set()
+        self._additional_collision_pairs = set()
+        self._void_collision_pairs = set()
+        self._pairs_revision = 0
+        self.self_collision_pairs()
+
+        # --- device side -----------------------------------------------------------------
+        self._margin_model = margin_model
+        self._arrays = descriptor.flatten_chain(chain, margin_model)
+        self._device = device
+        self._chain_handle = None
+        self._scene_handle = None
+        self._scene_key = None
+        self._scene_arrays = None
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def base_pose(self):
+        return self._chain.base_pose
+
+    @property
+    def joint_limits(self):
+        return self._chain.joint_limits
+
+    @property
+    def dof(self):
+        return self._chain.dof
+
+    @property
+    def device_index(self) -> int:
+        if self._device is None:
+            if torch is None or not torch.cuda.is_available():
+                raise RuntimeError(
+                    "numbotics_b200 needs a CUDA device: the batched kinematics / collision path has "
+                    "no CPU fallback")
+            self._device = torch.cuda.current_device()
+        return self._device
+
+    # ------------------------------------------------------------------ handles
+    def _handle(self) -> _cabi.ChainHandle:
+        if self._chain_handle is None:
+            self._chain_handle = _cabi.ChainHandle(self._arrays, self.device_index)
+        return self._chain_handle
+
+    def _scene(self) -> _cabi.SceneHandle:
+        world = self._chain.world
+        key = (world.revision, self._pairs_revision)
+        if self._scene_handle is None or key != self._scene_key:
+            self._scene_arrays = self.scene_arrays()
+            self._scene_handle = _cabi.SceneHandle(self._handle(), self._scene_arrays)
+            self._scene_key = key
+        return self._scene_handle
+
+    def scene_arrays(self) -> dict:
+        """Current obstacles + allowed pairs as nbx_scene_desc arrays (also used by the tests)."""
+        self_pairs = self.self_collision_pairs()
+        env_pairs = [p for p in self.collision_pairs().difference(self_pairs)
+                     if isinstance(p[1], PhysicsObject)]
+        return descriptor.flatten_scene(self._arrays, self_pairs, env_pairs, self._margin_model)
+
+    # ------------------------------------------------------------------ pair bookkeeping
+    def self_collision_pairs(self):
+        """Effective rule of reference arm.py:190-223.
+
+        The reference's "at least two non-fixed joints apart" filter never runs: it asks
+        networkx for a path between `link.name` strings ("world:body:link") that are not graph
+        nodes, `NodeNotFound` is swallowed (arm.py:202-214), and what remains is: every unordered
+        pair of non-EMPTY links that are not joined by a direct edge (arm.py:216-217).
+        """
+        if not hasattr(self, "_self_collision_pairs"):
+            self._self_collision_pairs = set()
+            Gu = self._chain._G.to_undirected()
+            for link_a in self._chain._links:
+                if link_a._collision_shape.shape == Shape.EMPTY:
+                    continue
+                for link_b in self._chain._links:
+                    if link_a is link_b or link_b._collision_shape.shape == Shape.EMPTY:
+                        continue
+                    if not Gu.has_edge(link_a._name, link_b._name) and (link_b, link_a) not in self._self_collision_pairs:
+                        self._self_collision_pairs.add((link_a, link_b))
+        return self._self_collision_pairs.union(
+            self._additional_self_collision_pairs).difference(self._void_self_collision_pairs)
+
+    def collision_pairs(self):
+        """reference arm.py:226-250 (other chains in the world are not supported on this path)."""
+        pairs = set()
+        for link in self._chain._links:
+            if link._collision_shape.shape == Shape.EMPTY:
+                continue
+            for obj in self._chain.world.objects():
+                if obj is self._chain:
+                    continue
+                if isinstance(obj, PhysicsObject):
+                    if obj._collision_shape.shape == Shape.EMPTY:
+                        continue
+                    pairs.add((link, obj))
+        return pairs.union(self.self_collision_pairs()).union(
+            self._additional_collision_pairs).difference(self._void_collision_pairs)
+
+    def _resolve(self, ref):
+        if isinstance(ref, str):
+            obj = self._links_from_nodes.get(ref)
+            if obj is None:
+                obj = self._chain.world.get_object(ref)
+                if obj is None:
+                    raise ValueError(f"Object name: {ref} must be a valid object in the world")
+            return obj
+        return ref
+
+    def add_collision_pair(self, link_a, link_b):
+        """reference arm.py:253-308."""
+        link_a, link_b = self._resolve(link_a), self._resolve(link_b)
+        a_in, b_in = link_a in self._chain._links, link_b in self._chain._links
+        if not a_in and not b_in:
+            return
+        if not a_in and b_in:
+            link_a, link_b = link_b, link_a
+            a_in, b_in = b_in, a_in
+        if b_in:
+            cur = self.self_collision_pairs()
+            if (link_a, link_b) not in cur and (link_b, link_a) not in cur:
+                if (link_a, link_b) not in self._additional_self_collision_pairs and \
+                        (link_b, link_a) not in self._additional_self_collision_pairs:
+                    # the reference files this under `_additional_collision_pairs` (arm.py:290)
+                    self._additional_collision_pairs.add((link_a, link_b))
+            self._void_self_collision_pairs.discard((link_a, link_b))
+            self._void_self_collision_pairs.discard((link_b, link_a))
+        else:
+            cur = self.collision_pairs()
+            if (link_a, link_b) not in cur and (link_b, link_a) not in cur:
+                if (link_a, link_b) not in self._additional_collision_pairs and \
+                        (link_b, link_a) not in self._additional_collision_pairs:
+                    self._additional_collision_pairs.add((link_a, link_b))
+            self._void_collision_pairs.discard((link_a, link_b))
+            self._void_collision_pairs.discard((link_b, link_a))
+        self._pairs_revision += 1
+
+    def remove_collision_pair(self, link_a, link_b):
+        """reference arm.py:311-366."""
+        link_a, link_b = self._resolve(link_a), self._resolve(link_b)
+        a_in, b_in = link_a in self._chain._links, link_b in self._chain._links
+        if not a_in and not b_in:
+            return
+        if not a_in and b_in:
+            link_a, link_b = link_b, link_a
+            a_in, b_in = b_in, a_in
+        if b_in:
+            self._additional_self_collision_pairs.discard((link_a, link_b))
+            self._additional_self_collision_pairs.discard((link_b, link_a))
+            # pairs added through add_collision_pair live in the other set (see above)
+            self._additional_collision_pairs.discard((link_a, link_b))
+            self._additional_collision_pairs.discard((link_b, link_a))
+            if (link_a, link_b) not in self._void_self_collision_pairs and \
+                    (link_b, link_a) not in self._void_self_collision_pairs:
+                cur = self.self_collision_pairs()
+                if (link_a, link_b) in cur:
+                    self._void_self_collision_pairs.add((link_a, link_b))
+                elif (link_b, link_a) in cur:
+                    self._void_self_collision_pairs.add((link_b, link_a))
+        else:
+            self._additional_collision_pairs.discard((link_a, link_b))
+            self._additional_collision_pairs.discard((link_b, link_a))
+            if (link_a, link_b) not in self._void_collision_pairs and \
+                    (link_b, link_a) not in self._void_collision_pairs:
+                cur = self.collision_pairs()
+                if (link_a, link_b) in cur:
+                    self._void_collision_pairs.add((link_a, link_b))
+                elif (link_b, link_a) in cur:
+                    self._void_collision_pairs.add((link_b, link_a))
+        self._pairs_revision += 1
+
+    # ------------------------------------------------------------------ argument handling
+    def _frame_id(self, frame):
+        if self._link_joint_sequence.get(frame) is None:
+            raise ValueError(f"Frame {frame} not found in chain")
+        return self._arrays["frame_id"][frame]
+
+    def _check_q(self, q, what="q"):
+        if q.shape[-1] != self.dof:
+            raise ValueError(f"{what} must have {self.dof} elements")
+
+    @staticmethod
+    def _check_pose_arg(pose, name, q_shape):
+        """Shape rules of arm.py:384-392 / 432-447.  Returns (array-like (n,4,4) or (4,4), stride)."""
+        if tuple(pose.shape[-2:]) != (4, 4):
+            raise ValueError(f"{name} must be a 4x4 matrix")
+        if pose.ndim == 2:
+            return pose, 0
+        if tuple(pose.shape[:-2]) != tuple(q_shape[:-1]):
+            raise ValueError(f"{name} must have the same batch dimensions as q")
+        return pose.reshape(-1, 4, 4), 16
+
+    def _to_device(self, x, dtype):
+        """NumPy / torch (any device) -> contiguous torch tensor on this arm's CUDA device."""
+        dev = torch.device("cuda", self.device_index)
+        if _is_torch(x):
+            return x.to(device=dev, dtype=dtype).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(x)).to(device=dev, dtype=dtype)
+
+    def _fkjac(self, q, frame, use_com, local_pose, global_pose, want_T, want_J):
+        """Shared driver of forward_kinematics / jacobian / fk_jacobian."""
+        fid = self._frame_id(frame)
+        self._check_q(q)
+        in_torch = _is_torch(q)
+        q_shape = tuple(q.shape)
+        single = len(q_shape) == 1
+        if local_pose is not None and global_pose is not None:
+            raise ValueError("local_pose and global_pose cannot both be provided")
+        lp = gp = None
+        lps = gps = 0
+        if local_pose is not None:
+            lp, lps = self._check_pose_arg(local_pose, "local_pose", q_shape)
+        if global_pose is not None:
+            gp, gps = self._check_pose_arg(global_pose, "global_pose", q_shape)
+
+        if in_torch:
+            if q.dtype not in (torch.float32, torch.float64):
+                raise TypeError("q must be float32 or float64")
+            tdtype, out_np = q.dtype, None
+        else:
+            q = np.asarray(q)
+            if q.dtype not in (np.float32, np.float64):
+                q = q.astype(np.float64)
+            tdtype, out_np = (torch.float32 if q.dtype == np.float32 else torch.float64), q.dtype
+        f64 = tdtype == torch.float64
+        B = int(np.prod(q_shape[:-1])) if not single else 1
+        base_keep, base_ptr = _cabi.base_pose_arg(self.base_pose)
+        lib = _cabi.load()
+        h = self._handle()
+        dof = self.dof
+
+        host_path = (not in_torch or q.device.type == "cpu") and lp is None and gp is None
+        if host_path:
+            # HOST buffers straight through the C-ABI: chunked H2D / kernel / D2H pipeline in C++
+            qn = q.detach().numpy() if in_torch else q
+            qn = np.ascontiguousarray(qn.reshape(B, dof))
+            Tn = np.empty((B, 4, 4), qn.dtype) if want_T else None
+            Jn = np.empty((B, 6, dof), qn.dtype) if want_J else None
+            fn = lib.nbx_fk_jac_host_f64 if f64 else lib.nbx_fk_jac_host_f32
+            _cabi.check(fn(h.ptr, fid, qn.ctypes.data, B, base_ptr, int(bool(use_com)),
+                           Tn.ctypes.data if want_T else None, Jn.ctypes.data if want_J else None))
+            if in_torch:
+                Tn = torch.from_numpy(Tn) if want_T else None
+                Jn = torch.from_numpy(Jn) if want_J else None
+            T_out, J_out = Tn, Jn
+        else:
+            dev_index = self.device_index
+            qd = self._to_device(q, tdtype).reshape(B, dof)
+            lpd = self._to_device(lp, tdtype) if lp is not None else None
+            gpd = self._to_device(gp, tdtype) if gp is not None else None
+            with torch.cuda.device(dev_index):
+                Td = torch.empty((B, 4, 4), dtype=tdtype, device=qd.device) if want_T else None
+                Jd = torch.empty((B, 6, dof), dtype=tdtype, device=qd.device) if want_J else None
+                fn = lib.nbx_fk_jac_f64 if f64 else lib.nbx_fk_jac_f32
+                _cabi.check(fn(h.ptr, fid, qd.data_ptr(), B, base_ptr, int(bool(use_com)),
+                               lpd.data_ptr() if lpd is not None else None, lps,
+                               gpd.data_ptr() if gpd is not None else None, gps,
+                               Td.data_ptr() if want_T else None, Jd.data_ptr() if want_J else None,
+                               _cuda_stream_ptr(dev_index)))
+            if in_torch and q.device.type == "cuda":
+                T_out, J_out = Td, Jd
+            elif in_torch:
+                T_out = Td.cpu() if want_T else None
+                J_out = Jd.cpu() if want_J else None
+            else:
+                T_out = Td.cpu().numpy().astype(out_np, copy=False) if want_T else None
+                J_out = Jd.cpu().numpy().astype(out_np, copy=False) if want_J else None
+        del base_keep
+        if want_T:
+            T_out = T_out[0] if single else T_out.reshape(*q_shape[:-1], 4, 4)
+        if want_J:
+            J_out = J_out[0] if single else J_out.reshape(*q_shape[:-1], 6, dof)
+        return T_out, J_out
+
+    # ------------------------------------------------------------------ kinematics
+    def forward_kinematics(self, q, frame: str, use_com: bool = False, local_pose=None):
+        return self._fkjac(q, frame, use_com, local_pose, None, True, False)[0]
+
+    def jacobian(self, q, frame: str, use_com: bool = False, local_pose=None, global_pose=False):
+        if global_pose is False:   # the reference's default value; it cannot be used as a pose
+            global_pose = None
+        return self._fkjac(q, frame, use_com, local_pose, global_pose, False, True)[1]
+
+    def fk_jacobian(self, q, frame: str, use_com: bool = False, local_pose=None):
+        """Pose and Jacobian from ONE pass over q (what the fused kernel natively produces)."""
+        return self._fkjac(q, frame, use_com, local_pose, None, True, True)
+
+    # ------------------------------------------------------------------ collision validity
+    def in_collision(self, q, threshold: float = 0.0):
+        """`min over allowed pairs of distance < threshold` (reference arm.py:603-604), batched.
+
+        q `(dof,)` -> Python bool (reference behaviour); `(..., dof)` -> bool array / tensor.
+        """
+        verdict = self._collide(q, threshold, want_dist=False)[0]
+        if verdict.ndim == 0:
+            return bool(verdict)
+        return verdict
+
+    def min_distance(self, q, threshold: float = 0.0):
+        """Minimum distance over the allowed pairs (clamped at overlap)."""
+        return self._collide(q, threshold, want_dist=True)[1]
+
+    def _collide(self, q, threshold, want_dist):
+        self._check_q(q)
+        if threshold < 0:
+            raise NotImplementedError("negative thresholds need penetration depth (EPA), which this path does not compute")
+        in_torch = _is_torch(q)
+        q_shape = tuple(q.shape)
+        single = len(q_shape) == 1
+        B = int(np.prod(q_shape[:-1])) if not single else 1
+        scene = self._scene()
+        if self._scene_arrays["self_pairs"].shape[0] + self._scene_arrays["env_pairs"].shape[0] == 0:
+            # reference: min([]) -> ValueError (arm.py:600)
+            raise ValueError("min() arg is an empty sequence")
+        dev_index = self.device_index
+        base_keep, base_ptr = _cabi.base_pose_arg(self.base_pose)
+        qd = self._to_device(q, torch.float32).reshape(B, self.dof)
+        lib = _cabi.load()
+        with torch.cuda.device(dev_index):
+            vd = torch.empty((B,), dtype=torch.uint8, device=qd.device)
+            dd = torch.empty((B,), dtype=torch.float32, device=qd.device) if want_dist else None
+            _cabi.check(lib.nbx_in_collision_f32(
+                self._handle().ptr, scene.ptr, qd.data_ptr(), B, base_ptr, float(threshold),
+                vd.data_ptr(), dd.data_ptr() if want_dist else None, _cuda_stream_ptr(dev_index)))
+        del base_keep
+        verdict = vd.to(torch.bool)
+        if in_torch:
+            verdict = verdict.to(q.device)
+            dist = dd.to(q.device) if want_dist else None
+        else:
+            verdict = verdict.cpu().numpy()
+            dist = dd.cpu().numpy() if want_dist else None
+        shape = q_shape[:-1]
+        verdict = verdict.reshape(shape) if not single else verdict.reshape(())
+        if want_dist:
+            dist = dist.reshape(shape) if not single else dist.reshape(())
+        return verdict, dist
+
+    # ------------------------------------------------------------------ edge validation
+    def edges_valid(self, starts, goals, resolution: float, max_distance: float | None = None,
+                    threshold: float = 0.0, return_samples: bool = False):
+        """Batched DiscreteConnector verdicts for edges start[e] -> goal[e] (see planning.sampling_based).
+
+        `max_distance=None` = `connect` semantics, otherwise `steer` semantics.
+        """
+        self._check_q(starts, "start")
+        self._check_q(goals, "goal")
+        if tuple(starts.shape) != tuple(goals.shape):
+            raise ValueError("starts and goals must have the same shape")
+        if resolution <= 0:
+            raise ValueError("Resolution must be positive")
+        if threshold < 0:
+            raise NotImplementedError("negative thresholds need penetration depth (EPA), which this path does not compute")
+        in_torch = _is_torch(starts)
+        shape = tuple(starts.shape[:-1])
+        E = int(np.prod(shape)) if len(shape) else 1
+        scene = self._scene()
+        if self._scene_arrays["self_pairs"].shape[0] + self._scene_arrays["env_pairs"].shape[0] == 0:
+            raise ValueError("min() arg is an empty sequence")
+        dev_index = self.device_index
+        base_keep, base_ptr = _cabi.base_pose_arg(self.base_pose)
+        sd = self._to_device(starts, torch.float32).reshape(E, self.dof)
+        gd = self._to_device(goals, torch.float32).reshape(E, self.dof)
+        lib = _cabi.load()
+        with torch.cuda.device(dev_index):
+            vd = torch.empty((E,), dtype=torch.uint8, device=sd.device)
+            nd = torch.empty((E,), dtype=torch.int32, device=sd.device) if return_samples else None
+            _cabi.check(lib.nbx_edges_valid_f32(
+                self._handle().ptr, scene.ptr, sd.data_ptr(), gd.data_ptr(), E, base_ptr,
+                float(resolution), float(max_distance) if max_distance is not None else 0.0,
+                float(threshold), vd.data_ptr(), nd.data_ptr() if return_samples else None,
+                _cuda_stream_ptr(dev_index)))
+        del base_keep
+        valid = vd.to(torch.bool)
+        if in_torch:
+            valid = valid.to(starts.device).reshape(shape)
+            ns = nd.to(starts.device).reshape(shape) if return_samples else None
+        else:
+            valid = valid.cpu().numpy().reshape(shape)
+            ns = nd.cpu().numpy().reshape(shape) if return_samples else None
+        return (valid, ns) if return_samples else valid

@@ -1,0 +1,187 @@
+"""Flatten a GraphChain (+ world obstacles + pair sets) into the arrays of include/nbx.h.
+
+This is the B200-side form of the "GraphChain kinematics caching" that
+reference numbotics/robots/arm.py:20-62 performs in `Arm.__init__`: per frame, the
+run of FIXED joints in front of a movable joint is folded into that joint's offset
+(arm.py:36-52) and the trailing FIXED run becomes an extra last offset (arm.py:54-58).
+In a tree every movable joint has exactly one path from the root, so the folded
+offset is a property of the joint and the trailing offset a property of the frame;
+that is how the descriptor stores them (once, instead of once per frame).
+"""
+import numpy as np
+
+from ..physics import Constraint, Shape
+from .. import _cabi
+
+_BULLET_DEFAULT_MARGIN = 0.04   # CONVEX_DISTANCE_MARGIN
+_BULLET_SAFE_MARGIN_MULT = 0.1  # btConvexInternalShape::setSafeMargin
+
+
+def pose12(T):
+    return np.asarray(T, dtype=np.float64)[:3, :4].reshape(12).copy()
+
+
+def primitive_params(cshape, margin_model: str):
+    """CollisionShape -> (nbx type, dims[3], margin).
+
+    margin_model:
+      'bullet' -- rounded cores the way Bullet builds btBoxShape / btCylinderShapeZ
+                  (margin = min(0.04, 0.1 * smallest half extent), core = shape - margin);
+                  third-party behaviour restated from the Bullet sources as remembered,
+                  NOT verifiable offline: see DESIGN.md "parity unpinned".
+      'sharp'  -- exact sharp primitives (margin 0).
+    """
+    info = cshape._shape_info
+    if cshape.shape in (Shape.CUBE, Shape.CUBOID):
+        he = np.asarray(info["half_extents"], dtype=np.float64).reshape(3)
+        if np.any(he <= 0):
+            raise ValueError("box half extents must be positive")
+        m = min(_BULLET_DEFAULT_MARGIN, _BULLET_SAFE_MARGIN_MULT * float(he.min())) if margin_model == "bullet" else 0.0
+        return _cabi.NBX_PRIM_BOX, he, m
+    if cshape.shape == Shape.SPHERE:
+        r = float(info["radius"])
+        if r <= 0:
+            raise ValueError("sphere radius must be positive")
+        return _cabi.NBX_PRIM_SPHERE, np.array([r, 0.0, 0.0]), r
+    if cshape.shape == Shape.CYLINDER:
+        r, hh = float(info["radius"]), 0.5 * float(info["height"])
+        if r <= 0 or hh <= 0:
+            raise ValueError("cylinder radius and height must be positive")
+        m = min(_BULLET_DEFAULT_MARGIN, _BULLET_SAFE_MARGIN_MULT * min(r, hh)) if margin_model == "bullet" else 0.0
+        return _cabi.NBX_PRIM_CYLINDER, np.array([r, hh, 0.0]), m
+    raise NotImplementedError(
+        f"collision shape {cshape.shape.name} is outside the batched collision path "
+        "(cylinders, boxes and spheres only)")
+
+
+def flatten_chain(chain, margin_model: str = "bullet") -> dict:
+    """GraphChain -> dict of arrays matching nbx_chain_desc (plus name maps)."""
+    if margin_model not in ("bullet", "sharp"):
+        raise ValueError("margin_model must be 'bullet' or 'sharp'")
+    G = chain._G
+    order = chain._node_order
+    root = order[0]
+    frame_id = {node: i for i, node in enumerate(order)}
+    parent_of = {node: next(iter(G.predecessors(node))) for node in order[1:]}
+
+    # movable joints in the reference's q order (physics/chain.py:516-534)
+    mov_of_joint = {}
+    for joint in chain._joints:
+        if joint.type == Constraint.FIXED:
+            continue
+        if joint.type == Constraint.SPHERICAL:
+            raise NotImplementedError(
+                "SPHERICAL joints are not supported by the batched path (the reference's batched "
+                "helpers cannot evaluate them either: robots/helpers.py:101-102, 144-145)")
+        mov_of_joint[joint] = len(mov_of_joint)
+    n_mov = len(mov_of_joint)
+
+    mov_parent = np.full(n_mov, -1, np.int32)
+    mov_type = np.zeros(n_mov, np.int32)
+    mov_qidx = np.zeros(n_mov, np.int32)
+    mov_offset = np.zeros((n_mov, 12))
+    mov_axis = np.zeros((n_mov, 3))
+    frame_mov = np.full(len(order), -1, np.int32)
+    frame_tail = np.zeros((len(order), 12))
+    frame_com = np.zeros((len(order), 12))
+
+    # walk in topological order carrying (last movable joint, accumulated fixed run)
+    state = {root: (-1, np.eye(4))}
+    for node in order:
+        if node != root:
+            par = parent_of[node]
+            last, run = state[par]
+            joint = G.edges[(par, node)]["joint"]
+            if joint.type == Constraint.FIXED:
+                state[node] = (last, run @ joint.offset)
+            else:
+                m = mov_of_joint[joint]
+                mov_parent[m] = last
+                mov_type[m] = joint.type.value
+                mov_qidx[m] = chain._joint_to_index[joint]
+                mov_offset[m] = pose12(run @ joint.offset)
+                mov_axis[m] = joint.axis
+                state[node] = (m, np.eye(4))
+        last, run = state[node]
+        f = frame_id[node]
+        frame_mov[f] = last
+        frame_tail[f] = pose12(run)
+        frame_com[f] = pose12(G.nodes[node]["link"]._offset)
+
+    # the device walk needs parents before children; topological node order guarantees the same
+    # for joints only if their indices follow that order, which they do (chain._joints is in it).
+    prim_frame, prim_type, prim_dims, prim_offset, prim_margin, prim_link = [], [], [], [], [], []
+    for node in order:
+        link = G.nodes[node]["link"]
+        cs = link._collision_shape
+        if cs.shape == Shape.EMPTY:
+            continue
+        t, dims, m = primitive_params(cs, margin_model)
+        prim_frame.append(frame_id[node])
+        prim_type.append(t)
+        prim_dims.append(dims)
+        prim_offset.append(pose12(cs.offset))
+        prim_margin.append(m)
+        prim_link.append(link)
+
+    return {
+        "dof": chain.dof,
+        "mov_parent": mov_parent, "mov_type": mov_type, "mov_qidx": mov_qidx,
+        "mov_offset": mov_offset.reshape(-1), "mov_axis": mov_axis.reshape(-1),
+        "frame_mov": frame_mov, "frame_tail": frame_tail.reshape(-1), "frame_com": frame_com.reshape(-1),
+        "prim_frame": np.asarray(prim_frame, np.int32), "prim_type": np.asarray(prim_type, np.int32),
+        "prim_dims": np.asarray(prim_dims, np.float64).reshape(-1),
+        "prim_offset": np.asarray(prim_offset, np.float64).reshape(-1),
+        "prim_margin": np.asarray(prim_margin, np.float64),
+        # host-side maps (not part of the C descriptor)
+        "frame_id": frame_id,
+        "prim_of_link": {link: i for i, link in enumerate(prim_link)},
+        "margin_model": margin_model,
+    }
+
+
+def flatten_scene(chain_arrays: dict, self_pairs, env_pairs, margin_model: str = "bullet") -> dict:
+    """Pair sets of Link / PhysicsObject tuples -> arrays matching nbx_scene_desc.
+
+    self_pairs: iterable of (Link, Link); env_pairs: iterable of (Link, PhysicsObject).
+    Pairs whose link has no primitive (EMPTY shape) can never produce a proximity in
+    the reference either and are dropped.
+    """
+    prim_of_link = chain_arrays["prim_of_link"]
+    prim_type = chain_arrays["prim_type"]
+    obstacles, obs_index = [], {}
+    env_idx = []
+    for link, obj in env_pairs:
+        if link not in prim_of_link:
+            continue
+        if obj not in obs_index:
+            obs_index[obj] = len(obstacles)
+            obstacles.append(obj)
+        env_idx.append((prim_of_link[link], obs_index[obj]))
+    # deterministic order independent of set iteration order
+    env_idx = sorted(set(env_idx))
+    self_idx = sorted({tuple(sorted((prim_of_link[a], prim_of_link[b])))
+                       for a, b in self_pairs if a in prim_of_link and b in prim_of_link})
+
+    obs_type, obs_dims, obs_pose, obs_margin = [], [], [], []
+    for obj in obstacles:
+        t, dims, m = primitive_params(obj._collision_shape, margin_model)
+        obs_type.append(t)
+        obs_dims.append(dims)
+        obs_pose.append(pose12(obj.pose @ obj._collision_shape.offset))
+        obs_margin.append(m)
+    obs_type = np.asarray(obs_type, np.int32)
+    box = _cabi.NBX_PRIM_BOX
+    # Bullet dispatches box-box to btBoxBoxCollisionAlgorithm, which works on the sharp boxes
+    self_sharp = np.array([prim_type[a] == box and prim_type[b] == box for a, b in self_idx], np.uint8)
+    env_sharp = np.array([prim_type[a] == box and obs_type[o] == box for a, o in env_idx], np.uint8)
+    return {
+        "obs_type": obs_type,
+        "obs_dims": np.asarray(obs_dims, np.float64).reshape(-1),
+        "obs_pose": np.asarray(obs_pose, np.float64).reshape(-1),
+        "obs_margin": np.asarray(obs_margin, np.float64),
+        "self_pairs": np.asarray(self_idx, np.int32).reshape(-1, 2),
+        "env_pairs": np.asarray(env_idx, np.int32).reshape(-1, 2),
+        "self_sharp": self_sharp, "env_sharp": env_sharp,
+        "obstacles": obstacles,
+    }

@@ -1,0 +1,439 @@
+/*
+ * nbx_oracle.c -- float64 CPU restatement of the hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Nothing under numbotics_b200/ may import, link or execute this file; it exists so that
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs have
+ * something to compare the CUDA path with (and to time beside it).
+ *
+ * What it restates (paths relative to the reference checkout):
+ *   - forward kinematics + geometric Jacobian      numbotics/robots/helpers.py:33-187
+ *     (Rodrigues joint transform :43-55, chain product :105-108, Jacobian columns :172-185)
+ *   - Arm.in_collision verdict                      numbotics/robots/arm.py:555-604
+ *     min over allowed pairs of closest distance < threshold.  The distance itself comes from
+ *     PyBullet 3.2.7 (poetry.lock:1659) getClosestPoints -- third-party, not vendored, not
+ *     installable offline -- so it is restated from the published algorithm: GJK closest
+ *     distance between convex cores, minus the two collision margins (Bullet's
+ *     btGjkPairDetector convention).  PARITY UNPINNED against real Bullet; pinned instead
+ *     by analytic known answers and Monte-Carlo / SLSQP cross-checks in tests/.
+ *   - DiscreteConnector.connect / steer             numbotics/planning/sampling_based/connectors.py:57-100
+ *
+ * The GJK here is deliberately NOT the one in numbotics_b200/csrc/nbx_gjk.cuh: the closest
+ * point of a simplex is found by enumerating all its sub-simplices and solving the affine
+ * projection of each (Johnson's sub-algorithm in its brute-force form), in float64, run to
+ * convergence.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define PRIM_SPHERE 0
+#define PRIM_BOX 1
+#define PRIM_CYL 2
+#define JOINT_REVOLUTE 0
+#define JOINT_PRISMATIC 1
+
+typedef struct {
+    int type;
+    double c[3];
+    double R[9];    /* world rotation, row-major; column k = local axis k */
+    double d[3];    /* core dims */
+} oshape;
+
+static double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+static void support(const oshape* S, const double* dir, double* out) {
+    out[0] = S->c[0]; out[1] = S->c[1]; out[2] = S->c[2];
+    if (S->type == PRIM_SPHERE) return;
+    if (S->type == PRIM_BOX) {
+        for (int k = 0; k < 3; ++k) {
+            const double a[3] = {S->R[k], S->R[3 + k], S->R[6 + k]};
+            const double s = dot3(dir, a) >= 0.0 ? S->d[k] : -S->d[k];
+            for (int i = 0; i < 3; ++i) out[i] += s * a[i];
+        }
+        return;
+    }
+    {
+        const double u[3] = {S->R[2], S->R[5], S->R[8]};
+        const double du = dot3(dir, u);
+        double perp[3] = {dir[0] - du * u[0], dir[1] - du * u[1], dir[2] - du * u[2]};
+        const double l = sqrt(dot3(perp, perp));
+        const double s = du >= 0.0 ? S->d[1] : -S->d[1];
+        for (int i = 0; i < 3; ++i) out[i] += s * u[i];
+        if (l > 1e-300)
+            for (int i = 0; i < 3; ++i) out[i] += S->d[0] / l * perp[i];
+    }
+}
+
+/* Solve the k x k system for the affine projection of the origin on the hull of pts[idx[0..k-1]].
+ * Returns 1 and barycentric weights lam if the system is regular. */
+static int affine_project(const double pts[4][3], const int* idx, int k, double* lam) {
+    if (k == 1) { lam[0] = 1.0; return 1; }
+    /* unknowns lam_1..lam_{k-1} relative to p0:  x = p0 + sum lam_i (p_i - p0),  (p_j - p0).x = 0 */
+    double E[3][3], G[3][3], r[3];
+    const double* p0 = pts[idx[0]];
+    const int m = k - 1;
+    for (int i = 0; i < m; ++i)
+        for (int c = 0; c < 3; ++c) E[i][c] = pts[idx[i + 1]][c] - p0[c];
+    for (int i = 0; i < m; ++i) {
+        for (int j = 0; j < m; ++j) G[i][j] = dot3(E[i], E[j]);
+        r[i] = -dot3(E[i], p0);
+    }
+    /* Gaussian elimination with partial pivoting on the (<= 3x3) Gram system */
+    double scale = 0.0;
+    for (int i = 0; i < m; ++i) if (G[i][i] > scale) scale = G[i][i];
+    if (scale <= 0.0) return 0;
+    for (int c = 0; c < m; ++c) {
+        int piv = c;
+        for (int i = c + 1; i < m; ++i) if (fabs(G[i][c]) > fabs(G[piv][c])) piv = i;
+        if (fabs(G[piv][c]) <= 1e-14 * scale) return 0;
+        if (piv != c) {
+            for (int j = 0; j < m; ++j) { double t = G[c][j]; G[c][j] = G[piv][j]; G[piv][j] = t; }
+            double t = r[c]; r[c] = r[piv]; r[piv] = t;
+        }
+        for (int i = c + 1; i < m; ++i) {
+            const double f = G[i][c] / G[c][c];
+            for (int j = c; j < m; ++j) G[i][j] -= f * G[c][j];
+            r[i] -= f * r[c];
+        }
+    }
+    double x[3];
+    for (int i = m - 1; i >= 0; --i) {
+        double s = r[i];
+        for (int j = i + 1; j < m; ++j) s -= G[i][j] * x[j];
+        x[i] = s / G[i][i];
+    }
+    double sum = 0.0;
+    for (int i = 0; i < m; ++i) { lam[i + 1] = x[i]; sum += x[i]; }
+    lam[0] = 1.0 - sum;
+    return 1;
+}
+
+/* closest point of conv(pts[0..n-1]) to the origin by sub-simplex enumeration; shrinks the simplex. */
+static void simplex_closest(double pts[4][3], int* n, double* v) {
+    double best = INFINITY;
+    int best_mask = 1;
+    double best_lam[4] = {1, 0, 0, 0};
+    for (int mask = 1; mask < (1 << *n); ++mask) {
+        int idx[4], k = 0;
+        for (int i = 0; i < *n; ++i) if (mask & (1 << i)) idx[k++] = i;
+        double lam[4];
+        if (!affine_project(pts, idx, k, lam)) continue;
+        int ok = 1;
+        for (int i = 0; i < k; ++i) if (lam[i] < -1e-12) { ok = 0; break; }
+        if (!ok) continue;
+        double x[3] = {0, 0, 0};
+        for (int i = 0; i < k; ++i)
+            for (int c = 0; c < 3; ++c) x[c] += lam[i] * pts[idx[i]][c];
+        const double dd = dot3(x, x);
+        if (dd < best) {
+            best = dd; best_mask = mask;
+            for (int i = 0; i < 4; ++i) best_lam[i] = 0.0;
+            for (int i = 0; i < k; ++i) best_lam[idx[i]] = lam[i];
+        }
+    }
+    double np[4][3];
+    int m = 0;
+    v[0] = v[1] = v[2] = 0.0;
+    for (int i = 0; i < *n; ++i) {
+        if (!(best_mask & (1 << i))) continue;
+        for (int c = 0; c < 3; ++c) { v[c] += best_lam[i] * pts[i][c]; np[m][c] = pts[i][c]; }
+        ++m;
+    }
+    for (int i = 0; i < m; ++i) for (int c = 0; c < 3; ++c) pts[i][c] = np[i][c];
+    *n = m;
+}
+
+/* GJK distance between two convex cores, run to convergence.  *overlap = 1 when they intersect. */
+static double core_distance(const oshape* A, const oshape* B, int* overlap) {
+    double v[3] = {A->c[0] - B->c[0], A->c[1] - B->c[1], A->c[2] - B->c[2]};
+    double pts[4][3];
+    int n = 0;
+    *overlap = 0;
+    if (dot3(v, v) < 1e-30) { v[0] = 1.0; v[1] = v[2] = 0.0; }
+    double vv = dot3(v, v);
+    int have = 0;
+    for (int it = 0; it < 500; ++it) {
+        double nd[3] = {-v[0], -v[1], -v[2]}, sa[3], sb[3], w[3];
+        support(A, nd, sa);
+        support(B, v, sb);
+        for (int c = 0; c < 3; ++c) w[c] = sa[c] - sb[c];
+        const double vw = dot3(v, w);
+        if (have && vv - vw <= 1e-14 * vv + 1e-300) break;      /* |v|^2 - v.w is the duality gap */
+        int dup = 0;
+        for (int i = 0; i < n; ++i) {
+            double e[3] = {pts[i][0] - w[0], pts[i][1] - w[1], pts[i][2] - w[2]};
+            if (dot3(e, e) <= 1e-28) dup = 1;
+        }
+        if (dup) break;
+        for (int c = 0; c < 3; ++c) pts[n][c] = w[c];
+        ++n;
+        double nv[3];
+        simplex_closest(pts, &n, nv);
+        const double nvv = dot3(nv, nv);
+        if (n == 4 || nvv <= 1e-24) { *overlap = 1; return 0.0; }
+        if (have && nvv >= vv) break;
+        v[0] = nv[0]; v[1] = nv[1]; v[2] = nv[2];
+        vv = nvv; have = 1;
+    }
+    return sqrt(vv);
+}
+
+static void make_shape(oshape* S, int type, const double* pose12, const double* dims_full, double margin, int sharp) {
+    S->type = type;
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) S->R[r * 3 + c] = pose12[r * 4 + c];
+        S->c[r] = pose12[r * 4 + 3];
+    }
+    const double m = (sharp || type == PRIM_SPHERE) ? 0.0 : margin;
+    if (type == PRIM_SPHERE) { S->d[0] = S->d[1] = S->d[2] = 0.0; }
+    else if (type == PRIM_BOX) { for (int k = 0; k < 3; ++k) S->d[k] = dims_full[k] - m; }
+    else { S->d[0] = dims_full[0] - m; S->d[1] = dims_full[1] - m; S->d[2] = 0.0; }
+}
+
+/* distance of one pair under the rounded-core model; sharp => margins ignored except for spheres */
+static double pair_distance(int ta, const double* pa, const double* da, double ma, int tb, const double* pb,
+                            const double* db, double mb, int sharp) {
+    oshape A, B;
+    make_shape(&A, ta, pa, da, ma, sharp);
+    make_shape(&B, tb, pb, db, mb, sharp);
+    const double mA = ta == PRIM_SPHERE ? da[0] : (sharp ? 0.0 : ma);
+    const double mB = tb == PRIM_SPHERE ? db[0] : (sharp ? 0.0 : mb);
+    int ov;
+    const double d = core_distance(&A, &B, &ov);
+    if (ov) return -(mA + mB) - 1e-9;
+    return d - mA - mB;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * exported: pair distances for given world poses (the checker path: FK comes from the NumPy
+ * oracle, only the narrow phase runs here)
+ *   poses  (n, n_link, 12) link-primitive world poses per configuration
+ *   sposes (n_static, 12)  obstacle poses; shape index space = [0,n_link) U [n_link, n_link+n_static)
+ *   out    (n, n_pairs)
+ * ------------------------------------------------------------------------------------------ */
+int oracle_pair_distances(int64_t n, int n_link, const double* poses, int n_static, const double* sposes,
+                          const int32_t* types, const double* dims, const double* margins, int n_pairs,
+                          const int32_t* pairs, const uint8_t* sharp, double* out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        for (int p = 0; p < n_pairs; ++p) {
+            const int a = pairs[2 * p], b = pairs[2 * p + 1];
+            const double* pa = a < n_link ? poses + ((size_t)i * n_link + a) * 12 : sposes + (size_t)(a - n_link) * 12;
+            const double* pb = b < n_link ? poses + ((size_t)i * n_link + b) * 12 : sposes + (size_t)(b - n_link) * 12;
+            out[(size_t)i * n_pairs + p] = pair_distance(types[a], pa, dims + 3 * a, margins[a], types[b], pb,
+                                                         dims + 3 * b, margins[b], sharp ? sharp[p] : 0);
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * full pipeline on the flattened descriptor (same arrays as include/nbx.h); used for the CPU
+ * baseline timing and cross-checked against the checker path in tests/.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int dof, n_mov, n_frames, n_prims;
+    const int32_t *mov_parent, *mov_type, *mov_qidx;
+    const double *mov_offset, *mov_axis;
+    const int32_t* frame_mov;
+    const double *frame_tail, *frame_com;
+    const int32_t *prim_frame, *prim_type;
+    const double *prim_dims, *prim_offset, *prim_margin;
+} ochain;
+
+typedef struct {
+    int n_obs;
+    const int32_t* obs_type;
+    const double *obs_dims, *obs_pose, *obs_margin;
+    int n_self;
+    const int32_t* self_pairs;
+    int n_env;
+    const int32_t* env_pairs;
+    const uint8_t *self_sharp, *env_sharp;
+} oscene;
+
+static void mul12(const double* a, const double* b, double* o) {
+    double r[12];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) r[i * 4 + j] = a[i * 4] * b[j] + a[i * 4 + 1] * b[4 + j] + a[i * 4 + 2] * b[8 + j];
+        r[i * 4 + 3] = a[i * 4] * b[3] + a[i * 4 + 1] * b[7] + a[i * 4 + 2] * b[11] + a[i * 4 + 3];
+    }
+    memcpy(o, r, sizeof(r));
+}
+
+/* X(q) of one joint: helpers.py:43-55 (revolute), intended form of :57-65 (prismatic) */
+static void joint_x(const double* off, const double* a, int type, double q, double* X) {
+    if (type == JOINT_REVOLUTE) {
+        const double s = sin(q), c = cos(q);
+        double M[9];
+        const double K[9] = {a[0] * a[0], a[0] * a[1], a[0] * a[2], a[1] * a[0], a[1] * a[1], a[1] * a[2], a[2] * a[0], a[2] * a[1], a[2] * a[2]};
+        const double S[9] = {0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0};
+        for (int i = 0; i < 9; ++i) M[i] = K[i] - c * (K[i] - ((i % 4) == 0 ? 1.0 : 0.0)) + s * S[i];
+        for (int r = 0; r < 3; ++r) {
+            for (int cc = 0; cc < 3; ++cc) X[r * 4 + cc] = off[r * 4] * M[cc] + off[r * 4 + 1] * M[3 + cc] + off[r * 4 + 2] * M[6 + cc];
+            X[r * 4 + 3] = off[r * 4 + 3];
+        }
+    } else {
+        for (int r = 0; r < 3; ++r) {
+            for (int cc = 0; cc < 3; ++cc) X[r * 4 + cc] = off[r * 4 + cc];
+            X[r * 4 + 3] = off[r * 4 + 3] + q * (off[r * 4] * a[0] + off[r * 4 + 1] * a[1] + off[r * 4 + 2] * a[2]);
+        }
+    }
+}
+
+/* FK + Jacobian of one frame, float64.  T_out (n,4,4), J_out (n,6,dof), both nullable. */
+int oracle_fk_jac(const ochain* ch, int frame, const double* q, int64_t n, const double* base16, int use_com,
+                  double* T_out, double* J_out) {
+    int path[256], np = 0;
+    for (int j = ch->frame_mov[frame]; j >= 0; j = ch->mov_parent[j]) path[np++] = j;
+    const int dof = ch->dof;
+#pragma omp parallel for schedule(static)
+    for (int64_t b = 0; b < n; ++b) {
+        double T[12], X[12], frames[256][12];
+        memcpy(T, base16, sizeof(T));
+        for (int i = np - 1; i >= 0; --i) {
+            const int j = path[i];
+            joint_x(ch->mov_offset + 12 * j, ch->mov_axis + 3 * j, ch->mov_type[j], q[b * dof + ch->mov_qidx[j]], X);
+            mul12(T, X, T);
+            memcpy(frames[i], T, sizeof(T));
+        }
+        mul12(T, ch->frame_tail + 12 * frame, T);
+        if (use_com) mul12(T, ch->frame_com + 12 * frame, T);
+        if (T_out) {
+            double* o = T_out + b * 16;
+            memcpy(o, T, sizeof(T));
+            o[12] = o[13] = o[14] = 0.0; o[15] = 1.0;
+        }
+        if (J_out) {
+            double* J = J_out + b * 6 * dof;
+            memset(J, 0, sizeof(double) * 6 * dof);
+            for (int i = np - 1; i >= 0; --i) {
+                const int j = path[i];
+                const double* F = frames[i];
+                const double* a = ch->mov_axis + 3 * j;
+                const double w[3] = {F[0] * a[0] + F[1] * a[1] + F[2] * a[2], F[4] * a[0] + F[5] * a[1] + F[6] * a[2],
+                                     F[8] * a[0] + F[9] * a[1] + F[10] * a[2]};
+                const int col = ch->mov_qidx[j];
+                if (ch->mov_type[j] == JOINT_REVOLUTE) {
+                    const double r[3] = {T[3] - F[3], T[7] - F[7], T[11] - F[11]};
+                    J[0 * dof + col] = w[1] * r[2] - w[2] * r[1];
+                    J[1 * dof + col] = w[2] * r[0] - w[0] * r[2];
+                    J[2 * dof + col] = w[0] * r[1] - w[1] * r[0];
+                    J[3 * dof + col] = w[0]; J[4 * dof + col] = w[1]; J[5 * dof + col] = w[2];
+                } else {
+                    J[0 * dof + col] = w[0]; J[1 * dof + col] = w[1]; J[2 * dof + col] = w[2];
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+/* world poses of every link primitive for one configuration */
+static void prim_poses(const ochain* ch, const double* q, const double* base16, double* out /* n_prims x 12 */) {
+    double jf[256][12];
+    for (int j = 0; j < ch->n_mov; ++j) {
+        double X[12];
+        joint_x(ch->mov_offset + 12 * j, ch->mov_axis + 3 * j, ch->mov_type[j], q[ch->mov_qidx[j]], X);
+        mul12(ch->mov_parent[j] < 0 ? base16 : jf[ch->mov_parent[j]], X, jf[j]);
+    }
+    for (int p = 0; p < ch->n_prims; ++p) {
+        const int f = ch->prim_frame[p];
+        const int j = ch->frame_mov[f];
+        double L[12];
+        mul12(j < 0 ? base16 : jf[j], ch->frame_tail + 12 * f, L);
+        mul12(L, ch->prim_offset + 12 * p, out + 12 * p);
+    }
+}
+
+static double config_min_distance(const ochain* ch, const oscene* sc, const double* q, const double* base16, double stop_below) {
+    double P[64 * 12];
+    prim_poses(ch, q, base16, P);
+    double best = INFINITY;
+    for (int e = 0; e < sc->n_env; ++e) {
+        const int a = sc->env_pairs[2 * e], o = sc->env_pairs[2 * e + 1];
+        const double d = pair_distance(ch->prim_type[a], P + 12 * a, ch->prim_dims + 3 * a, ch->prim_margin[a], sc->obs_type[o],
+                                       sc->obs_pose + 12 * o, sc->obs_dims + 3 * o, sc->obs_margin[o], sc->env_sharp ? sc->env_sharp[e] : 0);
+        if (d < best) best = d;
+        if (best < stop_below) return best;
+    }
+    for (int e = 0; e < sc->n_self; ++e) {
+        const int a = sc->self_pairs[2 * e], b = sc->self_pairs[2 * e + 1];
+        const double d = pair_distance(ch->prim_type[a], P + 12 * a, ch->prim_dims + 3 * a, ch->prim_margin[a], ch->prim_type[b],
+                                       P + 12 * b, ch->prim_dims + 3 * b, ch->prim_margin[b], sc->self_sharp ? sc->self_sharp[e] : 0);
+        if (d < best) best = d;
+        if (best < stop_below) return best;
+    }
+    return best;
+}
+
+/* verdict[b] = min distance < threshold; min_dist nullable (then early exit on the first hit) */
+int oracle_in_collision(const ochain* ch, const oscene* sc, const double* q, int64_t n, const double* base16,
+                        double threshold, uint8_t* verdict, double* min_dist) {
+    if (ch->n_prims > 64 || ch->n_mov > 256) return -1;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t b = 0; b < n; ++b) {
+        const double d = config_min_distance(ch, sc, q + b * ch->dof, base16, min_dist ? -INFINITY : threshold);
+        verdict[b] = d < threshold;
+        if (min_dist) min_dist[b] = d;
+    }
+    return 0;
+}
+
+/* connectors.py:57-100.  valid[e] = 1 iff the reference would return a state.  n_samples / n_useful nullable:
+ * samples of the edge, and samples the sequential reference evaluates (up to and including the first invalid). */
+int oracle_edges_valid(const ochain* ch, const oscene* sc, const double* starts, const double* goals, int64_t E,
+                       const double* base16, double resolution, double max_distance, double threshold, uint8_t* valid,
+                       int32_t* n_samples, int32_t* n_useful) {
+    if (ch->n_prims > 64 || ch->n_mov > 256 || ch->dof > 256) return -1;
+    const int dof = ch->dof;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t e = 0; e < E; ++e) {
+        const double* s = starts + e * dof;
+        const double* g = goals + e * dof;
+        double ss = 0.0;
+        for (int k = 0; k < dof; ++k) ss += (s[k] - g[k]) * (s[k] - g[k]);
+        const double dist = sqrt(ss);
+        int ok = 1, cnt = 0, used = 0;
+        if (dist <= 1.1920928955078125e-07) {
+            ok = 0;
+        } else {
+            const double step = resolution / dist;
+            double tf = 1.0;
+            if (max_distance > 0.0 && dist > max_distance) tf = max_distance / dist;
+            const int len = (int)ceil(tf / step);   /* numpy.arange length rule */
+            cnt = len + 1;
+            double qv[256];
+            for (int k = 0; k <= len && ok; ++k) {
+                const double t = k == len ? tf : k * step;
+                for (int c = 0; c < dof; ++c) qv[c] = (1.0 - t) * s[c] + t * g[c];
+                ++used;
+                if (config_min_distance(ch, sc, qv, base16, threshold) < threshold) ok = 0;
+            }
+        }
+        valid[e] = (uint8_t)ok;
+        if (n_samples) n_samples[e] = cnt;
+        if (n_useful) n_useful[e] = used;
+    }
+    return 0;
+}
+
+int oracle_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

@@ -1,0 +1,142 @@
+"""CUDA FK / Jacobian vs the reference's golden vectors and the float64 oracle (through the C-ABI)."""
+import numpy as np
+import pytest
+
+from numbotics_b200 import workloads
+from oracle import fkjac
+
+pytestmark = pytest.mark.gpu
+
+RTOL32 = 1e-5   # north star: 1e-5 relative (fp32), relative to max(|x|, 1) per matrix
+RTOL64 = 1e-12
+
+
+def rel_err(a, b):
+    """max over the batch of ||a-b||_max / max(||b||_max, 1) per matrix."""
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    num = np.abs(a - b).reshape(a.shape[0], -1).max(axis=1)
+    den = np.maximum(np.abs(b).reshape(b.shape[0], -1).max(axis=1), 1.0)
+    return float((num / den).max())
+
+
+@pytest.fixture(scope="module")
+def kinova(cuda):
+    return workloads.kinova_arm(device=0)
+
+
+@pytest.mark.parametrize("frame", ["tool_frame", "end_effector_link", "camera", "gripper"])
+@pytest.mark.parametrize("dtype,tol", [(np.float32, RTOL32), (np.float64, RTOL64)])
+def test_golden_numpy_path(kinova, golden_kinova, frame, dtype, tol):
+    g = golden_kinova
+    q = g["q"].astype(dtype)
+    T = kinova.forward_kinematics(q, frame)
+    J = kinova.jacobian(q, frame)
+    assert T.dtype == dtype and J.dtype == dtype
+    assert T.shape == (q.shape[0], 4, 4) and J.shape == (q.shape[0], 6, 7)
+    assert rel_err(T, g[f"{frame}/T"]) <= tol
+    assert rel_err(J, g[f"{frame}/J"]) <= tol
+    Tc = kinova.forward_kinematics(q, frame, use_com=True)
+    Jc = kinova.jacobian(q, frame, use_com=True)
+    assert rel_err(Tc, g[f"{frame}/T_com"]) <= tol
+    assert rel_err(Jc, g[f"{frame}/J_com"]) <= tol
+
+
+@pytest.mark.parametrize("tdtype,tol", [("float32", RTOL32), ("float64", RTOL64)])
+def test_golden_torch_cuda_path(kinova, golden_kinova, cuda, tdtype, tol):
+    import torch
+    g = golden_kinova
+    dt = getattr(torch, tdtype)
+    q = torch.as_tensor(g["q"], dtype=dt, device=cuda)
+    T, J = kinova.fk_jacobian(q, "tool_frame")
+    assert T.is_cuda and J.is_cuda and T.dtype == dt
+    assert rel_err(T.cpu().numpy(), g["tool_frame/T"]) <= tol
+    assert rel_err(J.cpu().numpy(), g["tool_frame/J"]) <= tol
+    lp = torch.as_tensor(g["local_pose"], dtype=dt, device=cuda)
+    gp = torch.as_tensor(g["global_pose"], dtype=dt, device=cuda)
+    assert rel_err(kinova.forward_kinematics(q, "tool_frame", local_pose=lp).cpu().numpy(), g["tool_frame/T_lp"]) <= tol
+    assert rel_err(kinova.jacobian(q, "tool_frame", local_pose=lp).cpu().numpy(), g["tool_frame/J_lp"]) <= tol
+    assert rel_err(kinova.jacobian(q, "tool_frame", global_pose=gp).cpu().numpy(), g["tool_frame/J_gp"]) <= tol
+    assert rel_err(kinova.forward_kinematics(q, "tool_frame", local_pose=lp[0]).cpu().numpy(), g["tool_frame/T_lp1"]) <= tol
+
+
+def test_shapes_and_batch_dims(kinova, golden_kinova):
+    g = golden_kinova
+    q = g["q"][:24]
+    T1 = kinova.forward_kinematics(q[0], "tool_frame")
+    J1 = kinova.jacobian(q[0], "tool_frame")
+    assert T1.shape == (4, 4) and J1.shape == (6, 7)
+    assert rel_err(T1[None], g["tool_frame/T"][:1]) <= RTOL64
+    q3 = q.reshape(2, 3, 4, 7)
+    T3 = kinova.forward_kinematics(q3, "tool_frame")
+    J3 = kinova.jacobian(q3, "tool_frame")
+    assert T3.shape == (2, 3, 4, 4, 4) and J3.shape == (2, 3, 4, 6, 7)
+    assert rel_err(T3.reshape(-1, 4, 4), g["tool_frame/T"][:24]) <= RTOL64
+    assert rel_err(J3.reshape(-1, 6, 7), g["tool_frame/J"][:24]) <= RTOL64
+    # bottom row is exactly [0 0 0 1]
+    assert np.array_equal(T3[..., 3, :], np.broadcast_to([0.0, 0.0, 0.0, 1.0], T3[..., 3, :].shape))
+
+
+def test_errors_match_reference(kinova):
+    q = np.zeros((3, 7))
+    with pytest.raises(ValueError, match="Frame nope not found in chain"):
+        kinova.forward_kinematics(q, "nope")
+    with pytest.raises(ValueError, match="q must have 7 elements"):
+        kinova.forward_kinematics(np.zeros((3, 6)), "tool_frame")
+    with pytest.raises(ValueError, match="local_pose must be a 4x4 matrix"):
+        kinova.forward_kinematics(q, "tool_frame", local_pose=np.zeros((3, 3)))
+    with pytest.raises(ValueError, match="local_pose must have the same batch dimensions as q"):
+        kinova.forward_kinematics(q, "tool_frame", local_pose=np.zeros((2, 4, 4)))
+    with pytest.raises(ValueError, match="local_pose and global_pose cannot both be provided"):
+        kinova.jacobian(q, "tool_frame", local_pose=np.eye(4), global_pose=np.eye(4))
+    with pytest.raises(ValueError, match="global_pose must be a 4x4 matrix"):
+        kinova.jacobian(q, "tool_frame", global_pose=np.zeros((3, 3)))
+
+
+def test_every_frame_against_oracle(kinova):
+    """All 16 link frames (dense and sparse paths, frames ending in a movable joint included) vs the
+    float64 oracle in its geometrically-correct mode."""
+    q = workloads.random_configs_np(kinova, 1000 + 37, seed=3)   # ragged last tile
+    com = {n: l._offset for n, l in kinova._links_from_nodes.items()}
+    ora = fkjac.ArmOracle(kinova._link_joint_sequence, 7, kinova.base_pose, com)
+    for frame in kinova._link_joint_sequence:
+        To, Jo = ora.forward_kinematics(q, frame), ora.jacobian(q, frame)
+        T64, J64 = kinova.fk_jacobian(q, frame)
+        assert rel_err(T64, To) <= RTOL64, frame
+        assert rel_err(J64, Jo) <= RTOL64, frame
+        T32, J32 = kinova.fk_jacobian(q.astype(np.float32), frame)
+        assert rel_err(T32, To) <= RTOL32, frame
+        assert rel_err(J32, Jo) <= RTOL32, frame
+
+
+def test_serial30_golden(cuda, golden_serial30):
+    g = golden_serial30
+    arm = workloads.serial_arm(30, device=0)
+    for dtype, tol in ((np.float64, RTOL64), (np.float32, 3e-5)):
+        # 30 chained fp32 rotations: the stated tolerance for the deep chain is 3e-5
+        T, J = arm.fk_jacobian(g["q"].astype(dtype), "tool")
+        assert rel_err(T, g["tool/T"]) <= tol
+        assert rel_err(J, g["tool/J"]) <= tol
+
+
+def test_large_batch_properties(kinova, cuda):
+    """BASELINE-size style checks that do not need the oracle at full size: rigid-body invariants and
+    agreement between the one-pass fused call and the two separate calls."""
+    import torch
+    q = workloads.random_configs_cuda(kinova, 1 << 20, seed=5)
+    T, J = kinova.fk_jacobian(q, "tool_frame")
+    R = T[:, :3, :3]
+    eye = torch.eye(3, device=cuda).expand_as(R)
+    assert float((R @ R.transpose(1, 2) - eye).abs().max()) < 2e-5
+    assert float((torch.linalg.det(R) - 1).abs().max()) < 2e-5
+    T2 = kinova.forward_kinematics(q, "tool_frame")
+    J2 = kinova.jacobian(q, "tool_frame")
+    assert torch.equal(T, T2) and torch.equal(J, J2)
+    # angular rows of a revolute column are unit vectors
+    assert float((J[:, 3:, :].norm(dim=1) - 1).abs().max()) < 2e-5
+    # spot check 4096 rows against the oracle
+    idx = torch.randint(0, q.shape[0], (4096,), device=cuda)
+    com = {n: l._offset for n, l in kinova._links_from_nodes.items()}
+    ora = fkjac.ArmOracle(kinova._link_joint_sequence, 7, kinova.base_pose, com)
+    qs = q[idx].double().cpu().numpy()
+    assert rel_err(T[idx].cpu().numpy(), ora.forward_kinematics(qs, "tool_frame")) <= RTOL32
+    assert rel_err(J[idx].cpu().numpy(), ora.jacobian(qs, "tool_frame")) <= RTOL32
