@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the batched FK + Jacobian hot path (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the fused FK+Jacobian kernel over one batch of 2^24 uniformly sampled
+fp32 Kinova-7 configurations per GPU (T (B,4,4) and J (B,6,7) both written).  Weak scaling: every
+rank owns its own 2^24 configurations (seed 0 + rank), no data-path collective.  Rank 0 prints ONE
+JSON line; see README / DESIGN.md section 7 for every key.
+
+`--impl reference` times the reference's algorithm on the host cores instead: the float64 C/OpenMP
+restatement under oracle/ (the reference itself is Python + numba + PyBullet and cannot travel to the
+GPU box), same metric and workload, each step a bounded sample.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CONFIGS_PER_GPU = 1 << 24          # BASELINE configs[1]: 16M configurations on one B200
+DOF = 7
+BYTES_PER_CFG = 4 * DOF + 64 + 24 * DOF     # q in + T out + J out, fp32 = 260
+FLOPS_PER_CFG = 7 * 137 + 72                # SURVEY.md section 8d accounting = 1031
+METRIC = "fk_jacobian_configs_per_sec"
+UNIT = "configs/s"
+WORKLOAD = "kinova7_fk_jacobian_2^24_fp32_per_gpu (BASELINE configs[1])"
+HBM_FALLBACK_GBS = 6650.0                   # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
+def recorded_traffic():
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return json.load(f).get("fkjac_dense_f32_7dof_2^24_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons DURING the timed region (NVML in a thread; the timed
+    region of a short run is only milliseconds long, too short for an nvidia-smi -lms loop)."""
+
+    REASONS = {
+        0x0000000000000002: "applications_clocks_setting", 0x0000000000000004: "sw_power_cap",
+        0x0000000000000008: "hw_slowdown", 0x0000000000000020: "sw_thermal_slowdown",
+        0x0000000000000040: "hw_thermal_slowdown", 0x0000000000000080: "hw_power_brake_slowdown",
+        0x0000000000000010: "sync_boost", 0x0000000000000100: "display_clock_setting",
+    }
+
+    def __init__(self, index: int):
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._h = None
+        try:
+            import pynvml
+            self._nv = pynvml
+            pynvml.nvmlInit()
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._h = None
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                break
+            time.sleep(0.001)
+
+    def start(self):
+        if self._h is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(2.0)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# -------------------------------------------------------------------------------------------------
+def cpu_port_rate(arm, n_cfg: int, threads: int | None = None, repeats: int = 1):
+    """configs/s of the float64 C/OpenMP restatement (FK + Jacobian, tool_frame) on `n_cfg` configs."""
+    import numpy as np
+    from numbotics_b200 import workloads
+    from oracle import collision
+    if threads:
+        collision.set_threads(threads)
+    desc = collision.CDesc(arm._arrays)
+    fid = arm._arrays["frame_id"]["tool_frame"]
+    q = workloads.random_configs_np(arm, n_cfg, seed=0)
+    best = float("inf")
+    out = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        out = collision.c_fk_jac(desc, fid, q, arm.base_pose)
+        best = min(best, time.perf_counter() - t0)
+    return n_cfg / best, collision.num_threads(), q, out
+
+
+def run_reference(args, rank):
+    """`--impl reference`: the CPU restatement of the reference's algorithm, all host threads."""
+    if rank != 0:
+        return
+    from numbotics_b200 import workloads
+    arm = workloads.kinova_arm(device=0)       # no device call is made on this arm
+    sample = 1 << 20
+    for _ in range(max(args.warmup, 1)):
+        cpu_port_rate(arm, sample)
+    t0 = time.perf_counter()
+    cores = 1
+    for _ in range(args.steps):
+        _, cores, _, _ = cpu_port_rate(arm, sample)
+    dt = time.perf_counter() - t0
+    value = args.steps * sample / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample_configs_per_step": sample, "frame": "tool_frame"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} uniformly sampled Kinova-7 configurations per step, float64 C/OpenMP restatement "
+                                   "of numbotics/robots/helpers.py:91-187 (the reference's numba kernels cannot travel to the GPU box)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# -------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="nbx", choices=["nbx", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary collision / edge / 30-DoF measurements")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from numbotics_b200 import _cabi, workloads
+    from numbotics_b200.dist import init_from_env, max_over_ranks
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: numbotics_b200 has no CPU path")
+    lib = _cabi.load()
+    if world > 1:
+        init_from_env("nccl")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    arm, cubes = workloads.prm_scene(device=local_rank)
+    B = CONFIGS_PER_GPU
+    q = workloads.random_configs_cuda(arm, B, seed=rank)
+    T = torch.empty((B, 4, 4), dtype=torch.float32, device=dev)
+    J = torch.empty((B, 6, DOF), dtype=torch.float32, device=dev)
+    h = arm._handle()
+    fid = arm._arrays["frame_id"]["tool_frame"]
+    base_keep, base_ptr = _cabi.base_pose_arg(arm.base_pose)
+    stream = torch.cuda.current_stream(dev)
+
+    def step():
+        _cabi.check(lib.nbx_fk_jac_f32(h.ptr, fid, q.data_ptr(), B, base_ptr, 0, None, 0, None, 0,
+                                       T.data_ptr(), J.data_ptr(), stream.cuda_stream))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    launches0 = _cabi.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    clocks.start()
+    barrier()
+    ev[0].record(stream)
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record(stream)
+    barrier()
+    clock_info = clocks.stop()
+    gpu_launches = _cabi.launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_step = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps))
+    total_ms_max = max_over_ranks(total_ms, dev)
+    ms_per_step = total_ms_max / args.steps
+    value = world * B * args.steps / (total_ms_max * 1e-3)
+
+    # ---- end to end: HOST (pinned) buffers through the C-ABI, copies inside the timed region ---------
+    e2e_steps = min(args.steps, 8)
+    qh = torch.empty((B, DOF), dtype=torch.float32).pin_memory()
+    qh.copy_(q)
+    Th = torch.empty((B, 4, 4), dtype=torch.float32).pin_memory()
+    Jh = torch.empty((B, 6, DOF), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        _cabi.check(lib.nbx_fk_jac_host_f32(h.ptr, fid, qh.data_ptr(), B, base_ptr, 0, Th.data_ptr(), Jh.data_ptr()))
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
+    e2e_value = world * B * e2e_steps / e2e_s
+    e2e_ok = bool(torch.equal(Th[:4096], T[:4096].cpu()) and torch.equal(Jh[-4096:], J[-4096:].cpu()))
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant (only) kernel ---------------------------------------------------------
+    peak, peak_src = measured_hbm_peak()
+    avg_launch_ms = total_ms / args.steps
+    achieved = BYTES_PER_CFG * B / (avg_launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": recorded_traffic(), "kernel": "fkjac_dense_kernel<float,7,128>",
+                "algorithmic_bytes_per_launch": BYTES_PER_CFG * B, "avg_launch_ms": avg_launch_ms,
+                "best_launch_ms": per_step[0], "median_launch_ms": per_step[len(per_step) // 2],
+                "peak_source": peak_src, "fp32_tflops": FLOPS_PER_CFG * B / (avg_launch_ms * 1e-3) / 1e12}
+
+    # ---- CPU baseline (oracle port) + parity gate, rank 0, N = 1 only ------------------------------------------
+    cpu_baseline = None
+    parity = None
+    if world == 1:
+        rate0, cores, _, _ = cpu_port_rate(arm, 1 << 17)
+        sample = int(min(1 << 24, max(1 << 18, 2 ** int(np.log2(max(rate0 * 10.0, 1.0))))))   # about 10 s of CPU work
+        rate, cores, qs, (To, Jo) = cpu_port_rate(arm, sample)
+        rate1, _, _, _ = cpu_port_rate(arm, 1 << 17, threads=1)
+        from oracle import collision as _oc
+        _oc.set_threads(os.cpu_count() or 1)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{sample} uniformly sampled Kinova-7 configurations (seed 0), float64 C/OpenMP restatement of "
+                                  "numbotics/robots/helpers.py:91-187, FK + Jacobian of tool_frame",
+                        "single_thread_value": rate1,
+                        "reference_numba_survey_value": 4.0e4,
+                        "note": "the reference's own numba kernels measured 4.0e4 cfg/s on one core at survey time (BASELINE.md section 2); "
+                                "they cannot run on the GPU box"}
+        # parity gate on the first 4096 rows of that sample (fp32 kernel vs float64 oracle)
+        n = 4096
+        Tg, Jg = arm.fk_jacobian(torch.as_tensor(qs[:n], dtype=torch.float32, device=dev), "tool_frame")
+        qs32 = qs[:n].astype(np.float32).astype(np.float64)
+        To32, Jo32 = _oc.c_fk_jac(_oc.CDesc(arm._arrays), fid, qs32, arm.base_pose)
+        eT = float(np.abs(Tg.cpu().numpy() - To32).max())
+        eJ = float(np.abs(Jg.cpu().numpy() - Jo32).max())
+        parity = {"checked_rows": n, "max_abs_err_T": eT, "max_abs_err_J": eJ, "tolerance": 1e-5, "ok": bool(eT < 1e-5 and eJ < 1e-5),
+                  "e2e_host_path_bitwise_equal_to_device_path": e2e_ok}
+
+    extras = None
+    if world == 1 and not args.no_extras:
+        extras = secondary_measurements(arm, q, dev)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "configs_per_gpu": B, "frame": "tool_frame", "outputs": "T (B,4,4) and J (B,6,7)",
+                   "l2_policy": "inputs larger than L2: each step streams 4.36 GB per GPU (126 MB L2)",
+                   "parallelism": f"batch sharded over {world} GPU(s), no data-path collective"},
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * DOF * B, "d2h_bytes_per_step": (64 + 24 * DOF) * B,
+                "steps": e2e_steps, "api": "nbx_fk_jac_host_f32 (pinned host buffers, 3-slot H2D/kernel/D2H pipeline)"},
+        "gpu_launches": int(gpu_launches),
+        "clocks": clock_info,
+        "parity": parity,
+        "extras": extras,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def secondary_measurements(arm, q, dev):
+    """BASELINE configs 3-5 on one GPU (not the headline; reported for the roofline table in DESIGN.md)."""
+    import torch
+    from numbotics_b200 import workloads
+
+    def best_ms(fn, n=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(n):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize(dev)
+            ts.append(a.elapsed_time(b))
+        return min(ts)
+
+    out = {}
+    Bc = 1 << 22
+    qc = q[:Bc]
+    ms = best_ms(lambda: arm.in_collision(qc))
+    out["in_collision_configs_per_sec"] = {"value": Bc / ms * 1e3, "configs": Bc, "best_ms": ms,
+                                           "hit_fraction": float(arm.in_collision(qc).float().mean()),
+                                           "workload": "BASELINE configs[2]: Kinova-7 + 3 cubes, self + env pairs"}
+    nodes = q[:100000]
+    s, g = workloads.knn_edges_cuda(nodes, 10)
+    ms = best_ms(lambda: arm.edges_valid(s, g, 0.1))
+    v, ns = arm.edges_valid(s, g, 0.1, return_samples=True)
+    out["prm_edges_per_sec"] = {"value": s.shape[0] / ms * 1e3, "edges": int(s.shape[0]), "best_ms": ms,
+                                "valid_fraction": float(v.float().mean()), "mean_samples_per_edge": float(ns.float().mean()),
+                                "workload": "BASELINE configs[3]: 100k nodes x 10-NN, resolution 0.1, one GPU's worth"}
+    arm30 = workloads.serial_arm(30, device=dev.index)
+    B30 = 1 << 22
+    q30 = workloads.random_configs_cuda(arm30, B30, seed=1)
+    T30 = torch.empty((B30, 4, 4), dtype=torch.float32, device=dev)
+    ms = best_ms(lambda: arm30.fk_jacobian(q30, "tool"))
+    out["serial30_fk_jacobian_configs_per_sec"] = {"value": B30 / ms * 1e3, "configs": B30, "best_ms": ms,
+                                                   "hbm_gbs": 904 * B30 / ms / 1e6,
+                                                   "workload": "BASELINE configs[4] per-GPU slice (2^22 of 2^25)"}
+    del T30
+    return out
+
+
+if __name__ == "__main__":
+    main()

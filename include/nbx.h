@@ -162,8 +162,9 @@ NBX_API int nbx_fk_jac_host_f64(const nbx_chain* chain, int frame, const double*
 /*
  * Batched Arm.in_collision (numbotics/robots/arm.py:555-604): verdict[b] = 1 iff the
  * minimum distance over the allowed pairs is < threshold.  Optional min_dist[b]
- * (nullable) receives a clamped minimum distance: exact when >= 0, and
- * -(margin_a + margin_b) at most when the cores overlap (no EPA).
+ * (nullable) receives a clamped minimum distance: exact while the cores are apart
+ * (distance >= -(margin_a + margin_b)), and -(margin_a + margin_b) - 1e-3 when the cores
+ * overlap (no EPA: depth beyond the margins is not computed).
  */
 NBX_API int nbx_in_collision_f32(const nbx_chain* chain, const nbx_scene* scene, const float* q, int64_t B,
                          const double* base_pose, float threshold,

@@ -28,7 +28,8 @@ namespace {
 constexpr int kCTile = 128;       // configurations (threads) per CTA, in_collision
 constexpr int kETile = 128;       // edges per CTA, edge validation
 constexpr int kMaxSave = 8;
-constexpr int kGjkIters = 24;
+constexpr int kGjkIters = 48;        // verdict mode: only near-threshold pairs ever get this far
+constexpr int kGjkItersDist = 96;    // distance mode: run to convergence
 
 struct SceneDev {
     const TreeJointK* tree;
@@ -186,10 +187,10 @@ __device__ __forceinline__ float pair_distance(ShapeW& A, float mA, ShapeW& B, f
         m = (A.type == NBX_PRIM_SPHERE ? mA : 0.f) + (B.type == NBX_PRIM_SPHERE ? mB : 0.f);
     }
     GjkOut g;
-    if (WANT_DIST) g = gjk_distance<kGjkIters>(A, B, best + m, -FLT_MAX);
+    if (WANT_DIST) g = gjk_distance<kGjkItersDist>(A, B, best + m, -FLT_MAX);
     else g = gjk_distance<kGjkIters>(A, B, thr + m, thr + m);
     B.d[0] = bd0; B.d[1] = bd1; B.d[2] = bd2;   // B is reused by the caller's next pair
-    if (g.overlap) return -m - 1e-9f;
+    if (g.overlap) return -m - 1e-3f;   // cores overlap: depth beyond the margins is not computed (clamp)
     return g.d - m;
 }
 

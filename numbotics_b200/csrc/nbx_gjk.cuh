@@ -51,10 +51,15 @@ __device__ __forceinline__ V3 support(const ShapeW& S, V3 dir) {
     // cylinder: segment along u plus a disc of radius r orthogonal to u
     const V3 u = mk(S.ax[0], S.ax[1], S.ax[2]);
     const float du = dot(dir, u);
-    const V3 perp = madd(dir, -du, u);
+    V3 perp = madd(dir, -du, u);
+    // dir nearly parallel to the axis (cap contacts: the common case) leaves only rounding noise in
+    // `perp`, and that noise is NOT orthogonal to u: normalising it would push the support point up
+    // to one radius beyond the cap.  Re-orthogonalise once and drop it below fp32 resolution of dir;
+    // every cap point is a support point then, so the cap centre is exact to 1e-5 * radius.
+    perp = madd(perp, -dot(perp, u), u);
     const float l2 = dot(perp, perp);
     V3 p = madd(S.c, copysignf(S.d[1], du), u);
-    if (l2 > 1e-30f) p = madd(p, S.d[0] * rsqrtf(l2), perp);
+    if (l2 > 1e-10f * dot(dir, dir)) p = madd(p, S.d[0] * rsqrtf(l2), perp);
     return p;
 }
 
@@ -84,11 +89,13 @@ __device__ __forceinline__ V3 closest_tri(V3 a, V3 b, V3 c, int* mask) {
         return madd(b, (d4 - d3) / ((d4 - d3) + (d5 - d6)), c - b);
     }
     *mask = 7;
-    // interior: project the origin on the plane (numerically better than the barycentric sum)
-    const V3 n = cross(ab, ac);
-    const float nn = dot(n, n);
-    if (nn <= 0.f) { *mask = 3; return a; }
-    return (dot(n, a) / nn) * n;
+    // interior: barycentric combination.  Unlike the plane projection this is a point OF the triangle
+    // whatever the rounding in va/vb/vc did, so |result| stays a valid upper bound even on slivers
+    // (collinear support points are the norm on cylinder sides and box faces).
+    const float sum = va + vb + vc;
+    if (!(sum > 0.f)) { *mask = 1; return a; }
+    const float inv = 1.f / sum;
+    return madd(madd(a, vb * inv, ab), vc * inv, ac);
 }
 
 // Result of one GJK query on the cores.
@@ -157,7 +164,11 @@ __device__ GjkOut gjk_distance(const ShapeW& A, const ShapeW& B, float stop_abov
                 const V3 nrm = cross(P1 - P0, P2 - P0);                                \
                 const float sp = -dot(P0, nrm);                                        \
                 const float sd = dot(OPP - P0, nrm);                                   \
-                if (sp * sd < 0.f || sd == 0.f) {                                      \
+                /* height of OPP over the face below fp32 resolution of the coordinates: the   */ \
+                /* tetrahedron is flat (coplanar support points) and its 'inside' test is noise */ \
+                const float flat = 4e-6f * (fabsf(P0.x) + fabsf(P0.y) + fabsf(P0.z) + 1e-3f);  \
+                const bool degenerate = sd * sd <= flat * flat * dot(nrm, nrm);        \
+                if (degenerate || sp * sd < 0.f) {                                     \
                     outside_any = true;                                                \
                     int m3;                                                            \
                     const V3 cp = closest_tri(P0, P1, P2, &m3);                        \
@@ -184,8 +195,20 @@ __device__ GjkOut gjk_distance(const ShapeW& A, const ShapeW& B, float stop_abov
             s0 = q0; s1 = q1; s2 = q2; n = k;
             if (n == 4) { out.d = 0.f; out.overlap = true; return out; }
         }
-        const float nvv = dot(nv, nv);
-        if (have_ub && nvv >= vv) break;   // numerical stall: keep the previous (better) estimate
+        float nvv = dot(nv, nv);
+        if (have_ub && nvv >= vv) {
+            // The sub-simplex classification lost to rounding (flat / collinear simplices).  Fall back to
+            // one Frank-Wolfe step: the old closest point v is itself a point of the difference, so
+            // [v, w] is a valid simplex and its closest point is strictly closer whenever v.w < v.v.
+            const V3 e = v - w;
+            const float den = dot(e, e);
+            const float t = -dot(w, e);
+            if (!(den > 0.f) || t <= 0.f || t >= den) break;
+            nv = madd(w, t / den, e);
+            nvv = dot(nv, nv);
+            if (nvv >= vv) break;
+            s0 = v; s1 = w; n = 2;
+        }
         v = nv; vv = nvv; have_ub = true;
         ub = sqrtf(vv);
         if (vv <= 1e-14f) { out.d = 0.f; out.overlap = true; return out; }

@@ -149,15 +149,10 @@ def flatten_scene(chain_arrays: dict, self_pairs, env_pairs, margin_model: str =
     """
     prim_of_link = chain_arrays["prim_of_link"]
     prim_type = chain_arrays["prim_type"]
-    obstacles, obs_index = [], {}
-    env_idx = []
-    for link, obj in env_pairs:
-        if link not in prim_of_link:
-            continue
-        if obj not in obs_index:
-            obs_index[obj] = len(obstacles)
-            obstacles.append(obj)
-        env_idx.append((prim_of_link[link], obs_index[obj]))
+    env_pairs = [(link, obj) for link, obj in env_pairs if link in prim_of_link]
+    obstacles = sorted({obj for _, obj in env_pairs}, key=lambda o: o.name)   # independent of set order
+    obs_index = {obj: i for i, obj in enumerate(obstacles)}
+    env_idx = [(prim_of_link[link], obs_index[obj]) for link, obj in env_pairs]
     # deterministic order independent of set iteration order
     env_idx = sorted(set(env_idx))
     self_idx = sorted({tuple(sorted((prim_of_link[a], prim_of_link[b])))

@@ -60,10 +60,13 @@ static void support(const oshape* S, const double* dir, double* out) {
         const double u[3] = {S->R[2], S->R[5], S->R[8]};
         const double du = dot3(dir, u);
         double perp[3] = {dir[0] - du * u[0], dir[1] - du * u[1], dir[2] - du * u[2]};
+        /* remove the rounding residue along the axis (dir almost parallel to u: cap contacts) */
+        const double pu = dot3(perp, u);
+        for (int i = 0; i < 3; ++i) perp[i] -= pu * u[i];
         const double l = sqrt(dot3(perp, perp));
         const double s = du >= 0.0 ? S->d[1] : -S->d[1];
         for (int i = 0; i < 3; ++i) out[i] += s * u[i];
-        if (l > 1e-300)
+        if (l > 1e-13 * sqrt(dot3(dir, dir)))
             for (int i = 0; i < 3; ++i) out[i] += S->d[0] / l * perp[i];
     }
 }
@@ -204,7 +207,7 @@ static double pair_distance(int ta, const double* pa, const double* da, double m
     const double mB = tb == PRIM_SPHERE ? db[0] : (sharp ? 0.0 : mb);
     int ov;
     const double d = core_distance(&A, &B, &ov);
-    if (ov) return -(mA + mB) - 1e-9;
+    if (ov) return -(mA + mB) - 1e-3;   /* clamp: penetration beyond the margins is not computed */
     return d - mA - mB;
 }
 

@@ -1,0 +1,228 @@
+"""CUDA Arm.in_collision / edge validation vs the float64 oracle (checker route), through the C-ABI."""
+import numpy as np
+import pytest
+
+from numbotics_b200 import workloads
+from numbotics_b200.physics import Cube, Cuboid, Sphere, Cylinder
+from numbotics_b200.planning.sampling_based import ConnectorParams, DiscreteConnector, ArmValidityChecker
+from oracle import collision
+
+pytestmark = pytest.mark.gpu
+
+EPS = 1e-4   # stated contact band (metres): verdicts may differ only where |oracle distance - threshold| <= EPS
+
+
+@pytest.fixture(scope="module")
+def scene(cuda):
+    arm, cubes = workloads.prm_scene(device=0)
+    return arm, cubes, collision.SceneOracle(arm)
+
+
+def check_verdicts(hit, d, thr=0.0):
+    clear = np.abs(d - thr) > EPS
+    assert clear.mean() > 0.97
+    assert np.array_equal(hit[clear], (d < thr)[clear])
+
+
+@pytest.mark.parametrize("margin_model", ["bullet", "sharp"])
+def test_in_collision_matches_oracle(cuda, margin_model):
+    arm, cubes = workloads.prm_scene(device=0, margin_model=margin_model)
+    so = collision.SceneOracle(arm, margin_model)
+    q = workloads.random_configs_np(arm, 6000 + 13, seed=1)
+    hit = arm.in_collision(q.astype(np.float32))
+    d = so.min_distance(q.astype(np.float32).astype(np.float64))
+    assert hit.dtype == bool and hit.shape == (q.shape[0],)
+    assert 50 < hit.sum() < q.shape[0] // 2
+    check_verdicts(hit, d)
+
+
+def test_in_collision_dense_contacts(scene):
+    """Configurations concentrated where contacts happen: arm folded on itself / reaching into the cubes."""
+    arm, cubes, so = scene
+    rng = np.random.default_rng(7)
+    sgn = lambda n: rng.choice([-1.0, 1.0], n)
+    q = rng.normal(scale=0.5, size=(4000, 7))
+    q[:, 1] = rng.uniform(1.2, 2.41, 4000) * sgn(4000)     # shoulder down
+    q[:, 3] = rng.uniform(2.2, 2.66, 4000) * sgn(4000)     # elbow folded
+    q[:, 5] = rng.uniform(1.5, 2.23, 4000) * sgn(4000)     # wrist folded
+    q = q.astype(np.float32)
+    hit = arm.in_collision(q)
+    d = so.min_distance(q.astype(np.float64))
+    assert 0.15 < hit.mean() < 0.95
+    check_verdicts(hit, d)
+
+
+def test_min_distance_matches_oracle(scene):
+    arm, cubes, so = scene
+    q = workloads.random_configs_np(arm, 3000, seed=5).astype(np.float32)
+    dist = arm.min_distance(q)
+    d = so.min_distance(q.astype(np.float64))
+    sep = d > 0
+    err = np.abs(dist[sep] - d[sep])
+    assert err.max() < 5e-5, (err.max(), np.argmax(err), dist[sep][np.argmax(err)], d[sep][np.argmax(err)])
+    assert np.all(dist[~sep] < 0)
+
+
+def test_threshold_and_single_config_api(scene):
+    arm, cubes, so = scene
+    q = workloads.random_configs_np(arm, 2000, seed=6).astype(np.float32)
+    d = so.min_distance(q.astype(np.float64))
+    for thr in (0.02, 0.1):
+        check_verdicts(arm.in_collision(q, thr), d, thr)
+    one = arm.in_collision(q[0].astype(np.float64))
+    assert isinstance(one, bool) and one == bool(d[0] < 0)
+    q3 = q[:24].reshape(2, 3, 4, 7)
+    assert arm.in_collision(q3).shape == (2, 3, 4)
+    with pytest.raises(ValueError, match="q must have 7 elements"):
+        arm.in_collision(np.zeros(6))
+    with pytest.raises(NotImplementedError):
+        arm.in_collision(q[0], threshold=-0.01)
+
+
+def test_torch_in_torch_out(scene, cuda):
+    import torch
+    arm, cubes, so = scene
+    q = workloads.random_configs_cuda(arm, 5000, seed=2)
+    hit = arm.in_collision(q)
+    assert hit.is_cuda and hit.dtype == torch.bool and hit.shape == (5000,)
+    d = so.min_distance(q.double().cpu().numpy())
+    check_verdicts(hit.cpu().numpy(), d)
+
+
+def test_moving_an_obstacle_refreshes_the_scene(cuda):
+    arm, cubes = workloads.prm_scene(device=0)
+    q = np.zeros(7, np.float32)            # arm straight up
+    assert arm.in_collision(q) is False
+    cubes[2].position = np.array([0.0, 0.0, 1.0])   # drop a cube on the arm
+    assert arm.in_collision(q) is True
+    arm.remove_collision_pair("forearm_link", cubes[2].name)
+    so = collision.SceneOracle(arm)
+    qs = workloads.random_configs_np(arm, 1500, seed=8).astype(np.float32)
+    check_verdicts(arm.in_collision(qs), so.min_distance(qs.astype(np.float64)))
+
+
+def test_mixed_primitives_and_tree_branches(cuda):
+    """Spheres, boxes and cylinders on a branching tree with a prismatic joint, obstacles of all three kinds."""
+    import networkx as nx
+    from numbotics_b200.math import trans_mat
+    from numbotics_b200.physics import GraphChain, Joint, Constraint, BasicLink, Link, Shape, CollisionShape
+    from numbotics_b200.robots import Arm
+    w = workloads.fresh_world("mixed")
+    G = nx.DiGraph()
+    G.add_node("base", link=BasicLink(1.0, np.eye(4), Shape.CUBOID, half_extents=np.array([0.1, 0.1, 0.05]), name="base"))
+    G.add_node("l1", link=Link(1.0, np.eye(4), CollisionShape(Shape.CYLINDER, radius=0.04, height=0.3,
+                                                              offset=trans_mat(pos=np.array([0, 0, 0.15]))), name="l1"))
+    G.add_node("l2", link=BasicLink(1.0, np.eye(4), Shape.SPHERE, radius=0.06, name="l2"))
+    G.add_node("l3", link=Link(1.0, np.eye(4), CollisionShape(Shape.CUBOID, half_extents=np.array([0.05, 0.03, 0.12]),
+                                                              offset=trans_mat(pos=np.array([0, 0, 0.12]))), name="l3"))
+    G.add_node("l4", link=Link(1.0, np.eye(4), CollisionShape(
+        Shape.CYLINDER, radius=0.03, height=0.25,
+        offset=trans_mat(pos=np.array([0.125, 0, 0]), orn=np.array([[0, 0, 1.0], [0, 1, 0], [-1, 0, 0]]))), name="l4"))
+    G.add_node("l5", link=BasicLink(1.0, np.eye(4), Shape.SPHERE, radius=0.05, name="l5"))
+    R = lambda ax, **kw: Joint(kw.pop("off"), np.array(ax, float), kw.pop("t", Constraint.REVOLUTE), **kw)
+    G.add_edge("base", "l1", joint=R([0, 0, 1], off=trans_mat(pos=np.array([0, 0, 0.05])), lower_limit=-3, upper_limit=3))
+    G.add_edge("l1", "l2", joint=R([0, 1, 0], off=trans_mat(pos=np.array([0, 0, 0.3])), lower_limit=-2, upper_limit=2))
+    G.add_edge("l2", "l3", joint=R([0, 0, 1], off=trans_mat(pos=np.array([0, 0, 0.0])), t=Constraint.PRISMATIC, lower_limit=0.0, upper_limit=0.3))
+    G.add_edge("l2", "l4", joint=R([1, 0, 0], off=trans_mat(pos=np.array([0.05, 0, 0])), lower_limit=-2, upper_limit=2))   # branch
+    G.add_edge("l4", "l5", joint=R([0, 1, 0], off=trans_mat(pos=np.array([0.3, 0, 0])), lower_limit=-2, upper_limit=2))
+    arm = Arm(GraphChain(G, world_name=w.name), device=0)
+    obs = [Cuboid(mass=1.0, half_extents=np.array([0.2, 0.3, 0.1]), world_name=w.name),
+           Sphere(mass=1.0, radius=0.15, world_name=w.name), Cylinder(mass=1.0, radius=0.1, height=0.5, world_name=w.name)]
+    obs[0].pose = trans_mat(pos=np.array([0.45, 0.0, 0.4]), orn=np.array([[0.8, -0.6, 0], [0.6, 0.8, 0], [0, 0, 1.0]]))
+    obs[1].position = np.array([-0.3, 0.3, 0.5])
+    obs[2].pose = trans_mat(pos=np.array([0.0, -0.45, 0.45]), orn=np.array([[1.0, 0, 0], [0, 0, -1], [0, 1, 0]]))
+    assert arm.dof == 5
+    q = workloads.random_configs_np(arm, 5000, seed=3).astype(np.float32)
+    so = collision.SceneOracle(arm)
+    d = so.min_distance(q.astype(np.float64))
+    hit = arm.in_collision(q)
+    assert 0.05 < hit.mean() < 0.95
+    check_verdicts(hit, d)
+    dist = arm.min_distance(q)
+    assert np.abs(dist[d > 0] - d[d > 0]).max() < 5e-5
+
+
+def test_no_pairs_raises_like_min_of_empty(cuda):
+    arm = workloads.serial_arm(4, device=0)     # no geometry, no obstacles
+    with pytest.raises(ValueError, match="empty sequence"):
+        arm.in_collision(np.zeros(4))
+
+
+# ------------------------------------------------------------------------------------------------ edges
+def check_edges(valid, ov, md, thr=0.0):
+    clear = np.abs(md - thr) > EPS
+    assert np.array_equal(valid[clear], ov[clear])
+
+
+def test_edges_match_oracle(scene):
+    arm, cubes, so = scene
+    q = workloads.random_configs_np(arm, 700, seed=12).astype(np.float32)
+    s, g = q[:350], q[350:]
+    # shorten half of the edges so both valid and invalid ones occur
+    g[:200] = s[:200] + 0.15 * (g[:200] - s[:200])
+    valid, ns = arm.edges_valid(s, g, 0.1, return_samples=True)
+    ov, ons, md = so.edges_valid(s.astype(np.float64), g.astype(np.float64), 0.1, return_detail=True)
+    assert np.array_equal(ns, ons)                      # numpy.arange sample count reproduced exactly
+    assert (~valid).sum() >= 10 and valid.sum() >= 10
+    check_edges(valid, ov, md)
+    # steer semantics
+    valid2, ns2 = arm.edges_valid(s, g, 0.1, max_distance=1.0, return_samples=True)
+    ov2, ons2, md2 = so.edges_valid(s.astype(np.float64), g.astype(np.float64), 0.1, max_distance=1.0, return_detail=True)
+    assert np.array_equal(ns2, ons2)
+    check_edges(valid2, ov2, md2)
+    assert valid2.sum() >= valid.sum()
+
+
+def test_edge_corner_cases(scene):
+    arm, cubes, so = scene
+    free = np.zeros(7, np.float32)
+    assert arm.in_collision(free) is False
+    s = np.stack([free, free, free, free])
+    g = s.copy()
+    g[1, 0] = 1e-8          # distance <= float32 eps -> None
+    g[2, 0] = 0.5           # distance/resolution = 5 (arange boundary)
+    g[3, 0] = 0.05          # shorter than the resolution: samples {0, 1}
+    valid, ns = arm.edges_valid(s, g, 0.1, return_samples=True)
+    assert list(valid) == [False, False, True, True]
+    ov, ons, _ = so.edges_valid(s.astype(np.float64), g.astype(np.float64), 0.1, return_detail=True)
+    assert list(ns) == list(ons) and list(ns[:2]) == [0, 0] and ns[3] == 2
+    assert arm.edges_valid(np.zeros((0, 7), np.float32), np.zeros((0, 7), np.float32), 0.1).shape == (0,)
+    with pytest.raises(ValueError, match="same shape"):
+        arm.edges_valid(s, g[:2], 0.1)
+
+
+def test_discrete_connector_surface(scene, cuda):
+    arm, cubes, so = scene
+    chk = ArmValidityChecker(arm)
+    conn = DiscreteConnector(ConnectorParams(resolution=0.1, max_distance=np.pi, validity_checker=chk))
+    q = workloads.random_configs_np(arm, 80, seed=21)
+    free = q[~so.in_collision(q)]
+    a, b = free[0], free[0] + 0.2 * (free[1] - free[0])
+    out = conn.connect(a, b)
+    ov = so.edges_valid(a[None].astype(np.float32), b[None].astype(np.float32), 0.1)[0]
+    assert (out is not None) == bool(ov)
+    if out is not None:
+        assert np.array_equal(out, b) and out is not b
+    assert conn.connect(a, a) is None
+    assert conn.is_valid(a) is True
+    # a colliding goal can never connect
+    bad = q[so.in_collision(q)][0] if so.in_collision(q).any() else None
+    if bad is not None:
+        assert conn.connect(a, bad) is None
+    # steer returns the clipped state
+    far = free[2]
+    st = conn.steer(a, far)
+    dist = np.linalg.norm(far - a)
+    if st is not None:
+        t_f = min(1.0, np.pi / dist)
+        assert np.allclose(st, (1 - t_f) * a + t_f * far)
+    # custom distance function -> host sample grid + batched validity, same verdict as the oracle
+    out2 = conn.connect(a, b, distance_func=lambda x, y: float(np.linalg.norm(x - y)))
+    assert (out2 is not None) == (out is not None)
+    # batched surface
+    s, g = free[:20], free[20:40]
+    vb = conn.connect_batch(s, g)
+    ovb, _, md = so.edges_valid(s.astype(np.float32), g.astype(np.float32), 0.1, return_detail=True)
+    check_edges(vb, ovb, md)
+    vs, ends = conn.steer_batch(s, g)
+    assert ends.shape == s.shape
