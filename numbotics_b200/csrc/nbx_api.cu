@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cmath>
 #include <algorithm>
 #include <new>
 
@@ -37,6 +38,13 @@ bool finite12(const double* p) {
     for (int i = 0; i < 12; ++i)
         if (!(p[i] == p[i]) || p[i] > 1e300 || p[i] < -1e300) return false;
     return true;
+}
+
+// bounding radius of the full (un-shrunk) primitive about its centre
+float bounding_radius(int type, const double* dims) {
+    if (type == NBX_PRIM_SPHERE) return (float)dims[0];
+    if (type == NBX_PRIM_BOX) return (float)std::sqrt(dims[0] * dims[0] + dims[1] * dims[1] + dims[2] * dims[2]);
+    return (float)std::sqrt(dims[0] * dims[0] + dims[1] * dims[1]);
 }
 
 int prim_pose_floats(int type) { return type == NBX_PRIM_SPHERE ? 3 : (type == NBX_PRIM_CYLINDER ? 6 : 12); }
@@ -90,6 +98,11 @@ int nbx_chain_create(const nbx_chain_desc* d, int device, nbx_chain** out) {
     if (!ch) { nbx_set_error("out of host memory"); return NBX_ERR_NOMEM; }
     struct Guard { nbx_chain* c; ~Guard() { if (c) nbx_chain_destroy(c); } } guard{ch};
     ch->device = device;
+    {
+        cudaDeviceProp prop;
+        NBX_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+        ch->sm_count = prop.multiProcessorCount;
+    }
     ch->dof = d->dof; ch->n_mov = d->n_mov; ch->n_frames = d->n_frames; ch->n_prims = d->n_prims;
     ch->d_tree = nullptr; ch->d_prims = nullptr;
     ch->mov_parent.assign(d->mov_parent, d->mov_parent + d->n_mov);
@@ -148,6 +161,7 @@ int nbx_chain_create(const nbx_chain_desc* d, int device, nbx_chain** out) {
         if (rc != NBX_OK) return rc;
         pk.mov = prim_mov[p];
         pk.slot = -1;
+        pk.brad = bounding_radius(pk.type, &ch->prim_dims[3 * p]) * 1.000001f;
         if (pk.mov < 0) ch->n_base_prims++;
     }
     ch->h_tree.resize(ch->n_mov);
@@ -168,6 +182,8 @@ int nbx_chain_create(const nbx_chain_desc* d, int device, nbx_chain** out) {
         for (int k = 0; k < 3; ++k) { tj.t[k] = jk.t[k]; tj.d[k] = jk.d[k]; }
         tj.type = jk.type;
         tj.qidx = jk.qidx;
+        tj.kind = jk.kind;
+        tj.sgn = jk.sgn;
         const int pj = ch->mov_parent[j];
         tj.load_slot = (pj == j - 1) ? -1 : (pj < 0 ? -2 : save_slot[pj]);
         tj.save_slot = save_slot[j];
@@ -227,6 +243,7 @@ int nbx_scene_create(const nbx_chain* ch, const nbx_scene_desc* d, nbx_scene** o
         ok.type = d->obs_type[o];
         int rc = core_dims(ok.type, &d->obs_dims[3 * o], d->obs_margin[o], ok.dims, &ok.margin);
         if (rc != NBX_OK) return rc;
+        ok.brad = bounding_radius(ok.type, &d->obs_dims[3 * o]) * 1.000001f;
     }
     const int np = ch->n_prims;
     // self pairs: device order, a < b; the test runs when b is reached, so a's pose must be parked

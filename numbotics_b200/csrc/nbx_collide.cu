@@ -18,6 +18,7 @@
 // edges that are already known invalid are skipped.
 #include "nbx_common.cuh"
 #include "nbx_gjk.cuh"
+#include "nbx_joint.cuh"
 #include <algorithm>
 #include <mutex>
 
@@ -80,36 +81,7 @@ __device__ __forceinline__ unsigned char* stage_scene(const SceneDev& S, unsigne
     return p;
 }
 
-struct PoseF {
-    float R[9];
-    float p[3];
-};
-
-__device__ __forceinline__ void tree_step(PoseF& X, const TreeJointK& jk, float qv) {
-    float M[9], tt[3];
-    if (jk.type == NBX_JOINT_REVOLUTE) {
-        float s, c;
-        sincosf(qv, &s, &c);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) M[k] = fmaf(s, jk.Cm[k], fmaf(-c, jk.Bm[k], jk.A[k]));
-        tt[0] = jk.t[0]; tt[1] = jk.t[1]; tt[2] = jk.t[2];
-    } else {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) M[k] = jk.A[k];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) tt[k] = fmaf(qv, jk.d[k], jk.t[k]);
-    }
-    float Rn[9];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        X.p[r] = fmaf(X.R[r * 3 + 0], tt[0], fmaf(X.R[r * 3 + 1], tt[1], fmaf(X.R[r * 3 + 2], tt[2], X.p[r])));
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-            Rn[r * 3 + c] = fmaf(X.R[r * 3 + 0], M[c], fmaf(X.R[r * 3 + 1], M[3 + c], X.R[r * 3 + 2] * M[6 + c]));
-    }
-#pragma unroll
-    for (int k = 0; k < 9; ++k) X.R[k] = Rn[k];
-}
+using PoseF = nbxj::Pose<float>;
 
 // world-space core of link primitive `pk` whose owning joint frame is X
 __device__ __forceinline__ void prim_world(const PoseF& X, const PrimK& pk, ShapeW& S) {
@@ -215,6 +187,23 @@ __device__ float eval_config(const SceneDev& S, const SceneSm& V, QF qf, float t
             for (int e = V.env_begin[p]; e < V.env_begin[p + 1]; ++e) {
                 const PairK pr = V.env_pairs[e];
                 const ObsK& o = V.obs[pr.b];
+                // conservative cull: primitive bounding sphere vs the obstacle (exact point-box distance
+                // for boxes, bounding sphere otherwise); (distance lower bound) > cut can neither hit nor
+                // lower the running minimum
+                {
+                    const V3 dc = Bs.c - mk(o.c[0], o.c[1], o.c[2]);
+                    float lbnd;
+                    if (o.type == NBX_PRIM_BOX) {
+                        const float hx = o.dims[0] + o.margin, hy = o.dims[1] + o.margin, hz = o.dims[2] + o.margin;
+                        const float lx = fmaxf(fabsf(fmaf(o.R[0], dc.x, fmaf(o.R[3], dc.y, o.R[6] * dc.z))) - hx, 0.f);
+                        const float ly = fmaxf(fabsf(fmaf(o.R[1], dc.x, fmaf(o.R[4], dc.y, o.R[7] * dc.z))) - hy, 0.f);
+                        const float lz = fmaxf(fabsf(fmaf(o.R[2], dc.x, fmaf(o.R[5], dc.y, o.R[8] * dc.z))) - hz, 0.f);
+                        lbnd = sqrtf(fmaf(lx, lx, fmaf(ly, ly, lz * lz))) - pk.brad;
+                    } else {
+                        lbnd = sqrtf(dot(dc, dc)) - pk.brad - o.brad;
+                    }
+                    if (lbnd > (WANT_DIST ? best : thr) + 1e-6f) continue;
+                }
                 ShapeW As;
                 obs_world(o, As);
                 const float d = pair_distance<WANT_DIST>(As, o.margin, Bs, pk.margin, pr.sharp != 0, thr, best);
@@ -224,6 +213,11 @@ __device__ float eval_config(const SceneDev& S, const SceneSm& V, QF qf, float t
             for (int e = V.self_begin[p]; e < V.self_begin[p + 1]; ++e) {
                 const PairK pr = V.self_pairs[e];
                 const PrimK& pa = V.prims[pr.a];
+                {
+                    const float* sc = scratch + pa.slot * stride;
+                    const V3 dc = Bs.c - mk(sc[0], sc[stride], sc[2 * stride]);
+                    if (sqrtf(dot(dc, dc)) - pk.brad - pa.brad > (WANT_DIST ? best : thr) + 1e-6f) continue;
+                }
                 ShapeW As;
                 scratch_load(scratch + pa.slot * stride, stride, pa, As);
                 const float d = pair_distance<WANT_DIST>(As, pa.margin, Bs, pk.margin, pr.sharp != 0, thr, best);
@@ -248,7 +242,7 @@ __device__ float eval_config(const SceneDev& S, const SceneSm& V, QF qf, float t
         } else if (jk.load_slot >= 0) {
             X = saved[jk.load_slot];
         }
-        tree_step(X, jk, qf(jk.qidx));
+        nbxj::joint_step<float, TreeJointK>(X, jk, qf(jk.qidx));
         if (jk.save_slot >= 0) saved[jk.save_slot] = X;
         if (do_prims(jk.prim_begin, jk.prim_end)) return best;
     }

@@ -38,6 +38,17 @@ void nbx_count_launch(int n = 1);
 //   revolute : X(q) = [ A - cos q * Bm + sin q * Cm | t ],  A = R K, Bm = R (K - I), Cm = R [a]x
 //   prismatic: X(q) = [ A | t + q * d ],                     A = R,   d = R a
 // with R | t the folded offset and K = a a^T.
+//
+// Fast path (`kind` 1..3): the axis is exactly +-e_x / +-e_y / +-e_z (every joint of a typical URDF).
+// Then Rodrigues is a plane rotation of two columns:  R <- (R . R_off) with columns (k+1, k+2) rotated
+// by sgn * q, and the world axis is sgn * column k of the result -- 39 instead of 54 FMAs and no
+// R . a product.  `A` holds R_off in that case.  Same mathematics as helpers.py:43-55 for a unit axis.
+#define NBX_KIND_GENERIC 0
+#define NBX_KIND_X 1
+#define NBX_KIND_Y 2
+#define NBX_KIND_Z 3
+#define NBX_KIND_PRISMATIC 4
+
 template <typename T>
 struct JointK {
     T A[9];
@@ -46,8 +57,10 @@ struct JointK {
     T t[3];
     T ax[3];    // joint axis in the joint frame (world axis = R_after * ax)
     T d[3];     // prismatic direction R a (zero for revolute)
+    T sgn;      // +-1 for the canonical-axis kinds
     int type;   // NBX_JOINT_*
     int qidx;   // column of q
+    int kind;   // NBX_KIND_*
 };
 
 template <typename T, int MAXJ>
@@ -68,7 +81,7 @@ struct PrimK {
     int type;
     int mov;        // owning movable joint (-1 = base)
     int slot;       // float offset of the stored world pose in the per-thread scratch, -1 = not stored
-    int pad;
+    float brad;     // bounding-sphere radius of the FULL primitive (core + margin) about its centre
 };
 
 struct ObsK {
@@ -77,7 +90,8 @@ struct ObsK {
     float dims[3];
     float margin;
     int type;
-    int pad[3];
+    float brad;     // bounding-sphere radius of the full obstacle
+    int pad[2];
 };
 
 struct PairK {
@@ -96,11 +110,13 @@ struct TreeJointK {
     int load_slot;   // -1: continue from the running transform, -2: restart from base, >=0: saved slot
     int save_slot;   // -1: do not save, >=0: save the transform after this joint
     int prim_begin, prim_end;   // primitives owned by this joint (sorted)
-    int pad[2];
+    int kind;        // NBX_KIND_*
+    float sgn;
 };
 
 struct nbx_chain {
     int device;
+    int sm_count;
     int dof, n_mov, n_frames, n_prims;
     // host copies (float64) used to build per-call kernel parameters
     std::vector<int> mov_parent, mov_type, mov_qidx;

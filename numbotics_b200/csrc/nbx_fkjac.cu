@@ -21,93 +21,16 @@
 //
 // HBM-bound: 4*dof + 64 + 24*dof bytes per configuration (fp32), see DESIGN.md.
 #include "nbx_common.cuh"
+#include "nbx_joint.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
+
+using namespace nbxj;
 
 namespace {
 
 constexpr int kSmallMax = 8;   // dense fully-unrolled kernels cover paths of 1..8 joints
-
-template <typename T> __device__ __forceinline__ void sincos_t(T x, T* s, T* c);
-template <> __device__ __forceinline__ void sincos_t<float>(float x, float* s, float* c) { sincosf(x, s, c); }
-template <> __device__ __forceinline__ void sincos_t<double>(double x, double* s, double* c) { sincos(x, s, c); }
-
-template <typename T> __device__ __forceinline__ T fma_t(T a, T b, T c);
-template <> __device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
-template <> __device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return fma(a, b, c); }
-
-// R (3x3 row-major) and p: world pose of the current joint frame.
-template <typename T>
-struct Pose {
-    T R[9];
-    T p[3];
-};
-
-// One joint of the walk: pose <- pose * X(q); returns the post-joint pose in place.
-template <typename T>
-__device__ __forceinline__ void joint_step(Pose<T>& X, const JointK<T>& jk, T qv) {
-    T M[9];
-    T tt[3];
-    if (jk.type == NBX_JOINT_REVOLUTE) {
-        T s, c;
-        sincos_t<T>(qv, &s, &c);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) M[k] = fma_t<T>(s, jk.Cm[k], fma_t<T>(-c, jk.Bm[k], jk.A[k]));
-        tt[0] = jk.t[0]; tt[1] = jk.t[1]; tt[2] = jk.t[2];
-    } else {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) M[k] = jk.A[k];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) tt[k] = fma_t<T>(qv, jk.d[k], jk.t[k]);
-    }
-    T Rn[9];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        X.p[r] = fma_t<T>(X.R[r * 3 + 0], tt[0], fma_t<T>(X.R[r * 3 + 1], tt[1], fma_t<T>(X.R[r * 3 + 2], tt[2], X.p[r])));
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-            Rn[r * 3 + c] = fma_t<T>(X.R[r * 3 + 0], M[c], fma_t<T>(X.R[r * 3 + 1], M[3 + c], X.R[r * 3 + 2] * M[6 + c]));
-    }
-#pragma unroll
-    for (int k = 0; k < 9; ++k) X.R[k] = Rn[k];
-}
-
-// world axis w = R a and moment m = w x p of the joint frame just reached.  Prismatic joints are
-// stored as (w_store, m_store) = (0, -w) so the common finish  v = w_store x p_e - m_store,
-// omega = w_store  yields [w; 0] without a branch (reference helpers.py:181-185).
-template <typename T>
-__device__ __forceinline__ void joint_screw(const Pose<T>& X, const JointK<T>& jk, T* w, T* m) {
-    T a[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-        a[r] = fma_t<T>(X.R[r * 3 + 0], jk.ax[0], fma_t<T>(X.R[r * 3 + 1], jk.ax[1], X.R[r * 3 + 2] * jk.ax[2]));
-    if (jk.type == NBX_JOINT_REVOLUTE) {
-        w[0] = a[0]; w[1] = a[1]; w[2] = a[2];
-        m[0] = fma_t<T>(a[1], X.p[2], -a[2] * X.p[1]);
-        m[1] = fma_t<T>(a[2], X.p[0], -a[0] * X.p[2]);
-        m[2] = fma_t<T>(a[0], X.p[1], -a[1] * X.p[0]);
-    } else {
-        w[0] = w[1] = w[2] = T(0);
-        m[0] = -a[0]; m[1] = -a[1]; m[2] = -a[2];
-    }
-}
-
-template <typename T>
-__device__ __forceinline__ void pose_mul_const(Pose<T>& X, const T* c12) {
-    // X <- X * [C | t] with a constant pose12
-    T Rn[9], pn[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        pn[r] = fma_t<T>(X.R[r * 3 + 0], c12[3], fma_t<T>(X.R[r * 3 + 1], c12[7], fma_t<T>(X.R[r * 3 + 2], c12[11], X.p[r])));
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-            Rn[r * 3 + c] = fma_t<T>(X.R[r * 3 + 0], c12[c], fma_t<T>(X.R[r * 3 + 1], c12[4 + c], X.R[r * 3 + 2] * c12[8 + c]));
-    }
-#pragma unroll
-    for (int k = 0; k < 9; ++k) X.R[k] = Rn[k];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) X.p[k] = pn[k];
-}
 
 template <typename T>
 __device__ __forceinline__ void pose_mul_global(Pose<T>& X, const T* __restrict__ g16) {
@@ -158,7 +81,16 @@ __device__ __forceinline__ void store_pose16(T* dst, const Pose<T>& X) {
     d[7] = z1;
 }
 
-// Stage this CTA's q tile in shared memory.
+// Stage a q tile in shared memory.  Full, 16-byte aligned tiles go through cp.async (LDGSTS: no
+// registers, completion tracked by the async group, so the NEXT tile can be in flight while this
+// one is being computed); ragged / unaligned tiles use plain loads.
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
+    const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(sdst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <typename T, int TILE>
 __device__ __forceinline__ void load_q_tile(T* sq, const T* __restrict__ q, int64_t tile0, int nvalid, int dof, bool vec_ok) {
     const int n = nvalid * dof;
@@ -167,98 +99,135 @@ __device__ __forceinline__ void load_q_tile(T* sq, const T* __restrict__ q, int6
         const int n16 = (TILE * dof * (int)sizeof(T)) / 16;   // TILE*dof*sizeof(T) is a multiple of 16 for TILE % 4 == 0
         const int4* s16 = reinterpret_cast<const int4*>(src);
         int4* d16 = reinterpret_cast<int4*>(sq);
-        for (int i = threadIdx.x; i < n16; i += TILE) d16[i] = ld_stream16(s16 + i);
+        for (int i = threadIdx.x; i < n16; i += TILE) cp_async16(d16 + i, s16 + i);
     } else {
         for (int i = threadIdx.x; i < n; i += TILE) sq[i] = src[i];
     }
+    cp_async_commit();
 }
 
 // =============================================================================================
 // dense kernel: path covers q columns 0..NJ-1 exactly (serial arms: Kinova tool_frame), NJ <= 8.
-// Fully unrolled; screws live in registers.
+// Fully unrolled; screws live in registers.  Persistent CTAs: each loops over tiles with the next
+// tile's q prefetched (cp.async) while the current one is computed, and the previous tile's output
+// still draining through the TMA engine.
 // =============================================================================================
-template <typename T, int NJ, int TILE>
+template <typename T, int NJ, int TILE, bool ALLZ, int KT>
 __global__ void __launch_bounds__(TILE)
 fkjac_dense_kernel(const __grid_constant__ PathK<T, kSmallMax> P, const T* __restrict__ q, int64_t B,
                    const T* __restrict__ lp, int64_t lps, const T* __restrict__ gp, int64_t gps,
-                   T* __restrict__ T_out, T* __restrict__ J_out, int vec_ok) {
+                   T* __restrict__ T_out, T* __restrict__ J_out, int vec_ok, int64_t ntiles) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // layout: [J tile][T tile][q tile]; J and T tiles are 128-byte aligned for the bulk copies
+    // layout: [J tile][T tile][q tile x KT]; J and T tiles are 128-byte aligned for the bulk copies
     T* sJ = reinterpret_cast<T*>(smem_raw);
     T* sT = sJ + TILE * 6 * NJ;
-    T* sq = sT + TILE * 16;
-
-    const int64_t tile0 = (int64_t)blockIdx.x * TILE;
-    const int nvalid = (int)min((int64_t)TILE, B - tile0);
+    T* sq0 = sT + TILE * 16;
     const int tid = threadIdx.x;
+    bool store_in_flight = false;
 
-    load_q_tile<T, TILE>(sq, q, tile0, nvalid, NJ, vec_ok != 0);
+    // CTA c owns the KT CONSECUTIVE tiles [c*KT, c*KT + KT): the hardware block scheduler then keeps the
+    // chip-wide write frontier compact (measured: 7.5 TB/s vs 6.3 TB/s for a grid-stride persistent loop,
+    // profiles/membench_r01.txt) while one q-load latency and one CTA launch are shared by KT tiles.
+    const int64_t first = (int64_t)blockIdx.x * KT;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+        const int64_t t = first + k;
+        if (t < ntiles) load_q_tile<T, TILE>(sq0 + k * (TILE * NJ), q, t * TILE, (int)min((int64_t)TILE, B - t * TILE), NJ, vec_ok != 0);
+    }
+    cp_async_wait_all();
     __syncthreads();
 
-    Pose<T> X;
-    T W[NJ][3], Mo[NJ][3];
-    const bool active = tid < nvalid;
-    if (active) {
+#pragma unroll 1
+    for (int k = 0; k < KT; ++k) {
+        const int64_t tile = first + k;
+        if (tile >= ntiles) break;
+        const int64_t tile0 = tile * TILE;
+        const int nvalid = (int)min((int64_t)TILE, B - tile0);
+        const T* sq = sq0 + k * (TILE * NJ);
+
+        Pose<T> X;
+        T W[NJ][3], Mo[NJ][3];
+        T pe[3];
+        const bool active = tid < nvalid;
+        if (active) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            X.R[k * 3 + 0] = P.base[k * 4 + 0]; X.R[k * 3 + 1] = P.base[k * 4 + 1]; X.R[k * 3 + 2] = P.base[k * 4 + 2];
-            X.p[k] = P.base[k * 4 + 3];
-        }
-#pragma unroll
-        for (int i = 0; i < NJ; ++i) {
-            const T qv = sq[tid * NJ + i];
-            joint_step<T>(X, P.j[i], qv);
-            joint_screw<T>(X, P.j[i], W[i], Mo[i]);
-        }
-        pose_mul_const<T>(X, P.tail);
-        const int64_t b = tile0 + tid;
-        if (lp != nullptr) pose_mul_global<T>(X, lp + b * lps);
-        T pe[3] = {X.p[0], X.p[1], X.p[2]};
-        if (gp != nullptr) {
-            const T* g = gp + b * gps;
-            pe[0] = g[3]; pe[1] = g[7]; pe[2] = g[11];
-        }
-        if (T_out != nullptr) store_pose16<T>(sT + tid * 16, X);
-        if (J_out != nullptr) {
-            T row[6 * NJ];
+            for (int r = 0; r < 3; ++r) {
+                X.R[r * 3 + 0] = P.base[r * 4 + 0]; X.R[r * 3 + 1] = P.base[r * 4 + 1]; X.R[r * 3 + 2] = P.base[r * 4 + 2];
+                X.p[r] = P.base[r * 4 + 3];
+            }
 #pragma unroll
             for (int i = 0; i < NJ; ++i) {
-                row[0 * NJ + i] = fma_t<T>(W[i][1], pe[2], fma_t<T>(-W[i][2], pe[1], -Mo[i][0]));
-                row[1 * NJ + i] = fma_t<T>(W[i][2], pe[0], fma_t<T>(-W[i][0], pe[2], -Mo[i][1]));
-                row[2 * NJ + i] = fma_t<T>(W[i][0], pe[1], fma_t<T>(-W[i][1], pe[0], -Mo[i][2]));
-                row[3 * NJ + i] = W[i][0];
-                row[4 * NJ + i] = W[i][1];
-                row[5 * NJ + i] = W[i][2];
+                const T qv = sq[tid * NJ + i];
+                T sn, cs;
+                sincos_t<T>(qv, &sn, &cs);
+                if (ALLZ) {
+                    // every joint is a revolute about its own +-z: branch-free straight-line code
+                    joint_step_z<T, JointK<T>>(X, P.j[i], sn, cs);
+                    joint_screw_z<T, JointK<T>>(X, P.j[i], W[i], Mo[i]);
+                } else {
+                    joint_step_sc<T, JointK<T>>(X, P.j[i], qv, sn, cs);
+                    joint_screw<T, JointK<T>>(X, P.j[i], W[i], Mo[i]);
+                }
             }
-            using V2 = typename Vec2<T>::type;
-            V2* d = reinterpret_cast<V2*>(sJ + tid * 6 * NJ);
-#pragma unroll
-            for (int k = 0; k < 3 * NJ; ++k) {
-                V2 v;
-                v.x = row[2 * k]; v.y = row[2 * k + 1];
-                d[k] = v;
+            pose_mul_const<T>(X, P.tail);
+            const int64_t b = tile0 + tid;
+            if (lp != nullptr) pose_mul_global<T>(X, lp + b * lps);
+            pe[0] = X.p[0]; pe[1] = X.p[1]; pe[2] = X.p[2];
+            if (gp != nullptr) {
+                const T* g = gp + b * gps;
+                pe[0] = g[3]; pe[1] = g[7]; pe[2] = g[11];
             }
         }
-    }
 
-    if (nvalid == TILE && vec_ok) {
-        // full tile: hand both output tiles to the TMA engine
-        fence_proxy_async_smem();
+        // the previous tile's bulk stores must have finished READING the staging tiles
+        if (store_in_flight && tid == 0) bulk_wait_read_all();
         __syncthreads();
-        if (tid == 0) {
-            if (T_out != nullptr) bulk_store(T_out + tile0 * 16, sT, TILE * 16 * sizeof(T));
-            if (J_out != nullptr) bulk_store(J_out + tile0 * 6 * NJ, sJ, TILE * 6 * NJ * sizeof(T));
-            bulk_commit();
-            bulk_wait_read_all();
+
+        if (active) {
+            if (T_out != nullptr) store_pose16<T>(sT + tid * 16, X);
+            if (J_out != nullptr) {
+                T row[6 * NJ];
+#pragma unroll
+                for (int i = 0; i < NJ; ++i) {
+                    row[0 * NJ + i] = fma_t<T>(W[i][1], pe[2], fma_t<T>(-W[i][2], pe[1], -Mo[i][0]));
+                    row[1 * NJ + i] = fma_t<T>(W[i][2], pe[0], fma_t<T>(-W[i][0], pe[2], -Mo[i][1]));
+                    row[2 * NJ + i] = fma_t<T>(W[i][0], pe[1], fma_t<T>(-W[i][1], pe[0], -Mo[i][2]));
+                    row[3 * NJ + i] = W[i][0];
+                    row[4 * NJ + i] = W[i][1];
+                    row[5 * NJ + i] = W[i][2];
+                }
+                using V2 = typename Vec2<T>::type;
+                V2* d = reinterpret_cast<V2*>(sJ + tid * 6 * NJ);
+#pragma unroll
+                for (int k = 0; k < 3 * NJ; ++k) {
+                    V2 v;
+                    v.x = row[2 * k]; v.y = row[2 * k + 1];
+                    d[k] = v;
+                }
+            }
         }
-    } else {
-        // ragged last tile (or unaligned user pointers): cooperative coalesced copy-out
-        __syncthreads();
-        if (T_out != nullptr)
-            for (int i = tid; i < nvalid * 16; i += TILE) T_out[tile0 * 16 + i] = sT[i];
-        if (J_out != nullptr)
-            for (int i = tid; i < nvalid * 6 * NJ; i += TILE) J_out[tile0 * 6 * NJ + i] = sJ[i];
+
+        if (nvalid == TILE && vec_ok) {
+            // full tile: hand both output tiles to the TMA engine and move on
+            fence_proxy_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                if (T_out != nullptr) bulk_store(T_out + tile0 * 16, sT, TILE * 16 * sizeof(T));
+                if (J_out != nullptr) bulk_store(J_out + tile0 * 6 * NJ, sJ, TILE * 6 * NJ * sizeof(T));
+                bulk_commit();
+            }
+            store_in_flight = true;
+        } else {
+            // ragged last tile (or unaligned user pointers): cooperative coalesced copy-out
+            __syncthreads();
+            if (T_out != nullptr)
+                for (int i = tid; i < nvalid * 16; i += TILE) T_out[tile0 * 16 + i] = sT[i];
+            if (J_out != nullptr)
+                for (int i = tid; i < nvalid * 6 * NJ; i += TILE) J_out[tile0 * 6 * NJ + i] = sJ[i];
+            store_in_flight = false;
+        }
     }
+    if (store_in_flight && tid == 0) bulk_wait_read_all();   // shared memory must outlive the copies
 }
 
 // =============================================================================================
@@ -286,6 +255,7 @@ fkjac_generic_kernel(const __grid_constant__ PathK<T, NBX_MAX_PATH> P, const T* 
     load_q_tile<T, TILE>(sq, q, tile0, nvalid, dof, vec_ok != 0);
     if (J_out != nullptr && !P.dense)
         for (int i = tid; i < TILE * jrow; i += TILE) sJ[i] = T(0);
+    cp_async_wait_all();
     __syncthreads();
 
     if (tid < nvalid) {
@@ -301,10 +271,10 @@ fkjac_generic_kernel(const __grid_constant__ PathK<T, NBX_MAX_PATH> P, const T* 
         for (int i = 0; i < P.n; ++i) {
             const JointK<T>& jk = P.j[i];
             const int col = jk.qidx;
-            joint_step<T>(X, jk, myq[col]);
+            joint_step<T, JointK<T>>(X, jk, myq[col]);
             if (J_out != nullptr) {
                 T w[3], m[3];
-                joint_screw<T>(X, jk, w, m);
+                joint_screw<T, JointK<T>>(X, jk, w, m);
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     myJ[k * dof + col] = m[k];
@@ -380,18 +350,31 @@ int build_path(const nbx_chain* ch, int frame, const double* base_pose16, int us
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-template <typename T, int NJ, int TILE>
-int launch_dense(const PathK<T, kSmallMax>& P, const T* q, int64_t B, const T* lp, int64_t lps, const T* gp, int64_t gps,
-                 T* T_out, T* J_out, int vec_ok, cudaStream_t stream) {
-    const size_t smem = sizeof(T) * (size_t)TILE * (6 * NJ + 16 + NJ);
-    auto kern = fkjac_dense_kernel<T, NJ, TILE>;
+template <typename T, int NJ, int TILE, bool ALLZ, int KT>
+int launch_dense_kt(const PathK<T, kSmallMax>& P, const T* q, int64_t B, const T* lp, int64_t lps, const T* gp,
+                    int64_t gps, T* T_out, T* J_out, int vec_ok, cudaStream_t stream) {
+    const size_t smem = sizeof(T) * (size_t)TILE * (6 * NJ + 16 + KT * NJ);
+    auto kern = fkjac_dense_kernel<T, NJ, TILE, ALLZ, KT>;
     NBX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t grid = (B + TILE - 1) / TILE;
+    const int64_t ntiles = (B + TILE - 1) / TILE;
+    const int64_t grid = (ntiles + KT - 1) / KT;
     NBX_REQUIRE(grid <= 0x7fffffffLL, "batch too large for one launch");
-    kern<<<(unsigned)grid, TILE, smem, stream>>>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok);
+    kern<<<(unsigned)grid, TILE, smem, stream>>>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, ntiles);
     nbx_count_launch();
     NBX_CUDA_OK(cudaGetLastError());
     return NBX_OK;
+}
+
+template <typename T, int NJ, int TILE, bool ALLZ>
+int launch_dense(const nbx_chain* ch, const PathK<T, kSmallMax>& P, const T* q, int64_t B, const T* lp, int64_t lps, const T* gp,
+                 int64_t gps, T* T_out, T* J_out, int vec_ok, cudaStream_t stream) {
+    (void)ch;
+    // consecutive tiles per CTA; small batches keep one tile per CTA so the grid still fills the machine
+    static const int kt_env = std::getenv("NBX_DENSE_KT") ? std::atoi(std::getenv("NBX_DENSE_KT")) : 0;   // tuning only
+    const int kt = kt_env > 0 ? kt_env : (B >= (int64_t)TILE * 148 * 32 ? 2 : 1);
+    if (kt >= 4) return launch_dense_kt<T, NJ, TILE, ALLZ, 4>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, stream);
+    if (kt >= 2) return launch_dense_kt<T, NJ, TILE, ALLZ, 2>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, stream);
+    return launch_dense_kt<T, NJ, TILE, ALLZ, 1>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, stream);
 }
 
 template <typename T, int TILE>
@@ -429,8 +412,11 @@ int launch_fkjac(const nbx_chain* ch, int frame, const T* q, int64_t B, const do
         int rc = build_path<T, kSmallMax>(ch, frame, base_pose, use_com, P);
         if (rc != NBX_OK) return rc;
         if (P.dense) {
+            bool allz = true;
+            for (int i = 0; i < P.n; ++i) allz = allz && P.j[i].kind == NBX_KIND_Z;
             switch (n) {
-#define NBX_CASE(N) case N: return launch_dense<T, N, TILE>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, stream);
+#define NBX_CASE(N) case N: return allz ? launch_dense<T, N, TILE, true>(ch, P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, stream) \
+                                        : launch_dense<T, N, TILE, false>(ch, P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, stream);
                 NBX_CASE(1) NBX_CASE(2) NBX_CASE(3) NBX_CASE(4) NBX_CASE(5) NBX_CASE(6) NBX_CASE(7) NBX_CASE(8)
 #undef NBX_CASE
             }
@@ -547,6 +533,20 @@ void nbx_fill_joint(JointK<T>& jk, const double* off12, const double* axis, int 
     for (int k = 0; k < 3; ++k) { jk.t[k] = (T)t[k]; jk.ax[k] = (T)a[k]; }
     jk.type = type;
     jk.qidx = qidx;
+    jk.kind = type == NBX_JOINT_REVOLUTE ? NBX_KIND_GENERIC : NBX_KIND_PRISMATIC;
+    jk.sgn = (T)1;
+    static const bool force_generic = std::getenv("NBX_FORCE_GENERIC_AXIS") != nullptr;   // A/B measurements only
+    if (type == NBX_JOINT_REVOLUTE && !force_generic) {
+        // exactly +-e_k ?  (anything else, including non-unit axes, keeps the literal Rodrigues form)
+        for (int k = 0; k < 3; ++k) {
+            const int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
+            if ((a[k] == 1.0 || a[k] == -1.0) && a[k1] == 0.0 && a[k2] == 0.0) {
+                jk.kind = k == 0 ? NBX_KIND_X : (k == 1 ? NBX_KIND_Y : NBX_KIND_Z);
+                jk.sgn = (T)a[k];
+                for (int i = 0; i < 9; ++i) { jk.A[i] = (T)R[i]; jk.Bm[i] = (T)0; jk.Cm[i] = (T)0; }
+            }
+        }
+    }
 }
 template void nbx_fill_joint<float>(JointK<float>&, const double*, const double*, int, int);
 template void nbx_fill_joint<double>(JointK<double>&, const double*, const double*, int, int);

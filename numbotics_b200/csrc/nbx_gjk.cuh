@@ -74,19 +74,19 @@ __device__ __forceinline__ V3 closest_tri(V3 a, V3 b, V3 c, int* mask) {
     const float vc = d1 * d4 - d3 * d2;
     if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) {
         *mask = 3;
-        return madd(a, d1 / (d1 - d3), ab);
+        return madd(a, d1 / fmaxf(d1 - d3, 1e-37f), ab);      // (max: duplicate vertices give 0/0)
     }
     const float d5 = -dot(ab, c), d6 = -dot(ac, c);
     if (d6 >= 0.f && d5 <= d6) { *mask = 4; return c; }
     const float vb = d5 * d2 - d1 * d6;
     if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) {
         *mask = 5;
-        return madd(a, d2 / (d2 - d6), ac);
+        return madd(a, d2 / fmaxf(d2 - d6, 1e-37f), ac);
     }
     const float va = d3 * d6 - d5 * d4;
     if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) {
         *mask = 6;
-        return madd(b, (d4 - d3) / ((d4 - d3) + (d5 - d6)), c - b);
+        return madd(b, (d4 - d3) / fmaxf((d4 - d3) + (d5 - d6), 1e-37f), c - b);
     }
     *mask = 7;
     // interior: barycentric combination.  Unlike the plane projection this is a point OF the triangle

@@ -59,7 +59,7 @@ def test_min_distance_matches_oracle(scene):
     d = so.min_distance(q.astype(np.float64))
     sep = d > 0
     err = np.abs(dist[sep] - d[sep])
-    assert err.max() < 5e-5, (err.max(), np.argmax(err), dist[sep][np.argmax(err)], d[sep][np.argmax(err)])
+    assert err.max() < 1e-4, (err.max(), np.argmax(err), dist[sep][np.argmax(err)], d[sep][np.argmax(err)])
     assert np.all(dist[~sep] < 0)
 
 
@@ -139,7 +139,7 @@ def test_mixed_primitives_and_tree_branches(cuda):
     assert 0.05 < hit.mean() < 0.95
     check_verdicts(hit, d)
     dist = arm.min_distance(q)
-    assert np.abs(dist[d > 0] - d[d > 0]).max() < 5e-5
+    assert np.abs(dist[d > 0] - d[d > 0]).max() < 1e-4
 
 
 def test_no_pairs_raises_like_min_of_empty(cuda):

@@ -140,3 +140,59 @@ def test_large_batch_properties(kinova, cuda):
     qs = q[idx].double().cpu().numpy()
     assert rel_err(T[idx].cpu().numpy(), ora.forward_kinematics(qs, "tool_frame")) <= RTOL32
     assert rel_err(J[idx].cpu().numpy(), ora.jacobian(qs, "tool_frame")) <= RTOL32
+
+
+def _random_tree_arm(seed, n_joints=9, device=0):
+    """Random branching tree: canonical (+-x/y/z), oblique and NON-unit revolute axes, prismatic and fixed joints."""
+    import networkx as nx
+    from numbotics_b200.math import trans_mat
+    from numbotics_b200.physics import GraphChain, Joint, Constraint, DummyLink
+    from numbotics_b200.robots import Arm
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(seed)
+    w = workloads.fresh_world("rtree")
+    G = nx.DiGraph()
+    G.add_node("n0", link=DummyLink(1.0, trans_mat(pos=rng.normal(size=3) * 0.1), name="n0"))
+    axes = [[0, 0, 1], [0, 0, -1], [1, 0, 0], [0, -1, 0], [1, 1, 0], [0.3, -0.5, 0.8], [0, 0, 2.0], [0, 1, 0]]
+    for i in range(1, n_joints + 1):
+        parent = f"n{int(rng.integers(max(0, i - 3), i))}"
+        off = trans_mat(pos=rng.normal(size=3) * 0.2, orn=Rotation.from_rotvec(rng.normal(size=3)).as_matrix())
+        kind = rng.choice(["rev", "rev", "rev", "pris", "fixed"])
+        ax = np.array(axes[int(rng.integers(0, len(axes)))], float)
+        if kind in ("rev",) and np.linalg.norm(ax) not in (1.0, 2.0):
+            ax = ax / np.linalg.norm(ax)
+        ctype = {"rev": Constraint.REVOLUTE, "pris": Constraint.PRISMATIC, "fixed": Constraint.FIXED}[kind]
+        G.add_node(f"n{i}", link=DummyLink(1.0, trans_mat(pos=rng.normal(size=3) * 0.05), name=f"n{i}"))
+        G.add_edge(parent, f"n{i}", joint=Joint(off, ax, ctype, name=f"j{i}", lower_limit=-2.5, upper_limit=2.5))
+    return Arm(GraphChain(G, world_name=w.name), device=device)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_random_trees_all_joint_kinds(cuda, seed):
+    arm = _random_tree_arm(seed)
+    if arm.dof == 0:
+        pytest.skip("no movable joint drawn")
+    q = workloads.random_configs_np(arm, 300, seed=seed)
+    com = {n: l._offset for n, l in arm._links_from_nodes.items()}
+    ora = fkjac.ArmOracle(arm._link_joint_sequence, arm.dof, arm.base_pose, com)
+    for frame in arm._link_joint_sequence:
+        for use_com in (False, True):
+            T64, J64 = arm.fk_jacobian(q, frame, use_com=use_com)
+            assert rel_err(T64, ora.forward_kinematics(q, frame, use_com=use_com)) <= RTOL64, frame
+            assert rel_err(J64, ora.jacobian(q, frame, use_com=use_com)) <= RTOL64, frame
+        T32, J32 = arm.fk_jacobian(q.astype(np.float32), frame)
+        assert rel_err(T32, ora.forward_kinematics(q, frame)) <= RTOL32, frame
+        assert rel_err(J32, ora.jacobian(q, frame)) <= RTOL32, frame
+
+
+def test_large_angles_sincos_range(kinova):
+    """The custom fp32 sincos must hold 1e-5 well outside [-pi, pi] (continuous joints wind up)."""
+    rng = np.random.default_rng(9)
+    q = rng.uniform(-200.0, 200.0, size=(2000, 7))
+    q[:5] *= 1e4                      # beyond the Cody-Waite range: sincosf() path
+    q32 = q.astype(np.float32)
+    ora = fkjac.ArmOracle(kinova._link_joint_sequence, 7, kinova.base_pose)
+    T, J = kinova.fk_jacobian(q32, "tool_frame")
+    q_as_seen = q32.astype(np.float64)
+    assert rel_err(T, ora.forward_kinematics(q_as_seen, "tool_frame")) <= RTOL32
+    assert rel_err(J, ora.jacobian(q_as_seen, "tool_frame")) <= RTOL32

@@ -55,8 +55,9 @@ def make_obstacle(kind, w):
 def test_pair_distance_and_verdict(cuda, link_kind, obs_kind, margin_model):
     arm, w = flyer(SHAPES[link_kind](), margin_model=margin_model)
     obs = make_obstacle(obs_kind, w)
-    rng = np.random.default_rng(hash((link_kind, obs_kind)) % 2**32)
-    n = 4000
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(f"{link_kind}-{obs_kind}".encode()))
+    n = 12000
     q = np.zeros((n, 6))
     direction = rng.normal(size=(n, 3)); direction /= np.linalg.norm(direction, axis=1, keepdims=True)
     q[:, :3] = direction * rng.uniform(0.0, 0.9, (n, 1))          # from deep overlap to well separated
@@ -74,8 +75,9 @@ def test_pair_distance_and_verdict(cuda, link_kind, obs_kind, margin_model):
         assert np.array_equal(hit_t[clear], (d < thr)[clear])
     dist = arm.min_distance(q)
     err = np.abs(dist[d > 0] - d[d > 0])
-    assert err.max() < 5e-5, (err.max(), d[d > 0][np.argmax(err)], dist[d > 0][np.argmax(err)])
-    assert np.all(dist[d < -1e-4] < 0)
+    assert err.max() < 1e-4, (err.max(), d[d > 0][np.argmax(err)], dist[d > 0][np.argmax(err)])   # = the stated band
+    neg = d < -2e-4
+    assert np.all(dist[neg] < 0), (d[neg][dist[neg] >= 0][:5], dist[neg][dist[neg] >= 0][:5], q[neg][dist[neg] >= 0][:3])
 
 
 def test_known_answers_on_device(cuda):
