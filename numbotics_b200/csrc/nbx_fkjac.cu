@@ -231,54 +231,88 @@ fkjac_dense_kernel(const __grid_constant__ PathK<T, kSmallMax> P, const T* __res
 }
 
 // =============================================================================================
-// generic kernel: any path length <= NBX_MAX_PATH, any dof, sparse columns.
-// Screws are parked in the Jacobian's own shared-memory tile (w in rows 3..5, m in rows 0..2
-// of the joint's column) and fixed up in place once p_e is known: registers stay O(1) in the
-// chain depth (BASELINE config 5, 30-DoF).
+// generic kernel: any path length <= NBX_MAX_PATH, any dof, sparse columns (BASELINE config 5, 30-DoF).
+//
+// Registers stay O(1) in the chain depth.  Two phases per tile:
+//   A  one thread per configuration walks the path and parks each joint's screw (w_i, m_i) in a
+//      shared-memory scratch laid out [component][joint][configuration] with an ODD configuration
+//      stride: the phase-A writes (lanes = configurations) and the phase-B reads (lanes = joints)
+//      are both bank-conflict free;
+//   B  one warp per configuration, lanes over the dof COLUMNS: v = w x p_e - m, and the six rows of
+//      that configuration's Jacobian go straight to global memory as six coalesced runs of 4*dof
+//      bytes (the 24*dof-byte block of one configuration is contiguous, so L2 sees full lines).
+//      Columns of joints that are not on the path are written as zeros in the same pass.
+// The 64-byte pose rows still leave through a TMA bulk copy of the whole tile.
 // =============================================================================================
-template <typename T, int TILE>
+template <typename T, int TILE, bool ALLZ>
 __global__ void __launch_bounds__(TILE)
 fkjac_generic_kernel(const __grid_constant__ PathK<T, NBX_MAX_PATH> P, const T* __restrict__ q, int64_t B,
                      const T* __restrict__ lp, int64_t lps, const T* __restrict__ gp, int64_t gps,
                      T* __restrict__ T_out, T* __restrict__ J_out, int vec_ok) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int SW = TILE + 1;                  // odd stride between components
+    constexpr int SJ = 6 * SW + 1;                // odd stride between joints
     const int dof = P.dof;
-    const int jrow = 6 * dof;
-    T* sJ = reinterpret_cast<T*>(smem_raw);
-    T* sT = sJ + TILE * jrow;
-    T* sq = sT + TILE * 16;
+    const int n = P.n;
+    T* sT = reinterpret_cast<T*>(smem_raw);       // [TILE][16]   (first: 128-byte aligned for the bulk copy)
+    T* sq = sT + TILE * 16;                       // [TILE][dof]  q, overwritten in place by sin(q)
+    T* sc = sq + TILE * dof;                      // [TILE][dof]  cos(q)
+    T* spe = sc + TILE * dof;                     // [3][TILE]
+    T* sW = spe + 3 * TILE;                       // [n][SJ]: joint-major, then component (stride SW), then configuration
+    short* colmap = reinterpret_cast<short*>(sW + (size_t)n * SJ);   // [dof] column -> path index or -1
 
     const int64_t tile0 = (int64_t)blockIdx.x * TILE;
     const int nvalid = (int)min((int64_t)TILE, B - tile0);
     const int tid = threadIdx.x;
 
     load_q_tile<T, TILE>(sq, q, tile0, nvalid, dof, vec_ok != 0);
-    if (J_out != nullptr && !P.dense)
-        for (int i = tid; i < TILE * jrow; i += TILE) sJ[i] = T(0);
+    for (int c = tid; c < dof; c += TILE) colmap[c] = -1;
     cp_async_wait_all();
     __syncthreads();
+    for (int i = tid; i < n; i += TILE) colmap[P.j[i].qidx] = (short)i;
 
     if (tid < nvalid) {
+        T* myq = sq + tid * dof;
+        T* myc = sc + tid * dof;
+        // ---- phase 0: every sine / cosine of this configuration.  No loop-carried dependency, so the
+        // transcendental latency overlaps across joints instead of sitting on the serial walk below.
+#pragma unroll 4
+        for (int i = 0; i < n; ++i) {
+            const int col = P.dense ? i : P.j[i].qidx;
+            if (ALLZ || P.j[i].kind != NBX_KIND_PRISMATIC) {
+                T sn, cs;
+                sincos_t<T>(myq[col], &sn, &cs);
+                myq[col] = sn;
+                myc[col] = cs;
+            }
+        }
+        // ---- phase A: the walk ------------------------------------------------------------------
         Pose<T> X;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            X.R[k * 3 + 0] = P.base[k * 4 + 0]; X.R[k * 3 + 1] = P.base[k * 4 + 1]; X.R[k * 3 + 2] = P.base[k * 4 + 2];
-            X.p[k] = P.base[k * 4 + 3];
+        for (int r = 0; r < 3; ++r) {
+            X.R[r * 3 + 0] = P.base[r * 4 + 0]; X.R[r * 3 + 1] = P.base[r * 4 + 1]; X.R[r * 3 + 2] = P.base[r * 4 + 2];
+            X.p[r] = P.base[r * 4 + 3];
         }
-        T* myJ = sJ + tid * jrow;
-        const T* myq = sq + tid * dof;
-#pragma unroll 1
-        for (int i = 0; i < P.n; ++i) {
+        T* pw = sW + tid;
+        const bool want_j = J_out != nullptr;
+#pragma unroll 2
+        for (int i = 0; i < n; ++i, pw += SJ) {
             const JointK<T>& jk = P.j[i];
-            const int col = jk.qidx;
-            joint_step<T, JointK<T>>(X, jk, myq[col]);
-            if (J_out != nullptr) {
-                T w[3], m[3];
+            const int col = P.dense ? i : jk.qidx;
+            T w[3], m[3];
+            if (ALLZ) {
+                joint_step_z<T, JointK<T>>(X, jk, myq[col], myc[col]);
+                joint_screw_z<T, JointK<T>>(X, jk, w, m);
+            } else {
+                // prismatic joints kept q itself in myq[col]
+                joint_step_sc<T, JointK<T>>(X, jk, myq[col], myq[col], myc[col]);
                 joint_screw<T, JointK<T>>(X, jk, w, m);
+            }
+            if (want_j) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    myJ[k * dof + col] = m[k];
-                    myJ[(3 + k) * dof + col] = w[k];
+                    pw[k * SW] = m[k];
+                    pw[(3 + k) * SW] = w[k];
                 }
             }
         }
@@ -290,36 +324,47 @@ fkjac_generic_kernel(const __grid_constant__ PathK<T, NBX_MAX_PATH> P, const T* 
             const T* g = gp + b * gps;
             pe[0] = g[3]; pe[1] = g[7]; pe[2] = g[11];
         }
+        spe[0 * TILE + tid] = pe[0]; spe[1 * TILE + tid] = pe[1]; spe[2 * TILE + tid] = pe[2];
         if (T_out != nullptr) store_pose16<T>(sT + tid * 16, X);
-        if (J_out != nullptr) {
-#pragma unroll 2
-            for (int i = 0; i < P.n; ++i) {
-                const int col = P.j[i].qidx;
-                const T w0 = myJ[3 * dof + col], w1 = myJ[4 * dof + col], w2 = myJ[5 * dof + col];
-                const T m0 = myJ[0 * dof + col], m1 = myJ[1 * dof + col], m2 = myJ[2 * dof + col];
-                myJ[0 * dof + col] = fma_t<T>(w1, pe[2], fma_t<T>(-w2, pe[1], -m0));
-                myJ[1 * dof + col] = fma_t<T>(w2, pe[0], fma_t<T>(-w0, pe[2], -m1));
-                myJ[2 * dof + col] = fma_t<T>(w0, pe[1], fma_t<T>(-w1, pe[0], -m2));
-            }
+    }
+
+    const bool bulk = (nvalid == TILE) && vec_ok;
+    if (bulk) fence_proxy_async_smem();
+    __syncthreads();
+    if (T_out != nullptr) {
+        if (bulk) {
+            if (tid == 0) { bulk_store(T_out + tile0 * 16, sT, TILE * 16 * sizeof(T)); bulk_commit(); }
+        } else {
+            for (int i = tid; i < nvalid * 16; i += TILE) T_out[tile0 * 16 + i] = sT[i];
         }
     }
 
-    if (nvalid == TILE && vec_ok) {
-        fence_proxy_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            if (T_out != nullptr) bulk_store(T_out + tile0 * 16, sT, TILE * 16 * sizeof(T));
-            if (J_out != nullptr) bulk_store(J_out + tile0 * jrow, sJ, (uint32_t)(TILE * jrow * sizeof(T)));
-            bulk_commit();
-            bulk_wait_read_all();
+    // ---- phase B: one warp per configuration, lanes over the Jacobian's columns -------------------
+    if (J_out != nullptr) {
+        const int lane = tid & 31, wid = tid >> 5;
+        constexpr int NW = TILE / 32;
+        for (int col = lane; col < dof; col += 32) {
+            const int i = P.dense ? col : (int)colmap[col];
+            const T* Wi = sW + (i < 0 ? 0 : i) * SJ;
+            T* Jcol = J_out + tile0 * 6 * (int64_t)dof + col;
+#pragma unroll 2
+            for (int c = wid; c < nvalid; c += NW) {
+                T v0 = T(0), v1 = T(0), v2 = T(0), w0 = T(0), w1 = T(0), w2 = T(0);
+                if (i >= 0) {
+                    const T pe0 = spe[c], pe1 = spe[TILE + c], pe2 = spe[2 * TILE + c];
+                    const T m0 = Wi[0 * SW + c], m1 = Wi[1 * SW + c], m2 = Wi[2 * SW + c];
+                    w0 = Wi[3 * SW + c]; w1 = Wi[4 * SW + c]; w2 = Wi[5 * SW + c];
+                    v0 = fma_t<T>(w1, pe2, fma_t<T>(-w2, pe1, -m0));
+                    v1 = fma_t<T>(w2, pe0, fma_t<T>(-w0, pe2, -m1));
+                    v2 = fma_t<T>(w0, pe1, fma_t<T>(-w1, pe0, -m2));
+                }
+                T* Jc = Jcol + (int64_t)c * (6 * dof);
+                Jc[0] = v0; Jc[dof] = v1; Jc[2 * dof] = v2;
+                Jc[3 * dof] = w0; Jc[4 * dof] = w1; Jc[5 * dof] = w2;
+            }
         }
-    } else {
-        __syncthreads();
-        if (T_out != nullptr)
-            for (int i = tid; i < nvalid * 16; i += TILE) T_out[tile0 * 16 + i] = sT[i];
-        if (J_out != nullptr)
-            for (int i = tid; i < nvalid * jrow; i += TILE) J_out[tile0 * jrow + i] = sJ[i];
     }
+    if (T_out != nullptr && bulk && tid == 0) bulk_wait_read_all();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -377,10 +422,10 @@ int launch_dense(const nbx_chain* ch, const PathK<T, kSmallMax>& P, const T* q, 
     return launch_dense_kt<T, NJ, TILE, ALLZ, 1>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, stream);
 }
 
-template <typename T, int TILE>
-int launch_generic(const PathK<T, NBX_MAX_PATH>& P, const T* q, int64_t B, const T* lp, int64_t lps, const T* gp, int64_t gps,
-                   T* T_out, T* J_out, int vec_ok, size_t smem, cudaStream_t stream) {
-    auto kern = fkjac_generic_kernel<T, TILE>;
+template <typename T, int TILE, bool ALLZ>
+int launch_generic_t(const PathK<T, NBX_MAX_PATH>& P, const T* q, int64_t B, const T* lp, int64_t lps, const T* gp, int64_t gps,
+                     T* T_out, T* J_out, int vec_ok, size_t smem, cudaStream_t stream) {
+    auto kern = fkjac_generic_kernel<T, TILE, ALLZ>;
     NBX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = (B + TILE - 1) / TILE;
     NBX_REQUIRE(grid <= 0x7fffffffLL, "batch too large for one launch");
@@ -388,6 +433,21 @@ int launch_generic(const PathK<T, NBX_MAX_PATH>& P, const T* q, int64_t B, const
     nbx_count_launch();
     NBX_CUDA_OK(cudaGetLastError());
     return NBX_OK;
+}
+
+template <typename T>
+size_t generic_smem(int tile, int dof, int n) {
+    return sizeof(T) * ((size_t)tile * 16 + 2 * (size_t)tile * dof + 3 * (size_t)tile + (size_t)n * (6 * (tile + 1) + 1)) + 2 * (size_t)dof + 16;
+}
+
+template <typename T, int TILE>
+int launch_generic(const PathK<T, NBX_MAX_PATH>& P, const T* q, int64_t B, const T* lp, int64_t lps, const T* gp, int64_t gps,
+                   T* T_out, T* J_out, int vec_ok, cudaStream_t stream) {
+    const size_t smem = generic_smem<T>(TILE, P.dof, P.n);
+    bool allz = P.n > 0;
+    for (int i = 0; i < P.n; ++i) allz = allz && P.j[i].kind == NBX_KIND_Z;
+    if (allz) return launch_generic_t<T, TILE, true>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, smem, stream);
+    return launch_generic_t<T, TILE, false>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, smem, stream);
 }
 
 template <typename T>
@@ -425,13 +485,17 @@ int launch_fkjac(const nbx_chain* ch, int frame, const T* q, int64_t B, const do
     PathK<T, NBX_MAX_PATH> P;
     int rc = build_path<T, NBX_MAX_PATH>(ch, frame, base_pose, use_com, P);
     if (rc != NBX_OK) return rc;
-    // tile size: keep >= 2 CTAs per SM when the per-thread tile row allows it
-    const size_t per_thread = sizeof(T) * (size_t)(6 * ch->dof + 16 + ch->dof);
-    const size_t budget = 100 * 1024;
-    if (per_thread * 128 <= budget) return launch_generic<T, 128>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, per_thread * 128, stream);
-    if (per_thread * 64 <= budget) return launch_generic<T, 64>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, per_thread * 64, stream);
-    NBX_REQUIRE(per_thread * 32 <= 220 * 1024, "dof %d too large for the shared-memory staged Jacobian", ch->dof);
-    return launch_generic<T, 32>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, per_thread * 32, stream);
+    // tile size: the largest tile that still leaves room for >= 3 CTAs per SM (tuning knob NBX_GENERIC_TILE)
+    static const int tile_env = std::getenv("NBX_GENERIC_TILE") ? std::atoi(std::getenv("NBX_GENERIC_TILE")) : 0;
+    const size_t budget = 72 * 1024;
+    int tile = 128;
+    if (generic_smem<T>(128, ch->dof, n) > budget) tile = 64;
+    if (generic_smem<T>(64, ch->dof, n) > budget) tile = 32;
+    if (tile_env == 32 || tile_env == 64 || tile_env == 128) tile = tile_env;
+    NBX_REQUIRE(generic_smem<T>(tile, ch->dof, n) <= 220 * 1024, "dof %d / path %d too large for the shared-memory staged Jacobian", ch->dof, n);
+    if (tile == 128) return launch_generic<T, 128>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, stream);
+    if (tile == 64) return launch_generic<T, 64>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, stream);
+    return launch_generic<T, 32>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, stream);
 }
 
 // ---- host-buffer pipeline ------------------------------------------------------------------
