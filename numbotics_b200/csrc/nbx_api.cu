@@ -148,6 +148,7 @@ int nbx_chain_create(const nbx_chain_desc* d, int device, nbx_chain** out) {
     ch->prim_rank.assign(ch->n_prims, 0);
     for (int i = 0; i < ch->n_prims; ++i) ch->prim_rank[ch->prim_order[i]] = i;
     ch->n_base_prims = 0;
+    ch->pose_floats = 0;
     ch->h_prims.resize(ch->n_prims);
     for (int i = 0; i < ch->n_prims; ++i) {
         const int p = ch->prim_order[i];
@@ -160,7 +161,8 @@ int nbx_chain_create(const nbx_chain_desc* d, int device, nbx_chain** out) {
         int rc = core_dims(pk.type, &ch->prim_dims[3 * p], ch->prim_margin[p], pk.dims, &pk.margin);
         if (rc != NBX_OK) return rc;
         pk.mov = prim_mov[p];
-        pk.slot = -1;
+        pk.slot = ch->pose_floats;
+        ch->pose_floats += prim_pose_floats(pk.type);
         pk.brad = bounding_radius(pk.type, &ch->prim_dims[3 * p]) * 1.000001f;
         if (pk.mov < 0) ch->n_base_prims++;
     }
@@ -246,43 +248,44 @@ int nbx_scene_create(const nbx_chain* ch, const nbx_scene_desc* d, nbx_scene** o
         ok.brad = bounding_radius(ok.type, &d->obs_dims[3 * o]) * 1.000001f;
     }
     const int np = ch->n_prims;
-    // self pairs: device order, a < b; the test runs when b is reached, so a's pose must be parked
     std::vector<PairK> self(d->n_self_pairs);
     for (int i = 0; i < d->n_self_pairs; ++i) {
         int a = d->self_pairs[2 * i], b = d->self_pairs[2 * i + 1];
         NBX_REQUIRE(a >= 0 && a < np && b >= 0 && b < np && a != b, "self pair %d: bad primitive index", i);
         a = ch->prim_rank[a]; b = ch->prim_rank[b];
         if (a > b) std::swap(a, b);
-        std::memset(&self[i], 0, sizeof(PairK));
-        self[i].a = (int16_t)a; self[i].b = (int16_t)b;
-        self[i].sharp = d->self_sharp ? d->self_sharp[i] : 0;
+        PairK& pr = self[i];
+        std::memset(&pr, 0, sizeof(PairK));
+        pr.a = (int16_t)a; pr.b = (int16_t)b;
+        pr.sharp = d->self_sharp ? d->self_sharp[i] : 0;
+        const PrimK& pa = sc->h_prims[a];
+        const PrimK& pb = sc->h_prims[b];
+        pr.both_cyl = (pa.type == NBX_PRIM_CYLINDER && pb.type == NBX_PRIM_CYLINDER) ? 1 : 0;
+        pr.slot_a = (int16_t)pa.slot; pr.slot_b = (int16_t)pb.slot;
+        pr.rsum = pa.brad + pb.brad;
     }
     std::stable_sort(self.begin(), self.end(), [](const PairK& x, const PairK& y) { return x.b != y.b ? x.b < y.b : x.a < y.a; });
     std::vector<PairK> env(d->n_env_pairs);
     for (int i = 0; i < d->n_env_pairs; ++i) {
         const int a = d->env_pairs[2 * i], o = d->env_pairs[2 * i + 1];
         NBX_REQUIRE(a >= 0 && a < np && o >= 0 && o < d->n_obs, "env pair %d: bad index", i);
-        std::memset(&env[i], 0, sizeof(PairK));
-        env[i].a = (int16_t)ch->prim_rank[a]; env[i].b = (int16_t)o;
-        env[i].sharp = d->env_sharp ? d->env_sharp[i] : 0;
+        PairK& pr = env[i];
+        std::memset(&pr, 0, sizeof(PairK));
+        pr.a = (int16_t)ch->prim_rank[a]; pr.b = (int16_t)o;
+        pr.sharp = d->env_sharp ? d->env_sharp[i] : 0;
+        const PrimK& pa = sc->h_prims[pr.a];
+        pr.slot_a = (int16_t)pa.slot;
+        pr.rsum = pa.brad;
     }
-    std::stable_sort(env.begin(), env.end(), [](const PairK& x, const PairK& y) { return x.a != y.a ? x.a < y.a : x.b < y.b; });
+    // obstacle-major: the broad phase keeps one obstacle in registers and streams the primitives past it
+    std::stable_sort(env.begin(), env.end(), [](const PairK& x, const PairK& y) { return x.b != y.b ? x.b < y.b : x.a < y.a; });
     sc->h_self = self;
     sc->h_env = env;
-    sc->h_self_begin.assign(np + 1, 0);
-    sc->h_env_begin.assign(np + 1, 0);
-    for (const PairK& p : self) sc->h_self_begin[p.b + 1]++;
-    for (const PairK& p : env) sc->h_env_begin[p.a + 1]++;
-    for (int i = 0; i < np; ++i) {
-        sc->h_self_begin[i + 1] += sc->h_self_begin[i];
-        sc->h_env_begin[i + 1] += sc->h_env_begin[i];
-    }
-    int off = 0;
-    for (const PairK& p : self) {
-        PrimK& pa = sc->h_prims[p.a];
-        if (pa.slot < 0) { pa.slot = off; off += prim_pose_floats(pa.type); }
-    }
-    sc->scratch_floats = off;
+    sc->h_self_begin.assign(1, 0);
+    sc->h_env_begin.assign(d->n_obs + 1, 0);
+    for (const PairK& p : env) sc->h_env_begin[p.b + 1]++;
+    for (int i = 0; i < d->n_obs; ++i) sc->h_env_begin[i + 1] += sc->h_env_begin[i];
+    sc->scratch_floats = ch->pose_floats;
 
     int rc;
     if ((rc = upload(sc->h_prims, &sc->d_prims)) != NBX_OK) return rc;

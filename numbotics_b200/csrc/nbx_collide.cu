@@ -59,7 +59,7 @@ __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t
 
 __host__ __device__ inline size_t scene_smem_bytes(int n_mov, int n_prims, int n_obs, int n_self, int n_env) {
     return align16(sizeof(TreeJointK) * n_mov) + align16(sizeof(PrimK) * n_prims) + align16(sizeof(ObsK) * n_obs) +
-           align16(sizeof(PairK) * n_self) + align16(sizeof(PairK) * n_env) + 2 * align16(sizeof(int) * (n_prims + 1));
+           align16(sizeof(PairK) * n_self) + align16(sizeof(PairK) * n_env) + align16(sizeof(int) * (n_obs + 1));
 }
 
 __device__ __forceinline__ void copy_words(void* dst, const void* src, size_t bytes) {
@@ -76,8 +76,8 @@ __device__ __forceinline__ unsigned char* stage_scene(const SceneDev& S, unsigne
     V.obs = reinterpret_cast<const ObsK*>(p);         copy_words(p, S.obs, sizeof(ObsK) * S.n_obs);         p += align16(sizeof(ObsK) * S.n_obs);
     V.self_pairs = reinterpret_cast<const PairK*>(p); copy_words(p, S.self_pairs, sizeof(PairK) * S.n_self); p += align16(sizeof(PairK) * S.n_self);
     V.env_pairs = reinterpret_cast<const PairK*>(p);  copy_words(p, S.env_pairs, sizeof(PairK) * S.n_env);   p += align16(sizeof(PairK) * S.n_env);
-    V.self_begin = reinterpret_cast<const int*>(p);   copy_words(p, S.self_begin, sizeof(int) * (S.n_prims + 1)); p += align16(sizeof(int) * (S.n_prims + 1));
-    V.env_begin = reinterpret_cast<const int*>(p);    copy_words(p, S.env_begin, sizeof(int) * (S.n_prims + 1));  p += align16(sizeof(int) * (S.n_prims + 1));
+    V.env_begin = reinterpret_cast<const int*>(p);    copy_words(p, S.env_begin, sizeof(int) * (S.n_obs + 1));    p += align16(sizeof(int) * (S.n_obs + 1));
+    V.self_begin = nullptr;
     return p;
 }
 
@@ -122,7 +122,43 @@ __device__ __forceinline__ void unround(ShapeW& S, float margin) {
     else if (S.type == NBX_PRIM_CYLINDER) { S.d[0] += margin; S.d[1] += margin; }
 }
 
-__device__ __forceinline__ void scratch_store(float* scr, int stride, const ShapeW& S) {
+// ---------------------------------------------------------------------------------------------
+// Block-cooperative evaluation of NT items (configurations or interpolation samples), two phases:
+//
+//   phase 1  thread = item.  Walk the whole tree, park EVERY primitive's world core in shared memory
+//            ([value][thread], conflict free), and run the cheap conservative culls on every allowed
+//            pair.  All lanes walk the same scene in lockstep, so survivors are appended to a block
+//            queue with one warp-aggregated shared-memory atomic per (pair, warp).
+//   phase 2  thread = queue entry.  Surviving (pair, item) candidates -- typically a handful per
+//            item out of ~60 pairs -- go through the GJK narrow phase.  Entries are ordered by pair,
+//            so a warp works on one pair type at a time and lanes only diverge in iteration count.
+//
+// The per-thread version of this (cull and GJK interleaved in one loop) ran at 72 % SIMT efficiency
+// and 229 KB of inlined code; see profiles/.
+// ---------------------------------------------------------------------------------------------
+constexpr int kQueuePerThread = 20;
+constexpr uint32_t kEnvFlag = 0x80000000u;
+
+struct Ctx {
+    SceneSm V;
+    const float* base;        // 12 floats (kernel parameter)
+    float* poses;             // [pose_floats][NT]
+    uint32_t* queue;          // [qcap]
+    int* qcount;
+    int* flag;                // verdict mode: [n_flags] 1 = hit ; distance mode: ordered-int keys of the running minimum
+    const int* item_flag;     // [NT] item -> flag index (nullptr = identity)
+    int qcap;
+    int n_mov, n_prims, n_base_prims;
+    float thr;
+};
+
+__device__ __forceinline__ int float_key(float f) {            // order-preserving float -> int
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
+__device__ __forceinline__ void pose_store(float* scr, int stride, const ShapeW& S) {
     scr[0 * stride] = S.c.x; scr[1 * stride] = S.c.y; scr[2 * stride] = S.c.z;
     if (S.type == NBX_PRIM_CYLINDER) {
         scr[3 * stride] = S.ax[0]; scr[4 * stride] = S.ax[1]; scr[5 * stride] = S.ax[2];
@@ -132,7 +168,7 @@ __device__ __forceinline__ void scratch_store(float* scr, int stride, const Shap
     }
 }
 
-__device__ __forceinline__ void scratch_load(const float* scr, int stride, const PrimK& pk, ShapeW& S) {
+__device__ __forceinline__ void pose_load(const float* scr, int stride, const PrimK& pk, ShapeW& S) {
     S.type = pk.type;
     S.c = mk(scr[0 * stride], scr[1 * stride], scr[2 * stride]);
     S.d[0] = pk.dims[0]; S.d[1] = pk.dims[1]; S.d[2] = pk.dims[2];
@@ -144,120 +180,223 @@ __device__ __forceinline__ void scratch_load(const float* scr, int stride, const
     }
 }
 
-// Distance of one pair minus margins, with verdict-style early outs:
-//   returns a value d with  (d < thr) == (true pair distance < thr)  whenever the true distance is
-//   outside the convergence band; when WANT_DIST the value itself is the pair distance
-//   (lower-bounded by `best` pruning).
-template <bool WANT_DIST>
-__device__ __forceinline__ float pair_distance(ShapeW& A, float mA, ShapeW& B, float mB, bool sharp, float thr, float best) {
+// Narrow phase of one queued candidate.  The ONLY place the GJK is instantiated (per mode).
+template <bool WANT_DIST, int NT>
+__device__ __forceinline__ void eval_candidate(const Ctx& C, uint32_t entry) {
+    const int item = (int)(entry & 0xffu);
+    const int e = (int)((entry & ~kEnvFlag) >> 8);
+    const int fi = C.item_flag ? C.item_flag[item] : item;
+    float best = FLT_MAX;
+    if (WANT_DIST) best = key_float(C.flag[fi]);
+    else if (((volatile int*)C.flag)[fi]) return;          // this item is already decided
+    ShapeW A, Bs;
+    float mA, mB;
+    bool sharp;
+    if (entry & kEnvFlag) {
+        const PairK pr = C.V.env_pairs[e];
+        const PrimK& pb = C.V.prims[pr.a];
+        const ObsK& o = C.V.obs[pr.b];
+        obs_world(o, A);
+        pose_load(C.poses + (size_t)pb.slot * NT + item, NT, pb, Bs);
+        mA = o.margin; mB = pb.margin; sharp = pr.sharp != 0;
+    } else {
+        const PairK pr = C.V.self_pairs[e];
+        const PrimK& pa = C.V.prims[pr.a];
+        const PrimK& pb = C.V.prims[pr.b];
+        pose_load(C.poses + (size_t)pa.slot * NT + item, NT, pa, A);
+        pose_load(C.poses + (size_t)pb.slot * NT + item, NT, pb, Bs);
+        mA = pa.margin; mB = pb.margin; sharp = pr.sharp != 0;
+    }
     float m = mA + mB;
-    const float bd0 = B.d[0], bd1 = B.d[1], bd2 = B.d[2];
     if (sharp) {
+        // box-box under the Bullet margin model: sharp boxes (spheres keep their radius: point cores)
         unround(A, mA);
-        unround(B, mB);
-        // spheres keep their radius (their core is a point)
-        m = (A.type == NBX_PRIM_SPHERE ? mA : 0.f) + (B.type == NBX_PRIM_SPHERE ? mB : 0.f);
+        unround(Bs, mB);
+        m = (A.type == NBX_PRIM_SPHERE ? mA : 0.f) + (Bs.type == NBX_PRIM_SPHERE ? mB : 0.f);
     }
     GjkOut g;
-    if (WANT_DIST) g = gjk_distance<kGjkItersDist>(A, B, best + m, -FLT_MAX);
-    else g = gjk_distance<kGjkIters>(A, B, thr + m, thr + m);
-    B.d[0] = bd0; B.d[1] = bd1; B.d[2] = bd2;   // B is reused by the caller's next pair
-    if (g.overlap) return -m - 1e-3f;   // cores overlap: depth beyond the margins is not computed (clamp)
-    return g.d - m;
+    if (WANT_DIST) g = gjk_distance<kGjkItersDist>(A, Bs, best + m, -FLT_MAX);
+    else g = gjk_distance<kGjkIters>(A, Bs, C.thr + m, C.thr + m);
+    // overlapping cores: depth beyond the margins is not computed (clamp)
+    const float d = g.overlap ? (-m - 1e-3f) : (g.contact ? (-m - 1e-6f) : (g.d - m));
+    if (WANT_DIST) {
+        if (!g.pruned) atomicMin(&C.flag[fi], float_key(d));
+    } else if (d < C.thr) {
+        ((volatile int*)C.flag)[fi] = 1;
+    }
 }
 
-// Evaluate one configuration.  QF: float operator()(int col) returns q[col].
-// Returns the minimum distance (WANT_DIST) or any value < thr as soon as a pair is in contact.
-template <bool WANT_DIST, typename QF>
-__device__ float eval_config(const SceneDev& S, const SceneSm& V, QF qf, float thr, float* scratch, int stride) {
-    float best = FLT_MAX;
-    PoseF X;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        X.R[r * 3 + 0] = S.base[r * 4 + 0]; X.R[r * 3 + 1] = S.base[r * 4 + 1]; X.R[r * 3 + 2] = S.base[r * 4 + 2];
-        X.p[r] = S.base[r * 4 + 3];
+// cold copy for the queue-overflow path, kept out of line so phase 1 stays small
+template <bool WANT_DIST, int NT>
+__device__ __noinline__ void eval_candidate_cold(const Ctx& C, uint32_t entry) { eval_candidate<WANT_DIST, NT>(C, entry); }
+
+// distance between segments {ca + s ua, |s| <= ha} and {cb + t ub, |t| <= hb} (unit directions)
+__device__ __forceinline__ float seg_seg_distance(V3 ca, V3 ua, float ha, V3 cb, V3 ub, float hb) {
+    const V3 r = ca - cb;
+    const float b = dot(ua, ub), c = dot(ua, r), f = dot(ub, r);
+    const float den = 1.f - b * b;
+    float s = den > 1e-9f ? fminf(fmaxf((b * f - c) / den, -ha), ha) : 0.f;
+    float t = fminf(fmaxf(fmaf(b, s, f), -hb), hb);
+    s = fminf(fmaxf(fmaf(b, t, -c), -ha), ha);
+    t = fminf(fmaxf(fmaf(b, s, f), -hb), hb);      // one more alternation: exact for clamped cases
+    const V3 d = madd(madd(r, s, ua), -t, ub);
+    return sqrtf(dot(d, d));
+}
+
+// warp-aggregated append of the surviving lanes' candidates; lanes that do not fit evaluate inline
+template <bool WANT_DIST, int NT>
+__device__ __forceinline__ void push_candidates(const Ctx& C, bool surv, uint32_t code) {
+    const unsigned mask = __ballot_sync(0xffffffffu, surv);
+    if (mask == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    int pos = 0;
+    if (lane == leader) pos = atomicAdd(C.qcount, __popc(mask));
+    pos = __shfl_sync(0xffffffffu, pos, leader) + __popc(mask & ((1u << lane) - 1u));
+    if (surv) {
+        const uint32_t entry = code | (uint32_t)threadIdx.x;
+        if (pos < C.qcap) C.queue[pos] = entry;
+        else eval_candidate_cold<WANT_DIST, NT>(C, entry);     // queue full (pathological scenes): no loss, just slower
     }
-    PoseF saved[kMaxSave];
+}
 
-    auto do_prims = [&](int p0, int p1) -> bool {
-        for (int p = p0; p < p1; ++p) {
-            const PrimK& pk = V.prims[p];
-            ShapeW Bs;
-            prim_world(X, pk, Bs);
-            for (int e = V.env_begin[p]; e < V.env_begin[p + 1]; ++e) {
-                const PairK pr = V.env_pairs[e];
-                const ObsK& o = V.obs[pr.b];
-                // conservative cull: primitive bounding sphere vs the obstacle (exact point-box distance
-                // for boxes, bounding sphere otherwise); (distance lower bound) > cut can neither hit nor
-                // lower the running minimum
-                {
-                    const V3 dc = Bs.c - mk(o.c[0], o.c[1], o.c[2]);
-                    float lbnd;
-                    if (o.type == NBX_PRIM_BOX) {
-                        const float hx = o.dims[0] + o.margin, hy = o.dims[1] + o.margin, hz = o.dims[2] + o.margin;
-                        const float lx = fmaxf(fabsf(fmaf(o.R[0], dc.x, fmaf(o.R[3], dc.y, o.R[6] * dc.z))) - hx, 0.f);
-                        const float ly = fmaxf(fabsf(fmaf(o.R[1], dc.x, fmaf(o.R[4], dc.y, o.R[7] * dc.z))) - hy, 0.f);
-                        const float lz = fmaxf(fabsf(fmaf(o.R[2], dc.x, fmaf(o.R[5], dc.y, o.R[8] * dc.z))) - hz, 0.f);
-                        lbnd = sqrtf(fmaf(lx, lx, fmaf(ly, ly, lz * lz))) - pk.brad;
-                    } else {
-                        lbnd = sqrtf(dot(dc, dc)) - pk.brad - o.brad;
-                    }
-                    if (lbnd > (WANT_DIST ? best : thr) + 1e-6f) continue;
-                }
-                ShapeW As;
-                obs_world(o, As);
-                const float d = pair_distance<WANT_DIST>(As, o.margin, Bs, pk.margin, pr.sharp != 0, thr, best);
-                best = fminf(best, d);
-                if (!WANT_DIST && d < thr) return true;
-            }
-            for (int e = V.self_begin[p]; e < V.self_begin[p + 1]; ++e) {
-                const PairK pr = V.self_pairs[e];
-                const PrimK& pa = V.prims[pr.a];
-                {
-                    const float* sc = scratch + pa.slot * stride;
-                    const V3 dc = Bs.c - mk(sc[0], sc[stride], sc[2 * stride]);
-                    if (sqrtf(dot(dc, dc)) - pk.brad - pa.brad > (WANT_DIST ? best : thr) + 1e-6f) continue;
-                }
-                ShapeW As;
-                scratch_load(scratch + pa.slot * stride, stride, pa, As);
-                const float d = pair_distance<WANT_DIST>(As, pa.margin, Bs, pk.margin, pr.sharp != 0, thr, best);
-                best = fminf(best, d);
-                if (!WANT_DIST && d < thr) return true;
-            }
-            if (pk.slot >= 0) scratch_store(scratch + pk.slot * stride, stride, Bs);
+// phase 1 for this thread's item.  `valid` = the thread has an item; invalid lanes still take part in the ballots.
+//   1a  walk the tree, park every primitive's world core in shared memory;
+//   1b  broad phase.  Obstacle-major for the environment pairs (one obstacle's frame stays in registers
+//       while the primitives paired with it stream past: exact point-to-box distance minus the primitive's
+//       bounding radius), then the self pairs (bounding spheres, refined by the capsule bound for
+//       cylinder-cylinder pairs that survive).  Every pair record is one 16-byte shared-memory load.
+template <bool WANT_DIST, int NT, typename QF>
+__device__ __forceinline__ void phase1(const Ctx& C, bool valid, QF qf, int n_obs, int n_self) {
+    const int tid = threadIdx.x;
+    float* my = C.poses + tid;
+    {
+        PoseF X;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            X.R[r * 3 + 0] = C.base[r * 4 + 0]; X.R[r * 3 + 1] = C.base[r * 4 + 1]; X.R[r * 3 + 2] = C.base[r * 4 + 2];
+            X.p[r] = C.base[r * 4 + 3];
         }
-        return false;
-    };
-
-    if (do_prims(0, S.n_base_prims)) return best;
+        PoseF saved[kMaxSave];
+        auto do_prims = [&](int p0, int p1) {
+            for (int p = p0; p < p1; ++p) {
+                const PrimK& pk = C.V.prims[p];
+                ShapeW Bs;
+                prim_world(X, pk, Bs);
+                pose_store(my + (size_t)pk.slot * NT, NT, Bs);
+            }
+        };
+        do_prims(0, C.n_base_prims);
 #pragma unroll 1
-    for (int j = 0; j < S.n_mov; ++j) {
-        const TreeJointK& jk = V.tree[j];
-        if (jk.load_slot == -2) {
+        for (int j = 0; j < C.n_mov; ++j) {
+            const TreeJointK& jk = C.V.tree[j];
+            if (jk.load_slot == -2) {
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                X.R[r * 3 + 0] = S.base[r * 4 + 0]; X.R[r * 3 + 1] = S.base[r * 4 + 1]; X.R[r * 3 + 2] = S.base[r * 4 + 2];
-                X.p[r] = S.base[r * 4 + 3];
+                for (int r = 0; r < 3; ++r) {
+                    X.R[r * 3 + 0] = C.base[r * 4 + 0]; X.R[r * 3 + 1] = C.base[r * 4 + 1]; X.R[r * 3 + 2] = C.base[r * 4 + 2];
+                    X.p[r] = C.base[r * 4 + 3];
+                }
+            } else if (jk.load_slot >= 0) {
+                X = saved[jk.load_slot];
             }
-        } else if (jk.load_slot >= 0) {
-            X = saved[jk.load_slot];
+            nbxj::joint_step<float, TreeJointK>(X, jk, valid ? qf(jk.qidx) : 0.f);
+            if (jk.save_slot >= 0) saved[jk.save_slot] = X;
+            do_prims(jk.prim_begin, jk.prim_end);
         }
-        nbxj::joint_step<float, TreeJointK>(X, jk, qf(jk.qidx));
-        if (jk.save_slot >= 0) saved[jk.save_slot] = X;
-        if (do_prims(jk.prim_begin, jk.prim_end)) return best;
     }
-    return best;
+
+    float run_ub = FLT_MAX;      // distance mode: no pair can beat the smallest centre distance seen so far
+    const float4* env4 = reinterpret_cast<const float4*>(C.V.env_pairs);
+    const float4* self4 = reinterpret_cast<const float4*>(C.V.self_pairs);
+#pragma unroll 1
+    for (int o = 0; o < n_obs; ++o) {
+        const ObsK& ob = C.V.obs[o];
+        const V3 oc = mk(ob.c[0], ob.c[1], ob.c[2]);
+        const bool is_box = ob.type == NBX_PRIM_BOX;
+        float R[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[k] = ob.R[k];
+        const float hx = ob.dims[0] + ob.margin, hy = ob.dims[1] + ob.margin, hz = ob.dims[2] + ob.margin;
+        const float orad = ob.brad;
+        const int e1 = C.V.env_begin[o + 1];
+#pragma unroll 2
+        for (int e = C.V.env_begin[o]; e < e1; ++e) {
+            const float4 rec = env4[e];                          // {a|b, sharp|flags|slot_a, slot_b|pad, rsum}
+            const int slot_a = (int)(short)(__float_as_uint(rec.y) >> 16);
+            const float* pc = my + (size_t)slot_a * NT;
+            const V3 dc = mk(pc[0], pc[NT], pc[2 * NT]) - oc;
+            float lbnd;
+            if (is_box) {
+                const float lx = fmaxf(fabsf(fmaf(R[0], dc.x, fmaf(R[3], dc.y, R[6] * dc.z))) - hx, 0.f);
+                const float ly = fmaxf(fabsf(fmaf(R[1], dc.x, fmaf(R[4], dc.y, R[7] * dc.z))) - hy, 0.f);
+                const float lz = fmaxf(fabsf(fmaf(R[2], dc.x, fmaf(R[5], dc.y, R[8] * dc.z))) - hz, 0.f);
+                lbnd = sqrtf(fmaf(lx, lx, fmaf(ly, ly, lz * lz))) - rec.w;
+            } else {
+                lbnd = sqrtf(dot(dc, dc)) - rec.w - orad;
+            }
+            if (WANT_DIST) run_ub = fminf(run_ub, sqrtf(dot(dc, dc)));
+            const bool surv = valid && lbnd <= (WANT_DIST ? run_ub : C.thr) + 1e-6f;
+            push_candidates<WANT_DIST, NT>(C, surv, kEnvFlag | ((uint32_t)e << 8));
+        }
+    }
+#pragma unroll 2
+    for (int e = 0; e < n_self; ++e) {
+        const float4 rec = self4[e];
+        const uint32_t w1 = __float_as_uint(rec.y), w2 = __float_as_uint(rec.z);
+        const int slot_a = (int)(short)(w1 >> 16), slot_b = (int)(short)(w2 & 0xffffu);
+        const float* pa = my + (size_t)slot_a * NT;
+        const float* pb = my + (size_t)slot_b * NT;
+        const V3 ca = mk(pa[0], pa[NT], pa[2 * NT]);
+        const V3 cb = mk(pb[0], pb[NT], pb[2 * NT]);
+        const V3 dc = cb - ca;
+        const float cd = sqrtf(dot(dc, dc));
+        if (WANT_DIST) run_ub = fminf(run_ub, cd);
+        const float cut = (WANT_DIST ? run_ub : C.thr) + 1e-6f;
+        bool surv = valid && cd - rec.w <= cut;
+        if (surv && ((w1 >> 8) & 0xffu)) {
+            // thin links: capsule bound  d(cyl, cyl) >= d(axis segment, axis segment) - rA - rB
+            const PairK pr = C.V.self_pairs[e];
+            const PrimK& ka = C.V.prims[pr.a];
+            const PrimK& kb = C.V.prims[pr.b];
+            const V3 ua = mk(pa[3 * NT], pa[4 * NT], pa[5 * NT]);
+            const V3 ub = mk(pb[3 * NT], pb[4 * NT], pb[5 * NT]);
+            const float d = seg_seg_distance(ca, ua, ka.dims[1] + ka.margin, cb, ub, kb.dims[1] + kb.margin) -
+                            (ka.dims[0] + ka.margin) - (kb.dims[0] + kb.margin);
+            surv = d <= cut;
+        }
+        push_candidates<WANT_DIST, NT>(C, surv, (uint32_t)e << 8);
+    }
+}
+
+template <bool WANT_DIST, int NT>
+__device__ __forceinline__ void phase2(const Ctx& C) {
+    const int count = min(*C.qcount, C.qcap);
+    for (int k = threadIdx.x; k < count; k += NT) eval_candidate<WANT_DIST, NT>(C, C.queue[k]);
+}
+
+__host__ __device__ inline size_t work_smem_bytes(int nt, int pose_floats, int dof_floats_per_item) {
+    return align16(sizeof(float) * (size_t)nt * (pose_floats > 0 ? pose_floats : 1)) + align16(sizeof(uint32_t) * (size_t)nt * kQueuePerThread) +
+           align16(sizeof(float) * (size_t)nt * dof_floats_per_item) + align16(sizeof(int) * (size_t)(2 * nt + 4));
 }
 
 // ---------------------------------------------------------------------------------------------
+template <bool WANT_DIST>
 __global__ void __launch_bounds__(kCTile)
 in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ q, int64_t B, int dof, float thr,
                     uint8_t* __restrict__ verdict, float* __restrict__ min_dist) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SceneSm V;
-    unsigned char* p = stage_scene(S, smem_raw, V);
-    float* sq = reinterpret_cast<float*>(p);
-    float* scratch = sq + (size_t)kCTile * dof;
+    Ctx C;
+    unsigned char* p = stage_scene(S, smem_raw, C.V);
+    C.poses = reinterpret_cast<float*>(p);              p += align16(sizeof(float) * (size_t)kCTile * max(S.scratch_floats, 1));
+    C.queue = reinterpret_cast<uint32_t*>(p);           p += align16(sizeof(uint32_t) * (size_t)kCTile * kQueuePerThread);
+    float* sq = reinterpret_cast<float*>(p);            p += align16(sizeof(float) * (size_t)kCTile * dof);
+    C.flag = reinterpret_cast<int*>(p);
+    C.qcount = C.flag + kCTile;
+    C.item_flag = nullptr;
+    C.qcap = kCTile * kQueuePerThread;
+    C.base = S.base;
+    C.n_mov = S.n_mov; C.n_prims = S.n_prims; C.n_base_prims = S.n_base_prims;
+    C.thr = thr;
 
     const int64_t tile0 = (int64_t)blockIdx.x * kCTile;
     const int nvalid = (int)min((int64_t)kCTile, B - tile0);
@@ -274,15 +413,24 @@ in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict_
             for (int i = tid; i < n; i += kCTile) sq[i] = src[i];
         }
     }
+    C.flag[tid] = WANT_DIST ? float_key(FLT_MAX) : 0;
+    if (tid == 0) *C.qcount = 0;
     __syncthreads();
-    if (tid >= nvalid) return;
+
     const float* myq = sq + tid * dof;
-    auto qf = [myq](int col) { return myq[col]; };
-    float d;
-    if (min_dist != nullptr) d = eval_config<true>(S, V, qf, thr, scratch + tid, kCTile);
-    else d = eval_config<false>(S, V, qf, thr, scratch + tid, kCTile);
-    verdict[tile0 + tid] = d < thr ? 1 : 0;
-    if (min_dist != nullptr) min_dist[tile0 + tid] = d;
+    phase1<WANT_DIST, kCTile>(C, tid < nvalid, [myq](int col) { return myq[col]; }, S.n_obs, S.n_self);
+    __syncthreads();
+    phase2<WANT_DIST, kCTile>(C);
+    __syncthreads();
+    if (tid < nvalid) {
+        if (WANT_DIST) {
+            const float d = key_float(C.flag[tid]);
+            min_dist[tile0 + tid] = d;
+            verdict[tile0 + tid] = d < thr ? 1 : 0;
+        } else {
+            verdict[tile0 + tid] = (uint8_t)C.flag[tid];
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -291,21 +439,33 @@ in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict_
 //   distance = ||goal - start||_2 ; distance <= float32 eps -> invalid
 //   step = resolution / distance ; T_f = 1 (connect) or min(1, max_distance / distance) (steer)
 //   samples: t_k = k * step for k < ceil(T_f / step)  (numpy.arange length rule), then t = T_f.
+// A block prefix sum flattens the (edge, sample) space of the CTA's edges; rounds of kETile samples go
+// through phase 1 / phase 2.  Samples of an edge that is already invalid are skipped, as the sequential
+// reference does by returning None.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kETile)
 edges_valid_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ starts, const float* __restrict__ goals,
                    int64_t E, int dof, double resolution, double max_distance, float thr,
                    uint8_t* __restrict__ valid, int32_t* __restrict__ n_samples) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SceneSm V;
-    unsigned char* p = stage_scene(S, smem_raw, V);
-    float* s_start = reinterpret_cast<float*>(p);
+    Ctx C;
+    unsigned char* p = stage_scene(S, smem_raw, C.V);
+    C.poses = reinterpret_cast<float*>(p);              p += align16(sizeof(float) * (size_t)kETile * max(S.scratch_floats, 1));
+    C.queue = reinterpret_cast<uint32_t*>(p);           p += align16(sizeof(uint32_t) * (size_t)kETile * kQueuePerThread);
+    float* s_start = reinterpret_cast<float*>(p);       p += align16(sizeof(float) * (size_t)kETile * 2 * dof);
     float* s_goal = s_start + (size_t)kETile * dof;
-    double* s_step = reinterpret_cast<double*>(s_goal + (size_t)kETile * dof + ((kETile * dof) & 1));
-    double* s_tf = s_step + kETile;
-    int* s_off = reinterpret_cast<int*>(s_tf + kETile);      // [kETile + 1] exclusive prefix of sample counts
-    volatile int* s_ok = s_off + kETile + 1;                 // [kETile]
-    float* scratch = reinterpret_cast<float*>(s_off + 2 * kETile + 1);
+    int* s_hit = reinterpret_cast<int*>(p);             // [kETile] per EDGE: 1 = some sample collides
+    int* s_item_edge = s_hit + kETile;                  // [kETile] per ITEM of the current round: its edge
+    C.qcount = s_item_edge + kETile;                    p += align16(sizeof(int) * (size_t)(2 * kETile + 4));
+    double* s_step = reinterpret_cast<double*>(p);      p += sizeof(double) * kETile;
+    double* s_tf = reinterpret_cast<double*>(p);        p += sizeof(double) * kETile;
+    int* s_off = reinterpret_cast<int*>(p);             // [kETile + 1] exclusive prefix of sample counts
+    C.flag = s_hit;
+    C.item_flag = s_item_edge;
+    C.qcap = kETile * kQueuePerThread;
+    C.base = S.base;
+    C.n_mov = S.n_mov; C.n_prims = S.n_prims; C.n_base_prims = S.n_base_prims;
+    C.thr = thr;
 
     const int64_t tile0 = (int64_t)blockIdx.x * kETile;
     const int nvalid = (int)min((int64_t)kETile, E - tile0);
@@ -317,6 +477,7 @@ edges_valid_kernel(const __grid_constant__ SceneDev S, const float* __restrict__
     __syncthreads();
 
     int cnt = 0;
+    int dead = 1;            // edges beyond nvalid, and edges shorter than float32 eps, have no samples and are invalid
     if (tid < nvalid) {
         double ss = 0.0;
         for (int k = 0; k < dof; ++k) {
@@ -324,10 +485,7 @@ edges_valid_kernel(const __grid_constant__ SceneDev S, const float* __restrict__
             ss = fma(dlt, dlt, ss);
         }
         const double dist = sqrt(ss);
-        int ok = 1;
-        if (dist <= (double)1.1920928955078125e-07f) {
-            ok = 0;
-        } else {
+        if (dist > (double)1.1920928955078125e-07f) {
             const double step = resolution / dist;
             double tf = 1.0;
             if (max_distance > 0.0 && dist > max_distance) tf = max_distance / dist;
@@ -335,10 +493,11 @@ edges_valid_kernel(const __grid_constant__ SceneDev S, const float* __restrict__
             cnt = (int)fmin(len, 1.0e9) + 1;
             s_step[tid] = step;
             s_tf[tid] = tf;
+            dead = 0;
         }
-        s_ok[tid] = ok;
         if (n_samples != nullptr) n_samples[tile0 + tid] = cnt;
     }
+    s_hit[tid] = dead;
     // block exclusive scan of cnt (kETile = 128: warp scans + 4 partials)
     {
         __shared__ int warp_tot[kETile / 32];
@@ -358,27 +517,35 @@ edges_valid_kernel(const __grid_constant__ SceneDev S, const float* __restrict__
     __syncthreads();
     const int total = s_off[kETile];
 
-    for (int s = tid; s < total; s += kETile) {
-        // owning edge: last e with s_off[e] <= s
-        int lo = 0, hi = kETile - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (s_off[mid] <= s) lo = mid; else hi = mid - 1;
+    for (int round0 = 0; round0 < total; round0 += kETile) {
+        const int s = round0 + tid;
+        bool have = s < total;
+        int e = 0;
+        float t = 0.f;
+        if (have) {
+            // owning edge: last e with s_off[e] <= s
+            int lo = 0, hi = kETile - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (s_off[mid] <= s) lo = mid; else hi = mid - 1;
+            }
+            e = lo;
+            const int k = s - s_off[e];
+            const int last = s_off[e + 1] - s_off[e] - 1;
+            t = (float)((k == last) ? s_tf[e] : (double)k * s_step[e]);
+            have = ((volatile int*)s_hit)[e] == 0;      // already invalid: skip (the sequential reference stops there too)
         }
-        const int e = lo;
-        if (s_ok[e] == 0) continue;   // already invalid (the sequential reference stops there too)
-        const int k = s - s_off[e];
-        const int last = s_off[e + 1] - s_off[e] - 1;
-        const double td = (k == last) ? s_tf[e] : (double)k * s_step[e];
-        const float t = (float)td;
+        s_item_edge[tid] = e;
+        if (tid == 0) *C.qcount = 0;
+        __syncthreads();
         const float* a = s_start + e * dof;
         const float* g = s_goal + e * dof;
-        auto qf = [a, g, t](int col) { return fmaf(t, g[col], fmaf(-t, a[col], a[col])); };
-        const float d = eval_config<false>(S, V, qf, thr, scratch + tid, kETile);
-        if (d < thr) s_ok[e] = 0;
+        phase1<false, kETile>(C, have, [a, g, t](int col) { return fmaf(t, g[col], fmaf(-t, a[col], a[col])); }, S.n_obs, S.n_self);
+        __syncthreads();
+        phase2<false, kETile>(C);
+        __syncthreads();
     }
-    __syncthreads();
-    if (tid < nvalid) valid[tile0 + tid] = (uint8_t)s_ok[tid];
+    if (tid < nvalid) valid[tile0 + tid] = (uint8_t)(s_hit[tid] == 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -399,7 +566,7 @@ int fill_scene_dev(const nbx_chain* ch, const nbx_scene* sc, const double* base_
     S.n_obs = sc->n_obs;
     S.n_self = sc->n_self;
     S.n_env = sc->n_env;
-    S.scratch_floats = sc->scratch_floats;
+    S.scratch_floats = ch->pose_floats;
     for (int k = 0; k < 12; ++k) S.base[k] = (float)base_pose[k];
     return NBX_OK;
 }
@@ -414,13 +581,17 @@ int launch_in_collision(const nbx_chain* ch, const nbx_scene* sc, const float* q
     NBX_REQUIRE(q != nullptr && verdict != nullptr, "q / verdict is NULL");
     NBX_REQUIRE(thr >= 0.f, "negative thresholds need penetration depth, which this path does not compute");
     NBX_CUDA_OK(cudaSetDevice(ch->device));
-    const size_t smem = scene_smem_bytes(S.n_mov, S.n_prims, S.n_obs, S.n_self, S.n_env) +
-                        sizeof(float) * (size_t)kCTile * ch->dof + sizeof(float) * (size_t)kCTile * std::max(1, S.scratch_floats);
+    const size_t smem = scene_smem_bytes(S.n_mov, S.n_prims, S.n_obs, S.n_self, S.n_env) + work_smem_bytes(kCTile, S.scratch_floats, ch->dof);
     NBX_REQUIRE(smem <= 220 * 1024, "scene too large for shared memory (%zu bytes)", smem);
-    NBX_CUDA_OK(cudaFuncSetAttribute(in_collision_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = (B + kCTile - 1) / kCTile;
     NBX_REQUIRE(grid <= 0x7fffffffLL, "batch too large for one launch");
-    in_collision_kernel<<<(unsigned)grid, kCTile, smem, stream>>>(S, q, B, ch->dof, thr, verdict, min_dist);
+    if (min_dist != nullptr) {
+        NBX_CUDA_OK(cudaFuncSetAttribute(in_collision_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        in_collision_kernel<true><<<(unsigned)grid, kCTile, smem, stream>>>(S, q, B, ch->dof, thr, verdict, min_dist);
+    } else {
+        NBX_CUDA_OK(cudaFuncSetAttribute(in_collision_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        in_collision_kernel<false><<<(unsigned)grid, kCTile, smem, stream>>>(S, q, B, ch->dof, thr, verdict, min_dist);
+    }
     nbx_count_launch();
     NBX_CUDA_OK(cudaGetLastError());
     return NBX_OK;
@@ -439,9 +610,8 @@ int launch_edges(const nbx_chain* ch, const nbx_scene* sc, const float* starts, 
     NBX_REQUIRE(thr >= 0.f, "negative thresholds need penetration depth, which this path does not compute");
     NBX_CUDA_OK(cudaSetDevice(ch->device));
     const int dof = ch->dof;
-    const size_t smem = scene_smem_bytes(S.n_mov, S.n_prims, S.n_obs, S.n_self, S.n_env) +
-                        sizeof(float) * (2 * (size_t)kETile * dof + ((kETile * dof) & 1)) + sizeof(double) * 2 * kETile +
-                        sizeof(int) * (2 * kETile + 1) + 16 + sizeof(float) * (size_t)kETile * std::max(1, S.scratch_floats);
+    const size_t smem = scene_smem_bytes(S.n_mov, S.n_prims, S.n_obs, S.n_self, S.n_env) + work_smem_bytes(kETile, S.scratch_floats, 2 * dof) +
+                        sizeof(double) * 2 * kETile + sizeof(int) * (kETile + 4);
     NBX_REQUIRE(smem <= 220 * 1024, "scene too large for shared memory (%zu bytes)", smem);
     NBX_CUDA_OK(cudaFuncSetAttribute(edges_valid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = (E + kETile - 1) / kETile;

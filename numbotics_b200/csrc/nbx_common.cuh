@@ -94,11 +94,16 @@ struct ObsK {
     int pad[2];
 };
 
+// One allowed pair, 16 bytes so the broad phase reads it with a single LDS.128.
 struct PairK {
-    int16_t a;       // link primitive (for self pairs: the one with the smaller index)
-    int16_t b;       // link primitive (self) or obstacle (env)
-    uint8_t sharp;
-    uint8_t pad[3];
+    int16_t a;        // link primitive (self pairs: the one with the smaller device index)
+    int16_t b;        // link primitive (self) or obstacle (env)
+    uint8_t sharp;    // 1 = ignore margins (box-box under the Bullet model)
+    uint8_t both_cyl; // self pairs: both primitives are cylinders -> capsule bound available
+    int16_t slot_a;   // float offset of a's world core in the per-item pose scratch
+    int16_t slot_b;   // same for b (self pairs only)
+    int16_t pad;
+    float rsum;       // self: bounding radius a + bounding radius b ; env: bounding radius of the link primitive
 };
 
 // Whole-tree walk used by the collision kernels.  Lives in global memory; blocks stage it in
@@ -129,6 +134,7 @@ struct nbx_chain {
     // collision walk
     int n_save_slots;
     int n_base_prims;                // primitives attached to the base (sorted first)
+    int pose_floats;                 // per-item floats needed to park every primitive's world core
     std::vector<int> prim_order;     // device primitive index -> descriptor primitive index
     std::vector<int> prim_rank;      // descriptor primitive index -> device primitive index
     std::vector<TreeJointK> h_tree;
@@ -143,8 +149,8 @@ struct nbx_scene {
     int scratch_floats;              // per-thread scratch for stored primitive poses
     std::vector<PrimK> h_prims;      // chain prims with `slot` resolved for this pair set
     std::vector<ObsK> h_obs;
-    std::vector<PairK> h_self, h_env;   // sorted by the primitive that triggers the test
-    std::vector<int> h_self_begin, h_env_begin;   // [n_prims+1] ranges per triggering primitive
+    std::vector<PairK> h_self, h_env;   // self: sorted by (b, a); env: sorted by (obstacle, primitive)
+    std::vector<int> h_self_begin, h_env_begin;   // h_env_begin: [n_obs+1] ranges per obstacle (h_self_begin unused)
     PrimK* d_prims;
     ObsK* d_obs;
     PairK* d_self;
