@@ -264,7 +264,7 @@ def main():
     avg_launch_ms = total_ms / args.steps
     achieved = BYTES_PER_CFG * B / (avg_launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": recorded_traffic(), "kernel": "fkjac_dense_kernel<float,7,128>",
+                "traffic": recorded_traffic(), "kernel": "fkjac_dense_kernel<float, 7, 128, ALLZ=true, KT=2>",
                 "algorithmic_bytes_per_launch": BYTES_PER_CFG * B, "avg_launch_ms": avg_launch_ms,
                 "best_launch_ms": per_step[0], "median_launch_ms": per_step[len(per_step) // 2],
                 "peak_source": peak_src, "fp32_tflops": FLOPS_PER_CFG * B / (avg_launch_ms * 1e-3) / 1e12}

@@ -191,6 +191,24 @@ NBX_API int nbx_edges_valid_host_f32(const nbx_chain* chain, const nbx_scene* sc
                              const double* base_pose, double resolution, double max_distance,
                              float threshold, uint8_t* valid);
 
+/*
+ * Batched damped-least-squares inverse kinematics: the reference's whole iteration loop
+ * (numbotics/robots/arm.py:464-552, Arm.inverse_kinematics) on the device, one problem per thread.
+ *   target_pose (B,4,4) or (4,4) device; target_stride = 16 or 0 (broadcast)
+ *   q0          (B,dof) device, initial guess;   q_out (B,dof) device (may alias q0)
+ *   lower/upper HOST arrays [dof] (nullable unless use_limits)
+ *   success     (B,) u8: |error twist| < tol at exit;  iters_out (nullable) int32 (B,)
+ * Defaults of the reference: tol 1e-6, max_iter 100, max_failures 15.
+ */
+NBX_API int nbx_ik_dls_f64(const nbx_chain* chain, int frame, const double* target_pose, int64_t target_stride,
+                   const double* q0, int64_t B, const double* base_pose, int use_com, int use_limits,
+                   const double* lower, const double* upper, double tol, int max_iter, int max_failures,
+                   double* q_out, uint8_t* success, int32_t* iters_out, void* stream);
+NBX_API int nbx_ik_dls_f32(const nbx_chain* chain, int frame, const float* target_pose, int64_t target_stride,
+                   const float* q0, int64_t B, const double* base_pose, int use_com, int use_limits,
+                   const double* lower, const double* upper, double tol, int max_iter, int max_failures,
+                   float* q_out, uint8_t* success, int32_t* iters_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

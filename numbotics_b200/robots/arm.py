@@ -371,6 +371,71 @@ class Arm:
         """Pose and Jacobian from ONE pass over q (what the fused kernel natively produces)."""
         return self._fkjac(q, frame, use_com, local_pose, None, True, True)
 
+    def inverse_kinematics(self, pose, q0, frame: str, use_com: bool = False, use_limits: bool = False,
+                           tol: float = 1e-6, max_iter: int = 100, max_failures: int = 15, return_iters: bool = False):
+        """Batched damped-least-squares IK (reference arm.py:464-552), the whole loop on the device.
+
+        Returns `(converged, q)` like the reference: `converged = |error twist| < tol`; shapes follow the
+        reference's batch rules (pose `(...,4,4)` / `(4,4)`, q0 `(...,dof)` / `(dof,)`).
+        """
+        fid = self._frame_id(frame)
+        self._check_q(q0, "q0")
+        if max_iter < 1:
+            raise ValueError("max_iter must be greater than 0")
+        in_torch = _is_torch(q0) or _is_torch(pose)
+        pose_shape, q_shape = tuple(pose.shape), tuple(q0.shape)
+        if pose_shape[-2:] != (4, 4):
+            raise ValueError("pose must be a 4x4 matrix")
+        batch_dims = None
+        if len(pose_shape) > 2:
+            batch_dims = pose_shape[:-2]
+        if len(q_shape) > 1:
+            if batch_dims is not None:
+                if q_shape[:-1] != batch_dims:
+                    raise ValueError("pose and q0 must have the same batch dimensions")
+            else:
+                batch_dims = q_shape[:-1]
+        B = int(np.prod(batch_dims)) if batch_dims is not None else 1
+        f64 = (q0.dtype in (np.float64,)) if not _is_torch(q0) else (q0.dtype == torch.float64)
+        if not _is_torch(q0) and q0.dtype not in (np.float32, np.float64):
+            q0 = np.asarray(q0, dtype=np.float64)
+            f64 = True
+        tdtype = torch.float64 if f64 else torch.float32
+        dev_index = self.device_index
+        qd = self._to_device(q0, tdtype).reshape(-1, self.dof)
+        if qd.shape[0] != B:
+            qd = qd.expand(B, self.dof).contiguous()
+        pd = self._to_device(pose, tdtype).reshape(-1, 4, 4)
+        stride = 16 if pd.shape[0] == B and B > 1 else (0 if pd.shape[0] == 1 else 16)
+        lim = np.ascontiguousarray(self.joint_limits, dtype=np.float64)
+        lo = np.ascontiguousarray(lim[:, 0]) if lim.size else np.zeros(1)
+        hi = np.ascontiguousarray(lim[:, 1]) if lim.size else np.zeros(1)
+        base_keep, base_ptr = _cabi.base_pose_arg(self.base_pose)
+        lib = _cabi.load()
+        with torch.cuda.device(dev_index):
+            q_out = torch.empty_like(qd)
+            ok = torch.empty((B,), dtype=torch.uint8, device=qd.device)
+            iters = torch.empty((B,), dtype=torch.int32, device=qd.device) if return_iters else None
+            fn = lib.nbx_ik_dls_f64 if f64 else lib.nbx_ik_dls_f32
+            _cabi.check(fn(self._handle().ptr, fid, pd.data_ptr(), stride, qd.data_ptr(), B, base_ptr, int(bool(use_com)),
+                           int(bool(use_limits)), lo.ctypes.data_as(C.POINTER(C.c_double)), hi.ctypes.data_as(C.POINTER(C.c_double)),
+                           float(tol), int(max_iter), int(max_failures), q_out.data_ptr(), ok.data_ptr(),
+                           iters.data_ptr() if return_iters else None, _cuda_stream_ptr(dev_index)))
+        del base_keep
+        ok = ok.to(torch.bool)
+        if batch_dims is None:
+            q_res, ok_res = q_out[0], ok           # reference: q[0] and a (1,) bool array (arm.py:550-551)
+        else:
+            q_res, ok_res = q_out.reshape(*batch_dims, self.dof), ok.reshape(batch_dims)
+        it_res = None if iters is None else (iters if batch_dims is None else iters.reshape(batch_dims))
+        if not in_torch:
+            q_res, ok_res = q_res.cpu().numpy(), ok_res.cpu().numpy()
+            it_res = None if it_res is None else it_res.cpu().numpy()
+        elif _is_torch(q0) and q0.device.type != "cuda":
+            q_res, ok_res = q_res.cpu(), ok_res.cpu()
+            it_res = None if it_res is None else it_res.cpu()
+        return (ok_res, q_res, it_res) if return_iters else (ok_res, q_res)
+
     # ------------------------------------------------------------------ collision validity
     def in_collision(self, q, threshold: float = 0.0):
         """`min over allowed pairs of distance < threshold` (reference arm.py:603-604), batched.
