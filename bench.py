@@ -112,14 +112,21 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 # -------------------------------------------------------------------------------------------------
 def cpu_port_rate(arm, n_cfg: int, threads: int | None = None, repeats: int = 1):
     """configs/s of the float64 C/OpenMP restatement (FK + Jacobian, tool_frame) on `n_cfg` configs."""
     import numpy as np
     from numbotics_b200 import workloads
     from oracle import collision
-    if threads:
-        collision.set_threads(threads)
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: ask for every core this process may run on instead
+    collision.set_threads(threads if threads else host_threads())
     desc = collision.CDesc(arm._arrays)
     fid = arm._arrays["frame_id"]["tool_frame"]
     q = workloads.random_configs_np(arm, n_cfg, seed=0)
@@ -278,7 +285,7 @@ def main():
         rate, cores, qs, (To, Jo) = cpu_port_rate(arm, sample)
         rate1, _, _, _ = cpu_port_rate(arm, 1 << 17, threads=1)
         from oracle import collision as _oc
-        _oc.set_threads(os.cpu_count() or 1)
+        _oc.set_threads(host_threads())
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"{sample} uniformly sampled Kinova-7 configurations (seed 0), float64 C/OpenMP restatement of "
                                   "numbotics/robots/helpers.py:91-187, FK + Jacobian of tool_frame",

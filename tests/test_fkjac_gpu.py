@@ -196,3 +196,56 @@ def test_large_angles_sincos_range(kinova):
     q_as_seen = q32.astype(np.float64)
     assert rel_err(T, ora.forward_kinematics(q_as_seen, "tool_frame")) <= RTOL32
     assert rel_err(J, ora.jacobian(q_as_seen, "tool_frame")) <= RTOL32
+
+
+def test_empty_unaligned_and_noncontiguous_inputs(kinova, cuda):
+    """Edge cases of the boundary: B = 0, tensors that are views at odd offsets (pointers not 16-byte aligned:
+    the kernels must drop to their non-TMA path), non-contiguous inputs, and every ragged size around a tile."""
+    import torch
+    ora = fkjac.ArmOracle(kinova._link_joint_sequence, 7, kinova.base_pose)
+    T0, J0 = kinova.fk_jacobian(np.zeros((0, 7)), "tool_frame")
+    assert T0.shape == (0, 4, 4) and J0.shape == (0, 6, 7)
+    T0, J0 = kinova.fk_jacobian(torch.zeros((0, 7), device=cuda), "tool_frame")
+    assert T0.shape == (0, 4, 4) and J0.shape == (0, 6, 7)
+    q = workloads.random_configs_cuda(kinova, 1000, seed=11)
+    To, Jo = ora.forward_kinematics(q.double().cpu().numpy(), "tool_frame"), ora.jacobian(q.double().cpu().numpy(), "tool_frame")
+    # misaligned q: a view starting one float into a larger buffer
+    buf = torch.empty(1000 * 7 + 1, device=cuda)
+    qv = buf[1:].view(1000, 7)
+    qv.copy_(q)
+    assert qv.data_ptr() % 16 != 0
+    T, J = kinova.fk_jacobian(qv, "tool_frame")
+    assert rel_err(T.cpu().numpy(), To) <= RTOL32 and rel_err(J.cpu().numpy(), Jo) <= RTOL32
+    # non-contiguous q (every other row of a wider tensor)
+    wide = torch.zeros((2000, 7), device=cuda)
+    wide[::2] = q
+    T, J = kinova.fk_jacobian(wide[::2], "tool_frame")
+    assert rel_err(T.cpu().numpy(), To) <= RTOL32 and rel_err(J.cpu().numpy(), Jo) <= RTOL32
+    # ragged sizes around one and two tiles (two consecutive tiles per CTA)
+    for n in (1, 127, 128, 129, 255, 256, 257, 383):
+        T, J = kinova.fk_jacobian(q[:n], "tool_frame")
+        assert T.shape == (n, 4, 4)
+        assert rel_err(T.cpu().numpy(), To[:n]) <= RTOL32 and rel_err(J.cpu().numpy(), Jo[:n]) <= RTOL32
+    # sparse-column frame through the generic kernel, ragged
+    Tf, Jf = kinova.fk_jacobian(q[:333], "forearm_link")
+    assert rel_err(Tf.cpu().numpy(), ora.forward_kinematics(q[:333].double().cpu().numpy(), "forearm_link")) <= RTOL32
+    assert rel_err(Jf.cpu().numpy(), ora.jacobian(q[:333].double().cpu().numpy(), "forearm_link")) <= RTOL32
+    assert float(Jf[:, :, 4:].abs().max()) == 0.0     # joints past the forearm do not move it
+
+
+def test_cabi_rejects_bad_arguments(kinova, cuda):
+    """Status codes instead of crashes: the C-ABI validates what the Python layer cannot know."""
+    import torch
+    from numbotics_b200 import _cabi
+    lib = _cabi.load()
+    h = kinova._handle()
+    keep, base = _cabi.base_pose_arg(kinova.base_pose)
+    q = torch.zeros((4, 7), device=cuda)
+    T = torch.empty((4, 4, 4), device=cuda)
+    assert lib.nbx_fk_jac_f32(h.ptr, 999, q.data_ptr(), 4, base, 0, None, 0, None, 0, T.data_ptr(), None, None) == -1
+    assert "frame id" in _cabi.last_error()
+    assert lib.nbx_fk_jac_f32(h.ptr, 0, q.data_ptr(), -1, base, 0, None, 0, None, 0, T.data_ptr(), None, None) == -1
+    assert lib.nbx_fk_jac_f32(h.ptr, 0, None, 4, base, 0, None, 0, None, 0, T.data_ptr(), None, None) == -1
+    assert lib.nbx_fk_jac_f32(None, 0, q.data_ptr(), 4, base, 0, None, 0, None, 0, T.data_ptr(), None, None) == -1
+    with pytest.raises(_cabi.NbxError, match="frame id"):
+        _cabi.check(lib.nbx_fk_jac_f32(h.ptr, -3, q.data_ptr(), 4, base, 0, None, 0, None, 0, T.data_ptr(), None, None))
