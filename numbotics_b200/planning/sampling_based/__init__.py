@@ -1,4 +1,5 @@
 """Connectors of the sampling-based planners (reference planning/sampling_based/__init__.py)."""
 from .connectors import Connector, ConnectorParams, DiscreteConnector, ArmValidityChecker
+from .roadmap import BatchedPRM, Roadmap, knn_earlier
 
-__all__ = ["Connector", "ConnectorParams", "DiscreteConnector", "ArmValidityChecker"]
+__all__ = ["Connector", "ConnectorParams", "DiscreteConnector", "ArmValidityChecker", "BatchedPRM", "Roadmap", "knn_earlier"]

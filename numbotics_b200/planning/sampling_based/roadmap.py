@@ -1,0 +1,125 @@
+"""Batched PRM roadmap construction: the caller of the edge kernel.
+
+The reference builds a roadmap one sample at a time (numbotics/planning/sampling_based/planners/prm.py:19-47):
+sample a state, add it as a vertex, ask faiss for its k nearest earlier vertices
+(math/geometry/nearest_neighbors.py:6-85), and call `connector.connect(neighbor, new)` k times.  Here the same
+roadmap is built inside out: all samples are drawn at once, the k nearest *earlier* vertices of every sample
+come from one masked brute-force kNN on the device (plumbing: torch matmul + topk, like the reference's faiss
+IndexFlatL2), and all N*k candidate edges go through ONE launch of the fused edge kernel
+(`DiscreteConnector.connect_batch`).  Edge set and weights are those the sequential loop would produce for the
+same sample sequence (up to kNN ties).
+"""
+from dataclasses import dataclass
+
+import numpy as np
+
+try:
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+from .connectors import DiscreteConnector, ArmValidityChecker
+
+
+@dataclass
+class Roadmap:
+    nodes: "torch.Tensor"        # (N, dof) on the device
+    edges: "torch.Tensor"        # (M, 2) int64, edge (earlier vertex, later vertex), undirected
+    weights: "torch.Tensor"      # (M,) L2 length
+    candidates: int              # candidate edges that were validated
+    node_valid: "torch.Tensor"   # (N,) bool: the vertex itself is collision free
+
+    def to_networkx(self):
+        import networkx as nx
+        G = nx.Graph()
+        nodes = self.nodes.cpu().numpy()
+        for i, s in enumerate(nodes):
+            G.add_node(f"v_{i}", state=s)
+        e = self.edges.cpu().numpy()
+        w = self.weights.cpu().numpy()
+        for (u, v), wt in zip(e, w):
+            G.add_edge(f"v_{u}", f"v_{v}", weight=float(wt))
+        return G
+
+    def shortest_path(self, src: int, dst: int):
+        """Vertex indices of the shortest path src -> dst (None if disconnected); Dijkstra on the host."""
+        from scipy.sparse import coo_matrix
+        from scipy.sparse.csgraph import dijkstra
+        n = self.nodes.shape[0]
+        e = self.edges.cpu().numpy()
+        w = self.weights.cpu().numpy().astype(np.float64)
+        if e.shape[0] == 0:
+            return None
+        A = coo_matrix((np.concatenate([w, w]), (np.concatenate([e[:, 0], e[:, 1]]), np.concatenate([e[:, 1], e[:, 0]]))), shape=(n, n)).tocsr()
+        dist, pred = dijkstra(A, directed=False, indices=src, return_predecessors=True)
+        if not np.isfinite(dist[dst]):
+            return None
+        path = [dst]
+        while path[-1] != src:
+            path.append(int(pred[path[-1]]))
+        return path[::-1]
+
+
+def knn_earlier(nodes, k: int, chunk: int = 4096):
+    """For every vertex i > 0 its (up to) k nearest vertices among 0..i-1 (the reference's incremental kNN).
+    Returns (idx (N,k) int64, valid (N,k) bool)."""
+    N = nodes.shape[0]
+    idx = torch.zeros((N, k), dtype=torch.long, device=nodes.device)
+    ok = torch.zeros((N, k), dtype=torch.bool, device=nodes.device)
+    sq = (nodes * nodes).sum(-1)
+    cols = torch.arange(N, device=nodes.device)
+    for s in range(0, N, chunk):
+        e = min(s + chunk, N)
+        hi = e                                       # rows s..e-1 only look at columns < e
+        d2 = sq[s:e, None] - 2.0 * nodes[s:e] @ nodes[:hi].T + sq[None, :hi]
+        rows = torch.arange(s, e, device=nodes.device)
+        d2 = torch.where(cols[None, :hi] < rows[:, None], d2, torch.full_like(d2, float("inf")))
+        kk = min(k, hi)
+        val, ind = torch.topk(d2, kk, dim=1, largest=False)
+        idx[s:e, :kk] = ind
+        ok[s:e, :kk] = torch.isfinite(val)
+    return idx, ok
+
+
+class BatchedPRM:
+    """Roadmap over an Arm's configuration space with DiscreteConnector edge semantics."""
+
+    def __init__(self, connector: DiscreteConnector, lower_bounds, upper_bounds, k_nearest: int = 10):
+        chk = connector._params.validity_checker
+        if not isinstance(chk, ArmValidityChecker):
+            raise ValueError("BatchedPRM needs a DiscreteConnector whose validity checker is an ArmValidityChecker")
+        self.connector = connector
+        self.arm = chk.arm
+        self.lower = np.asarray(lower_bounds, dtype=np.float64)
+        self.upper = np.asarray(upper_bounds, dtype=np.float64)
+        if self.lower.shape != self.upper.shape or self.lower.ndim != 1:
+            raise ValueError("Lower and upper bounds must be 1D arrays of the same shape")
+        self.k = int(k_nearest)
+
+    def build(self, n_samples: int, start=None, goals=(), seed: int = 0, nodes=None) -> Roadmap:
+        """Vertices = [start] + goals + uniform samples (or the given `nodes`); edges as described above."""
+        dev = torch.device("cuda", self.arm.device_index)
+        if nodes is None:
+            g = torch.Generator(device=dev)
+            g.manual_seed(seed)
+            lo = torch.as_tensor(self.lower, dtype=torch.float32, device=dev)
+            hi = torch.as_tensor(self.upper, dtype=torch.float32, device=dev)
+            samples = lo + torch.rand((n_samples, lo.shape[0]), generator=g, dtype=torch.float32, device=dev) * (hi - lo)
+            fixed = [np.asarray(s, dtype=np.float32) for s in ([start] if start is not None else []) + list(goals)]
+            if fixed:
+                samples = torch.cat([torch.as_tensor(np.stack(fixed), device=dev), samples], dim=0)
+            nodes = samples
+        else:
+            nodes = torch.as_tensor(nodes, dtype=torch.float32, device=dev).contiguous()
+        N = nodes.shape[0]
+        node_valid = ~self.arm.in_collision(nodes, self.connector._params.validity_checker.threshold)
+        idx, ok = knn_earlier(nodes, self.k)
+        later = torch.arange(N, device=dev)[:, None].expand(N, self.k)
+        u = idx[ok]
+        v = later[ok]
+        starts = nodes[u].contiguous()      # connect(neighbor.state, new_node.state)
+        ends = nodes[v].contiguous()
+        valid = self.connector.connect_batch(starts, ends)
+        edges = torch.stack([u[valid], v[valid]], dim=1)
+        weights = (nodes[edges[:, 0]] - nodes[edges[:, 1]]).norm(dim=1)
+        return Roadmap(nodes=nodes, edges=edges, weights=weights, candidates=int(u.shape[0]), node_valid=node_valid)

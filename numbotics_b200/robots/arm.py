@@ -95,8 +95,7 @@ class Arm:
         self._arrays = descriptor.flatten_chain(chain, margin_model)
         self._device = device
         self._chain_handle = None
-        self._scene_handle = None
-        self._scene_key = None
+        self._scenes = {}
         self._scene_arrays = None
 
     # ------------------------------------------------------------------ properties
@@ -128,21 +127,32 @@ class Arm:
             self._chain_handle = _cabi.ChainHandle(self._arrays, self.device_index)
         return self._chain_handle
 
-    def _scene(self) -> _cabi.SceneHandle:
+    def _scene(self, threshold: float = 0.0, exact_distance: bool = False) -> _cabi.SceneHandle:
+        """Device scene for the current world / pair sets.  Verdict queries use a scene whose obstacle pairs are
+        statically pruned for thresholds up to `static_thr` (rebuilt when a larger threshold is asked for);
+        minimum-distance queries use the unpruned scene."""
         world = self._chain.world
-        key = (world.revision, self._pairs_revision)
-        if self._scene_handle is None or key != self._scene_key:
-            self._scene_arrays = self.scene_arrays()
-            self._scene_handle = _cabi.SceneHandle(self._handle(), self._scene_arrays)
-            self._scene_key = key
-        return self._scene_handle
+        base = self.base_pose
+        which = "dist" if exact_distance else "verdict"
+        cur = self._scenes.get(which)
+        key = (world.revision, self._pairs_revision, base.tobytes())
+        if cur is None or cur["key"] != key or (not exact_distance and threshold > cur["static_thr"]):
+            static_thr = None if exact_distance else max(0.05, 2.0 * float(threshold))
+            arrays = self.scene_arrays(static_thr)
+            cur = {"key": key, "static_thr": static_thr, "arrays": arrays,
+                   "handle": _cabi.SceneHandle(self._handle(), arrays)}
+            self._scenes[which] = cur
+        self._scene_arrays = cur["arrays"]
+        return cur["handle"]
 
-    def scene_arrays(self) -> dict:
-        """Current obstacles + allowed pairs as nbx_scene_desc arrays (also used by the tests)."""
+    def scene_arrays(self, static_threshold: float | None = None) -> dict:
+        """Current obstacles + allowed pairs as nbx_scene_desc arrays (also used by the tests).
+        `static_threshold` not None -> obstacle pairs that can never come within it are dropped."""
         self_pairs = self.self_collision_pairs()
         env_pairs = [p for p in self.collision_pairs().difference(self_pairs)
                      if isinstance(p[1], PhysicsObject)]
-        return descriptor.flatten_scene(self._arrays, self_pairs, env_pairs, self._margin_model)
+        prune = None if static_threshold is None else (self.base_pose, self.joint_limits, static_threshold)
+        return descriptor.flatten_scene(self._arrays, self_pairs, env_pairs, self._margin_model, prune)
 
     # ------------------------------------------------------------------ pair bookkeeping
     def self_collision_pairs(self):
@@ -459,8 +469,8 @@ class Arm:
         q_shape = tuple(q.shape)
         single = len(q_shape) == 1
         B = int(np.prod(q_shape[:-1])) if not single else 1
-        scene = self._scene()
-        if self._scene_arrays["self_pairs"].shape[0] + self._scene_arrays["env_pairs"].shape[0] == 0:
+        scene = self._scene(threshold, exact_distance=want_dist)
+        if self._scene_arrays["self_pairs"].shape[0] + self._scene_arrays["n_env_pairs_before_pruning"] == 0:
             # reference: min([]) -> ValueError (arm.py:600)
             raise ValueError("min() arg is an empty sequence")
         dev_index = self.device_index
@@ -505,8 +515,8 @@ class Arm:
         in_torch = _is_torch(starts)
         shape = tuple(starts.shape[:-1])
         E = int(np.prod(shape)) if len(shape) else 1
-        scene = self._scene()
-        if self._scene_arrays["self_pairs"].shape[0] + self._scene_arrays["env_pairs"].shape[0] == 0:
+        scene = self._scene(threshold)
+        if self._scene_arrays["self_pairs"].shape[0] + self._scene_arrays["n_env_pairs_before_pruning"] == 0:
             raise ValueError("min() arg is an empty sequence")
         dev_index = self.device_index
         base_keep, base_ptr = _cabi.base_pose_arg(self.base_pose)

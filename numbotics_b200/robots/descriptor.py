@@ -140,16 +140,79 @@ def flatten_chain(chain, margin_model: str = "bullet") -> dict:
     }
 
 
-def flatten_scene(chain_arrays: dict, self_pairs, env_pairs, margin_model: str = "bullet") -> dict:
+def primitive_reach(chain_arrays: dict, joint_limits) -> np.ndarray:
+    """Upper bound, per link primitive, on the distance of ANY of its points from the base-frame origin,
+    over every configuration: sum of the translation norms along the path (rotations preserve norms;
+    a prismatic joint adds its largest travel) + the primitive's own offset + its bounding radius."""
+    A = chain_arrays
+    n_mov = len(A["mov_type"])
+    off = np.asarray(A["mov_offset"]).reshape(n_mov, 12)
+    axis = np.asarray(A["mov_axis"]).reshape(n_mov, 3)
+    reach_j = np.zeros(n_mov)
+    for j in range(n_mov):
+        par = int(A["mov_parent"][j])
+        r = (reach_j[par] if par >= 0 else 0.0) + np.linalg.norm(off[j, [3, 7, 11]])
+        if int(A["mov_type"][j]) == _cabi.NBX_JOINT_PRISMATIC:
+            lo, hi = joint_limits[int(A["mov_qidx"][j])]
+            r += max(abs(lo), abs(hi)) * np.linalg.norm(axis[j])      # inf for an unlimited slider: never pruned
+        reach_j[j] = r
+    tail = np.asarray(A["frame_tail"]).reshape(-1, 12)
+    poff = np.asarray(A["prim_offset"]).reshape(-1, 12)
+    dims = np.asarray(A["prim_dims"]).reshape(-1, 3)
+    out = np.zeros(len(A["prim_type"]))
+    for p in range(len(out)):
+        f = int(A["prim_frame"][p])
+        j = int(A["frame_mov"][f])
+        t = int(A["prim_type"][p])
+        brad = dims[p, 0] if t == _cabi.NBX_PRIM_SPHERE else (np.linalg.norm(dims[p]) if t == _cabi.NBX_PRIM_BOX else np.hypot(dims[p, 0], dims[p, 1]))
+        out[p] = (reach_j[j] if j >= 0 else 0.0) + np.linalg.norm(tail[f, [3, 7, 11]]) + np.linalg.norm(poff[p, [3, 7, 11]]) + brad
+    return out
+
+
+def obstacle_gap_from(origin_pose, obj) -> float:
+    """Lower bound on the distance from the origin of `origin_pose` (4x4, world) to the obstacle."""
+    cs = obj._collision_shape
+    P = obj.pose @ cs.offset
+    o = origin_pose[:3, 3]
+    info = cs._shape_info
+    if cs.shape in (Shape.CUBE, Shape.CUBOID):
+        loc = P[:3, :3].T @ (o - P[:3, 3])
+        he = np.asarray(info["half_extents"], dtype=np.float64).reshape(3)
+        return float(np.linalg.norm(np.maximum(np.abs(loc) - he, 0.0)))
+    c = float(np.linalg.norm(o - P[:3, 3]))
+    if cs.shape == Shape.SPHERE:
+        return c - float(info["radius"])
+    return c - float(np.hypot(info["radius"], 0.5 * info["height"]))
+
+
+def flatten_scene(chain_arrays: dict, self_pairs, env_pairs, margin_model: str = "bullet",
+                  prune=None) -> dict:
     """Pair sets of Link / PhysicsObject tuples -> arrays matching nbx_scene_desc.
 
     self_pairs: iterable of (Link, Link); env_pairs: iterable of (Link, PhysicsObject).
     Pairs whose link has no primitive (EMPTY shape) can never produce a proximity in
     the reference either and are dropped.
+
+    prune = (base_pose, joint_limits, threshold) enables STATIC pruning of obstacle pairs: a pair is
+    dropped when, for every configuration, the primitive stays farther than `threshold` from the
+    obstacle (reach bound, `primitive_reach`).  Verdicts `distance < t` for any t <= threshold are
+    unchanged; the pruned scene must not be used for minimum-distance queries.
     """
     prim_of_link = chain_arrays["prim_of_link"]
     prim_type = chain_arrays["prim_type"]
     env_pairs = [(link, obj) for link, obj in env_pairs if link in prim_of_link]
+    n_before = len(env_pairs)
+    if prune is not None:
+        base_pose, joint_limits, thr = prune
+        reach = primitive_reach(chain_arrays, np.asarray(joint_limits, dtype=np.float64).reshape(-1, 2))
+        gaps = {}
+        kept = []
+        for link, obj in env_pairs:
+            if obj not in gaps:
+                gaps[obj] = obstacle_gap_from(np.asarray(base_pose, dtype=np.float64), obj)
+            if gaps[obj] - reach[prim_of_link[link]] <= thr + 1e-9:
+                kept.append((link, obj))
+        env_pairs = kept
     obstacles = sorted({obj for _, obj in env_pairs}, key=lambda o: o.name)   # independent of set order
     obs_index = {obj: i for i, obj in enumerate(obstacles)}
     env_idx = [(prim_of_link[link], obs_index[obj]) for link, obj in env_pairs]
@@ -179,4 +242,5 @@ def flatten_scene(chain_arrays: dict, self_pairs, env_pairs, margin_model: str =
         "env_pairs": np.asarray(env_idx, np.int32).reshape(-1, 2),
         "self_sharp": self_sharp, "env_sharp": env_sharp,
         "obstacles": obstacles,
+        "n_env_pairs_before_pruning": n_before,
     }

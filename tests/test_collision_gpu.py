@@ -226,3 +226,25 @@ def test_discrete_connector_surface(scene, cuda):
     check_edges(vb, ovb, md)
     vs, ends = conn.steer_batch(s, g)
     assert ends.shape == s.shape
+
+
+def test_static_pruning_never_changes_a_verdict(scene):
+    """Obstacle pairs that the reach bound proves can never come within the threshold are dropped from the
+    verdict scene; the unpruned scene (used by min_distance) must give the same answers."""
+    arm, cubes, so = scene
+    pruned = arm.scene_arrays(0.05)
+    assert pruned["env_pairs"].shape[0] < pruned["n_env_pairs_before_pruning"] == 30
+    q = workloads.random_configs_np(arm, 20000, seed=31).astype(np.float32)
+    for thr in (0.0, 0.04, 0.2):                     # 0.2 forces a rebuild with a larger static threshold
+        hit = arm.in_collision(q, thr)
+        dist = arm.min_distance(q)
+        clear = np.abs(dist - thr) > 1e-4
+        assert np.array_equal(hit[clear], (dist < thr)[clear])
+    # the reach bound itself, against sampled forward kinematics
+    from numbotics_b200.robots import descriptor
+    reach = descriptor.primitive_reach(arm._arrays, arm.joint_limits)
+    base = arm.base_pose[:3, 3]
+    for p, (node, off) in enumerate(zip(so.link_nodes, so.link_offsets)):
+        centers = (so.fk.forward_kinematics(q[:3000].astype(np.float64), node) @ off)[:, :3, 3]
+        link = arm._links_from_nodes[node]
+        assert np.linalg.norm(centers - base, axis=1).max() <= reach[arm._arrays["prim_of_link"][link]] + 1e-9
