@@ -330,8 +330,15 @@ class Arm:
             # HOST buffers straight through the C-ABI: chunked H2D / kernel / D2H pipeline in C++
             qn = q.detach().numpy() if in_torch else q
             qn = np.ascontiguousarray(qn.reshape(B, dof))
-            Tn = np.empty((B, 4, 4), qn.dtype) if want_T else None
-            Jn = np.empty((B, 6, dof), qn.dtype) if want_J else None
+            if B >= 32768:
+                # large results land in page-locked host memory (torch's caching pinned allocator): the D2H copies
+                # then run at PCIe rate instead of the ~5 GB/s of pageable first-touch memory.  The ndarray
+                # keeps the pinned block alive through its base.
+                Tn = torch.empty((B, 4, 4), dtype=tdtype, pin_memory=True).numpy() if want_T else None
+                Jn = torch.empty((B, 6, dof), dtype=tdtype, pin_memory=True).numpy() if want_J else None
+            else:
+                Tn = np.empty((B, 4, 4), qn.dtype) if want_T else None
+                Jn = np.empty((B, 6, dof), qn.dtype) if want_J else None
             fn = lib.nbx_fk_jac_host_f64 if f64 else lib.nbx_fk_jac_host_f32
             _cabi.check(fn(h.ptr, fid, qn.ctypes.data, B, base_ptr, int(bool(use_com)),
                            Tn.ctypes.data if want_T else None, Jn.ctypes.data if want_J else None))
