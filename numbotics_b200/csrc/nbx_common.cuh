@@ -178,6 +178,14 @@ static inline void pose12_identity(double* o) {
 template <typename T>
 void nbx_fill_joint(JointK<T>& jk, const double* off12, const double* axis, int type, int qidx);
 
+// float paths of 9..32 joints: register-resident dense kernels (nbx_fkjac_wide_a.cu: 9..22, _b.cu: 23..32)
+#define NBX_WIDE_CAP 32
+#define NBX_WIDE_SPLIT 22
+int nbx_launch_wide_a_f32(const PathK<float, NBX_WIDE_CAP>& P, bool allz, const float* q, int64_t B, const float* lp, int64_t lps,
+                          const float* gp, int64_t gps, float* T_out, float* J_out, int vec_ok, int sm_count, cudaStream_t stream);
+int nbx_launch_wide_b_f32(const PathK<float, NBX_WIDE_CAP>& P, bool allz, const float* q, int64_t B, const float* lp, int64_t lps,
+                          const float* gp, int64_t gps, float* T_out, float* J_out, int vec_ok, int sm_count, cudaStream_t stream);
+
 int nbx_launch_fkjac_f32(const nbx_chain* chain, int frame, const float* q, int64_t B, const double* base_pose,
                          int use_com, const float* lp, int64_t lps, const float* gp, int64_t gps, float* T_out,
                          float* J_out, cudaStream_t stream);

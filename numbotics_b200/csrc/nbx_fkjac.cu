@@ -22,213 +22,16 @@
 // HBM-bound: 4*dof + 64 + 24*dof bytes per configuration (fp32), see DESIGN.md.
 #include "nbx_common.cuh"
 #include "nbx_joint.cuh"
+#include "nbx_fkjac_dense.cuh"
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
+#include <type_traits>
 
 using namespace nbxj;
+using namespace nbxd;
 
 namespace {
-
-constexpr int kSmallMax = 8;   // dense fully-unrolled kernels cover paths of 1..8 joints
-
-template <typename T>
-__device__ __forceinline__ void pose_mul_global(Pose<T>& X, const T* __restrict__ g16) {
-    // X <- X * G, G a row-major 4x4 in global memory (per-configuration local_pose)
-    T c12[12];
-#pragma unroll
-    for (int k = 0; k < 12; ++k) c12[k] = g16[k];
-    pose_mul_const<T>(X, c12);
-}
-
-// ---- TMA bulk copy shared -> global --------------------------------------------------------
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
-    uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(ssrc));
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-
-// 16-byte streaming load (q is read exactly once)
-__device__ __forceinline__ int4 ld_stream16(const void* p) {
-    int4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-
-template <typename T> struct Vec2;
-template <> struct Vec2<float> { using type = float2; };
-template <> struct Vec2<double> { using type = double2; };
-
-template <typename T>
-__device__ __forceinline__ void store_pose16(T* dst, const Pose<T>& X) {
-    // row-major 4x4, vectorised as 4 x 16 bytes (float) / 8 x 16 bytes (double)
-    using V2 = typename Vec2<T>::type;
-    V2* d = reinterpret_cast<V2*>(dst);
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        V2 a, b;
-        a.x = X.R[r * 3 + 0]; a.y = X.R[r * 3 + 1];
-        b.x = X.R[r * 3 + 2]; b.y = X.p[r];
-        d[r * 2 + 0] = a;
-        d[r * 2 + 1] = b;
-    }
-    V2 z0, z1;
-    z0.x = T(0); z0.y = T(0); z1.x = T(0); z1.y = T(1);
-    d[6] = z0;
-    d[7] = z1;
-}
-
-// Stage a q tile in shared memory.  Full, 16-byte aligned tiles go through cp.async (LDGSTS: no
-// registers, completion tracked by the async group, so the NEXT tile can be in flight while this
-// one is being computed); ragged / unaligned tiles use plain loads.
-__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
-    const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(sdst));
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-template <typename T, int TILE>
-__device__ __forceinline__ void load_q_tile(T* sq, const T* __restrict__ q, int64_t tile0, int nvalid, int dof, bool vec_ok) {
-    const int n = nvalid * dof;
-    const T* src = q + tile0 * dof;
-    if (vec_ok && nvalid == TILE) {
-        const int n16 = (TILE * dof * (int)sizeof(T)) / 16;   // TILE*dof*sizeof(T) is a multiple of 16 for TILE % 4 == 0
-        const int4* s16 = reinterpret_cast<const int4*>(src);
-        int4* d16 = reinterpret_cast<int4*>(sq);
-        for (int i = threadIdx.x; i < n16; i += TILE) cp_async16(d16 + i, s16 + i);
-    } else {
-        for (int i = threadIdx.x; i < n; i += TILE) sq[i] = src[i];
-    }
-    cp_async_commit();
-}
-
-// =============================================================================================
-// dense kernel: path covers q columns 0..NJ-1 exactly (serial arms: Kinova tool_frame), NJ <= 8.
-// Fully unrolled; screws live in registers.  Persistent CTAs: each loops over tiles with the next
-// tile's q prefetched (cp.async) while the current one is computed, and the previous tile's output
-// still draining through the TMA engine.
-// =============================================================================================
-template <typename T, int NJ, int TILE, bool ALLZ, int KT>
-__global__ void __launch_bounds__(TILE)
-fkjac_dense_kernel(const __grid_constant__ PathK<T, kSmallMax> P, const T* __restrict__ q, int64_t B,
-                   const T* __restrict__ lp, int64_t lps, const T* __restrict__ gp, int64_t gps,
-                   T* __restrict__ T_out, T* __restrict__ J_out, int vec_ok, int64_t ntiles) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    // layout: [J tile][T tile][q tile x KT]; J and T tiles are 128-byte aligned for the bulk copies
-    T* sJ = reinterpret_cast<T*>(smem_raw);
-    T* sT = sJ + TILE * 6 * NJ;
-    T* sq0 = sT + TILE * 16;
-    const int tid = threadIdx.x;
-    bool store_in_flight = false;
-
-    // CTA c owns the KT CONSECUTIVE tiles [c*KT, c*KT + KT): the hardware block scheduler then keeps the
-    // chip-wide write frontier compact (measured: 7.5 TB/s vs 6.3 TB/s for a grid-stride persistent loop,
-    // profiles/membench_r01.txt) while one q-load latency and one CTA launch are shared by KT tiles.
-    const int64_t first = (int64_t)blockIdx.x * KT;
-#pragma unroll
-    for (int k = 0; k < KT; ++k) {
-        const int64_t t = first + k;
-        if (t < ntiles) load_q_tile<T, TILE>(sq0 + k * (TILE * NJ), q, t * TILE, (int)min((int64_t)TILE, B - t * TILE), NJ, vec_ok != 0);
-    }
-    cp_async_wait_all();
-    __syncthreads();
-
-#pragma unroll 1
-    for (int k = 0; k < KT; ++k) {
-        const int64_t tile = first + k;
-        if (tile >= ntiles) break;
-        const int64_t tile0 = tile * TILE;
-        const int nvalid = (int)min((int64_t)TILE, B - tile0);
-        const T* sq = sq0 + k * (TILE * NJ);
-
-        Pose<T> X;
-        T W[NJ][3], Mo[NJ][3];
-        T pe[3];
-        const bool active = tid < nvalid;
-        if (active) {
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                X.R[r * 3 + 0] = P.base[r * 4 + 0]; X.R[r * 3 + 1] = P.base[r * 4 + 1]; X.R[r * 3 + 2] = P.base[r * 4 + 2];
-                X.p[r] = P.base[r * 4 + 3];
-            }
-#pragma unroll
-            for (int i = 0; i < NJ; ++i) {
-                const T qv = sq[tid * NJ + i];
-                T sn, cs;
-                sincos_t<T>(qv, &sn, &cs);
-                if (ALLZ) {
-                    // every joint is a revolute about its own +-z: branch-free straight-line code
-                    joint_step_z<T, JointK<T>>(X, P.j[i], sn, cs);
-                    joint_screw_z<T, JointK<T>>(X, P.j[i], W[i], Mo[i]);
-                } else {
-                    joint_step_sc<T, JointK<T>>(X, P.j[i], qv, sn, cs);
-                    joint_screw<T, JointK<T>>(X, P.j[i], W[i], Mo[i]);
-                }
-            }
-            pose_mul_const<T>(X, P.tail);
-            const int64_t b = tile0 + tid;
-            if (lp != nullptr) pose_mul_global<T>(X, lp + b * lps);
-            pe[0] = X.p[0]; pe[1] = X.p[1]; pe[2] = X.p[2];
-            if (gp != nullptr) {
-                const T* g = gp + b * gps;
-                pe[0] = g[3]; pe[1] = g[7]; pe[2] = g[11];
-            }
-        }
-
-        // the previous tile's bulk stores must have finished READING the staging tiles
-        if (store_in_flight && tid == 0) bulk_wait_read_all();
-        __syncthreads();
-
-        if (active) {
-            if (T_out != nullptr) store_pose16<T>(sT + tid * 16, X);
-            if (J_out != nullptr) {
-                T row[6 * NJ];
-#pragma unroll
-                for (int i = 0; i < NJ; ++i) {
-                    row[0 * NJ + i] = fma_t<T>(W[i][1], pe[2], fma_t<T>(-W[i][2], pe[1], -Mo[i][0]));
-                    row[1 * NJ + i] = fma_t<T>(W[i][2], pe[0], fma_t<T>(-W[i][0], pe[2], -Mo[i][1]));
-                    row[2 * NJ + i] = fma_t<T>(W[i][0], pe[1], fma_t<T>(-W[i][1], pe[0], -Mo[i][2]));
-                    row[3 * NJ + i] = W[i][0];
-                    row[4 * NJ + i] = W[i][1];
-                    row[5 * NJ + i] = W[i][2];
-                }
-                using V2 = typename Vec2<T>::type;
-                V2* d = reinterpret_cast<V2*>(sJ + tid * 6 * NJ);
-#pragma unroll
-                for (int k = 0; k < 3 * NJ; ++k) {
-                    V2 v;
-                    v.x = row[2 * k]; v.y = row[2 * k + 1];
-                    d[k] = v;
-                }
-            }
-        }
-
-        if (nvalid == TILE && vec_ok) {
-            // full tile: hand both output tiles to the TMA engine and move on
-            fence_proxy_async_smem();
-            __syncthreads();
-            if (tid == 0) {
-                if (T_out != nullptr) bulk_store(T_out + tile0 * 16, sT, TILE * 16 * sizeof(T));
-                if (J_out != nullptr) bulk_store(J_out + tile0 * 6 * NJ, sJ, TILE * 6 * NJ * sizeof(T));
-                bulk_commit();
-            }
-            store_in_flight = true;
-        } else {
-            // ragged last tile (or unaligned user pointers): cooperative coalesced copy-out
-            __syncthreads();
-            if (T_out != nullptr)
-                for (int i = tid; i < nvalid * 16; i += TILE) T_out[tile0 * 16 + i] = sT[i];
-            if (J_out != nullptr)
-                for (int i = tid; i < nvalid * 6 * NJ; i += TILE) J_out[tile0 * 6 * NJ + i] = sJ[i];
-            store_in_flight = false;
-        }
-    }
-    if (store_in_flight && tid == 0) bulk_wait_read_all();   // shared memory must outlive the copies
-}
 
 // =============================================================================================
 // generic kernel: any path length <= NBX_MAX_PATH, any dof, sparse columns (BASELINE config 5, 30-DoF).
@@ -367,49 +170,243 @@ fkjac_generic_kernel(const __grid_constant__ PathK<T, NBX_MAX_PATH> P, const T* 
     if (T_out != nullptr && bulk && tid == 0) bulk_wait_read_all();
 }
 
+// =============================================================================================
+// deep kernel: long paths whose joints are all canonical-axis revolutes or prismatic (BASELINE
+// config 5, the 30-DoF chain).  The generic kernel above parks one screw (24 bytes) per joint and
+// configuration in shared memory until the end point p_e is known; at 30 joints that is ~1 KB per
+// configuration and bounds the occupancy at ~6 warps per SM.  This kernel needs no per-joint storage:
+//
+//   backward pass   e <- X_i(q_i) e  for i = n..1 starting from the trailing offset gives e_0, the
+//                   end point expressed in the base frame (vector recursion only: 13 FMA per joint),
+//                   hence p_e = base * e_0 BEFORE the forward walk starts;
+//   forward walk    carries the rotation R_i and the end point in the CURRENT joint frame,
+//                   e_i = X_i(q_i)^-1 e_{i-1}  (rigid inverse, 16 FMA), so the Jacobian column of joint i
+//                   is complete the moment the joint is reached:  [R_i (a x e_i) ; R_i a]
+//                   (= w x (p_e - p_i) of reference helpers.py:182-183, with p_e - p_i = R_i e_i).
+//
+// Columns are produced in q order (movable joints on a root->frame path have increasing q indices;
+// the host checks it), off-path columns are zeros, and K consecutive columns at a time go through a
+// small per-warp staging slab [row][column][configuration] and leave as coalesced runs.  Warps are
+// autonomous (their own 32 configurations, their own slab, __syncwarp only).  Shared memory per
+// configuration: 8 n bytes of sines / cosines + 24 K bytes of staging (K = 8: ~430 B at 30-DoF).
+// =============================================================================================
+template <typename T, bool ALLZ>
+__global__ void __launch_bounds__(128)
+fkjac_deep_kernel(const __grid_constant__ PathK<T, NBX_MAX_PATH> P, const T* __restrict__ q, int64_t B,
+                  const T* __restrict__ lp, int64_t lps, const T* __restrict__ gp, int64_t gps,
+                  T* __restrict__ T_out, T* __restrict__ J_out, int vec_ok, int K, int slab_elems) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int LS = 33;                         // configuration stride inside the staging slab (odd)
+    const int dof = P.dof;
+    const int n = P.n;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // per-warp slab: [sin n x 32][cos n x 32][union: q tile 32 x dof | staging 6 x K x 33]
+    T* slab = reinterpret_cast<T*>(smem_raw) + (size_t)wid * slab_elems;
+    T* ssin = slab;
+    T* scos = slab + n * 32;
+    T* stg = slab + 2 * n * 32;
+    short* colmap = reinterpret_cast<short*>(reinterpret_cast<T*>(smem_raw) + (size_t)4 * slab_elems);   // [dof]
+
+    const int64_t tile0 = ((int64_t)blockIdx.x * 4 + wid) * 32;
+    const int nvalid = (int)max((int64_t)0, min((int64_t)32, B - tile0));
+
+    for (int c = threadIdx.x; c < dof; c += 128) colmap[c] = -1;
+    // q tile of this warp -> staging area (row-major [configuration][dof], as in global memory)
+    if (nvalid > 0) {
+        const T* src = q + tile0 * dof;
+        if (vec_ok && nvalid == 32) {
+            const int n16 = (32 * dof * (int)sizeof(T)) / 16;
+            const int4* s16 = reinterpret_cast<const int4*>(src);
+            int4* d16 = reinterpret_cast<int4*>(stg);
+            for (int i = lane; i < n16; i += 32) cp_async16(d16 + i, s16 + i);
+        } else {
+            for (int i = lane; i < nvalid * dof; i += 32) stg[i] = src[i];
+        }
+    }
+    cp_async_commit();
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += 128) colmap[P.j[i].qidx] = (short)i;
+    cp_async_wait_all();
+    __syncthreads();
+    if (nvalid == 0) return;
+    const bool active = lane < nvalid;
+    const bool want_j = J_out != nullptr;
+
+    // ---- phase 0: every sine / cosine (prismatic joints keep q itself in the sine slot) ------------
+    {
+        const T* myq = stg + lane * dof;
+#pragma unroll 4
+        for (int i = 0; i < n; ++i) {
+            const T qv = active ? myq[P.j[i].qidx] : T(0);
+            T sn = qv, cs = T(1);
+            if (ALLZ || P.j[i].kind != NBX_KIND_PRISMATIC) {
+                sincos_t<T>(qv, &sn, &cs);
+                sn *= (T)P.j[i].sgn;               // rotation by sgn * q
+            }
+            ssin[i * 32 + lane] = sn;
+            scos[i * 32 + lane] = cs;
+        }
+    }
+    __syncwarp();                                   // the q tile is dead: its area becomes the staging slab
+
+    const int64_t b = tile0 + (active ? lane : 0);
+    // ---- backward pass: e_0 = end point in the base frame ---------------------------------------
+    T e[3] = {P.tail[3], P.tail[7], P.tail[11]};
+    if (lp != nullptr) {
+        const T* g = lp + b * lps;
+        const T l0 = g[3], l1 = g[7], l2 = g[11];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            e[r] = fma_t<T>(P.tail[r * 4 + 0], l0, fma_t<T>(P.tail[r * 4 + 1], l1, fma_t<T>(P.tail[r * 4 + 2], l2, e[r])));
+    }
+#pragma unroll 2
+    for (int i = n - 1; i >= 0; --i) {
+        const JointK<T>& jk = P.j[i];
+        const T s = ssin[i * 32 + lane], c = scos[i * 32 + lane];
+        T x[3] = {e[0], e[1], e[2]};
+        T tt[3] = {(T)jk.t[0], (T)jk.t[1], (T)jk.t[2]};
+        if (ALLZ || jk.kind == NBX_KIND_Z) {
+            x[0] = fma_t<T>(c, e[0], -(s * e[1])); x[1] = fma_t<T>(s, e[0], c * e[1]);
+        } else if (jk.kind == NBX_KIND_X) {
+            x[1] = fma_t<T>(c, e[1], -(s * e[2])); x[2] = fma_t<T>(s, e[1], c * e[2]);
+        } else if (jk.kind == NBX_KIND_Y) {
+            x[2] = fma_t<T>(c, e[2], -(s * e[0])); x[0] = fma_t<T>(s, e[2], c * e[0]);
+        } else {   // prismatic: s holds q
+#pragma unroll
+            for (int k = 0; k < 3; ++k) tt[k] = fma_t<T>(s, (T)jk.d[k], tt[k]);
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            e[r] = fma_t<T>((T)jk.A[r * 3 + 0], x[0], fma_t<T>((T)jk.A[r * 3 + 1], x[1], fma_t<T>((T)jk.A[r * 3 + 2], x[2], tt[r])));
+    }
+    // true end point (the pose's translation) and the point the Jacobian refers to
+    T pe[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+        pe[r] = fma_t<T>(P.base[r * 4 + 0], e[0], fma_t<T>(P.base[r * 4 + 1], e[1], fma_t<T>(P.base[r * 4 + 2], e[2], P.base[r * 4 + 3])));
+    if (gp != nullptr) {
+        // Jacobian of a given world point: e_0 = base^-1 * g
+        const T* g = gp + b * gps;
+        const T d0 = g[3] - P.base[3], d1 = g[7] - P.base[7], d2 = g[11] - P.base[11];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) e[k] = fma_t<T>(P.base[0 * 4 + k], d0, fma_t<T>(P.base[1 * 4 + k], d1, P.base[2 * 4 + k] * d2));
+    }
+
+    // ---- forward walk over the q columns -----------------------------------------------------
+    T R[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { R[r * 3 + 0] = P.base[r * 4 + 0]; R[r * 3 + 1] = P.base[r * 4 + 1]; R[r * 3 + 2] = P.base[r * 4 + 2]; }
+    int k = 0, c0 = 0;
+    const int ncols = want_j ? dof : 0;
+    int next = 0;                                   // next path joint (FK-only launches walk the path, not the columns)
+    const int steps = want_j ? dof : n;
+#pragma unroll 1
+    for (int c = 0; c < steps; ++c) {
+        const int i = want_j ? (int)colmap[c] : next++;
+        T v[3] = {T(0), T(0), T(0)}, w[3] = {T(0), T(0), T(0)};
+        if (i >= 0) {
+            const JointK<T>& jk = P.j[i];
+            const T s = ssin[i * 32 + lane], cs = scos[i * 32 + lane];
+            // R <- R * R_off
+            T Rn[9];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc)
+                    Rn[r * 3 + cc] = fma_t<T>(R[r * 3 + 0], (T)jk.A[cc], fma_t<T>(R[r * 3 + 1], (T)jk.A[3 + cc], R[r * 3 + 2] * (T)jk.A[6 + cc]));
+            // y = R_off^T (e - t [- q d])  (only the Jacobian needs the end point in the joint frame)
+            T y[3] = {T(0), T(0), T(0)};
+            const bool prism = !ALLZ && jk.kind == NBX_KIND_PRISMATIC;
+            if (want_j) {
+                T u[3] = {e[0] - (T)jk.t[0], e[1] - (T)jk.t[1], e[2] - (T)jk.t[2]};
+                if (prism) {
+#pragma unroll
+                    for (int kk = 0; kk < 3; ++kk) u[kk] = fma_t<T>(-s, (T)jk.d[kk], u[kk]);
+                }
+#pragma unroll
+                for (int kk = 0; kk < 3; ++kk) y[kk] = fma_t<T>((T)jk.A[0 + kk], u[0], fma_t<T>((T)jk.A[3 + kk], u[1], (T)jk.A[6 + kk] * u[2]));
+            }
+            // plane rotation of two columns of R and the inverse rotation of y; column of the Jacobian
+#define NBX_DEEP_ROT(A_, B_, C_)                                                                   \
+            {                                                                                      \
+                _Pragma("unroll") for (int r = 0; r < 3; ++r) {                                    \
+                    const T a_ = Rn[r * 3 + A_], b_ = Rn[r * 3 + B_];                              \
+                    Rn[r * 3 + A_] = fma_t<T>(cs, a_, s * b_);                                     \
+                    Rn[r * 3 + B_] = fma_t<T>(cs, b_, -(s * a_));                                  \
+                }                                                                                  \
+                if (want_j) {                                                                      \
+                    const T ya = y[A_], yb = y[B_];                                                \
+                    y[A_] = fma_t<T>(cs, ya, s * yb);                                              \
+                    y[B_] = fma_t<T>(cs, yb, -(s * ya));                                           \
+                    const T sg = (T)jk.sgn;                                                        \
+                    const T ea = sg * y[A_], eb = sg * y[B_];                                      \
+                    _Pragma("unroll") for (int r = 0; r < 3; ++r) {                                \
+                        v[r] = fma_t<T>(ea, Rn[r * 3 + B_], -(eb * Rn[r * 3 + A_]));               \
+                        w[r] = sg * Rn[r * 3 + C_];                                                \
+                    }                                                                              \
+                }                                                                                  \
+            }
+            if (ALLZ || jk.kind == NBX_KIND_Z) NBX_DEEP_ROT(0, 1, 2)
+            else if (jk.kind == NBX_KIND_X) NBX_DEEP_ROT(1, 2, 0)
+            else if (jk.kind == NBX_KIND_Y) NBX_DEEP_ROT(2, 0, 1)
+            else if (want_j) {
+                // prismatic: column = [R a ; 0]  (reference helpers.py:184-185)
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                    v[r] = fma_t<T>(Rn[r * 3 + 0], (T)jk.ax[0], fma_t<T>(Rn[r * 3 + 1], (T)jk.ax[1], Rn[r * 3 + 2] * (T)jk.ax[2]));
+            }
+#undef NBX_DEEP_ROT
+#pragma unroll
+            for (int kk = 0; kk < 9; ++kk) R[kk] = Rn[kk];
+            e[0] = y[0]; e[1] = y[1]; e[2] = y[2];
+        }
+        if (c < ncols) {
+            T* sp = stg + k * LS + lane;
+            const int rs = K * LS;
+            sp[0 * rs] = v[0]; sp[1 * rs] = v[1]; sp[2 * rs] = v[2];
+            sp[3 * rs] = w[0]; sp[4 * rs] = w[1]; sp[5 * rs] = w[2];
+            if (++k == K || c == dof - 1) {
+                // flush K columns of 32 configurations: lanes over (row, column), runs of 4*k bytes per row
+                __syncwarp();
+                const int tot = 6 * k;
+                T* Jt = J_out + tile0 * 6 * (int64_t)dof + c0;
+                for (int idx = lane; idx < tot; idx += 32) {
+                    const int r = idx / k, kk = idx - r * k;
+                    const T* sr = stg + (r * K + kk) * LS;
+                    T* Jc = Jt + r * dof + kk;
+                    int cf = 0;
+                    for (; cf + 4 <= nvalid; cf += 4) {
+                        const T a0 = sr[cf], a1 = sr[cf + 1], a2 = sr[cf + 2], a3 = sr[cf + 3];
+                        Jc[(int64_t)(cf + 0) * (6 * dof)] = a0;
+                        Jc[(int64_t)(cf + 1) * (6 * dof)] = a1;
+                        Jc[(int64_t)(cf + 2) * (6 * dof)] = a2;
+                        Jc[(int64_t)(cf + 3) * (6 * dof)] = a3;
+                    }
+                    for (; cf < nvalid; ++cf) Jc[(int64_t)cf * (6 * dof)] = sr[cf];
+                }
+                __syncwarp();
+                c0 = c + 1;
+                k = 0;
+            }
+        }
+    }
+
+    if (T_out != nullptr && active) {
+        // pose: R_n * tail.R (* local_pose.R), translation p_e
+        Pose<T> X;
+#pragma unroll
+        for (int kk = 0; kk < 9; ++kk) X.R[kk] = R[kk];
+        X.p[0] = X.p[1] = X.p[2] = T(0);
+        pose_mul_const<T>(X, P.tail);
+        if (lp != nullptr) pose_mul_global<T>(X, lp + b * lps);
+        X.p[0] = pe[0]; X.p[1] = pe[1]; X.p[2] = pe[2];
+        store_pose16<T>(T_out + b * 16, X);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <typename T, int MAXJ>
-int build_path(const nbx_chain* ch, int frame, const double* base_pose16, int use_com, PathK<T, MAXJ>& P) {
-    const std::vector<int>& path = ch->frame_path[frame];
-    NBX_REQUIRE((int)path.size() <= MAXJ, "path of frame %d has %d movable joints (max %d)", frame, (int)path.size(), MAXJ);
-    P.n = (int)path.size();
-    P.dof = ch->dof;
-    P.use_com = use_com;
-    bool dense = (P.n == ch->dof);
-    for (int i = 0; i < P.n; ++i) {
-        const int j = path[i];
-        nbx_fill_joint<T>(P.j[i], &ch->mov_offset[12 * j], &ch->mov_axis[3 * j], ch->mov_type[j], ch->mov_qidx[j]);
-        dense = dense && (ch->mov_qidx[j] == i);
-    }
-    P.dense = dense ? 1 : 0;
-    for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 4; ++c) P.base[r * 4 + c] = (T)base_pose16[r * 4 + c];
-    double tail[12];
-    for (int k = 0; k < 12; ++k) tail[k] = ch->frame_tail[12 * frame + k];
-    if (use_com) pose12_mul(tail, &ch->frame_com[12 * frame], tail);
-    for (int k = 0; k < 12; ++k) P.tail[k] = (T)tail[k];
-    return NBX_OK;
-}
-
-inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-
-template <typename T, int NJ, int TILE, bool ALLZ, int KT>
-int launch_dense_kt(const PathK<T, kSmallMax>& P, const T* q, int64_t B, const T* lp, int64_t lps, const T* gp,
-                    int64_t gps, T* T_out, T* J_out, int vec_ok, cudaStream_t stream) {
-    const size_t smem = sizeof(T) * (size_t)TILE * (6 * NJ + 16 + KT * NJ);
-    auto kern = fkjac_dense_kernel<T, NJ, TILE, ALLZ, KT>;
-    NBX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t ntiles = (B + TILE - 1) / TILE;
-    const int64_t grid = (ntiles + KT - 1) / KT;
-    NBX_REQUIRE(grid <= 0x7fffffffLL, "batch too large for one launch");
-    kern<<<(unsigned)grid, TILE, smem, stream>>>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, ntiles);
-    nbx_count_launch();
-    NBX_CUDA_OK(cudaGetLastError());
-    return NBX_OK;
-}
-
 template <typename T, int NJ, int TILE, bool ALLZ>
 int launch_dense(const nbx_chain* ch, const PathK<T, kSmallMax>& P, const T* q, int64_t B, const T* lp, int64_t lps, const T* gp,
                  int64_t gps, T* T_out, T* J_out, int vec_ok, cudaStream_t stream) {
@@ -417,9 +414,9 @@ int launch_dense(const nbx_chain* ch, const PathK<T, kSmallMax>& P, const T* q, 
     // consecutive tiles per CTA; small batches keep one tile per CTA so the grid still fills the machine
     static const int kt_env = std::getenv("NBX_DENSE_KT") ? std::atoi(std::getenv("NBX_DENSE_KT")) : 0;   // tuning only
     const int kt = kt_env > 0 ? kt_env : (B >= (int64_t)TILE * 148 * 32 ? 2 : 1);
-    if (kt >= 4) return launch_dense_kt<T, NJ, TILE, ALLZ, 4>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, stream);
-    if (kt >= 2) return launch_dense_kt<T, NJ, TILE, ALLZ, 2>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, stream);
-    return launch_dense_kt<T, NJ, TILE, ALLZ, 1>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, stream);
+    if (kt >= 4) return launch_dense_kt<T, NJ, TILE, ALLZ, 4, kSmallMax>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, stream);
+    if (kt >= 2) return launch_dense_kt<T, NJ, TILE, ALLZ, 2, kSmallMax>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, stream);
+    return launch_dense_kt<T, NJ, TILE, ALLZ, 1, kSmallMax>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, stream);
 }
 
 template <typename T, int TILE, bool ALLZ>
@@ -482,9 +479,50 @@ int launch_fkjac(const nbx_chain* ch, int frame, const T* q, int64_t B, const do
             }
         }
     }
+    if constexpr (std::is_same<T, float>::value) {
+        // float paths of 9..32 joints covering q columns 0..n-1: register-resident dense kernels, one warp per tile
+        static const bool no_wide = std::getenv("NBX_NO_WIDE") != nullptr;   // A/B measurements and tests only
+        if (n > kSmallMax && n <= NBX_WIDE_CAP && n == ch->dof && !no_wide) {
+            PathK<float, NBX_WIDE_CAP> P;
+            int rc = build_path<float, NBX_WIDE_CAP>(ch, frame, base_pose, use_com, P);
+            if (rc != NBX_OK) return rc;
+            if (P.dense) {
+                bool allz = true;
+                for (int i = 0; i < P.n; ++i) allz = allz && P.j[i].kind == NBX_KIND_Z;
+                return n <= NBX_WIDE_SPLIT ? nbx_launch_wide_a_f32(P, allz, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, ch->sm_count, stream)
+                                           : nbx_launch_wide_b_f32(P, allz, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, ch->sm_count, stream);
+            }
+        }
+    }
     PathK<T, NBX_MAX_PATH> P;
     int rc = build_path<T, NBX_MAX_PATH>(ch, frame, base_pose, use_com, P);
     if (rc != NBX_OK) return rc;
+    // deep kernel: canonical-axis / prismatic joints only, q columns increasing along the path
+    static const bool legacy = std::getenv("NBX_GENERIC_LEGACY") != nullptr;   // A/B measurements and tests only
+    bool deep_ok = n >= 1 && !legacy, allz = true;
+    for (int i = 0; i < n; ++i) {
+        deep_ok = deep_ok && P.j[i].kind != NBX_KIND_GENERIC && (i == 0 || P.j[i].qidx > P.j[i - 1].qidx);
+        allz = allz && P.j[i].kind == NBX_KIND_Z;
+    }
+    if (deep_ok) {
+        static const int k_env = std::getenv("NBX_DEEP_K") ? std::atoi(std::getenv("NBX_DEEP_K")) : 0;
+        const int dof = ch->dof;
+        int K = k_env > 0 ? k_env : 8;
+        K = std::min(K, dof);
+        auto slab = [&](int kk) { return ((2 * n * 32 + std::max(std::max(32 * dof, 6 * kk * 33), 64)) + 31) & ~31; };
+        auto bytes = [&](int kk) { return sizeof(T) * 4 * (size_t)slab(kk) + 2 * (size_t)dof + 16; };
+        while (K > 1 && bytes(K) > 200 * 1024) K /= 2;
+        NBX_REQUIRE(bytes(K) <= 220 * 1024, "dof %d / path %d too large for the shared-memory staged Jacobian", dof, n);
+        const size_t smem = bytes(K);
+        const int64_t grid = (B + 127) / 128;
+        NBX_REQUIRE(grid <= 0x7fffffffLL, "batch too large for one launch");
+        auto kern = allz ? fkjac_deep_kernel<T, true> : fkjac_deep_kernel<T, false>;
+        NBX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)grid, 128, smem, stream>>>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, K, slab(K));
+        nbx_count_launch();
+        NBX_CUDA_OK(cudaGetLastError());
+        return NBX_OK;
+    }
     // tile size: the largest tile that still leaves room for >= 3 CTAs per SM (tuning knob NBX_GENERIC_TILE)
     static const int tile_env = std::getenv("NBX_GENERIC_TILE") ? std::atoi(std::getenv("NBX_GENERIC_TILE")) : 0;
     const size_t budget = 72 * 1024;

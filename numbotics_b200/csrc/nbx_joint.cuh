@@ -15,10 +15,21 @@ template <> __device__ __forceinline__ double fma_t<double>(double a, double b, 
 // sin and cos with one shared Cody-Waite reduction (three-constant pi/2 split) and the classic
 // degree-7 / degree-8 minimax polynomials on [-pi/4, pi/4]: <= 1.5 ulp for |x| < 1e5, about half the
 // instructions of sincosf() (no Payne-Hanek path, no local stack).  Larger arguments take sincosf().
-static __device__ __noinline__ void sincos_huge(float x, float* sp, float* cp) { sincosf(x, sp, cp); }
+// (returned by value: results handed back through pointers would live in local memory and put an STL/LDL pair
+// on every call site's fast path as well)
+static __device__ __noinline__ float2 sincos_huge(float x) {
+    float s, c;
+    sincosf(x, &s, &c);
+    return make_float2(s, c);
+}
 
 __device__ __forceinline__ void sincos_fast(float x, float* sp, float* cp) {
-    if (fabsf(x) > 1.0e5f) { sincos_huge(x, sp, cp); return; }   // cold, kept out of line
+    if (fabsf(x) > 1.0e5f) {   // cold, kept out of line
+        const float2 r = sincos_huge(x);
+        *sp = r.x;
+        *cp = r.y;
+        return;
+    }
     // round-to-nearest via the 1.5 * 2^23 magic constant: FFMA / FADD only (no FRND / F2I on the XU pipe),
     // the integer part sits in the low mantissa bits of `t`
     const float t = fmaf(x, 0.636619747f, 12582912.0f);
