@@ -246,6 +246,9 @@ int nbx_scene_create(const nbx_chain* ch, const nbx_scene_desc* d, nbx_scene** o
         int rc = core_dims(ok.type, &d->obs_dims[3 * o], d->obs_margin[o], ok.dims, &ok.margin);
         if (rc != NBX_OK) return rc;
         ok.brad = bounding_radius(ok.type, &d->obs_dims[3 * o]) * 1.000001f;
+        // axis-aligned (rotation exactly the identity): the broad phase skips the rotation into the obstacle frame
+        ok.pad[0] = (P[0] == 1.0 && P[5] == 1.0 && P[10] == 1.0 && P[1] == 0.0 && P[2] == 0.0 && P[4] == 0.0 && P[6] == 0.0 &&
+                     P[8] == 0.0 && P[9] == 0.0) ? 1 : 0;
     }
     const int np = ch->n_prims;
     std::vector<PairK> self(d->n_self_pairs);

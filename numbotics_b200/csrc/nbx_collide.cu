@@ -20,14 +20,13 @@
 #include "nbx_gjk.cuh"
 #include "nbx_joint.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 using namespace nbxg;
 
 namespace {
 
-constexpr int kCTile = 128;       // configurations (threads) per CTA, in_collision
-constexpr int kETile = 128;       // edges per CTA, edge validation
 constexpr int kMaxSave = 8;
 constexpr int kGjkIters = 48;        // verdict mode: only near-threshold pairs ever get this far
 constexpr int kGjkItersDist = 96;    // distance mode: run to convergence
@@ -123,33 +122,56 @@ __device__ __forceinline__ void unround(ShapeW& S, float margin) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Block-cooperative evaluation of NT items (configurations or interpolation samples), two phases:
+// Warp-autonomous evaluation.  A warp owns a contiguous range of units (configurations, or edges) and works through
+// it in tiles of 32 items (configurations, or interpolation samples) without ever meeting a block barrier:
 //
-//   phase 1  thread = item.  Walk the whole tree, park EVERY primitive's world core in shared memory
-//            ([value][thread], conflict free), and run the cheap conservative culls on every allowed
-//            pair.  All lanes walk the same scene in lockstep, so survivors are appended to a block
-//            queue with one warp-aggregated shared-memory atomic per (pair, warp).
-//   phase 2  thread = queue entry.  Surviving (pair, item) candidates -- typically a handful per
-//            item out of ~60 pairs -- go through the GJK narrow phase.  Entries are ordered by pair,
-//            so a warp works on one pair type at a time and lanes only diverge in iteration count.
+//   phase 1      lane = item.  Walk the whole tree, park every primitive's world core in the warp's shared-memory
+//                scratch ([value][lane], conflict free), run the cheap conservative culls on every allowed pair.
+//                All lanes walk the same scene in lockstep; the rare survivors (~0.5 % of the pairs) are appended to
+//                the warp's pending list with one ballot per pair and no atomics (the count is warp-uniform).
+//   materialise  lane = pending survivor.  Its two world-space cores are copied from the scratch into a
+//                self-contained queue entry, so the entry outlives the tile.
+//   drain        lane = queue entry.  Whenever 32 entries have accumulated (typically every 3-4 tiles) they go
+//                through the GJK narrow phase with every lane busy; the remainder is drained at the end of the range.
 //
-// The per-thread version of this (cull and GJK interleaved in one loop) ran at 72 % SIMT efficiency
-// and 229 KB of inlined code; see profiles/.
+// Two arrangements of the narrow phase:
+//   * verdict queries (in_collision, edge validation) are SPLIT over two kernels: the broad kernel appends its
+//     entries to a global queue (env pairs in the first half, self pairs in the second, so that GJK warps see one
+//     kind of pair) and a second, small kernel runs the GJK over the queue at full lane utilisation.  The broad
+//     kernel then carries no GJK state: <= 96 registers and ~9 KB of shared memory per warp, 20 warps per SM.
+//   * distance queries (min_distance) stay FUSED: the warp keeps a shared-memory queue and drains it itself whenever
+//     32 entries have accumulated, because the running minimum of a configuration prunes its later candidates.
+// The block-cooperative predecessor (phase 2 right after each tile's phase 1, between two __syncthreads) spent 26 % of
+// its warp-cycles at the barrier behind the one or two warps that had candidates, and ran the GJK at ~30 % lane
+// utilisation; see profiles/README.md.
 // ---------------------------------------------------------------------------------------------
-constexpr int kQueuePerThread = 20;
+constexpr int kWarps = 4;            // autonomous warps per CTA (they only share the staged scene)
+constexpr int kWT = 32;              // items per tile
+constexpr int kQCap = 48;            // materialised candidates per warp
+constexpr int kPendCap = 64;         // survivors of one tile awaiting materialisation
+constexpr int kEW = 33;              // words per queue entry
+constexpr int kMaxRange = 256;       // units a warp owns (flags kept in shared memory until the range is done)
 constexpr uint32_t kEnvFlag = 0x80000000u;
 
-struct Ctx {
+constexpr int kSplit = 0;            // verdict query, global queue + narrow kernel
+constexpr int kDist = 1;             // distance query, fused
+
+struct WCtx {
     SceneSm V;
     const float* base;        // 12 floats (kernel parameter)
-    float* poses;             // [pose_floats][NT]
-    uint32_t* queue;          // [qcap]
-    int* qcount;
-    int* flag;                // verdict mode: [n_flags] 1 = hit ; distance mode: ordered-int keys of the running minimum
-    const int* item_flag;     // [NT] item -> flag index (nullptr = identity)
-    int qcap;
+    float* poses;             // [pose_floats][32]
+    float* queue;             // kDist: [kEW][kQCap] in shared memory, word-major so that lanes = entries is conflict free
+    uint32_t* pend;           // [kPendCap] survivor codes: env flag | pair << 8 | item lane
+    int* flag;                // kDist: [kMaxRange] ordered-int keys of the running minimum
+    int* item_fi;             // [32] item lane -> flag index (kDist: within the warp's range; kSplit: global unit index)
     int n_mov, n_prims, n_base_prims;
     float thr;
+    // kSplit
+    float* gq;                // [kEW][2 * gq_half] global queue, word-major: env entries [0, gq_half), self entries [gq_half, 2 gq_half)
+    int* gq_count;            // [2] entries requested so far (may exceed gq_half: the excess was evaluated in place)
+    int gq_half;
+    uint8_t* gflag;           // per unit: verdict (hit_value 1) or edge validity (hit_value 0)
+    int hit_value;
 };
 
 __device__ __forceinline__ int float_key(float f) {            // order-preserving float -> int
@@ -172,6 +194,8 @@ __device__ __forceinline__ void pose_load(const float* scr, int stride, const Pr
     S.type = pk.type;
     S.c = mk(scr[0 * stride], scr[1 * stride], scr[2 * stride]);
     S.d[0] = pk.dims[0]; S.d[1] = pk.dims[1]; S.d[2] = pk.dims[2];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) S.ax[k] = 0.f;
     if (pk.type == NBX_PRIM_CYLINDER) {
         S.ax[0] = scr[3 * stride]; S.ax[1] = scr[4 * stride]; S.ax[2] = scr[5 * stride];
     } else if (pk.type == NBX_PRIM_BOX) {
@@ -180,55 +204,101 @@ __device__ __forceinline__ void pose_load(const float* scr, int stride, const Pr
     }
 }
 
-// Narrow phase of one queued candidate.  The ONLY place the GJK is instantiated (per mode).
-template <bool WANT_DIST, int NT>
-__device__ __forceinline__ void eval_candidate(const Ctx& C, uint32_t entry) {
-    const int item = (int)(entry & 0xffu);
-    const int e = (int)((entry & ~kEnvFlag) >> 8);
-    const int fi = C.item_flag ? C.item_flag[item] : item;
-    float best = FLT_MAX;
-    if (WANT_DIST) best = key_float(C.flag[fi]);
-    else if (((volatile int*)C.flag)[fi]) return;          // this item is already decided
-    ShapeW A, Bs;
+// One narrow-phase candidate: the two world-space cores, the margins to subtract, the flag it reports to.
+struct Cand {
+    ShapeW A, B;
+    float m;
+    int fi;
+};
+
+// survivor code -> candidate, from the warp's pose scratch (valid until the next tile's phase 1)
+__device__ __forceinline__ void build_cand(const WCtx& C, uint32_t code, Cand& K) {
+    const int item = (int)(code & 0xffu);
+    const int e = (int)((code & ~kEnvFlag) >> 8);
+    K.fi = C.item_fi[item];
     float mA, mB;
     bool sharp;
-    if (entry & kEnvFlag) {
+    if (code & kEnvFlag) {
         const PairK pr = C.V.env_pairs[e];
         const PrimK& pb = C.V.prims[pr.a];
         const ObsK& o = C.V.obs[pr.b];
-        obs_world(o, A);
-        pose_load(C.poses + (size_t)pb.slot * NT + item, NT, pb, Bs);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) K.A.ax[k] = 0.f;
+        obs_world(o, K.A);
+        pose_load(C.poses + (size_t)pb.slot * kWT + item, kWT, pb, K.B);
         mA = o.margin; mB = pb.margin; sharp = pr.sharp != 0;
     } else {
         const PairK pr = C.V.self_pairs[e];
         const PrimK& pa = C.V.prims[pr.a];
         const PrimK& pb = C.V.prims[pr.b];
-        pose_load(C.poses + (size_t)pa.slot * NT + item, NT, pa, A);
-        pose_load(C.poses + (size_t)pb.slot * NT + item, NT, pb, Bs);
+        pose_load(C.poses + (size_t)pa.slot * kWT + item, kWT, pa, K.A);
+        pose_load(C.poses + (size_t)pb.slot * kWT + item, kWT, pb, K.B);
         mA = pa.margin; mB = pb.margin; sharp = pr.sharp != 0;
     }
-    float m = mA + mB;
+    K.m = mA + mB;
     if (sharp) {
         // box-box under the Bullet margin model: sharp boxes (spheres keep their radius: point cores)
-        unround(A, mA);
-        unround(Bs, mB);
-        m = (A.type == NBX_PRIM_SPHERE ? mA : 0.f) + (Bs.type == NBX_PRIM_SPHERE ? mB : 0.f);
-    }
-    GjkOut g;
-    if (WANT_DIST) g = gjk_distance<kGjkItersDist>(A, Bs, best + m, -FLT_MAX);
-    else g = gjk_distance<kGjkIters>(A, Bs, C.thr + m, C.thr + m);
-    // overlapping cores: depth beyond the margins is not computed (clamp)
-    const float d = g.overlap ? (-m - 1e-3f) : (g.contact ? (-m - 1e-6f) : (g.d - m));
-    if (WANT_DIST) {
-        if (!g.pruned) atomicMin(&C.flag[fi], float_key(d));
-    } else if (d < C.thr) {
-        ((volatile int*)C.flag)[fi] = 1;
+        unround(K.A, mA);
+        unround(K.B, mB);
+        K.m = (K.A.type == NBX_PRIM_SPHERE ? mA : 0.f) + (K.B.type == NBX_PRIM_SPHERE ? mB : 0.f);
     }
 }
 
-// cold copy for the queue-overflow path, kept out of line so phase 1 stays small
-template <bool WANT_DIST, int NT>
-__device__ __noinline__ void eval_candidate_cold(const Ctx& C, uint32_t entry) { eval_candidate<WANT_DIST, NT>(C, entry); }
+template <typename STRIDE>
+__device__ __forceinline__ void store_cand(float* qd, int slot, const Cand& K, const STRIDE kQCap) {
+    float* w = qd + slot;
+    w[0 * kQCap] = __int_as_float(K.fi);
+    w[1 * kQCap] = __int_as_float(K.A.type | (K.B.type << 8));
+    w[2 * kQCap] = K.m;
+    w[3 * kQCap] = K.A.c.x; w[4 * kQCap] = K.A.c.y; w[5 * kQCap] = K.A.c.z;
+    w[18 * kQCap] = K.B.c.x; w[19 * kQCap] = K.B.c.y; w[20 * kQCap] = K.B.c.z;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { w[(6 + k) * kQCap] = K.A.ax[k]; w[(21 + k) * kQCap] = K.B.ax[k]; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { w[(15 + k) * kQCap] = K.A.d[k]; w[(30 + k) * kQCap] = K.B.d[k]; }
+}
+
+template <typename STRIDE>
+__device__ __forceinline__ void load_cand(const float* qd, int slot, Cand& K, const STRIDE kQCap) {
+    const float* w = qd + slot;
+    K.fi = __float_as_int(w[0 * kQCap]);
+    const int ty = __float_as_int(w[1 * kQCap]);
+    K.A.type = ty & 0xff; K.B.type = (ty >> 8) & 0xff;
+    K.m = w[2 * kQCap];
+    K.A.c = mk(w[3 * kQCap], w[4 * kQCap], w[5 * kQCap]);
+    K.B.c = mk(w[18 * kQCap], w[19 * kQCap], w[20 * kQCap]);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { K.A.ax[k] = w[(6 + k) * kQCap]; K.B.ax[k] = w[(21 + k) * kQCap]; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { K.A.d[k] = w[(15 + k) * kQCap]; K.B.d[k] = w[(30 + k) * kQCap]; }
+}
+
+// Narrow phase of one candidate.
+template <int MODE>
+__device__ __forceinline__ void eval_cand(const WCtx& C, const Cand& K) {
+    if (MODE == kDist) {
+        const float best = key_float(((volatile int*)C.flag)[K.fi]);
+        const GjkOut g = gjk_distance<kGjkItersDist>(K.A, K.B, best + K.m, -FLT_MAX);
+        // overlapping cores: depth beyond the margins is not computed (clamp)
+        const float d = g.overlap ? (-K.m - 1e-3f) : (g.contact ? (-K.m - 1e-6f) : (g.d - K.m));
+        if (!g.pruned) atomicMin(&C.flag[K.fi], float_key(d));
+    } else {
+        volatile uint8_t* f = C.gflag + K.fi;
+        if (*f == (uint8_t)C.hit_value) return;              // this unit is already decided
+        const GjkOut g = gjk_distance<kGjkIters>(K.A, K.B, C.thr + K.m, C.thr + K.m);
+        const float d = g.overlap ? (-K.m - 1e-3f) : (g.contact ? (-K.m - 1e-6f) : (g.d - K.m));
+        if (d < C.thr) *f = (uint8_t)C.hit_value;
+    }
+}
+
+// Evaluate a survivor on the spot, out of line so that phase 1 stays small: overflow of the pending list (> 64
+// survivors in a tile of 32 items) or of the global queue.  Pathological scenes only; no loss, just slower.
+template <int MODE>
+__device__ __noinline__ void eval_now_cold(const WCtx& C, uint32_t code) {
+    Cand K;
+    build_cand(C, code, K);
+    eval_cand<MODE>(C, K);
+}
 
 // distance between segments {ca + s ua, |s| <= ha} and {cb + t ub, |t| <= hb} (unit directions)
 __device__ __forceinline__ float seg_seg_distance(V3 ca, V3 ua, float ha, V3 cb, V3 ub, float hb) {
@@ -243,33 +313,32 @@ __device__ __forceinline__ float seg_seg_distance(V3 ca, V3 ua, float ha, V3 cb,
     return sqrtf(dot(d, d));
 }
 
-// warp-aggregated append of the surviving lanes' candidates; lanes that do not fit evaluate inline
-template <bool WANT_DIST, int NT>
-__device__ __forceinline__ void push_candidates(const Ctx& C, bool surv, uint32_t code) {
+// append the surviving lanes' codes to the pending list: one ballot, no atomics (npend is warp-uniform)
+template <int MODE>
+__device__ __forceinline__ void push_pending(const WCtx& C, int& npend, bool surv, uint32_t code) {
     const unsigned mask = __ballot_sync(0xffffffffu, surv);
     if (mask == 0) return;
     const int lane = threadIdx.x & 31;
-    const int leader = __ffs(mask) - 1;
-    int pos = 0;
-    if (lane == leader) pos = atomicAdd(C.qcount, __popc(mask));
-    pos = __shfl_sync(0xffffffffu, pos, leader) + __popc(mask & ((1u << lane) - 1u));
+    const int pos = npend + __popc(mask & ((1u << lane) - 1u));
     if (surv) {
-        const uint32_t entry = code | (uint32_t)threadIdx.x;
-        if (pos < C.qcap) C.queue[pos] = entry;
-        else eval_candidate_cold<WANT_DIST, NT>(C, entry);     // queue full (pathological scenes): no loss, just slower
+        if (pos < kPendCap) C.pend[pos] = code | (uint32_t)lane;
+        else eval_now_cold<MODE>(C, code | (uint32_t)lane);
     }
+    npend = min(npend + __popc(mask), kPendCap);
 }
 
-// phase 1 for this thread's item.  `valid` = the thread has an item; invalid lanes still take part in the ballots.
-//   1a  walk the tree, park every primitive's world core in shared memory;
-//   1b  broad phase.  Obstacle-major for the environment pairs (one obstacle's frame stays in registers
-//       while the primitives paired with it stream past: exact point-to-box distance minus the primitive's
-//       bounding radius), then the self pairs (bounding spheres, refined by the capsule bound for
-//       cylinder-cylinder pairs that survive).  Every pair record is one 16-byte shared-memory load.
-template <bool WANT_DIST, int NT, typename QF>
-__device__ __forceinline__ void phase1(const Ctx& C, bool valid, QF qf, int n_obs, int n_self) {
-    const int tid = threadIdx.x;
-    float* my = C.poses + tid;
+// phase 1 for this lane's item.  `valid` = the lane has an item; invalid lanes still take part in the ballots.
+//   1a  walk the tree, park every primitive's world core in the warp's scratch;
+//   1b  broad phase.  Obstacle-major for the environment pairs (one obstacle's frame stays in registers while the
+//       primitives paired with it stream past: exact point-to-box distance against the primitive's bounding radius,
+//       compared squared -- no square root -- and without the rotation for axis-aligned boxes), then the self pairs
+//       (bounding spheres, refined by the capsule bound for cylinder-cylinder pairs that survive).
+template <int MODE, typename QF>
+__device__ __forceinline__ void phase1(const WCtx& C, bool valid, QF qf, int n_obs, int n_self, int& npend) {
+    constexpr bool WANT_DIST = MODE == kDist;
+    constexpr int NT = kWT;
+    const int lane = threadIdx.x & 31;
+    float* my = C.poses + lane;
     {
         PoseF X;
 #pragma unroll
@@ -304,20 +373,23 @@ __device__ __forceinline__ void phase1(const Ctx& C, bool valid, QF qf, int n_ob
             do_prims(jk.prim_begin, jk.prim_end);
         }
     }
+    __syncwarp();
 
     float run_ub = FLT_MAX;      // distance mode: no pair can beat the smallest centre distance seen so far
     const float4* env4 = reinterpret_cast<const float4*>(C.V.env_pairs);
     const float4* self4 = reinterpret_cast<const float4*>(C.V.self_pairs);
+    const float cut0 = C.thr + 1e-6f;
 #pragma unroll 1
     for (int o = 0; o < n_obs; ++o) {
         const ObsK& ob = C.V.obs[o];
         const V3 oc = mk(ob.c[0], ob.c[1], ob.c[2]);
         const bool is_box = ob.type == NBX_PRIM_BOX;
+        const bool aa = ob.pad[0] != 0;                          // rotation is exactly the identity
         float R[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) R[k] = ob.R[k];
         const float hx = ob.dims[0] + ob.margin, hy = ob.dims[1] + ob.margin, hz = ob.dims[2] + ob.margin;
-        const float orad = ob.brad;
+        const float orad = is_box ? 0.f : ob.brad;
         const int e1 = C.V.env_begin[o + 1];
 #pragma unroll 2
         for (int e = C.V.env_begin[o]; e < e1; ++e) {
@@ -325,18 +397,29 @@ __device__ __forceinline__ void phase1(const Ctx& C, bool valid, QF qf, int n_ob
             const int slot_a = (int)(short)(__float_as_uint(rec.y) >> 16);
             const float* pc = my + (size_t)slot_a * NT;
             const V3 dc = mk(pc[0], pc[NT], pc[2 * NT]) - oc;
-            float lbnd;
+            float l2;      // squared distance from the primitive's centre to the obstacle (box: exact; else: to its centre)
             if (is_box) {
-                const float lx = fmaxf(fabsf(fmaf(R[0], dc.x, fmaf(R[3], dc.y, R[6] * dc.z))) - hx, 0.f);
-                const float ly = fmaxf(fabsf(fmaf(R[1], dc.x, fmaf(R[4], dc.y, R[7] * dc.z))) - hy, 0.f);
-                const float lz = fmaxf(fabsf(fmaf(R[2], dc.x, fmaf(R[5], dc.y, R[8] * dc.z))) - hz, 0.f);
-                lbnd = sqrtf(fmaf(lx, lx, fmaf(ly, ly, lz * lz))) - rec.w;
+                float lx, ly, lz;
+                if (aa) {
+                    lx = fmaxf(fabsf(dc.x) - hx, 0.f); ly = fmaxf(fabsf(dc.y) - hy, 0.f); lz = fmaxf(fabsf(dc.z) - hz, 0.f);
+                } else {
+                    lx = fmaxf(fabsf(fmaf(R[0], dc.x, fmaf(R[3], dc.y, R[6] * dc.z))) - hx, 0.f);
+                    ly = fmaxf(fabsf(fmaf(R[1], dc.x, fmaf(R[4], dc.y, R[7] * dc.z))) - hy, 0.f);
+                    lz = fmaxf(fabsf(fmaf(R[2], dc.x, fmaf(R[5], dc.y, R[8] * dc.z))) - hz, 0.f);
+                }
+                l2 = fmaf(lx, lx, fmaf(ly, ly, lz * lz));
             } else {
-                lbnd = sqrtf(dot(dc, dc)) - rec.w - orad;
+                l2 = dot(dc, dc);
             }
-            if (WANT_DIST) run_ub = fminf(run_ub, sqrtf(dot(dc, dc)));
-            const bool surv = valid && lbnd <= (WANT_DIST ? run_ub : C.thr) + 1e-6f;
-            push_candidates<WANT_DIST, NT>(C, surv, kEnvFlag | ((uint32_t)e << 8));
+            bool surv;
+            if (WANT_DIST) {
+                run_ub = fminf(run_ub, sqrtf(dot(dc, dc)));
+                surv = valid && sqrtf(l2) - rec.w - orad <= run_ub + 1e-6f;
+            } else {
+                const float reach = rec.w + orad + cut0;         // >= 0: thresholds are non-negative
+                surv = valid && l2 <= reach * reach;
+            }
+            push_pending<MODE>(C, npend, surv, kEnvFlag | ((uint32_t)e << 8));
         }
     }
 #pragma unroll 2
@@ -349,10 +432,19 @@ __device__ __forceinline__ void phase1(const Ctx& C, bool valid, QF qf, int n_ob
         const V3 ca = mk(pa[0], pa[NT], pa[2 * NT]);
         const V3 cb = mk(pb[0], pb[NT], pb[2 * NT]);
         const V3 dc = cb - ca;
-        const float cd = sqrtf(dot(dc, dc));
-        if (WANT_DIST) run_ub = fminf(run_ub, cd);
-        const float cut = (WANT_DIST ? run_ub : C.thr) + 1e-6f;
-        bool surv = valid && cd - rec.w <= cut;
+        const float cd2 = dot(dc, dc);
+        float cut;
+        bool surv;
+        if (WANT_DIST) {
+            const float cd = sqrtf(cd2);
+            run_ub = fminf(run_ub, cd);
+            cut = run_ub + 1e-6f;
+            surv = valid && cd - rec.w <= cut;
+        } else {
+            cut = cut0;
+            const float reach = rec.w + cut0;
+            surv = valid && cd2 <= reach * reach;
+        }
         if (surv && ((w1 >> 8) & 0xffu)) {
             // thin links: capsule bound  d(cyl, cyl) >= d(axis segment, axis segment) - rA - rB
             const PairK pr = C.V.self_pairs[e];
@@ -364,188 +456,294 @@ __device__ __forceinline__ void phase1(const Ctx& C, bool valid, QF qf, int n_ob
                             (ka.dims[0] + ka.margin) - (kb.dims[0] + kb.margin);
             surv = d <= cut;
         }
-        push_candidates<WANT_DIST, NT>(C, surv, (uint32_t)e << 8);
+        push_pending<MODE>(C, npend, surv, (uint32_t)e << 8);
     }
 }
 
-template <bool WANT_DIST, int NT>
-__device__ __forceinline__ void phase2(const Ctx& C) {
-    const int count = min(*C.qcount, C.qcap);
-    for (int k = threadIdx.x; k < count; k += NT) eval_candidate<WANT_DIST, NT>(C, C.queue[k]);
+// kDist: GJK on the 32 newest queue entries (all lanes busy), or on what is left at the end of the range
+__device__ __forceinline__ void drain(const WCtx& C, int& qn, bool all) {
+    const int lane = threadIdx.x & 31;
+    while (qn >= 32 || (all && qn > 0)) {
+        const int take = min(qn, 32);
+        if (lane < take) {
+            Cand K;
+            load_cand(C.queue, qn - take + lane, K, kQCap);
+            eval_cand<kDist>(C, K);
+        }
+        qn -= take;
+        __syncwarp();
+    }
 }
 
-__host__ __device__ inline size_t work_smem_bytes(int nt, int pose_floats, int dof_floats_per_item) {
-    return align16(sizeof(float) * (size_t)nt * (pose_floats > 0 ? pose_floats : 1)) + align16(sizeof(uint32_t) * (size_t)nt * kQueuePerThread) +
-           align16(sizeof(float) * (size_t)nt * dof_floats_per_item) + align16(sizeof(int) * (size_t)(2 * nt + 4));
+// pending survivors of the tile just walked -> self-contained queue entries (the scratch is overwritten by the next
+// tile).  kDist: the warp's shared-memory queue, drained as soon as it holds 32 entries.  kSplit: the global queue;
+// one atomic per (tile, pair kind) reserves the slots.
+template <int MODE>
+__device__ __forceinline__ void materialise(const WCtx& C, int& npend, int& qn) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    int done = 0;
+    while (done < npend) {
+        if (MODE == kDist) {
+            const int chunk = min(min(32, npend - done), kQCap - qn);
+            if (lane < chunk) {
+                Cand K;
+                build_cand(C, C.pend[done + lane], K);
+                store_cand(C.queue, qn + lane, K, kQCap);
+            }
+            __syncwarp();
+            qn += chunk;
+            done += chunk;
+            drain(C, qn, false);
+        } else {
+            const int chunk = min(32, npend - done);
+            const bool have = lane < chunk;
+            const uint32_t code = have ? C.pend[done + lane] : 0u;
+            const bool env = have && (code & kEnvFlag) != 0;
+            const bool slf = have && !env;
+            const unsigned menv = __ballot_sync(0xffffffffu, env), mslf = __ballot_sync(0xffffffffu, slf);
+            int benv = 0, bslf = 0;
+            if (lane == 0) {
+                if (menv) benv = atomicAdd(&C.gq_count[0], __popc(menv));
+                if (mslf) bslf = atomicAdd(&C.gq_count[1], __popc(mslf));
+            }
+            benv = __shfl_sync(0xffffffffu, benv, 0);
+            bslf = __shfl_sync(0xffffffffu, bslf, 0);
+            if (have) {
+                const unsigned below = (1u << lane) - 1u;
+                const int pos = env ? benv + __popc(menv & below) : bslf + __popc(mslf & below);
+                if (pos < C.gq_half) {
+                    Cand K;
+                    build_cand(C, code, K);
+                    store_cand(C.gq, env ? pos : C.gq_half + pos, K, 2 * C.gq_half);
+                } else {
+                    eval_now_cold<MODE>(C, code);
+                }
+            }
+            done += chunk;
+        }
+    }
+    npend = 0;
 }
+
+// per-warp work area: pose scratch, queue, pending list, flags, item -> flag map, + `extra_floats` for the caller
+__host__ __device__ inline size_t warp_smem_bytes(int mode, int pose_floats, int extra_floats) {
+    return align16(sizeof(float) * (size_t)kWT * (pose_floats > 0 ? pose_floats : 1)) +
+           (mode == kDist ? align16(sizeof(float) * (size_t)kEW * kQCap) + align16(sizeof(int) * kMaxRange) : 0) +
+           align16(sizeof(uint32_t) * kPendCap) + align16(sizeof(int) * kWT) + align16(sizeof(float) * (size_t)extra_floats);
+}
+
+template <int MODE>
+__device__ __forceinline__ unsigned char* carve_warp(WCtx& C, unsigned char* p, int pose_floats) {
+    C.poses = reinterpret_cast<float*>(p);      p += align16(sizeof(float) * (size_t)kWT * max(pose_floats, 1));
+    C.queue = nullptr;
+    C.flag = nullptr;
+    if (MODE == kDist) {
+        C.queue = reinterpret_cast<float*>(p);  p += align16(sizeof(float) * (size_t)kEW * kQCap);
+        C.flag = reinterpret_cast<int*>(p);     p += align16(sizeof(int) * kMaxRange);
+    }
+    C.pend = reinterpret_cast<uint32_t*>(p);    p += align16(sizeof(uint32_t) * kPendCap);
+    C.item_fi = reinterpret_cast<int*>(p);      p += align16(sizeof(int) * kWT);
+    return p;
+}
+
+struct SplitArgs {
+    float* gq;
+    int* gq_count;
+    int gq_half;
+};
 
 // ---------------------------------------------------------------------------------------------
-template <bool WANT_DIST>
-__global__ void __launch_bounds__(kCTile)
+// in_collision.  MODE kSplit: broad kernel of the verdict query (verdict[b] = 0 here, the narrow kernel raises it);
+// MODE kDist: fused distance query (min_dist[b] and the verdict at the end of the warp's range).
+template <int MODE>
+__global__ void __launch_bounds__(kWarps * 32, MODE == kSplit ? 5 : 1)
 in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ q, int64_t B, int dof, float thr,
-                    uint8_t* __restrict__ verdict, float* __restrict__ min_dist) {
+                    uint8_t* __restrict__ verdict, float* __restrict__ min_dist, int upw, const SplitArgs G) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Ctx C;
+    WCtx C;
     unsigned char* p = stage_scene(S, smem_raw, C.V);
-    C.poses = reinterpret_cast<float*>(p);              p += align16(sizeof(float) * (size_t)kCTile * max(S.scratch_floats, 1));
-    C.queue = reinterpret_cast<uint32_t*>(p);           p += align16(sizeof(uint32_t) * (size_t)kCTile * kQueuePerThread);
-    float* sq = reinterpret_cast<float*>(p);            p += align16(sizeof(float) * (size_t)kCTile * dof);
-    C.flag = reinterpret_cast<int*>(p);
-    C.qcount = C.flag + kCTile;
-    C.item_flag = nullptr;
-    C.qcap = kCTile * kQueuePerThread;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const size_t wbytes = warp_smem_bytes(MODE, S.scratch_floats, kWT * dof);
+    p = carve_warp<MODE>(C, p + (size_t)wid * wbytes, S.scratch_floats);
+    float* sq = reinterpret_cast<float*>(p);             // [32][dof]
     C.base = S.base;
     C.n_mov = S.n_mov; C.n_prims = S.n_prims; C.n_base_prims = S.n_base_prims;
     C.thr = thr;
+    C.gq = G.gq; C.gq_count = G.gq_count; C.gq_half = G.gq_half;
+    C.gflag = verdict; C.hit_value = 1;
+    __syncthreads();                                     // the staged scene is the only thing the warps share
 
-    const int64_t tile0 = (int64_t)blockIdx.x * kCTile;
-    const int nvalid = (int)min((int64_t)kCTile, B - tile0);
-    const int tid = threadIdx.x;
-    {
-        const float* src = q + tile0 * dof;
-        const int n = nvalid * dof;
-        if (nvalid == kCTile && ((reinterpret_cast<uintptr_t>(q) & 15u) == 0)) {
-            const int n16 = n / 4;
+    const int64_t range0 = ((int64_t)blockIdx.x * kWarps + wid) * upw;
+    const int rangeN = (int)max((int64_t)0, min((int64_t)upw, B - range0));
+    if (rangeN == 0) return;
+    for (int i = lane; i < rangeN; i += 32) {
+        if (MODE == kDist) C.flag[i] = float_key(FLT_MAX);
+        else verdict[range0 + i] = 0;
+    }
+    int npend = 0, qn = 0;
+    const bool vec = (reinterpret_cast<uintptr_t>(q) & 15u) == 0;
+#pragma unroll 1
+    for (int t0 = 0; t0 < rangeN; t0 += kWT) {
+        const int nv = min(kWT, rangeN - t0);
+        const float* src = q + (range0 + t0) * dof;
+        const int n = nv * dof;
+        __syncwarp();
+        if (nv == kWT && vec && (((range0 + t0) * dof) & 3) == 0) {
             const float4* s16 = reinterpret_cast<const float4*>(src);
             float4* d16 = reinterpret_cast<float4*>(sq);
-            for (int i = tid; i < n16; i += kCTile) d16[i] = __ldg(s16 + i);
+            for (int i = lane; i < n / 4; i += 32) d16[i] = __ldg(s16 + i);
         } else {
-            for (int i = tid; i < n; i += kCTile) sq[i] = src[i];
+            for (int i = lane; i < n; i += 32) sq[i] = src[i];
         }
+        C.item_fi[lane] = (MODE == kDist) ? t0 + lane : (int)(range0 + t0 + lane);
+        __syncwarp();
+        const float* myq = sq + lane * dof;
+        phase1<MODE>(C, lane < nv, [myq](int col) { return myq[col]; }, S.n_obs, S.n_self, npend);
+        materialise<MODE>(C, npend, qn);
     }
-    C.flag[tid] = WANT_DIST ? float_key(FLT_MAX) : 0;
-    if (tid == 0) *C.qcount = 0;
-    __syncthreads();
-
-    const float* myq = sq + tid * dof;
-    phase1<WANT_DIST, kCTile>(C, tid < nvalid, [myq](int col) { return myq[col]; }, S.n_obs, S.n_self);
-    __syncthreads();
-    phase2<WANT_DIST, kCTile>(C);
-    __syncthreads();
-    if (tid < nvalid) {
-        if (WANT_DIST) {
-            const float d = key_float(C.flag[tid]);
-            min_dist[tile0 + tid] = d;
-            verdict[tile0 + tid] = d < thr ? 1 : 0;
-        } else {
-            verdict[tile0 + tid] = (uint8_t)C.flag[tid];
+    if (MODE == kDist) {
+        drain(C, qn, true);
+        __syncwarp();
+        for (int i = lane; i < rangeN; i += 32) {
+            const float d = key_float(C.flag[i]);
+            min_dist[range0 + i] = d;
+            verdict[range0 + i] = d < thr ? 1 : 0;
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Edge validation.  Per edge (all float64, bit-for-bit the reference's NumPy arithmetic,
+// Edge validation, broad kernel.  Per edge (all float64, bit-for-bit the reference's NumPy arithmetic,
 // connectors.py:62-69 / :84-93):
 //   distance = ||goal - start||_2 ; distance <= float32 eps -> invalid
 //   step = resolution / distance ; T_f = 1 (connect) or min(1, max_distance / distance) (steer)
 //   samples: t_k = k * step for k < ceil(T_f / step)  (numpy.arange length rule), then t = T_f.
-// A block prefix sum flattens the (edge, sample) space of the CTA's edges; rounds of kETile samples go
-// through phase 1 / phase 2.  Samples of an edge that is already invalid are skipped, as the sequential
-// reference does by returning None.
+// A warp prefix sum flattens the (edge, sample) space of 32 edges, so every lane always has a sample; rounds of 32
+// samples go through phase 1 with the configuration interpolated on the fly.  valid[e] starts as 1 (0 for an edge
+// shorter than float32 eps) and the narrow kernel clears it when one of the edge's candidates collides.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kETile)
+__global__ void __launch_bounds__(kWarps * 32, 5)
 edges_valid_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ starts, const float* __restrict__ goals,
                    int64_t E, int dof, double resolution, double max_distance, float thr,
-                   uint8_t* __restrict__ valid, int32_t* __restrict__ n_samples) {
+                   uint8_t* __restrict__ valid, int32_t* __restrict__ n_samples, int upw, const SplitArgs G) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Ctx C;
+    WCtx C;
     unsigned char* p = stage_scene(S, smem_raw, C.V);
-    C.poses = reinterpret_cast<float*>(p);              p += align16(sizeof(float) * (size_t)kETile * max(S.scratch_floats, 1));
-    C.queue = reinterpret_cast<uint32_t*>(p);           p += align16(sizeof(uint32_t) * (size_t)kETile * kQueuePerThread);
-    float* s_start = reinterpret_cast<float*>(p);       p += align16(sizeof(float) * (size_t)kETile * 2 * dof);
-    float* s_goal = s_start + (size_t)kETile * dof;
-    int* s_hit = reinterpret_cast<int*>(p);             // [kETile] per EDGE: 1 = some sample collides
-    int* s_item_edge = s_hit + kETile;                  // [kETile] per ITEM of the current round: its edge
-    C.qcount = s_item_edge + kETile;                    p += align16(sizeof(int) * (size_t)(2 * kETile + 4));
-    double* s_step = reinterpret_cast<double*>(p);      p += sizeof(double) * kETile;
-    double* s_tf = reinterpret_cast<double*>(p);        p += sizeof(double) * kETile;
-    int* s_off = reinterpret_cast<int*>(p);             // [kETile + 1] exclusive prefix of sample counts
-    C.flag = s_hit;
-    C.item_flag = s_item_edge;
-    C.qcap = kETile * kQueuePerThread;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int extra = 2 * kWT * dof + 4 * kWT + (kWT + 4);       // start/goal tiles, step/tf (double), sample offsets
+    const size_t wbytes = warp_smem_bytes(kSplit, S.scratch_floats, extra);
+    p = carve_warp<kSplit>(C, p + (size_t)wid * wbytes, S.scratch_floats);
+    double* s_step = reinterpret_cast<double*>(p);       // [32]   (16-byte aligned: first in the extra area)
+    double* s_tf = s_step + kWT;                         // [32]
+    float* s_start = reinterpret_cast<float*>(s_tf + kWT);   // [32][dof]
+    float* s_goal = s_start + (size_t)kWT * dof;         // [32][dof]
+    int* s_off = reinterpret_cast<int*>(s_goal + (size_t)kWT * dof);   // [33] exclusive prefix of sample counts
     C.base = S.base;
     C.n_mov = S.n_mov; C.n_prims = S.n_prims; C.n_base_prims = S.n_base_prims;
     C.thr = thr;
-
-    const int64_t tile0 = (int64_t)blockIdx.x * kETile;
-    const int nvalid = (int)min((int64_t)kETile, E - tile0);
-    const int tid = threadIdx.x;
-    for (int i = tid; i < nvalid * dof; i += kETile) {
-        s_start[i] = starts[tile0 * dof + i];
-        s_goal[i] = goals[tile0 * dof + i];
-    }
+    C.gq = G.gq; C.gq_count = G.gq_count; C.gq_half = G.gq_half;
+    C.gflag = valid; C.hit_value = 0;
     __syncthreads();
 
-    int cnt = 0;
-    int dead = 1;            // edges beyond nvalid, and edges shorter than float32 eps, have no samples and are invalid
-    if (tid < nvalid) {
-        double ss = 0.0;
-        for (int k = 0; k < dof; ++k) {
-            const double dlt = (double)s_start[tid * dof + k] - (double)s_goal[tid * dof + k];
-            ss = fma(dlt, dlt, ss);
+    const int64_t range0 = ((int64_t)blockIdx.x * kWarps + wid) * upw;
+    const int rangeN = (int)max((int64_t)0, min((int64_t)upw, E - range0));
+    if (rangeN == 0) return;
+    int npend = 0, qn = 0;
+#pragma unroll 1
+    for (int t0 = 0; t0 < rangeN; t0 += kWT) {
+        const int nv = min(kWT, rangeN - t0);
+        __syncwarp();
+        for (int i = lane; i < nv * dof; i += 32) {
+            s_start[i] = starts[(range0 + t0) * dof + i];
+            s_goal[i] = goals[(range0 + t0) * dof + i];
         }
-        const double dist = sqrt(ss);
-        if (dist > (double)1.1920928955078125e-07f) {
-            const double step = resolution / dist;
-            double tf = 1.0;
-            if (max_distance > 0.0 && dist > max_distance) tf = max_distance / dist;
-            const double len = ceil(tf / step);
-            cnt = (int)fmin(len, 1.0e9) + 1;
-            s_step[tid] = step;
-            s_tf[tid] = tf;
-            dead = 0;
+        __syncwarp();
+        int cnt = 0;
+        if (lane < nv) {
+            int dead = 1;            // edges shorter than float32 eps have no samples and are invalid
+            double ss = 0.0;
+            for (int k = 0; k < dof; ++k) {
+                const double dlt = (double)s_start[lane * dof + k] - (double)s_goal[lane * dof + k];
+                ss = fma(dlt, dlt, ss);
+            }
+            const double dist = sqrt(ss);
+            if (dist > (double)1.1920928955078125e-07f) {
+                const double step = resolution / dist;
+                double tf = 1.0;
+                if (max_distance > 0.0 && dist > max_distance) tf = max_distance / dist;
+                const double len = ceil(tf / step);
+                cnt = (int)fmin(len, 1.0e9) + 1;
+                s_step[lane] = step;
+                s_tf[lane] = tf;
+                dead = 0;
+            }
+            if (n_samples != nullptr) n_samples[range0 + t0 + lane] = cnt;
+            valid[range0 + t0 + lane] = (uint8_t)(dead ? 0 : 1);
         }
-        if (n_samples != nullptr) n_samples[tile0 + tid] = cnt;
-    }
-    s_hit[tid] = dead;
-    // block exclusive scan of cnt (kETile = 128: warp scans + 4 partials)
-    {
-        __shared__ int warp_tot[kETile / 32];
+        // warp exclusive scan of cnt
         int x = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int y = __shfl_up_sync(0xffffffffu, x, o);
-            if ((tid & 31) >= o) x += y;
+            if (lane >= o) x += y;
         }
-        if ((tid & 31) == 31) warp_tot[tid >> 5] = x;
-        __syncthreads();
-        int base = 0;
-        for (int w = 0; w < (tid >> 5); ++w) base += warp_tot[w];
-        s_off[tid] = base + x - cnt;
-        if (tid == kETile - 1) s_off[kETile] = base + x;
-    }
-    __syncthreads();
-    const int total = s_off[kETile];
+        s_off[lane] = x - cnt;
+        if (lane == 31) s_off[32] = x;
+        __syncwarp();
+        const int total = s_off[32];
 
-    for (int round0 = 0; round0 < total; round0 += kETile) {
-        const int s = round0 + tid;
-        bool have = s < total;
-        int e = 0;
-        float t = 0.f;
-        if (have) {
-            // owning edge: last e with s_off[e] <= s
-            int lo = 0, hi = kETile - 1;
-            while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (s_off[mid] <= s) lo = mid; else hi = mid - 1;
+#pragma unroll 1
+        for (int round0 = 0; round0 < total; round0 += kWT) {
+            const int s = round0 + lane;
+            const bool have = s < total;
+            int e = 0;
+            float t = 0.f;
+            if (have) {
+                // owning edge: last e with s_off[e] <= s
+                int lo = 0, hi = kWT - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (s_off[mid] <= s) lo = mid; else hi = mid - 1;
+                }
+                e = lo;
+                const int k = s - s_off[e];
+                const int last = s_off[e + 1] - s_off[e] - 1;
+                t = (float)((k == last) ? s_tf[e] : (double)k * s_step[e]);
             }
-            e = lo;
-            const int k = s - s_off[e];
-            const int last = s_off[e + 1] - s_off[e] - 1;
-            t = (float)((k == last) ? s_tf[e] : (double)k * s_step[e]);
-            have = ((volatile int*)s_hit)[e] == 0;      // already invalid: skip (the sequential reference stops there too)
+            __syncwarp();
+            C.item_fi[lane] = (int)(range0 + t0 + e);
+            __syncwarp();
+            const float* a = s_start + e * dof;
+            const float* g = s_goal + e * dof;
+            phase1<kSplit>(C, have, [a, g, t](int col) { return fmaf(t, g[col], fmaf(-t, a[col], a[col])); }, S.n_obs, S.n_self, npend);
+            materialise<kSplit>(C, npend, qn);
         }
-        s_item_edge[tid] = e;
-        if (tid == 0) *C.qcount = 0;
-        __syncthreads();
-        const float* a = s_start + e * dof;
-        const float* g = s_goal + e * dof;
-        phase1<false, kETile>(C, have, [a, g, t](int col) { return fmaf(t, g[col], fmaf(-t, a[col], a[col])); }, S.n_obs, S.n_self);
-        __syncthreads();
-        phase2<false, kETile>(C);
-        __syncthreads();
     }
-    if (tid < nvalid) valid[tile0 + tid] = (uint8_t)(s_hit[tid] == 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Narrow kernel of the verdict queries: one thread per queue entry, grid-stride, first the environment pairs, then
+// the self pairs (a warp works on one kind of pair).  The entry count lives on the device: no host round trip.
+__global__ void __launch_bounds__(128)
+narrow_kernel(const float* __restrict__ gq, const int* __restrict__ gq_count, int gq_half, float thr,
+              uint8_t* __restrict__ gflag, int hit_value) {
+    WCtx C;
+    C.thr = thr;
+    C.gflag = gflag;
+    C.hit_value = hit_value;
+    const int n_env = min(gq_count[0], gq_half), n_self = min(gq_count[1], gq_half);
+    const int stride = gridDim.x * blockDim.x;
+    const int first = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int half = 0; half < 2; ++half) {
+        const int n = half == 0 ? n_env : n_self;
+        const int off = half == 0 ? 0 : gq_half;
+        for (int i = first; i < n; i += stride) {
+            Cand K;
+            load_cand(gq, off + i, K, 2 * gq_half);
+            eval_cand<kSplit>(C, K);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -571,6 +769,44 @@ int fill_scene_dev(const nbx_chain* ch, const nbx_scene* sc, const double* base_
     return NBX_OK;
 }
 
+// units (configurations / edges) per warp: long ranges amortise the final partial drain, but the grid must keep
+// every SM busy for several waves
+int units_per_warp(int64_t n_units, int sm_count, int warps_per_sm) {
+    static const int env = std::getenv("NBX_COLLIDE_UPW") ? std::atoi(std::getenv("NBX_COLLIDE_UPW")) : 0;   // tuning only
+    int64_t u = n_units / ((int64_t)sm_count * warps_per_sm * 6 * kWT);
+    u = std::max<int64_t>(1, std::min<int64_t>(u, kMaxRange / kWT));
+    if (env > 0) u = std::min(env, kMaxRange / kWT);
+    return (int)u * kWT;
+}
+
+// stream-ordered workspace of a verdict query: the global queue and its two counters
+struct SplitWs {
+    void* p = nullptr;
+    cudaStream_t st = nullptr;
+    SplitArgs args{nullptr, nullptr, 0};
+    int alloc(int64_t n_items, cudaStream_t stream) {
+        st = stream;
+        // ~0.3 candidates per item on the PRM scene; what does not fit is evaluated in place by the broad kernel
+        int64_t half = std::max<int64_t>(4096, std::min<int64_t>(n_items / 2, 1 << 20));
+        half = (half + 31) & ~(int64_t)31;
+        const size_t bytes = 256 + sizeof(float) * (size_t)kEW * 2 * (size_t)half;
+        NBX_CUDA_OK(cudaMallocAsync(&p, bytes, stream));
+        NBX_CUDA_OK(cudaMemsetAsync(p, 0, 256, stream));
+        args.gq_count = static_cast<int*>(p);
+        args.gq = reinterpret_cast<float*>(static_cast<unsigned char*>(p) + 256);
+        args.gq_half = (int)half;
+        return NBX_OK;
+    }
+    ~SplitWs() { if (p) cudaFreeAsync(p, st); }
+};
+
+int launch_narrow(const nbx_chain* ch, const SplitArgs& G, float thr, uint8_t* gflag, int hit_value, cudaStream_t stream) {
+    narrow_kernel<<<(unsigned)(ch->sm_count * 8), 128, 0, stream>>>(G.gq, G.gq_count, G.gq_half, thr, gflag, hit_value);
+    nbx_count_launch();
+    NBX_CUDA_OK(cudaGetLastError());
+    return NBX_OK;
+}
+
 int launch_in_collision(const nbx_chain* ch, const nbx_scene* sc, const float* q, int64_t B, const double* base_pose,
                         float thr, uint8_t* verdict, float* min_dist, cudaStream_t stream) {
     SceneDev S;
@@ -580,21 +816,27 @@ int launch_in_collision(const nbx_chain* ch, const nbx_scene* sc, const float* q
     if (B == 0) return NBX_OK;
     NBX_REQUIRE(q != nullptr && verdict != nullptr, "q / verdict is NULL");
     NBX_REQUIRE(thr >= 0.f, "negative thresholds need penetration depth, which this path does not compute");
+    NBX_REQUIRE(B <= 0x7fffffffLL, "batch too large for one launch");
     NBX_CUDA_OK(cudaSetDevice(ch->device));
-    const size_t smem = scene_smem_bytes(S.n_mov, S.n_prims, S.n_obs, S.n_self, S.n_env) + work_smem_bytes(kCTile, S.scratch_floats, ch->dof);
+    const int mode = min_dist != nullptr ? kDist : kSplit;
+    const size_t smem = scene_smem_bytes(S.n_mov, S.n_prims, S.n_obs, S.n_self, S.n_env) + kWarps * warp_smem_bytes(mode, S.scratch_floats, kWT * ch->dof);
     NBX_REQUIRE(smem <= 220 * 1024, "scene too large for shared memory (%zu bytes)", smem);
-    const int64_t grid = (B + kCTile - 1) / kCTile;
-    NBX_REQUIRE(grid <= 0x7fffffffLL, "batch too large for one launch");
-    if (min_dist != nullptr) {
-        NBX_CUDA_OK(cudaFuncSetAttribute(in_collision_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        in_collision_kernel<true><<<(unsigned)grid, kCTile, smem, stream>>>(S, q, B, ch->dof, thr, verdict, min_dist);
-    } else {
-        NBX_CUDA_OK(cudaFuncSetAttribute(in_collision_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        in_collision_kernel<false><<<(unsigned)grid, kCTile, smem, stream>>>(S, q, B, ch->dof, thr, verdict, min_dist);
+    const int upw = units_per_warp(B, ch->sm_count, mode == kDist ? 12 : 20);
+    const int64_t grid = (B + (int64_t)kWarps * upw - 1) / ((int64_t)kWarps * upw);
+    if (mode == kDist) {
+        NBX_CUDA_OK(cudaFuncSetAttribute(in_collision_kernel<kDist>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        in_collision_kernel<kDist><<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, q, B, ch->dof, thr, verdict, min_dist, upw, SplitArgs{nullptr, nullptr, 0});
+        nbx_count_launch();
+        NBX_CUDA_OK(cudaGetLastError());
+        return NBX_OK;
     }
+    SplitWs ws;
+    if ((rc = ws.alloc(B, stream)) != NBX_OK) return rc;
+    NBX_CUDA_OK(cudaFuncSetAttribute(in_collision_kernel<kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    in_collision_kernel<kSplit><<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, q, B, ch->dof, thr, verdict, nullptr, upw, ws.args);
     nbx_count_launch();
     NBX_CUDA_OK(cudaGetLastError());
-    return NBX_OK;
+    return launch_narrow(ch, ws.args, thr, verdict, 1, stream);
 }
 
 int launch_edges(const nbx_chain* ch, const nbx_scene* sc, const float* starts, const float* goals, int64_t E,
@@ -608,18 +850,21 @@ int launch_edges(const nbx_chain* ch, const nbx_scene* sc, const float* starts, 
     NBX_REQUIRE(starts != nullptr && goals != nullptr && valid != nullptr, "starts / goals / valid is NULL");
     NBX_REQUIRE(resolution > 0.0, "Resolution must be positive");
     NBX_REQUIRE(thr >= 0.f, "negative thresholds need penetration depth, which this path does not compute");
+    NBX_REQUIRE(E <= 0x7fffffffLL, "too many edges for one launch");
     NBX_CUDA_OK(cudaSetDevice(ch->device));
     const int dof = ch->dof;
-    const size_t smem = scene_smem_bytes(S.n_mov, S.n_prims, S.n_obs, S.n_self, S.n_env) + work_smem_bytes(kETile, S.scratch_floats, 2 * dof) +
-                        sizeof(double) * 2 * kETile + sizeof(int) * (kETile + 4);
+    const size_t smem = scene_smem_bytes(S.n_mov, S.n_prims, S.n_obs, S.n_self, S.n_env) +
+                        kWarps * warp_smem_bytes(kSplit, S.scratch_floats, 2 * kWT * dof + 4 * kWT + (kWT + 4));
     NBX_REQUIRE(smem <= 220 * 1024, "scene too large for shared memory (%zu bytes)", smem);
+    SplitWs ws;
+    if ((rc = ws.alloc(E * 8, stream)) != NBX_OK) return rc;
     NBX_CUDA_OK(cudaFuncSetAttribute(edges_valid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t grid = (E + kETile - 1) / kETile;
-    NBX_REQUIRE(grid <= 0x7fffffffLL, "too many edges for one launch");
-    edges_valid_kernel<<<(unsigned)grid, kETile, smem, stream>>>(S, starts, goals, E, dof, resolution, max_distance, thr, valid, n_samples);
+    const int upw = units_per_warp(E * 8, ch->sm_count, 20);      // an edge is ~13 samples: smaller ranges for the same balance
+    const int64_t grid = (E + (int64_t)kWarps * upw - 1) / ((int64_t)kWarps * upw);
+    edges_valid_kernel<<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, starts, goals, E, dof, resolution, max_distance, thr, valid, n_samples, upw, ws.args);
     nbx_count_launch();
     NBX_CUDA_OK(cudaGetLastError());
-    return NBX_OK;
+    return launch_narrow(ch, ws.args, thr, valid, 0, stream);
 }
 
 // host-buffer variants: one staging allocation per call is acceptable here (verdict bytes are tiny,

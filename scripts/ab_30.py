@@ -21,3 +21,13 @@ arm, cubes = workloads.prm_scene(device=0)
 q = workloads.random_configs_cuda(arm, 1 << 22, seed=0)
 b = timeit(lambda: arm.fk_jacobian(q, "forearm_link"))
 print(f"{tag} kinova forearm_link (sparse, generic kernel) fk+jac 4M: {b:.3f} ms")
+import numpy as np
+q64 = q30[: 1 << 20].double()
+b = timeit(lambda: arm30.fk_jacobian(q64, "tool"), n=5)
+print(f"{tag} 30dof f64 fk+jac 1M: {b:.3f} ms -> {q64.shape[0]/b*1e3:.3e} cfg/s")
+arm48 = workloads.serial_arm(48, device=0)
+q48 = workloads.random_configs_cuda(arm48, 1 << 21, seed=1)
+b = timeit(lambda: arm48.fk_jacobian(q48, "tool"), n=5)
+print(f"{tag} 48dof f32 fk+jac 2M: {b:.3f} ms -> {q48.shape[0]/b*1e3:.3e} cfg/s, {(48*28+64)*q48.shape[0]/b/1e6:.0f} GB/s")
+b = timeit(lambda: arm48.fk_jacobian(q48, "link_24"), n=5)
+print(f"{tag} 48dof f32 link_24 (sparse) fk+jac 2M: {b:.3f} ms")
