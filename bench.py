@@ -260,6 +260,11 @@ def main():
     e2e_value = world * B * e2e_steps / e2e_s
     e2e_ok = bool(torch.equal(Th[:4096], T[:4096].cpu()) and torch.equal(Jh[-4096:], J[-4096:].cpu()))
 
+    extras = None
+    if not args.no_extras:
+        del qh, Th, Jh
+        extras = secondary_measurements(arm, q, dev, rank, world, float(clock_info.get("sm_mhz") or 1965.0))
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -303,10 +308,6 @@ def main():
         parity = {"checked_rows": n, "max_abs_err_T": eT, "max_abs_err_J": eJ, "tolerance": 1e-5, "ok": bool(eT < 1e-5 and eJ < 1e-5),
                   "e2e_host_path_bitwise_equal_to_device_path": e2e_ok}
 
-    extras = None
-    if world == 1 and not args.no_extras:
-        extras = secondary_measurements(arm, q, dev)
-
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -329,46 +330,91 @@ def main():
         dist.destroy_process_group()
 
 
-def secondary_measurements(arm, q, dev):
-    """BASELINE configs 3-5 on one GPU (not the headline; reported for the roofline table in DESIGN.md)."""
-    import torch
-    from numbotics_b200 import workloads
+def fp32_convention_flops_per_config(arm):
+    """SURVEY.md section 8(d) accounting convention for one collision-checked configuration:
+    110 flop per movable joint (sincos 2 + Rodrigues 36 + rigid product 72), 72 per collision primitive (world pose
+    of the primitive), 256 per allowed convex pair (64 when a sphere is involved)."""
+    from numbotics_b200 import _cabi
+    sc = arm.scene_arrays(None)                      # the allowed pair sets, before static pruning
+    types = [int(t) for t in arm._arrays["prim_type"]]
+    sphere = _cabi.NBX_PRIM_SPHERE
+    flops = 110 * arm.dof + 72 * len(types)
+    for a, b_ in sc["self_pairs"]:
+        flops += 64 if (types[a] == sphere or types[b_] == sphere) else 256
+    for a, o in sc["env_pairs"]:
+        flops += 64 if (types[a] == sphere or int(sc["obs_type"][o]) == sphere) else 256
+    return flops, len(types), int(sc["self_pairs"].shape[0]), int(sc["env_pairs"].shape[0])
 
-    def best_ms(fn, n=5, warm=2):
+
+def secondary_measurements(arm, q, dev, rank, world, clocks_mhz):
+    """BASELINE configs 3-5 (not the headline; reported for the roofline table in DESIGN.md).  Every rank runs its
+    shard; times are the max over ranks between two barriers, values are whole-job aggregates."""
+    import torch
+    import torch.distributed as dist
+    from numbotics_b200 import workloads
+    from numbotics_b200.dist import max_over_ranks, shard_bounds
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def best_ms(fn, n=5, warm=3):
         for _ in range(warm):
             fn()
-        torch.cuda.synchronize(dev)
         ts = []
         for _ in range(n):
+            barrier()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); fn(); b.record()
             torch.cuda.synchronize(dev)
-            ts.append(a.elapsed_time(b))
+            ts.append(max_over_ranks(a.elapsed_time(b), dev))
         return min(ts)
 
     out = {}
+    # configs[2]: 4 Mi configurations per GPU (weak)
     Bc = 1 << 22
     qc = q[:Bc]
     ms = best_ms(lambda: arm.in_collision(qc))
-    out["in_collision_configs_per_sec"] = {"value": Bc / ms * 1e3, "configs": Bc, "best_ms": ms,
-                                           "hit_fraction": float(arm.in_collision(qc).float().mean()),
-                                           "workload": "BASELINE configs[2]: Kinova-7 + 3 cubes, self + env pairs"}
-    nodes = q[:100000]
-    s, g = workloads.knn_edges_cuda(nodes, 10)
+    flops, n_prims, n_self, n_env = fp32_convention_flops_per_config(arm)
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    fp32_peak = sms * 128 * 2 * clocks_mhz * 1e6 / 1e12
+    rate = world * Bc / ms * 1e3
+    out["in_collision_configs_per_sec"] = {
+        "value": rate, "configs_per_gpu": Bc, "best_ms": ms, "scaling": "weak",
+        "hit_fraction": float(arm.in_collision(qc).float().mean()),
+        "workload": "BASELINE configs[2]: Kinova-7 + 3 cubes, self + env pairs, 2^22 configurations per GPU",
+        "kernels": "in_collision_kernel<split> (tree walk + broad phase) + narrow_kernel (GJK over the candidate queue)",
+        "roofline": {"bound": "fp32", "convention_flops_per_config": flops, "n_prims": n_prims, "self_pairs": n_self, "env_pairs": n_env,
+                     "achieved": flops * rate / world / 1e12, "peak": fp32_peak, "unit": "TFLOP/s", "frac": flops * rate / world / 1e12 / fp32_peak,
+                     "note": "SURVEY 8(d) accounting convention (256 flop charged per allowed pair); culled pairs execute ~20 flop, "
+                             "see profiles/ for executed FFMA counts"}}
+    # configs[3]: 1 M candidate edges in total, sharded over the GPUs (strong)
+    nodes = workloads.random_configs_cuda(arm, 100000, seed=0)
+    s_all, g_all = workloads.knn_edges_cuda(nodes, 10)
+    lo, hi = shard_bounds(s_all.shape[0], rank, world)
+    s, g = s_all[lo:hi].contiguous(), g_all[lo:hi].contiguous()
     ms = best_ms(lambda: arm.edges_valid(s, g, 0.1))
     v, ns = arm.edges_valid(s, g, 0.1, return_samples=True)
-    out["prm_edges_per_sec"] = {"value": s.shape[0] / ms * 1e3, "edges": int(s.shape[0]), "best_ms": ms,
-                                "valid_fraction": float(v.float().mean()), "mean_samples_per_edge": float(ns.float().mean()),
-                                "workload": "BASELINE configs[3]: 100k nodes x 10-NN, resolution 0.1, one GPU's worth"}
+    out["prm_edges_per_sec"] = {"value": s_all.shape[0] / ms * 1e3, "edges_total": int(s_all.shape[0]), "edges_this_rank": int(hi - lo),
+                                "best_ms": ms, "scaling": "strong",
+                                "valid_fraction_rank0": float(v.float().mean()), "mean_samples_per_edge_rank0": float(ns.float().mean()),
+                                "samples_per_sec": float(ns.sum()) * world / ms * 1e3,
+                                "workload": "BASELINE configs[3]: 100k nodes x 10-NN = 1M edges, resolution 0.1, contiguous E/G slices"}
+    del s_all, g_all, s, g, nodes
+    # configs[4]: 2^25 configurations of the 30-DoF chain per GPU (2^28 over 8 GPUs), J alone is 24 GB per GPU
     arm30 = workloads.serial_arm(30, device=dev.index)
-    B30 = 1 << 22
-    q30 = workloads.random_configs_cuda(arm30, B30, seed=1)
-    T30 = torch.empty((B30, 4, 4), dtype=torch.float32, device=dev)
-    ms = best_ms(lambda: arm30.fk_jacobian(q30, "tool"))
-    out["serial30_fk_jacobian_configs_per_sec"] = {"value": B30 / ms * 1e3, "configs": B30, "best_ms": ms,
-                                                   "hbm_gbs": 904 * B30 / ms / 1e6,
-                                                   "workload": "BASELINE configs[4] per-GPU slice (2^22 of 2^25)"}
-    del T30
+    B30 = 1 << 25
+    q30 = workloads.random_configs_cuda(arm30, B30, seed=1 + rank)
+    ms = best_ms(lambda: arm30.fk_jacobian(q30, "tool"), n=3, warm=2)
+    peak, _ = measured_hbm_peak()
+    out["serial30_fk_jacobian_configs_per_sec"] = {
+        "value": world * B30 / ms * 1e3, "configs_per_gpu": B30, "best_ms": ms, "scaling": "weak",
+        "workload": "BASELINE configs[4]: programmatic 30-DoF serial chain, 2^25 configurations per GPU (2^28 on 8)",
+        "kernel": "fkjac_wide_kernel<30, ALLZ>",
+        "roofline": {"bound": "hbm", "achieved": 904 * B30 / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": 904 * B30 / ms / 1e6 / peak,
+                     "algorithmic_bytes_per_config": 904}}
+    del q30
     return out
 
 

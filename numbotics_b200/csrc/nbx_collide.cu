@@ -779,18 +779,44 @@ int units_per_warp(int64_t n_units, int sm_count, int warps_per_sm) {
     return (int)u * kWT;
 }
 
+// The library's own memory pool per device, with an unbounded release threshold: the default pool hands its memory
+// back to the driver at every synchronisation, which turned each call's 100+ MB workspace into a ~10 ms allocation.
+int workspace_pool(int device, cudaMemPool_t* out) {
+    static std::mutex mu;
+    static cudaMemPool_t pools[64] = {};
+    NBX_REQUIRE(device >= 0 && device < 64, "device index out of range");
+    std::lock_guard<std::mutex> lock(mu);
+    if (pools[device] == nullptr) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaMemPool_t pool = nullptr;
+        NBX_CUDA_OK(cudaMemPoolCreate(&pool, &props));
+        uint64_t keep = ~0ull;
+        NBX_CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        pools[device] = pool;
+    }
+    *out = pools[device];
+    return NBX_OK;
+}
+
 // stream-ordered workspace of a verdict query: the global queue and its two counters
 struct SplitWs {
     void* p = nullptr;
     cudaStream_t st = nullptr;
     SplitArgs args{nullptr, nullptr, 0};
-    int alloc(int64_t n_items, cudaStream_t stream) {
+    int alloc(int device, int64_t n_items, cudaStream_t stream) {
         st = stream;
+        cudaMemPool_t pool = nullptr;
+        int rc = workspace_pool(device, &pool);
+        if (rc != NBX_OK) return rc;
         // ~0.3 candidates per item on the PRM scene; what does not fit is evaluated in place by the broad kernel
         int64_t half = std::max<int64_t>(4096, std::min<int64_t>(n_items / 2, 1 << 20));
         half = (half + 31) & ~(int64_t)31;
         const size_t bytes = 256 + sizeof(float) * (size_t)kEW * 2 * (size_t)half;
-        NBX_CUDA_OK(cudaMallocAsync(&p, bytes, stream));
+        NBX_CUDA_OK(cudaMallocFromPoolAsync(&p, bytes, pool, stream));
         NBX_CUDA_OK(cudaMemsetAsync(p, 0, 256, stream));
         args.gq_count = static_cast<int*>(p);
         args.gq = reinterpret_cast<float*>(static_cast<unsigned char*>(p) + 256);
@@ -831,7 +857,7 @@ int launch_in_collision(const nbx_chain* ch, const nbx_scene* sc, const float* q
         return NBX_OK;
     }
     SplitWs ws;
-    if ((rc = ws.alloc(B, stream)) != NBX_OK) return rc;
+    if ((rc = ws.alloc(ch->device, B, stream)) != NBX_OK) return rc;
     NBX_CUDA_OK(cudaFuncSetAttribute(in_collision_kernel<kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     in_collision_kernel<kSplit><<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, q, B, ch->dof, thr, verdict, nullptr, upw, ws.args);
     nbx_count_launch();
@@ -857,7 +883,7 @@ int launch_edges(const nbx_chain* ch, const nbx_scene* sc, const float* starts, 
                         kWarps * warp_smem_bytes(kSplit, S.scratch_floats, 2 * kWT * dof + 4 * kWT + (kWT + 4));
     NBX_REQUIRE(smem <= 220 * 1024, "scene too large for shared memory (%zu bytes)", smem);
     SplitWs ws;
-    if ((rc = ws.alloc(E * 8, stream)) != NBX_OK) return rc;
+    if ((rc = ws.alloc(ch->device, E * 8, stream)) != NBX_OK) return rc;
     NBX_CUDA_OK(cudaFuncSetAttribute(edges_valid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int upw = units_per_warp(E * 8, ch->sm_count, 20);      // an edge is ~13 samples: smaller ranges for the same balance
     const int64_t grid = (E + (int64_t)kWarps * upw - 1) / ((int64_t)kWarps * upw);
