@@ -192,6 +192,21 @@ NBX_API int nbx_edges_valid_host_f32(const nbx_chain* chain, const nbx_scene* sc
                              float threshold, uint8_t* valid);
 
 /*
+ * Batched bisection towards the collision boundary: the zero-order-hold counter-example search of IRIS
+ * (numbotics/planning/safe_sets.py:124-134, IrisSolver.counter_ex_search_bisection; its caller maps it over the
+ * colliding samples with a thread pool, safe_sets.py:198-199).  Per sample b the interval [inside, outside[b]]
+ * (inside: one shared point, stride 0 -- the ellipsoid centre -- or one per sample, stride dof) is halved
+ * n_bisections times: the half whose far end still satisfies `min distance < threshold` is kept; out[b] is the
+ * colliding end.  Interval arithmetic in float64 like the reference; all buffers on the device.
+ */
+NBX_API int nbx_bisect_f32(const nbx_chain* chain, const nbx_scene* scene, const float* inside, int64_t inside_stride,
+                   const float* outside, int64_t B, const double* base_pose, int n_bisections, float threshold,
+                   float* out, void* stream);
+NBX_API int nbx_bisect_f64(const nbx_chain* chain, const nbx_scene* scene, const double* inside, int64_t inside_stride,
+                   const double* outside, int64_t B, const double* base_pose, int n_bisections, float threshold,
+                   double* out, void* stream);
+
+/*
  * Batched damped-least-squares inverse kinematics: the reference's whole iteration loop
  * (numbotics/robots/arm.py:464-552, Arm.inverse_kinematics) on the device, one problem per thread.
  *   target_pose (B,4,4) or (4,4) device; target_stride = 16 or 0 (broadcast)

@@ -747,6 +747,33 @@ narrow_kernel(const float* __restrict__ gq, const int* __restrict__ gq_count, in
 }
 
 // ---------------------------------------------------------------------------------------------
+// Bisection towards the collision boundary (IRIS "zero-order hold" counter-example search, reference
+// numbotics/planning/safe_sets.py:124-134): per sample an interval [lo, hi] in configuration space, lo free, hi
+// colliding; each round tests the midpoint and keeps the half that still straddles the boundary.  Interval
+// arithmetic in float64 exactly as the reference's NumPy ((lo + hi) / 2.0); the collision test sees the midpoint
+// rounded to float32.  One elementwise kernel per round applies the previous verdict and emits the next midpoints.
+template <typename T>
+__global__ void bisect_step_kernel(double* __restrict__ lo, double* __restrict__ hi, const T* __restrict__ inside, int64_t inside_stride,
+                                   const T* __restrict__ outside, const uint8_t* __restrict__ verdict, float* __restrict__ mid32,
+                                   T* __restrict__ out, int64_t B, int dof, int round, int last) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * dof) return;
+    const int64_t b = i / dof;
+    double l, h;
+    if (round == 0) {
+        l = (double)inside[inside_stride ? i : i - b * dof];
+        h = (double)outside[i];
+    } else {
+        l = lo[i]; h = hi[i];
+        const double m = (l + h) / 2.0;
+        if (verdict[b]) h = m; else l = m;
+    }
+    if (last) { out[i] = (T)h; return; }
+    lo[i] = l; hi[i] = h;
+    mid32[i] = (float)((l + h) / 2.0);
+}
+
+// ---------------------------------------------------------------------------------------------
 int fill_scene_dev(const nbx_chain* ch, const nbx_scene* sc, const double* base_pose, SceneDev& S) {
     NBX_REQUIRE(ch != nullptr && sc != nullptr, "NULL handle");
     NBX_REQUIRE(sc->chain == ch, "scene was created for a different chain");
@@ -893,6 +920,44 @@ int launch_edges(const nbx_chain* ch, const nbx_scene* sc, const float* starts, 
     return launch_narrow(ch, ws.args, thr, valid, 0, stream);
 }
 
+template <typename T>
+int launch_bisect(const nbx_chain* ch, const nbx_scene* sc, const T* inside, int64_t inside_stride, const T* outside, int64_t B,
+                  const double* base_pose, int n_bisections, float thr, T* out, cudaStream_t stream) {
+    NBX_REQUIRE(ch != nullptr && sc != nullptr, "NULL handle");
+    NBX_REQUIRE(B >= 0, "negative batch size");
+    NBX_REQUIRE(n_bisections >= 1, "num_bisections must be greater than 0");
+    if (B == 0) return NBX_OK;
+    NBX_REQUIRE(inside != nullptr && outside != nullptr && out != nullptr, "inside / outside / out is NULL");
+    NBX_REQUIRE(inside_stride == 0 || inside_stride == ch->dof, "inside_stride must be 0 (one shared point) or dof");
+    NBX_CUDA_OK(cudaSetDevice(ch->device));
+    const int dof = ch->dof;
+    const size_t n = (size_t)B * dof;
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t bytes = 2 * up(sizeof(double) * n) + up(sizeof(float) * n) + up((size_t)B);
+    cudaMemPool_t pool = nullptr;
+    int rc = workspace_pool(ch->device, &pool);
+    if (rc != NBX_OK) return rc;
+    struct Tmp { void* p = nullptr; cudaStream_t st = nullptr; ~Tmp() { if (p) cudaFreeAsync(p, st); } } tmp;
+    tmp.st = stream;
+    NBX_CUDA_OK(cudaMallocFromPoolAsync(&tmp.p, bytes, pool, stream));
+    unsigned char* w = static_cast<unsigned char*>(tmp.p);
+    double* lo = reinterpret_cast<double*>(w);
+    double* hi = reinterpret_cast<double*>(w + up(sizeof(double) * n));
+    float* mid = reinterpret_cast<float*>(w + 2 * up(sizeof(double) * n));
+    uint8_t* verdict = w + 2 * up(sizeof(double) * n) + up(sizeof(float) * n);
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    for (int r = 0; r <= n_bisections; ++r) {
+        const int last = r == n_bisections;
+        bisect_step_kernel<T><<<grid, 256, 0, stream>>>(lo, hi, inside, inside_stride, outside, verdict, mid, out, B, dof, r, last);
+        nbx_count_launch();
+        NBX_CUDA_OK(cudaGetLastError());
+        if (last) break;
+        rc = launch_in_collision(ch, sc, mid, B, base_pose, thr, verdict, nullptr, stream);
+        if (rc != NBX_OK) return rc;
+    }
+    return NBX_OK;
+}
+
 // host-buffer variants: one staging allocation per call is acceptable here (verdict bytes are tiny,
 // the copies are the dominant term); stream-ordered allocation keeps it asynchronous.
 struct DevTmp {
@@ -926,6 +991,18 @@ int nbx_in_collision_host_f32(const nbx_chain* chain, const nbx_scene* scene, co
     NBX_CUDA_OK(cudaMemcpyAsync(verdict, dv.p, (size_t)B, cudaMemcpyDeviceToHost, st));
     NBX_CUDA_OK(cudaStreamSynchronize(st));
     return NBX_OK;
+}
+
+int nbx_bisect_f32(const nbx_chain* chain, const nbx_scene* scene, const float* inside, int64_t inside_stride, const float* outside,
+                   int64_t B, const double* base_pose, int n_bisections, float threshold, float* out, void* stream) {
+    return launch_bisect<float>(chain, scene, inside, inside_stride, outside, B, base_pose, n_bisections, threshold, out,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int nbx_bisect_f64(const nbx_chain* chain, const nbx_scene* scene, const double* inside, int64_t inside_stride, const double* outside,
+                   int64_t B, const double* base_pose, int n_bisections, float threshold, double* out, void* stream) {
+    return launch_bisect<double>(chain, scene, inside, inside_stride, outside, B, base_pose, n_bisections, threshold, out,
+                                 static_cast<cudaStream_t>(stream));
 }
 
 int nbx_edges_valid_f32(const nbx_chain* chain, const nbx_scene* scene, const float* starts, const float* goals, int64_t E,

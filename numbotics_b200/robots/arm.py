@@ -504,6 +504,56 @@ class Arm:
             dist = dist.reshape(shape) if not single else dist.reshape(())
         return verdict, dist
 
+    # ------------------------------------------------------------------ bisection to the collision boundary
+    def bisect_to_collision(self, inside, outside, num_bisections: int = 15, threshold: float = 1e-6):
+        """Batched `IrisSolver.counter_ex_search_bisection` (reference safe_sets.py:124-134).
+
+        `inside` (dof,) (shared, e.g. the ellipsoid centre) or (..., dof); `outside` (..., dof), colliding samples.
+        Per sample the interval [inside, outside] is halved `num_bisections` times, keeping the half whose far end
+        has `min distance < threshold`; returns the far (colliding) ends, same type / dtype / shape as `outside`.
+        """
+        self._check_q(outside, "outside")
+        self._check_q(inside, "inside")
+        if num_bisections < 1:
+            raise ValueError("num_bisections must be greater than 0")
+        if threshold < 0:
+            raise NotImplementedError("negative thresholds need penetration depth (EPA), which this path does not compute")
+        in_torch = _is_torch(outside)
+        o_shape = tuple(outside.shape)
+        i_shape = tuple(inside.shape)
+        if len(i_shape) > 1 and i_shape != o_shape:
+            raise ValueError("inside must be one configuration or have the same shape as outside")
+        B = int(np.prod(o_shape[:-1])) if len(o_shape) > 1 else 1
+        if in_torch:
+            if outside.dtype not in (torch.float32, torch.float64):
+                raise TypeError("outside must be float32 or float64")
+            tdtype, out_np = outside.dtype, None
+        else:
+            outside = np.asarray(outside)
+            if outside.dtype not in (np.float32, np.float64):
+                outside = outside.astype(np.float64)
+            tdtype, out_np = (torch.float32 if outside.dtype == np.float32 else torch.float64), outside.dtype
+        scene = self._scene(threshold)
+        if self._scene_arrays["self_pairs"].shape[0] + self._scene_arrays["n_env_pairs_before_pruning"] == 0:
+            raise ValueError("min() arg is an empty sequence")
+        dev_index = self.device_index
+        base_keep, base_ptr = _cabi.base_pose_arg(self.base_pose)
+        od = self._to_device(outside, tdtype).reshape(B, self.dof)
+        idv = self._to_device(inside if _is_torch(inside) else np.asarray(inside), tdtype)
+        idv = idv.reshape(B, self.dof) if len(i_shape) > 1 else idv.reshape(self.dof)
+        lib = _cabi.load()
+        fn = lib.nbx_bisect_f64 if tdtype == torch.float64 else lib.nbx_bisect_f32
+        with torch.cuda.device(dev_index):
+            out = torch.empty_like(od)
+            _cabi.check(fn(self._handle().ptr, scene.ptr, idv.data_ptr(), self.dof if len(i_shape) > 1 else 0,
+                           od.data_ptr(), B, base_ptr, int(num_bisections), float(threshold), out.data_ptr(),
+                           _cuda_stream_ptr(dev_index)))
+        del base_keep
+        out = out.reshape(o_shape)
+        if in_torch:
+            return out.to(outside.device)
+        return out.cpu().numpy().astype(out_np, copy=False)
+
     # ------------------------------------------------------------------ edge validation
     def edges_valid(self, starts, goals, resolution: float, max_distance: float | None = None,
                     threshold: float = 0.0, return_samples: bool = False):
