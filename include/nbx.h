@@ -192,6 +192,23 @@ NBX_API int nbx_edges_valid_host_f32(const nbx_chain* chain, const nbx_scene* sc
                              float threshold, uint8_t* valid);
 
 /*
+ * Batched Arm.closest_to (numbotics/robots/arm.py:599-600): per configuration the allowed pair with the smallest
+ * distance, as the fields of the reference's Proximity record (numbotics/physics/chain.py:952-968), plus the
+ * gradient of that distance with respect to q, which is Arm.jacobian_proximity for the closest pair
+ * (numbotics/robots/arm.py:621-632:  n . J_v(subject, p_subject) - n . J_v(target, p_target)).
+ *   distance (B,), position_on_subject / position_on_target / normal_target_to_subject (B,3) world frame,
+ *   subject_prim (B,) index of the link primitive in the chain descriptor,
+ *   target (B,): obstacle index in the scene descriptor when the pair is (link, obstacle) -- then is_env bit 30 is
+ *   set: target = obstacle | 0x40000000 -- else the chain-descriptor index of the other link primitive,
+ *   valid (B,) u8: 0 when the two cores overlap (no EPA: distance is the clamp of nbx_in_collision_f32's min_dist,
+ *   points are the centres), gradient (nullable, (B,dof)).
+ * The scene must be unpruned (every allowed pair present).
+ */
+NBX_API int nbx_closest_f32(const nbx_chain* chain, const nbx_scene* scene, const float* q, int64_t B, const double* base_pose,
+                    float* distance, float* position_on_subject, float* position_on_target, float* normal_target_to_subject,
+                    int32_t* subject_prim, int32_t* target, uint8_t* valid, float* gradient, void* stream);
+
+/*
  * Batched bisection towards the collision boundary: the zero-order-hold counter-example search of IRIS
  * (numbotics/planning/safe_sets.py:124-134, IrisSolver.counter_ex_search_bisection; its caller maps it over the
  * colliding samples with a thread pool, safe_sets.py:198-199).  Per sample b the interval [inside, outside[b]]

@@ -164,6 +164,10 @@ int nbx_chain_create(const nbx_chain_desc* d, int device, nbx_chain** out) {
         pk.slot = ch->pose_floats;
         ch->pose_floats += prim_pose_floats(pk.type);
         pk.brad = bounding_radius(pk.type, &ch->prim_dims[3 * p]) * 1.000001f;
+        pk.desc = p;
+        pk.anc = 0ull;
+        if (ch->n_mov <= 64)
+            for (int j = pk.mov; j >= 0; j = ch->mov_parent[j]) pk.anc |= 1ull << j;
         if (pk.mov < 0) ch->n_base_prims++;
     }
     ch->h_tree.resize(ch->n_mov);
@@ -181,7 +185,7 @@ int nbx_chain_create(const nbx_chain_desc* d, int device, nbx_chain** out) {
         JointK<float> jk;
         nbx_fill_joint<float>(jk, &ch->mov_offset[12 * j], &ch->mov_axis[3 * j], ch->mov_type[j], ch->mov_qidx[j]);
         for (int k = 0; k < 9; ++k) { tj.A[k] = jk.A[k]; tj.Bm[k] = jk.Bm[k]; tj.Cm[k] = jk.Cm[k]; }
-        for (int k = 0; k < 3; ++k) { tj.t[k] = jk.t[k]; tj.d[k] = jk.d[k]; }
+        for (int k = 0; k < 3; ++k) { tj.t[k] = jk.t[k]; tj.d[k] = jk.d[k]; tj.ax[k] = jk.ax[k]; }
         tj.type = jk.type;
         tj.qidx = jk.qidx;
         tj.kind = jk.kind;

@@ -149,7 +149,7 @@ constexpr int kWarps = 4;            // autonomous warps per CTA (they only shar
 constexpr int kWT = 32;              // items per tile
 constexpr int kQCap = 48;            // materialised candidates per warp
 constexpr int kPendCap = 64;         // survivors of one tile awaiting materialisation
-constexpr int kEW = 33;              // words per queue entry
+constexpr int kEW = 34;              // words per queue entry
 constexpr int kMaxRange = 256;       // units a warp owns (flags kept in shared memory until the range is done)
 constexpr uint32_t kEnvFlag = 0x80000000u;
 
@@ -162,7 +162,7 @@ struct WCtx {
     float* poses;             // [pose_floats][32]
     float* queue;             // kDist: [kEW][kQCap] in shared memory, word-major so that lanes = entries is conflict free
     uint32_t* pend;           // [kPendCap] survivor codes: env flag | pair << 8 | item lane
-    int* flag;                // kDist: [kMaxRange] ordered-int keys of the running minimum
+    unsigned long long* flag; // kDist: [kMaxRange] running minimum: (ordered key of the distance) << 32 | pair code
     int* item_fi;             // [32] item lane -> flag index (kDist: within the warp's range; kSplit: global unit index)
     int n_mov, n_prims, n_base_prims;
     float thr;
@@ -179,6 +179,11 @@ __device__ __forceinline__ int float_key(float f) {            // order-preservi
     return i >= 0 ? i : i ^ 0x7fffffff;
 }
 __device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+// running minimum of a distance query: distance key in the high word (unsigned order), pair code in the low word
+__device__ __forceinline__ unsigned long long dist_entry(float d, uint32_t pc) {
+    return ((unsigned long long)((uint32_t)float_key(d) ^ 0x80000000u) << 32) | pc;
+}
+__device__ __forceinline__ float entry_dist(unsigned long long e) { return key_float((int)((uint32_t)(e >> 32) ^ 0x80000000u)); }
 
 __device__ __forceinline__ void pose_store(float* scr, int stride, const ShapeW& S) {
     scr[0 * stride] = S.c.x; scr[1 * stride] = S.c.y; scr[2 * stride] = S.c.z;
@@ -209,6 +214,7 @@ struct Cand {
     ShapeW A, B;
     float m;
     int fi;
+    uint32_t pc;    // pair code: kEnvFlag | index into the scene's env / self pair array
 };
 
 // survivor code -> candidate, from the warp's pose scratch (valid until the next tile's phase 1)
@@ -216,6 +222,7 @@ __device__ __forceinline__ void build_cand(const WCtx& C, uint32_t code, Cand& K
     const int item = (int)(code & 0xffu);
     const int e = (int)((code & ~kEnvFlag) >> 8);
     K.fi = C.item_fi[item];
+    K.pc = (code & kEnvFlag) | (uint32_t)e;
     float mA, mB;
     bool sharp;
     if (code & kEnvFlag) {
@@ -250,6 +257,7 @@ __device__ __forceinline__ void store_cand(float* qd, int slot, const Cand& K, c
     w[0 * kQCap] = __int_as_float(K.fi);
     w[1 * kQCap] = __int_as_float(K.A.type | (K.B.type << 8));
     w[2 * kQCap] = K.m;
+    w[33 * kQCap] = __uint_as_float(K.pc);
     w[3 * kQCap] = K.A.c.x; w[4 * kQCap] = K.A.c.y; w[5 * kQCap] = K.A.c.z;
     w[18 * kQCap] = K.B.c.x; w[19 * kQCap] = K.B.c.y; w[20 * kQCap] = K.B.c.z;
 #pragma unroll
@@ -265,6 +273,7 @@ __device__ __forceinline__ void load_cand(const float* qd, int slot, Cand& K, co
     const int ty = __float_as_int(w[1 * kQCap]);
     K.A.type = ty & 0xff; K.B.type = (ty >> 8) & 0xff;
     K.m = w[2 * kQCap];
+    K.pc = __float_as_uint(w[33 * kQCap]);
     K.A.c = mk(w[3 * kQCap], w[4 * kQCap], w[5 * kQCap]);
     K.B.c = mk(w[18 * kQCap], w[19 * kQCap], w[20 * kQCap]);
 #pragma unroll
@@ -277,11 +286,11 @@ __device__ __forceinline__ void load_cand(const float* qd, int slot, Cand& K, co
 template <int MODE>
 __device__ __forceinline__ void eval_cand(const WCtx& C, const Cand& K) {
     if (MODE == kDist) {
-        const float best = key_float(((volatile int*)C.flag)[K.fi]);
+        const float best = entry_dist(((volatile unsigned long long*)C.flag)[K.fi]);
         const GjkOut g = gjk_distance<kGjkItersDist>(K.A, K.B, best + K.m, -FLT_MAX);
         // overlapping cores: depth beyond the margins is not computed (clamp)
         const float d = g.overlap ? (-K.m - 1e-3f) : (g.contact ? (-K.m - 1e-6f) : (g.d - K.m));
-        if (!g.pruned) atomicMin(&C.flag[K.fi], float_key(d));
+        if (!g.pruned) atomicMin(&C.flag[K.fi], dist_entry(d, K.pc));
     } else {
         volatile uint8_t* f = C.gflag + K.fi;
         if (*f == (uint8_t)C.hit_value) return;              // this unit is already decided
@@ -529,7 +538,7 @@ __device__ __forceinline__ void materialise(const WCtx& C, int& npend, int& qn) 
 // per-warp work area: pose scratch, queue, pending list, flags, item -> flag map, + `extra_floats` for the caller
 __host__ __device__ inline size_t warp_smem_bytes(int mode, int pose_floats, int extra_floats) {
     return align16(sizeof(float) * (size_t)kWT * (pose_floats > 0 ? pose_floats : 1)) +
-           (mode == kDist ? align16(sizeof(float) * (size_t)kEW * kQCap) + align16(sizeof(int) * kMaxRange) : 0) +
+           (mode == kDist ? align16(sizeof(float) * (size_t)kEW * kQCap) + align16(sizeof(unsigned long long) * kMaxRange) : 0) +
            align16(sizeof(uint32_t) * kPendCap) + align16(sizeof(int) * kWT) + align16(sizeof(float) * (size_t)extra_floats);
 }
 
@@ -540,7 +549,7 @@ __device__ __forceinline__ unsigned char* carve_warp(WCtx& C, unsigned char* p, 
     C.flag = nullptr;
     if (MODE == kDist) {
         C.queue = reinterpret_cast<float*>(p);  p += align16(sizeof(float) * (size_t)kEW * kQCap);
-        C.flag = reinterpret_cast<int*>(p);     p += align16(sizeof(int) * kMaxRange);
+        C.flag = reinterpret_cast<unsigned long long*>(p);   p += align16(sizeof(unsigned long long) * kMaxRange);
     }
     C.pend = reinterpret_cast<uint32_t*>(p);    p += align16(sizeof(uint32_t) * kPendCap);
     C.item_fi = reinterpret_cast<int*>(p);      p += align16(sizeof(int) * kWT);
@@ -559,7 +568,8 @@ struct SplitArgs {
 template <int MODE>
 __global__ void __launch_bounds__(kWarps * 32, MODE == kSplit ? 5 : 1)
 in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ q, int64_t B, int dof, float thr,
-                    uint8_t* __restrict__ verdict, float* __restrict__ min_dist, int upw, const SplitArgs G) {
+                    uint8_t* __restrict__ verdict, float* __restrict__ min_dist, uint32_t* __restrict__ pair_code, int upw,
+                    const SplitArgs G) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WCtx C;
     unsigned char* p = stage_scene(S, smem_raw, C.V);
@@ -578,7 +588,7 @@ in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict_
     const int rangeN = (int)max((int64_t)0, min((int64_t)upw, B - range0));
     if (rangeN == 0) return;
     for (int i = lane; i < rangeN; i += 32) {
-        if (MODE == kDist) C.flag[i] = float_key(FLT_MAX);
+        if (MODE == kDist) C.flag[i] = dist_entry(FLT_MAX, 0xffffffffu);
         else verdict[range0 + i] = 0;
     }
     int npend = 0, qn = 0;
@@ -606,9 +616,11 @@ in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict_
         drain(C, qn, true);
         __syncwarp();
         for (int i = lane; i < rangeN; i += 32) {
-            const float d = key_float(C.flag[i]);
+            const unsigned long long e = C.flag[i];
+            const float d = entry_dist(e);
             min_dist[range0 + i] = d;
             verdict[range0 + i] = d < thr ? 1 : 0;
+            if (pair_code != nullptr) pair_code[range0 + i] = (uint32_t)e;
         }
     }
 }
@@ -747,6 +759,133 @@ narrow_kernel(const float* __restrict__ gq, const int* __restrict__ gq_count, in
 }
 
 // ---------------------------------------------------------------------------------------------
+// Closest pair of a configuration with witness points, contact normal and the gradient of the distance
+// (reference Arm.closest_to, robots/arm.py:599-600; Proximity of physics/chain.py:952-968; Arm.jacobian_proximity,
+// robots/arm.py:621-632 for the closest pair).  One thread per configuration; `pair_code` comes from the distance
+// query (kDist kernel).  Walk 1 rebuilds the two primitives of that pair and runs the witness GJK; walk 2 (only when
+// the gradient is wanted) accumulates  n . (w_j x (p_S - p_j))  over the joints above the subject, minus the same
+// over the joints above the target when the target is a link of the arm.
+// Subject / target: link primitive / obstacle for environment pairs; the pair's two link primitives (device
+// order) for self pairs.  The normal points from the target to the subject.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+closest_witness_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ q, int64_t B, int dof,
+                       const uint32_t* __restrict__ pair_code, float* __restrict__ dist, float* __restrict__ p_subject,
+                       float* __restrict__ p_target, float* __restrict__ normal, int32_t* __restrict__ subject,
+                       int32_t* __restrict__ target, uint8_t* __restrict__ valid, float* __restrict__ grad) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SceneSm V;
+    stage_scene(S, smem_raw, V);
+    __syncthreads();
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const uint32_t code = pair_code[b];
+    const float* myq = q + b * dof;
+    if (grad != nullptr)
+        for (int k = 0; k < dof; ++k) grad[b * dof + k] = 0.f;
+    if (code == 0xffffffffu) {              // no allowed pair produced a distance (every pair pruned): nothing to report
+        dist[b] = FLT_MAX; valid[b] = 0; subject[b] = -1; target[b] = -1;
+        for (int k = 0; k < 3; ++k) { p_subject[b * 3 + k] = 0.f; p_target[b * 3 + k] = 0.f; normal[b * 3 + k] = 0.f; }
+        return;
+    }
+    const bool env = (code & kEnvFlag) != 0;
+    const int e = (int)(code & ~kEnvFlag);
+    const PairK pr = env ? V.env_pairs[e] : V.self_pairs[e];
+    const int ia = pr.a;                        // link primitive (subject)
+    const int ib = env ? -1 : pr.b;             // link primitive (target) or none
+    ShapeW Ssub, Stgt;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { Ssub.ax[k] = 0.f; Stgt.ax[k] = 0.f; }
+    float m_sub = V.prims[ia].margin, m_tgt;
+    if (env) { obs_world(V.obs[pr.b], Stgt); m_tgt = V.obs[pr.b].margin; }
+    else m_tgt = V.prims[ib].margin;
+
+    auto walk = [&](auto&& on_prims, auto&& on_joint) {
+        PoseF X;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            X.R[r * 3 + 0] = S.base[r * 4 + 0]; X.R[r * 3 + 1] = S.base[r * 4 + 1]; X.R[r * 3 + 2] = S.base[r * 4 + 2];
+            X.p[r] = S.base[r * 4 + 3];
+        }
+        PoseF saved[kMaxSave];
+        on_prims(X, 0, S.n_base_prims);
+#pragma unroll 1
+        for (int j = 0; j < S.n_mov; ++j) {
+            const TreeJointK& jk = V.tree[j];
+            if (jk.load_slot == -2) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    X.R[r * 3 + 0] = S.base[r * 4 + 0]; X.R[r * 3 + 1] = S.base[r * 4 + 1]; X.R[r * 3 + 2] = S.base[r * 4 + 2];
+                    X.p[r] = S.base[r * 4 + 3];
+                }
+            } else if (jk.load_slot >= 0) {
+                X = saved[jk.load_slot];
+            }
+            nbxj::joint_step<float, TreeJointK>(X, jk, myq[jk.qidx]);
+            if (jk.save_slot >= 0) saved[jk.save_slot] = X;
+            on_joint(X, jk, j);
+            on_prims(X, jk.prim_begin, jk.prim_end);
+        }
+    };
+    walk([&](const PoseF& X, int p0, int p1) {
+             for (int p = p0; p < p1; ++p) {
+                 if (p == ia) prim_world(X, V.prims[p], Ssub);
+                 if (p == ib) prim_world(X, V.prims[p], Stgt);
+             }
+         },
+         [](const PoseF&, const TreeJointK&, int) {});
+    if (pr.sharp) {
+        unround(Ssub, m_sub);
+        unround(Stgt, m_tgt);
+        m_sub = Ssub.type == NBX_PRIM_SPHERE ? m_sub : 0.f;
+        m_tgt = Stgt.type == NBX_PRIM_SPHERE ? m_tgt : 0.f;
+    }
+    const GjkWit g = gjk_witness<96>(Ssub, Stgt);
+    subject[b] = V.prims[ia].desc;
+    target[b] = env ? ((int)pr.b | 0x40000000) : V.prims[ib].desc;
+    V3 n, ps, pt;
+    if (g.overlap) {
+        // cores overlap: depth beyond the margins needs EPA; the distance is the clamp that
+        // min_distance reports, the points are the centres and the normal joins them
+        const V3 dc = Ssub.c - Stgt.c;
+        const float l = sqrtf(dot(dc, dc));
+        n = l > 0.f ? (1.f / l) * dc : mk(0.f, 0.f, 1.f);
+        ps = Ssub.c; pt = Stgt.c;
+        dist[b] = -(m_sub + m_tgt) - 1e-3f;
+        valid[b] = 0;
+    } else {
+        n = (1.f / g.d) * (g.pa - g.pb);            // target -> subject
+        ps = madd(g.pa, -m_sub, n);
+        pt = madd(g.pb, m_tgt, n);
+        dist[b] = g.d - m_sub - m_tgt;
+        valid[b] = 1;
+    }
+    p_subject[b * 3 + 0] = ps.x; p_subject[b * 3 + 1] = ps.y; p_subject[b * 3 + 2] = ps.z;
+    p_target[b * 3 + 0] = pt.x; p_target[b * 3 + 1] = pt.y; p_target[b * 3 + 2] = pt.z;
+    normal[b * 3 + 0] = n.x; normal[b * 3 + 1] = n.y; normal[b * 3 + 2] = n.z;
+    if (grad == nullptr) return;
+    const unsigned long long anc_s = V.prims[ia].anc, anc_t = env ? 0ull : V.prims[ib].anc;
+    walk([](const PoseF&, int, int) {},
+         [&](const PoseF& X, const TreeJointK& jk, int j) {
+             const bool on_s = (anc_s >> j) & 1ull, on_t = (anc_t >> j) & 1ull;
+             if (on_s == on_t) return;             // above neither, or above both (the relative motion cancels)
+             V3 w;
+             if (jk.kind == NBX_KIND_X) w = mk(X.R[0], X.R[3], X.R[6]);
+             else if (jk.kind == NBX_KIND_Y) w = mk(X.R[1], X.R[4], X.R[7]);
+             else if (jk.kind == NBX_KIND_Z) w = mk(X.R[2], X.R[5], X.R[8]);
+             else w = mk(fmaf(X.R[0], jk.ax[0], fmaf(X.R[1], jk.ax[1], X.R[2] * jk.ax[2])),
+                         fmaf(X.R[3], jk.ax[0], fmaf(X.R[4], jk.ax[1], X.R[5] * jk.ax[2])),
+                         fmaf(X.R[6], jk.ax[0], fmaf(X.R[7], jk.ax[1], X.R[8] * jk.ax[2])));
+             if (jk.kind == NBX_KIND_X || jk.kind == NBX_KIND_Y || jk.kind == NBX_KIND_Z) w = jk.sgn * w;
+             const V3 pj = mk(X.p[0], X.p[1], X.p[2]);
+             float gj;
+             if (jk.type == NBX_JOINT_REVOLUTE) gj = dot(n, cross(w, (on_s ? ps : pt) - pj));
+             else gj = dot(n, w);
+             grad[b * dof + jk.qidx] = on_s ? gj : -gj;
+         });
+}
+
+// ---------------------------------------------------------------------------------------------
 // Bisection towards the collision boundary (IRIS "zero-order hold" counter-example search, reference
 // numbotics/planning/safe_sets.py:124-134): per sample an interval [lo, hi] in configuration space, lo free, hi
 // colliding; each round tests the midpoint and keeps the half that still straddles the boundary.  Interval
@@ -861,7 +1000,7 @@ int launch_narrow(const nbx_chain* ch, const SplitArgs& G, float thr, uint8_t* g
 }
 
 int launch_in_collision(const nbx_chain* ch, const nbx_scene* sc, const float* q, int64_t B, const double* base_pose,
-                        float thr, uint8_t* verdict, float* min_dist, cudaStream_t stream) {
+                        float thr, uint8_t* verdict, float* min_dist, cudaStream_t stream, uint32_t* pair_code = nullptr) {
     SceneDev S;
     int rc = fill_scene_dev(ch, sc, base_pose, S);
     if (rc != NBX_OK) return rc;
@@ -878,7 +1017,7 @@ int launch_in_collision(const nbx_chain* ch, const nbx_scene* sc, const float* q
     const int64_t grid = (B + (int64_t)kWarps * upw - 1) / ((int64_t)kWarps * upw);
     if (mode == kDist) {
         NBX_CUDA_OK(cudaFuncSetAttribute(in_collision_kernel<kDist>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        in_collision_kernel<kDist><<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, q, B, ch->dof, thr, verdict, min_dist, upw, SplitArgs{nullptr, nullptr, 0});
+        in_collision_kernel<kDist><<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, q, B, ch->dof, thr, verdict, min_dist, pair_code, upw, SplitArgs{nullptr, nullptr, 0});
         nbx_count_launch();
         NBX_CUDA_OK(cudaGetLastError());
         return NBX_OK;
@@ -886,7 +1025,7 @@ int launch_in_collision(const nbx_chain* ch, const nbx_scene* sc, const float* q
     SplitWs ws;
     if ((rc = ws.alloc(ch->device, B, stream)) != NBX_OK) return rc;
     NBX_CUDA_OK(cudaFuncSetAttribute(in_collision_kernel<kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    in_collision_kernel<kSplit><<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, q, B, ch->dof, thr, verdict, nullptr, upw, ws.args);
+    in_collision_kernel<kSplit><<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, q, B, ch->dof, thr, verdict, nullptr, nullptr, upw, ws.args);
     nbx_count_launch();
     NBX_CUDA_OK(cudaGetLastError());
     return launch_narrow(ch, ws.args, thr, verdict, 1, stream);
@@ -918,6 +1057,41 @@ int launch_edges(const nbx_chain* ch, const nbx_scene* sc, const float* starts, 
     nbx_count_launch();
     NBX_CUDA_OK(cudaGetLastError());
     return launch_narrow(ch, ws.args, thr, valid, 0, stream);
+}
+
+int launch_closest(const nbx_chain* ch, const nbx_scene* sc, const float* q, int64_t B, const double* base_pose,
+                   float* dist, float* p_subject, float* p_target, float* normal, int32_t* subject, int32_t* target,
+                   uint8_t* valid, float* grad, cudaStream_t stream) {
+    NBX_REQUIRE(ch != nullptr && sc != nullptr, "NULL handle");
+    NBX_REQUIRE(B >= 0, "negative batch size");
+    if (B == 0) return NBX_OK;
+    NBX_REQUIRE(q != nullptr && dist != nullptr && p_subject != nullptr && p_target != nullptr && normal != nullptr &&
+                subject != nullptr && target != nullptr && valid != nullptr, "NULL output buffer");
+    NBX_REQUIRE(grad == nullptr || ch->n_mov <= 64, "distance gradients support chains of at most 64 movable joints");
+    NBX_CUDA_OK(cudaSetDevice(ch->device));
+    cudaMemPool_t pool = nullptr;
+    int rc = workspace_pool(ch->device, &pool);
+    if (rc != NBX_OK) return rc;
+    struct Tmp { void* p = nullptr; cudaStream_t st = nullptr; ~Tmp() { if (p) cudaFreeAsync(p, st); } } tmp;
+    tmp.st = stream;
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    NBX_CUDA_OK(cudaMallocFromPoolAsync(&tmp.p, up(sizeof(uint32_t) * (size_t)B) + up((size_t)B), pool, stream));
+    uint32_t* code = static_cast<uint32_t*>(tmp.p);
+    uint8_t* verdict = static_cast<unsigned char*>(tmp.p) + up(sizeof(uint32_t) * (size_t)B);
+    // distance pass (fused kDist kernel): minimum distance and the pair that attains it; `dist` is rewritten below
+    rc = launch_in_collision(ch, sc, q, B, base_pose, 0.f, verdict, dist, stream, code);
+    if (rc != NBX_OK) return rc;
+    SceneDev S;
+    rc = fill_scene_dev(ch, sc, base_pose, S);
+    if (rc != NBX_OK) return rc;
+    const size_t smem = scene_smem_bytes(S.n_mov, S.n_prims, S.n_obs, S.n_self, S.n_env);
+    NBX_REQUIRE(smem <= 220 * 1024, "scene too large for shared memory (%zu bytes)", smem);
+    NBX_CUDA_OK(cudaFuncSetAttribute(closest_witness_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    closest_witness_kernel<<<(unsigned)((B + 127) / 128), 128, smem, stream>>>(S, q, B, ch->dof, code, dist, p_subject, p_target, normal,
+                                                                              subject, target, valid, grad);
+    nbx_count_launch();
+    NBX_CUDA_OK(cudaGetLastError());
+    return NBX_OK;
 }
 
 template <typename T>
@@ -991,6 +1165,13 @@ int nbx_in_collision_host_f32(const nbx_chain* chain, const nbx_scene* scene, co
     NBX_CUDA_OK(cudaMemcpyAsync(verdict, dv.p, (size_t)B, cudaMemcpyDeviceToHost, st));
     NBX_CUDA_OK(cudaStreamSynchronize(st));
     return NBX_OK;
+}
+
+int nbx_closest_f32(const nbx_chain* chain, const nbx_scene* scene, const float* q, int64_t B, const double* base_pose,
+                    float* distance, float* position_on_subject, float* position_on_target, float* normal_target_to_subject,
+                    int32_t* subject_prim, int32_t* target, uint8_t* valid, float* gradient, void* stream) {
+    return launch_closest(chain, scene, q, B, base_pose, distance, position_on_subject, position_on_target, normal_target_to_subject,
+                          subject_prim, target, valid, gradient, static_cast<cudaStream_t>(stream));
 }
 
 int nbx_bisect_f32(const nbx_chain* chain, const nbx_scene* scene, const float* inside, int64_t inside_stride, const float* outside,

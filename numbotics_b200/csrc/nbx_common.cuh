@@ -82,6 +82,8 @@ struct PrimK {
     int mov;        // owning movable joint (-1 = base)
     int slot;       // float offset of the stored world pose in the per-thread scratch, -1 = not stored
     float brad;     // bounding-sphere radius of the FULL primitive (core + margin) about its centre
+    int desc;       // index of this primitive in the chain descriptor (device order is sorted by owning joint)
+    unsigned long long anc;   // bit j: movable joint j is on the path root -> this primitive (chains of <= 64 movable joints)
 };
 
 struct ObsK {
@@ -117,6 +119,7 @@ struct TreeJointK {
     int prim_begin, prim_end;   // primitives owned by this joint (sorted)
     int kind;        // NBX_KIND_*
     float sgn;
+    float ax[3];     // joint axis in the joint frame (world axis = R_after * ax)
 };
 
 struct nbx_chain {

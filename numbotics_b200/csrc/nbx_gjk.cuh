@@ -223,4 +223,136 @@ __device__ GjkOut gjk_distance(const ShapeW& A, const ShapeW& B, float stop_abov
     return out;
 }
 
+// ---------------------------------------------------------------------------------------------
+// GJK with witness points (closest-pair query; reference Arm.closest_to / Proximity, robots/arm.py:599-601,
+// physics/chain.py:944-969).  Not a hot path: one call per configuration, on the pair that the distance pass found
+// closest.  The simplex carries, next to each vertex w_i = a_i - b_i of the Minkowski difference, the support point
+// a_i of A; the closest point v = sum lam_i w_i gives the witness pair  pA = sum lam_i a_i,  pB = pA - v.
+// ---------------------------------------------------------------------------------------------
+struct GjkWit {
+    float d;        // distance between the cores (0 when they overlap)
+    V3 pa, pb;      // closest points on core A / core B
+    bool overlap;
+};
+
+// barycentric coordinates of the point of triangle (a,b,c) closest to the origin (Ericson 5.1.5)
+__device__ __forceinline__ void closest_tri_bary(V3 a, V3 b, V3 c, float* la, float* lb, float* lc) {
+    const V3 ab = b - a, ac = c - a;
+    const float d1 = -dot(ab, a), d2 = -dot(ac, a);
+    *la = 1.f; *lb = 0.f; *lc = 0.f;
+    if (d1 <= 0.f && d2 <= 0.f) return;
+    const float d3 = -dot(ab, b), d4 = -dot(ac, b);
+    if (d3 >= 0.f && d4 <= d3) { *la = 0.f; *lb = 1.f; return; }
+    const float vc = d1 * d4 - d3 * d2;
+    if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) { const float t = d1 / fmaxf(d1 - d3, 1e-37f); *la = 1.f - t; *lb = t; return; }
+    const float d5 = -dot(ab, c), d6 = -dot(ac, c);
+    if (d6 >= 0.f && d5 <= d6) { *la = 0.f; *lc = 1.f; return; }
+    const float vb = d5 * d2 - d1 * d6;
+    if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) { const float t = d2 / fmaxf(d2 - d6, 1e-37f); *la = 1.f - t; *lc = t; return; }
+    const float va = d3 * d6 - d5 * d4;
+    if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) {
+        const float t = (d4 - d3) / fmaxf((d4 - d3) + (d5 - d6), 1e-37f);
+        *la = 0.f; *lb = 1.f - t; *lc = t;
+        return;
+    }
+    const float sum = va + vb + vc;
+    if (!(sum > 0.f)) return;
+    const float inv = 1.f / sum;
+    *lb = vb * inv; *lc = vc * inv; *la = 1.f - *lb - *lc;
+}
+
+template <int MAX_ITER>
+__device__ GjkWit gjk_witness(const ShapeW& A, const ShapeW& B) {
+    GjkWit out;
+    out.overlap = false;
+    V3 w[4], a[4];
+    float lam[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { w[i] = mk(0, 0, 0); a[i] = mk(0, 0, 0); lam[i] = 0.f; }
+    int n = 0;
+    V3 v = A.c - B.c;
+    float vv = dot(v, v);
+    if (vv < 1e-20f) { v = mk(1.f, 0.f, 0.f); vv = 1.f; }
+    V3 best_pa = A.c, best_v = v;
+    float best_vv = FLT_MAX;
+#pragma unroll 1
+    for (int it = 0; it < MAX_ITER; ++it) {
+        const V3 sa = support(A, -v);
+        const V3 sw = sa - support(B, v);
+        if (best_vv < FLT_MAX && vv - dot(v, sw) <= 1e-7f * vv) break;      // no support point beyond the current plane
+        // append the new vertex at index n (n <= 3 here)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (i == n) { w[i] = sw; a[i] = sa; }
+        ++n;
+        // closest point of the simplex to the origin, as barycentric weights
+#pragma unroll
+        for (int i = 0; i < 4; ++i) lam[i] = 0.f;
+        if (n == 1) {
+            lam[0] = 1.f;
+        } else if (n == 2) {
+            const V3 e = w[1] - w[0];
+            const float den = dot(e, e);
+            const float t = den > 0.f ? fminf(fmaxf(-dot(w[0], e) / den, 0.f), 1.f) : 0.f;
+            lam[0] = 1.f - t; lam[1] = t;
+        } else if (n == 3) {
+            closest_tri_bary(w[0], w[1], w[2], &lam[0], &lam[1], &lam[2]);
+        } else {
+            // tetrahedron: the closest of the faces the origin lies outside of; inside all four = overlap
+            float bd = FLT_MAX;
+            bool outside_any = false;
+#define NBX_WFACE(I0, I1, I2, IO)                                                             \
+            {                                                                                  \
+                const V3 nrm = cross(w[I1] - w[I0], w[I2] - w[I0]);                            \
+                const float sp = -dot(w[I0], nrm);                                             \
+                const float sd = dot(w[IO] - w[I0], nrm);                                      \
+                const float flat = 4e-6f * (fabsf(w[I0].x) + fabsf(w[I0].y) + fabsf(w[I0].z) + 1e-3f); \
+                if (sd * sd <= flat * flat * dot(nrm, nrm) || sp * sd < 0.f) {                 \
+                    outside_any = true;                                                        \
+                    float l0, l1, l2;                                                          \
+                    closest_tri_bary(w[I0], w[I1], w[I2], &l0, &l1, &l2);                      \
+                    const V3 cp = madd(madd(l0 * w[I0], l1, w[I1]), l2, w[I2]);                \
+                    const float dd = dot(cp, cp);                                              \
+                    if (dd < bd) { bd = dd; lam[I0] = l0; lam[I1] = l1; lam[I2] = l2; lam[IO] = 0.f; } \
+                }                                                                              \
+            }
+            NBX_WFACE(0, 1, 2, 3)
+            NBX_WFACE(0, 1, 3, 2)
+            NBX_WFACE(0, 2, 3, 1)
+            NBX_WFACE(1, 2, 3, 0)
+#undef NBX_WFACE
+            if (!outside_any) { out.overlap = true; break; }
+        }
+        V3 nv = mk(0, 0, 0), pa = mk(0, 0, 0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { nv = madd(nv, lam[i], w[i]); pa = madd(pa, lam[i], a[i]); }
+        const float nvv = dot(nv, nv);
+        if (nvv >= best_vv) break;                       // rounding stopped the descent: keep the best point so far
+        best_vv = nvv; best_v = nv; best_pa = pa;
+        v = nv; vv = nvv;
+        if (vv <= 2.5e-9f) { out.overlap = true; break; }   // contact regime (see gjk_distance)
+        // drop the vertices that do not support the closest point (stable compaction, static indices)
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass)
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                if (lam[i] <= 0.f && lam[i + 1] > 0.f) {
+                    const V3 tw = w[i]; w[i] = w[i + 1]; w[i + 1] = tw;
+                    const V3 ta = a[i]; a[i] = a[i + 1]; a[i + 1] = ta;
+                    lam[i] = lam[i + 1]; lam[i + 1] = 0.f;
+                }
+        n = (lam[0] > 0.f) + (lam[1] > 0.f) + (lam[2] > 0.f) + (lam[3] > 0.f);
+        if (n == 4) { out.overlap = true; break; }
+    }
+    if (out.overlap || best_vv == FLT_MAX) {
+        out.overlap = true;
+        out.d = 0.f;
+        out.pa = A.c; out.pb = B.c;
+        return out;
+    }
+    out.d = sqrtf(best_vv);
+    out.pa = best_pa;
+    out.pb = best_pa - best_v;
+    return out;
+}
+
 }  // namespace nbxg

@@ -23,6 +23,8 @@ deliberate and documented in DESIGN.md:
 """
 import ctypes as C
 
+from dataclasses import dataclass
+
 import numpy as np
 import networkx as nx
 
@@ -42,6 +44,30 @@ def _is_torch(x):
 
 def _cuda_stream_ptr(device_index: int) -> int:
     return int(torch.cuda.current_stream(device_index).cuda_stream)
+
+
+@dataclass
+class Proximity:
+    """The reference's record (numbotics/physics/collision.py:26-32)."""
+    subject: object
+    target: object
+    position_on_subject: np.ndarray
+    position_on_target: np.ndarray
+    normal_target_to_subject: np.ndarray
+    distance: float
+
+
+@dataclass
+class Proximities:
+    """Struct-of-arrays form of `Proximity` for a batch of configurations."""
+    subject: np.ndarray
+    target: np.ndarray
+    position_on_subject: object
+    position_on_target: object
+    normal_target_to_subject: object
+    distance: object
+    valid: object
+    gradient: object = None
 
 
 class Arm:
@@ -503,6 +529,71 @@ class Arm:
         if want_dist:
             dist = dist.reshape(shape) if not single else dist.reshape(())
         return verdict, dist
+
+    # ------------------------------------------------------------------ closest pair, witness points, distance gradient
+    def closest_to(self, q, gradient: bool = False):
+        """Batched `Arm.closest_to` (reference arm.py:599-600): the allowed pair with the smallest distance.
+
+        `q (dof,)` -> one `Proximity` (the reference's record: subject, target, position_on_subject,
+        position_on_target, normal_target_to_subject, distance); `q (..., dof)` -> a `Proximities` record whose
+        fields are arrays with the batch dimensions of q (`subject` / `target` are object arrays of Link /
+        PhysicsObject, `valid` is False where the two cores overlap: no EPA).
+        `gradient=True` adds `.gradient (..., dof)`: d distance / d q, i.e. `jacobian_proximity` of the closest pair.
+        """
+        self._check_q(q)
+        in_torch = _is_torch(q)
+        q_shape = tuple(q.shape)
+        single = len(q_shape) == 1
+        B = int(np.prod(q_shape[:-1])) if not single else 1
+        scene = self._scene(0.0, exact_distance=True)
+        arrays = self._scene_arrays
+        if arrays["self_pairs"].shape[0] + arrays["n_env_pairs_before_pruning"] == 0:
+            raise ValueError("min() arg is an empty sequence")
+        dev_index = self.device_index
+        base_keep, base_ptr = _cabi.base_pose_arg(self.base_pose)
+        qd = self._to_device(q, torch.float32).reshape(B, self.dof)
+        lib = _cabi.load()
+        with torch.cuda.device(dev_index):
+            f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=qd.device)
+            dist, ps, pt, nrm = f(B), f(B, 3), f(B, 3), f(B, 3)
+            grad = f(B, self.dof) if gradient else None
+            sub = torch.empty((B,), dtype=torch.int32, device=qd.device)
+            tgt = torch.empty((B,), dtype=torch.int32, device=qd.device)
+            ok = torch.empty((B,), dtype=torch.uint8, device=qd.device)
+            _cabi.check(lib.nbx_closest_f32(self._handle().ptr, scene.ptr, qd.data_ptr(), B, base_ptr, dist.data_ptr(),
+                                            ps.data_ptr(), pt.data_ptr(), nrm.data_ptr(), sub.data_ptr(), tgt.data_ptr(),
+                                            ok.data_ptr(), grad.data_ptr() if gradient else None, _cuda_stream_ptr(dev_index)))
+        del base_keep
+        link_of_prim = {p: l for l, p in self._arrays["prim_of_link"].items()}
+        obstacles = arrays["obstacles"]
+        sub_h, tgt_h = sub.cpu().numpy(), tgt.cpu().numpy()
+        subjects = np.empty(B, dtype=object)
+        targets = np.empty(B, dtype=object)
+        for i in range(B):
+            subjects[i] = link_of_prim.get(int(sub_h[i]))
+            t = int(tgt_h[i])
+            targets[i] = None if t < 0 else (obstacles[t & 0x3fffffff] if t & 0x40000000 else link_of_prim.get(t))
+        if in_torch:
+            conv = lambda x: x.to(q.device)
+        else:
+            out_dt = q.dtype if getattr(q, "dtype", None) in (np.float32, np.float64) else np.float64
+            conv = lambda x: x.cpu().numpy().astype(out_dt if x.dtype == torch.float32 else bool, copy=False)
+        shape = q_shape[:-1]
+        rec = Proximities(
+            subject=subjects.reshape(shape), target=targets.reshape(shape),
+            position_on_subject=conv(ps).reshape(*shape, 3), position_on_target=conv(pt).reshape(*shape, 3),
+            normal_target_to_subject=conv(nrm).reshape(*shape, 3), distance=conv(dist).reshape(shape),
+            valid=conv(ok.to(torch.bool)).reshape(shape), gradient=conv(grad).reshape(*shape, self.dof) if gradient else None)
+        if single:
+            return Proximity(subject=subjects[0], target=targets[0], position_on_subject=rec.position_on_subject,
+                             position_on_target=rec.position_on_target, normal_target_to_subject=rec.normal_target_to_subject,
+                             distance=float(rec.distance)) if not gradient else rec
+        return rec
+
+    def jacobian_proximity_closest(self, q):
+        """`Arm.jacobian_proximity` (reference arm.py:621-632) for the closest pair of each configuration:
+        `n . J_v(subject, p_subject) - n . J_v(target, p_target)`, shape `(..., dof)`."""
+        return self.closest_to(q, gradient=True).gradient
 
     # ------------------------------------------------------------------ bisection to the collision boundary
     def bisect_to_collision(self, inside, outside, num_bisections: int = 15, threshold: float = 1e-6):

@@ -206,6 +206,7 @@ class SceneOracle:
         self.pairs = np.asarray(pairs, np.int32).reshape(-1, 2)
         self.sharp = np.array([self.types[a] == PRIM_BOX and self.types[b] == PRIM_BOX for a, b in pairs], np.uint8)
         self.n_link = len(links)
+        self.links, self.objs = links, objs
 
     def pair_distances(self, q):
         q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, self.dof)
@@ -221,6 +222,35 @@ class SceneOracle:
                                          _p(_arr(self.sharp, np.uint8), C.c_uint8), _p(out, C.c_double))
         assert rc == 0
         return out
+
+    def link_poses(self, q):
+        """World poses (n, n_link, 12) of the link primitives."""
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, self.dof)
+        poses = np.empty((q.shape[0], max(self.n_link, 1), 12))
+        for i, (node, off) in enumerate(zip(self.link_nodes, self.link_offsets)):
+            poses[:, i] = (self.fk.forward_kinematics(q, node) @ off)[:, :3, :4].reshape(-1, 12)
+        return poses
+
+    def point_to_shape(self, shape_index, shape_poses12, points, sharp=False):
+        """Distance from world points (n,3) to shape `shape_index` (link or obstacle index space of `pairs`) posed at
+        `shape_poses12 (n,12)`, through the same C narrow phase (a point is a sphere of radius 0).  `sharp`: the shape
+        without its rounding margin (box-box pairs under the Bullet model)."""
+        n = points.shape[0]
+        poses = np.zeros((n, 2, 12))
+        poses[:, 0] = shape_poses12
+        poses[:, 1, [0, 5, 10]] = 1.0
+        poses[:, 1, [3, 7, 11]] = points
+        types = _arr([self.types[shape_index], PRIM_SPHERE], np.int32)
+        dims = np.ascontiguousarray(np.vstack([self.dims[shape_index], np.zeros(3)]), dtype=np.float64)
+        margins = _arr([self.margins[shape_index], 0.0], np.float64)
+        pairs = _arr([[0, 1]], np.int32)
+        out = np.empty((n, 1))
+        sp = np.zeros((1, 12))
+        rc = lib().oracle_pair_distances(C.c_int64(n), C.c_int(2), _p(np.ascontiguousarray(poses), C.c_double), C.c_int(0),
+                                         _p(sp, C.c_double), _p(types, C.c_int32), _p(dims, C.c_double), _p(margins, C.c_double),
+                                         C.c_int(1), _p(pairs, C.c_int32), _p(_arr([1 if sharp else 0], np.uint8), C.c_uint8), _p(out, C.c_double))
+        assert rc == 0
+        return out[:, 0]
 
     def min_distance(self, q):
         shape = np.shape(q)[:-1]
