@@ -1132,11 +1132,23 @@ int launch_bisect(const nbx_chain* ch, const nbx_scene* sc, const T* inside, int
     return NBX_OK;
 }
 
-// host-buffer variants: one staging allocation per call is acceptable here (verdict bytes are tiny,
-// the copies are the dominant term); stream-ordered allocation keeps it asynchronous.
-struct DevTmp {
+// host-buffer variants: stream-ordered staging buffers from the library's pool (no cudaMalloc per call), one private
+// stream per call so that concurrent host threads overlap.
+struct HostStage {
     void* p = nullptr;
-    ~DevTmp() { if (p) cudaFree(p); }
+    cudaStream_t st = nullptr;
+    int open(int device, size_t bytes) {
+        cudaMemPool_t pool = nullptr;
+        int rc = workspace_pool(device, &pool);
+        if (rc != NBX_OK) return rc;
+        NBX_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        NBX_CUDA_OK(cudaMallocFromPoolAsync(&p, bytes, pool, st));
+        return NBX_OK;
+    }
+    ~HostStage() {
+        if (p) cudaFreeAsync(p, st);
+        if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    }
 };
 
 }  // namespace
@@ -1152,18 +1164,19 @@ int nbx_in_collision_host_f32(const nbx_chain* chain, const nbx_scene* scene, co
                               float threshold, uint8_t* verdict) {
     NBX_REQUIRE(chain != nullptr, "chain handle is NULL");
     if (B <= 0) return NBX_OK;
+    NBX_REQUIRE(q != nullptr && verdict != nullptr, "q / verdict is NULL");
     NBX_CUDA_OK(cudaSetDevice(chain->device));
-    DevTmp dq, dv;
-    const size_t qb = sizeof(float) * (size_t)B * chain->dof;
-    NBX_CUDA_OK(cudaMalloc(&dq.p, qb));
-    NBX_CUDA_OK(cudaMalloc(&dv.p, (size_t)B));
-    cudaStream_t st = nullptr;
-    NBX_CUDA_OK(cudaMemcpyAsync(dq.p, q, qb, cudaMemcpyHostToDevice, st));
-    int rc = launch_in_collision(chain, scene, static_cast<const float*>(dq.p), B, base_pose, threshold,
-                                 static_cast<uint8_t*>(dv.p), nullptr, st);
+    const size_t qb = (sizeof(float) * (size_t)B * chain->dof + 255) & ~(size_t)255;
+    HostStage hs;
+    int rc = hs.open(chain->device, qb + (size_t)B);
     if (rc != NBX_OK) return rc;
-    NBX_CUDA_OK(cudaMemcpyAsync(verdict, dv.p, (size_t)B, cudaMemcpyDeviceToHost, st));
-    NBX_CUDA_OK(cudaStreamSynchronize(st));
+    float* dq = static_cast<float*>(hs.p);
+    uint8_t* dv = static_cast<unsigned char*>(hs.p) + qb;
+    NBX_CUDA_OK(cudaMemcpyAsync(dq, q, sizeof(float) * (size_t)B * chain->dof, cudaMemcpyHostToDevice, hs.st));
+    rc = launch_in_collision(chain, scene, dq, B, base_pose, threshold, dv, nullptr, hs.st);
+    if (rc != NBX_OK) return rc;
+    NBX_CUDA_OK(cudaMemcpyAsync(verdict, dv, (size_t)B, cudaMemcpyDeviceToHost, hs.st));
+    NBX_CUDA_OK(cudaStreamSynchronize(hs.st));
     return NBX_OK;
 }
 
@@ -1197,20 +1210,22 @@ int nbx_edges_valid_host_f32(const nbx_chain* chain, const nbx_scene* scene, con
                              const double* base_pose, double resolution, double max_distance, float threshold, uint8_t* valid) {
     NBX_REQUIRE(chain != nullptr, "chain handle is NULL");
     if (E <= 0) return NBX_OK;
+    NBX_REQUIRE(starts != nullptr && goals != nullptr && valid != nullptr, "starts / goals / valid is NULL");
     NBX_CUDA_OK(cudaSetDevice(chain->device));
-    DevTmp ds, dg, dv;
-    const size_t qb = sizeof(float) * (size_t)E * chain->dof;
-    NBX_CUDA_OK(cudaMalloc(&ds.p, qb));
-    NBX_CUDA_OK(cudaMalloc(&dg.p, qb));
-    NBX_CUDA_OK(cudaMalloc(&dv.p, (size_t)E));
-    cudaStream_t st = nullptr;
-    NBX_CUDA_OK(cudaMemcpyAsync(ds.p, starts, qb, cudaMemcpyHostToDevice, st));
-    NBX_CUDA_OK(cudaMemcpyAsync(dg.p, goals, qb, cudaMemcpyHostToDevice, st));
-    int rc = launch_edges(chain, scene, static_cast<const float*>(ds.p), static_cast<const float*>(dg.p), E, base_pose,
-                          resolution, max_distance, threshold, static_cast<uint8_t*>(dv.p), nullptr, st);
+    const size_t raw = sizeof(float) * (size_t)E * chain->dof;
+    const size_t qb = (raw + 255) & ~(size_t)255;
+    HostStage hs;
+    int rc = hs.open(chain->device, 2 * qb + (size_t)E);
     if (rc != NBX_OK) return rc;
-    NBX_CUDA_OK(cudaMemcpyAsync(valid, dv.p, (size_t)E, cudaMemcpyDeviceToHost, st));
-    NBX_CUDA_OK(cudaStreamSynchronize(st));
+    float* ds = static_cast<float*>(hs.p);
+    float* dg = reinterpret_cast<float*>(static_cast<unsigned char*>(hs.p) + qb);
+    uint8_t* dv = static_cast<unsigned char*>(hs.p) + 2 * qb;
+    NBX_CUDA_OK(cudaMemcpyAsync(ds, starts, raw, cudaMemcpyHostToDevice, hs.st));
+    NBX_CUDA_OK(cudaMemcpyAsync(dg, goals, raw, cudaMemcpyHostToDevice, hs.st));
+    rc = launch_edges(chain, scene, ds, dg, E, base_pose, resolution, max_distance, threshold, dv, nullptr, hs.st);
+    if (rc != NBX_OK) return rc;
+    NBX_CUDA_OK(cudaMemcpyAsync(valid, dv, (size_t)E, cudaMemcpyDeviceToHost, hs.st));
+    NBX_CUDA_OK(cudaStreamSynchronize(hs.st));
     return NBX_OK;
 }
 

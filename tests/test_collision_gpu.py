@@ -248,3 +248,42 @@ def test_static_pruning_never_changes_a_verdict(scene):
         centers = (so.fk.forward_kinematics(q[:3000].astype(np.float64), node) @ off)[:, :3, 3]
         link = arm._links_from_nodes[node]
         assert np.linalg.norm(centers - base, axis=1).max() <= reach[arm._arrays["prim_of_link"][link]] + 1e-9
+
+
+def test_host_buffer_entry_points_and_concurrent_threads(scene):
+    """`nbx_in_collision_host_f32` / `nbx_edges_valid_host_f32` (HOST pointers in, HOST verdicts out) give the bits of the
+    device path, also when several host threads call at once on the same immutable handles (the IRIS thread-pool caller,
+    reference utils/threading.py:33-37)."""
+    import threading
+    from numbotics_b200 import _cabi
+    arm, cubes, so = scene
+    lib = _cabi.load()
+    q = workloads.random_configs_np(arm, 20000 + 7, seed=31).astype(np.float32)
+    expect = arm.in_collision(q)
+    sc = arm._scene(0.0)
+    keep, base = _cabi.base_pose_arg(arm.base_pose)
+    h = arm._handle()
+
+    def host_call(rows):
+        out = np.full(rows.shape[0], 7, np.uint8)
+        _cabi.check(lib.nbx_in_collision_host_f32(h.ptr, sc.ptr, rows.ctypes.data, rows.shape[0], base, 0.0, out.ctypes.data))
+        return out.astype(bool)
+
+    assert np.array_equal(host_call(q), expect)
+    s, g = np.ascontiguousarray(q[:5000]), np.ascontiguousarray(q[5000:10000])
+    ev = np.full(5000, 7, np.uint8)
+    _cabi.check(lib.nbx_edges_valid_host_f32(h.ptr, sc.ptr, s.ctypes.data, g.ctypes.data, 5000, base, 0.1, 0.0, 0.0, ev.ctypes.data))
+    assert np.array_equal(ev.astype(bool), arm.edges_valid(s, g, 0.1))
+    assert lib.nbx_in_collision_host_f32(h.ptr, sc.ptr, None, 4, base, 0.0, ev.ctypes.data) == -1      # NULL q: status, not a crash
+    # 8 threads, each its own slice, repeated
+    results = [None] * 8
+    def worker(i):
+        rows = np.ascontiguousarray(q[i::8])
+        ok = True
+        for _ in range(5):
+            ok = ok and np.array_equal(host_call(rows), expect[i::8])
+        results[i] = ok
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(8)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert all(results)
