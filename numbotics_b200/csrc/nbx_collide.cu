@@ -322,18 +322,26 @@ __device__ __forceinline__ float seg_seg_distance(V3 ca, V3 ua, float ha, V3 cb,
     return sqrtf(dot(d, d));
 }
 
-// append the surviving lanes' codes to the pending list: one ballot, no atomics (npend is warp-uniform)
-template <int MODE>
+// append the surviving lanes' codes to the pending list: one ballot, no atomics (npend is warp-uniform).  A full list
+// (> 64 survivors in a tile of 32 items: pathological scenes) only raises `npend` past the capacity; the tile is then
+// evaluated exhaustively after the culls (tile_exhaustive_cold) -- no call inside the cull loops, whose loop invariants
+// would otherwise be spilled around it.
 __device__ __forceinline__ void push_pending(const WCtx& C, int& npend, bool surv, uint32_t code) {
     const unsigned mask = __ballot_sync(0xffffffffu, surv);
     if (mask == 0) return;
     const int lane = threadIdx.x & 31;
     const int pos = npend + __popc(mask & ((1u << lane) - 1u));
-    if (surv) {
-        if (pos < kPendCap) C.pend[pos] = code | (uint32_t)lane;
-        else eval_now_cold<MODE>(C, code | (uint32_t)lane);
-    }
-    npend = min(npend + __popc(mask), kPendCap);
+    if (surv && pos < kPendCap) C.pend[pos] = code | (uint32_t)lane;
+    npend += __popc(mask);
+}
+
+// every allowed pair of this lane's item through the narrow phase (the pose scratch of the tile is still valid)
+template <int MODE>
+__device__ __noinline__ void tile_exhaustive_cold(const WCtx& C, bool valid, int n_env, int n_self) {
+    if (!valid) return;
+    const uint32_t lane = threadIdx.x & 31;
+    for (int e = 0; e < n_env; ++e) eval_now_cold<MODE>(C, kEnvFlag | ((uint32_t)e << 8) | lane);
+    for (int e = 0; e < n_self; ++e) eval_now_cold<MODE>(C, ((uint32_t)e << 8) | lane);
 }
 
 // phase 1 for this lane's item.  `valid` = the lane has an item; invalid lanes still take part in the ballots.
@@ -428,7 +436,7 @@ __device__ __forceinline__ void phase1(const WCtx& C, bool valid, QF qf, int n_o
                 const float reach = rec.w + orad + cut0;         // >= 0: thresholds are non-negative
                 surv = valid && l2 <= reach * reach;
             }
-            push_pending<MODE>(C, npend, surv, kEnvFlag | ((uint32_t)e << 8));
+            push_pending(C, npend, surv, kEnvFlag | ((uint32_t)e << 8));
         }
     }
 #pragma unroll 2
@@ -465,7 +473,11 @@ __device__ __forceinline__ void phase1(const WCtx& C, bool valid, QF qf, int n_o
                             (ka.dims[0] + ka.margin) - (kb.dims[0] + kb.margin);
             surv = d <= cut;
         }
-        push_pending<MODE>(C, npend, surv, (uint32_t)e << 8);
+        push_pending(C, npend, surv, (uint32_t)e << 8);
+    }
+    if (npend > kPendCap) {          // warp-uniform
+        tile_exhaustive_cold<MODE>(C, valid, C.V.env_begin[n_obs], n_self);
+        npend = 0;
     }
 }
 
@@ -635,7 +647,7 @@ in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict_
 // samples go through phase 1 with the configuration interpolated on the fly.  valid[e] starts as 1 (0 for an edge
 // shorter than float32 eps) and the narrow kernel clears it when one of the edge's candidates collides.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kWarps * 32, 5)
+__global__ void __launch_bounds__(kWarps * 32, 4)
 edges_valid_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ starts, const float* __restrict__ goals,
                    int64_t E, int dof, double resolution, double max_distance, float thr,
                    uint8_t* __restrict__ valid, int32_t* __restrict__ n_samples, int upw, const SplitArgs G) {
@@ -937,9 +949,9 @@ int fill_scene_dev(const nbx_chain* ch, const nbx_scene* sc, const double* base_
 
 // units (configurations / edges) per warp: long ranges amortise the final partial drain, but the grid must keep
 // every SM busy for several waves
-int units_per_warp(int64_t n_units, int sm_count, int warps_per_sm) {
+int units_per_warp(int64_t n_units, int sm_count, int warps_per_sm, int waves = 6) {
     static const int env = std::getenv("NBX_COLLIDE_UPW") ? std::atoi(std::getenv("NBX_COLLIDE_UPW")) : 0;   // tuning only
-    int64_t u = n_units / ((int64_t)sm_count * warps_per_sm * 6 * kWT);
+    int64_t u = n_units / ((int64_t)sm_count * warps_per_sm * waves * kWT);
     u = std::max<int64_t>(1, std::min<int64_t>(u, kMaxRange / kWT));
     if (env > 0) u = std::min(env, kMaxRange / kWT);
     return (int)u * kWT;
@@ -1051,7 +1063,9 @@ int launch_edges(const nbx_chain* ch, const nbx_scene* sc, const float* starts, 
     SplitWs ws;
     if ((rc = ws.alloc(ch->device, E * 8, stream)) != NBX_OK) return rc;
     NBX_CUDA_OK(cudaFuncSetAttribute(edges_valid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int upw = units_per_warp(E * 8, ch->sm_count, 20);      // an edge is ~13 samples: smaller ranges for the same balance
+    // an edge is ~13 tiles of work for its warp, so the per-CTA prologue is already amortised by one tile of edges; what
+    // matters is the tail: 10^6 edges in ranges of 256 were 977 CTAs = 1.65 waves of the 592 resident ones (ncu: +7 %)
+    const int upw = units_per_warp(E, ch->sm_count, 16, 8);
     const int64_t grid = (E + (int64_t)kWarps * upw - 1) / ((int64_t)kWarps * upw);
     edges_valid_kernel<<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, starts, goals, E, dof, resolution, max_distance, thr, valid, n_samples, upw, ws.args);
     nbx_count_launch();
