@@ -244,6 +244,17 @@ def main():
     value = world * B * args.steps / (total_ms_max * 1e-3)
 
     # ---- end to end: HOST (pinned) buffers through the C-ABI, copies inside the timed region ---------
+    # one process per GPU: run on the CPU cores next to this GPU, so that the pinned buffers are first touched (and the
+    # copies staged) on its NUMA node; without it 2 ranks reached 1.2x and 8 ranks 1.6x the one-GPU rate
+    numa = "unset"
+    if world > 1:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+            numa = f"{len(os.sched_getaffinity(0))} cores near GPU {local_rank}"
+        except Exception as exc:   # NVML missing or not permitted: measured as is
+            numa = f"unavailable ({type(exc).__name__})"
     e2e_steps = min(args.steps, 8)
     qh = torch.empty((B, DOF), dtype=torch.float32).pin_memory()
     qh.copy_(q)
@@ -321,7 +332,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * DOF * B, "d2h_bytes_per_step": (64 + 24 * DOF) * B,
-                "steps": e2e_steps, "api": "nbx_fk_jac_host_f32 (pinned host buffers, 3-slot H2D/kernel/D2H pipeline)"},
+                "steps": e2e_steps, "api": "nbx_fk_jac_host_f32 (pinned host buffers, 3-slot H2D/kernel/D2H pipeline)", "cpu_affinity": numa},
         "gpu_launches": int(gpu_launches),
         "clocks": clock_info,
         "parity": parity,
