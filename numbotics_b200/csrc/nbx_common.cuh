@@ -61,6 +61,9 @@ struct JointK {
     int type;   // NBX_JOINT_*
     int qidx;   // column of q
     int kind;   // NBX_KIND_*
+    int okind;  // structure of the offset rotation: 0 general, 1 rotation about x only (DH-style link offsets, URDF
+                // origins with rpy = (r, 0, 0)), 2 identity.  Then R <- R * R_off is a plane rotation of two columns.
+    T oc, os;   // cos / sin of that roll angle
 };
 
 template <typename T, int MAXJ>
@@ -184,9 +187,9 @@ void nbx_fill_joint(JointK<T>& jk, const double* off12, const double* axis, int 
 // float paths of 9..32 joints: register-resident dense kernels (nbx_fkjac_wide_a.cu: 9..22, _b.cu: 23..32)
 #define NBX_WIDE_CAP 32
 #define NBX_WIDE_SPLIT 22
-int nbx_launch_wide_a_f32(const PathK<float, NBX_WIDE_CAP>& P, bool allz, const float* q, int64_t B, const float* lp, int64_t lps,
+int nbx_launch_wide_a_f32(const PathK<float, NBX_WIDE_CAP>& P, int allz, const float* q, int64_t B, const float* lp, int64_t lps,
                           const float* gp, int64_t gps, float* T_out, float* J_out, int vec_ok, int sm_count, cudaStream_t stream);
-int nbx_launch_wide_b_f32(const PathK<float, NBX_WIDE_CAP>& P, bool allz, const float* q, int64_t B, const float* lp, int64_t lps,
+int nbx_launch_wide_b_f32(const PathK<float, NBX_WIDE_CAP>& P, int allz, const float* q, int64_t B, const float* lp, int64_t lps,
                           const float* gp, int64_t gps, float* T_out, float* J_out, int vec_ok, int sm_count, cudaStream_t stream);
 
 int nbx_launch_fkjac_f32(const nbx_chain* chain, int frame, const float* q, int64_t B, const double* base_pose,

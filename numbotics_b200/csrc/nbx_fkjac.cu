@@ -407,7 +407,7 @@ fkjac_deep_kernel(const __grid_constant__ PathK<T, NBX_MAX_PATH> P, const T* __r
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <typename T, int NJ, int TILE, bool ALLZ>
+template <typename T, int NJ, int TILE, int ALLZ>
 int launch_dense(const nbx_chain* ch, const PathK<T, kSmallMax>& P, const T* q, int64_t B, const T* lp, int64_t lps, const T* gp,
                  int64_t gps, T* T_out, T* J_out, int vec_ok, cudaStream_t stream) {
     (void)ch;
@@ -469,11 +469,14 @@ int launch_fkjac(const nbx_chain* ch, int frame, const T* q, int64_t B, const do
         int rc = build_path<T, kSmallMax>(ch, frame, base_pose, use_com, P);
         if (rc != NBX_OK) return rc;
         if (P.dense) {
-            bool allz = true;
-            for (int i = 0; i < P.n; ++i) allz = allz && P.j[i].kind == NBX_KIND_Z;
+            bool allz = true, roll = true;
+            for (int i = 0; i < P.n; ++i) { allz = allz && P.j[i].kind == NBX_KIND_Z; roll = roll && P.j[i].okind != 0; }
+            static const bool no_roll = std::getenv("NBX_NO_ROLL_FASTPATH") != nullptr;   // A/B measurements and tests only
+            const int mode = allz ? ((roll && !no_roll) ? 2 : 1) : 0;
             switch (n) {
-#define NBX_CASE(N) case N: return allz ? launch_dense<T, N, TILE, true>(ch, P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, stream) \
-                                        : launch_dense<T, N, TILE, false>(ch, P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, stream);
+#define NBX_CASE(N) case N: return mode == 2 ? launch_dense<T, N, TILE, 2>(ch, P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, stream) \
+                                 : mode == 1 ? launch_dense<T, N, TILE, 1>(ch, P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, stream) \
+                                             : launch_dense<T, N, TILE, 0>(ch, P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, stream);
                 NBX_CASE(1) NBX_CASE(2) NBX_CASE(3) NBX_CASE(4) NBX_CASE(5) NBX_CASE(6) NBX_CASE(7) NBX_CASE(8)
 #undef NBX_CASE
             }
@@ -487,8 +490,10 @@ int launch_fkjac(const nbx_chain* ch, int frame, const T* q, int64_t B, const do
             int rc = build_path<float, NBX_WIDE_CAP>(ch, frame, base_pose, use_com, P);
             if (rc != NBX_OK) return rc;
             if (P.dense) {
-                bool allz = true;
-                for (int i = 0; i < P.n; ++i) allz = allz && P.j[i].kind == NBX_KIND_Z;
+                bool allz_b = true, roll = true;
+                for (int i = 0; i < P.n; ++i) { allz_b = allz_b && P.j[i].kind == NBX_KIND_Z; roll = roll && P.j[i].okind != 0; }
+                static const bool no_roll = std::getenv("NBX_NO_ROLL_FASTPATH") != nullptr;   // A/B measurements and tests only
+                const int allz = allz_b ? ((roll && !no_roll) ? 2 : 1) : 0;
                 return n <= NBX_WIDE_SPLIT ? nbx_launch_wide_a_f32(P, allz, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, ch->sm_count, stream)
                                            : nbx_launch_wide_b_f32(P, allz, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, ch->sm_count, stream);
             }
@@ -635,6 +640,14 @@ void nbx_fill_joint(JointK<T>& jk, const double* off12, const double* axis, int 
     for (int k = 0; k < 3; ++k) { jk.t[k] = (T)t[k]; jk.ax[k] = (T)a[k]; }
     jk.type = type;
     jk.qidx = qidx;
+    {
+        // roll-only offset rotation?  (exact structure: rpy = (r, 0, 0) gives exact zeros and an exact one)
+        const bool roll = R[0] == 1.0 && R[1] == 0.0 && R[2] == 0.0 && R[3] == 0.0 && R[6] == 0.0;
+        const bool ident = roll && R[4] == 1.0 && R[8] == 1.0 && R[5] == 0.0 && R[7] == 0.0;
+        jk.okind = ident ? 2 : (roll ? 1 : 0);
+        jk.oc = roll ? (T)R[4] : (T)1;
+        jk.os = roll ? (T)R[7] : (T)0;
+    }
     jk.kind = type == NBX_JOINT_REVOLUTE ? NBX_KIND_GENERIC : NBX_KIND_PRISMATIC;
     jk.sgn = (T)1;
     static const bool force_generic = std::getenv("NBX_FORCE_GENERIC_AXIS") != nullptr;   // A/B measurements only

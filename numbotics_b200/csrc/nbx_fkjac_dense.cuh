@@ -94,7 +94,7 @@ __device__ __forceinline__ void load_q_tile(T* sq, const T* __restrict__ q, int6
 // tile's q prefetched (cp.async) while the current one is computed, and the previous tile's output
 // still draining through the TMA engine.
 // =============================================================================================
-template <typename T, int NJ, int TILE, bool ALLZ, int KT, int CAP>
+template <typename T, int NJ, int TILE, int ALLZ, int KT, int CAP>
 __global__ void __launch_bounds__(TILE, (sizeof(T) == 4 && TILE == 128) ? 5 : 1)   // float: <= 96 registers, 5 CTAs per SM
 fkjac_dense_kernel(const __grid_constant__ PathK<T, CAP> P, const T* __restrict__ q, int64_t B,
                    const T* __restrict__ lp, int64_t lps, const T* __restrict__ gp, int64_t gps,
@@ -144,7 +144,9 @@ fkjac_dense_kernel(const __grid_constant__ PathK<T, CAP> P, const T* __restrict_
                 sincos_t<T>(qv, &sn, &cs);
                 if (ALLZ) {
                     // every joint is a revolute about its own +-z: branch-free straight-line code
-                    joint_step_z<T, JointK<T>>(X, P.j[i], sn, cs);
+                    // (ALLZ == 2: and every offset rotation is a roll about x -- DH-style links)
+                    if (ALLZ == 2) joint_step_zx<T, JointK<T>>(X, P.j[i], sn, cs);
+                    else joint_step_z<T, JointK<T>>(X, P.j[i], sn, cs);
                     joint_screw_z<T, JointK<T>>(X, P.j[i], W[i], Mo[i]);
                 } else {
                     joint_step_sc<T, JointK<T>>(X, P.j[i], qv, sn, cs);
@@ -238,7 +240,7 @@ int build_path(const nbx_chain* ch, int frame, const double* base_pose16, int us
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-template <typename T, int NJ, int TILE, bool ALLZ, int KT, int CAP>
+template <typename T, int NJ, int TILE, int ALLZ, int KT, int CAP>
 int launch_dense_kt(const PathK<T, CAP>& P, const T* q, int64_t B, const T* lp, int64_t lps, const T* gp,
                     int64_t gps, T* T_out, T* J_out, int vec_ok, cudaStream_t stream) {
     const size_t smem = sizeof(T) * (size_t)TILE * (6 * NJ + 16 + KT * NJ);
