@@ -263,12 +263,12 @@ int nbx_scene_create(const nbx_chain* ch, const nbx_scene_desc* d, nbx_scene** o
         if (a > b) std::swap(a, b);
         PairK& pr = self[i];
         std::memset(&pr, 0, sizeof(PairK));
-        pr.a = (int16_t)a; pr.b = (int16_t)b;
+        pr.a = (uint8_t)a; pr.b = (uint8_t)b;
         pr.sharp = d->self_sharp ? d->self_sharp[i] : 0;
         const PrimK& pa = sc->h_prims[a];
         const PrimK& pb = sc->h_prims[b];
         pr.both_cyl = (pa.type == NBX_PRIM_CYLINDER && pb.type == NBX_PRIM_CYLINDER) ? 1 : 0;
-        pr.slot_a = (int16_t)pa.slot; pr.slot_b = (int16_t)pb.slot;
+        pr.off_a = pa.slot * NBX_WARP_TILE * 4; pr.off_b = pb.slot * NBX_WARP_TILE * 4;
         pr.rsum = pa.brad + pb.brad;
     }
     std::stable_sort(self.begin(), self.end(), [](const PairK& x, const PairK& y) { return x.b != y.b ? x.b < y.b : x.a < y.a; });
@@ -278,10 +278,10 @@ int nbx_scene_create(const nbx_chain* ch, const nbx_scene_desc* d, nbx_scene** o
         NBX_REQUIRE(a >= 0 && a < np && o >= 0 && o < d->n_obs, "env pair %d: bad index", i);
         PairK& pr = env[i];
         std::memset(&pr, 0, sizeof(PairK));
-        pr.a = (int16_t)ch->prim_rank[a]; pr.b = (int16_t)o;
+        pr.a = (uint8_t)ch->prim_rank[a]; pr.b = (uint8_t)o;
         pr.sharp = d->env_sharp ? d->env_sharp[i] : 0;
         const PrimK& pa = sc->h_prims[pr.a];
-        pr.slot_a = (int16_t)pa.slot;
+        pr.off_a = pa.slot * NBX_WARP_TILE * 4;
         pr.rsum = pa.brad;
     }
     // obstacle-major: the broad phase keeps one obstacle in registers and streams the primitives past it

@@ -146,7 +146,7 @@ __device__ __forceinline__ void unround(ShapeW& S, float margin) {
 // utilisation; see profiles/README.md.
 // ---------------------------------------------------------------------------------------------
 constexpr int kWarps = 4;            // autonomous warps per CTA (they only share the staged scene)
-constexpr int kWT = 32;              // items per tile
+constexpr int kWT = NBX_WARP_TILE;   // items per tile
 constexpr int kQCap = 48;            // materialised candidates per warp
 constexpr int kPendCap = 64;         // survivors of one tile awaiting materialisation
 constexpr int kEW = 34;              // words per queue entry
@@ -309,6 +309,8 @@ __device__ __noinline__ void eval_now_cold(const WCtx& C, uint32_t code) {
     eval_cand<MODE>(C, K);
 }
 
+__device__ __forceinline__ float sq3(float x, float y, float z) { return fmaf(x, x, fmaf(y, y, z * z)); }
+
 // distance between segments {ca + s ua, |s| <= ha} and {cb + t ub, |t| <= hb} (unit directions)
 __device__ __forceinline__ float seg_seg_distance(V3 ca, V3 ua, float ha, V3 cb, V3 ub, float hb) {
     const V3 r = ca - cb;
@@ -395,57 +397,59 @@ __device__ __forceinline__ void phase1(const WCtx& C, bool valid, QF qf, int n_o
     float run_ub = FLT_MAX;      // distance mode: no pair can beat the smallest centre distance seen so far
     const float4* env4 = reinterpret_cast<const float4*>(C.V.env_pairs);
     const float4* self4 = reinterpret_cast<const float4*>(C.V.self_pairs);
+    const char* myb = reinterpret_cast<const char*>(my);
     const float cut0 = C.thr + 1e-6f;
+    // one environment pair: squared distance l2 from the primitive's centre to the obstacle, against the reach
+#define NBX_ENV_PAIR(L2_EXPR, ORAD)                                                                      \
+    {                                                                                                    \
+        const float4 rec = env4[e];        /* {a|b|sharp|both_cyl, off_a, off_b, rsum} */                \
+        const float* pc = reinterpret_cast<const float*>(myb + __float_as_int(rec.y));                   \
+        const V3 dc = mk(pc[0], pc[NT], pc[2 * NT]) - oc;                                                \
+        const float l2 = (L2_EXPR);                                                                      \
+        bool surv;                                                                                       \
+        if (WANT_DIST) {                                                                                 \
+            run_ub = fminf(run_ub, sqrtf(dot(dc, dc)));                                                  \
+            surv = valid && sqrtf(l2) - rec.w - (ORAD) <= run_ub + 1e-6f;                                \
+        } else {                                                                                         \
+            const float reach = rec.w + (ORAD) + cut0;     /* >= 0: thresholds are non-negative */       \
+            surv = valid && l2 <= reach * reach;                                                         \
+        }                                                                                                \
+        push_pending(C, npend, surv, kEnvFlag | ((uint32_t)e << 8));                                     \
+    }
 #pragma unroll 1
     for (int o = 0; o < n_obs; ++o) {
         const ObsK& ob = C.V.obs[o];
         const V3 oc = mk(ob.c[0], ob.c[1], ob.c[2]);
-        const bool is_box = ob.type == NBX_PRIM_BOX;
-        const bool aa = ob.pad[0] != 0;                          // rotation is exactly the identity
-        float R[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) R[k] = ob.R[k];
-        const float hx = ob.dims[0] + ob.margin, hy = ob.dims[1] + ob.margin, hz = ob.dims[2] + ob.margin;
-        const float orad = is_box ? 0.f : ob.brad;
-        const int e1 = C.V.env_begin[o + 1];
+        const int e0 = C.V.env_begin[o], e1 = C.V.env_begin[o + 1];
+        // the obstacle's kind is warp-uniform: one specialised inner loop each, no branch per pair
+        if (ob.type == NBX_PRIM_BOX) {
+            const float hx = ob.dims[0] + ob.margin, hy = ob.dims[1] + ob.margin, hz = ob.dims[2] + ob.margin;
+            if (ob.pad[0] != 0) {              // axis-aligned box: exact point-to-box distance without the rotation
 #pragma unroll 2
-        for (int e = C.V.env_begin[o]; e < e1; ++e) {
-            const float4 rec = env4[e];                          // {a|b, sharp|flags|slot_a, slot_b|pad, rsum}
-            const int slot_a = (int)(short)(__float_as_uint(rec.y) >> 16);
-            const float* pc = my + (size_t)slot_a * NT;
-            const V3 dc = mk(pc[0], pc[NT], pc[2 * NT]) - oc;
-            float l2;      // squared distance from the primitive's centre to the obstacle (box: exact; else: to its centre)
-            if (is_box) {
-                float lx, ly, lz;
-                if (aa) {
-                    lx = fmaxf(fabsf(dc.x) - hx, 0.f); ly = fmaxf(fabsf(dc.y) - hy, 0.f); lz = fmaxf(fabsf(dc.z) - hz, 0.f);
-                } else {
-                    lx = fmaxf(fabsf(fmaf(R[0], dc.x, fmaf(R[3], dc.y, R[6] * dc.z))) - hx, 0.f);
-                    ly = fmaxf(fabsf(fmaf(R[1], dc.x, fmaf(R[4], dc.y, R[7] * dc.z))) - hy, 0.f);
-                    lz = fmaxf(fabsf(fmaf(R[2], dc.x, fmaf(R[5], dc.y, R[8] * dc.z))) - hz, 0.f);
-                }
-                l2 = fmaf(lx, lx, fmaf(ly, ly, lz * lz));
+                for (int e = e0; e < e1; ++e)
+                    NBX_ENV_PAIR(sq3(fmaxf(fabsf(dc.x) - hx, 0.f), fmaxf(fabsf(dc.y) - hy, 0.f), fmaxf(fabsf(dc.z) - hz, 0.f)), 0.f)
             } else {
-                l2 = dot(dc, dc);
+                float R[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) R[k] = ob.R[k];
+#pragma unroll 2
+                for (int e = e0; e < e1; ++e)
+                    NBX_ENV_PAIR(sq3(fmaxf(fabsf(fmaf(R[0], dc.x, fmaf(R[3], dc.y, R[6] * dc.z))) - hx, 0.f),
+                                     fmaxf(fabsf(fmaf(R[1], dc.x, fmaf(R[4], dc.y, R[7] * dc.z))) - hy, 0.f),
+                                     fmaxf(fabsf(fmaf(R[2], dc.x, fmaf(R[5], dc.y, R[8] * dc.z))) - hz, 0.f)), 0.f)
             }
-            bool surv;
-            if (WANT_DIST) {
-                run_ub = fminf(run_ub, sqrtf(dot(dc, dc)));
-                surv = valid && sqrtf(l2) - rec.w - orad <= run_ub + 1e-6f;
-            } else {
-                const float reach = rec.w + orad + cut0;         // >= 0: thresholds are non-negative
-                surv = valid && l2 <= reach * reach;
-            }
-            push_pending(C, npend, surv, kEnvFlag | ((uint32_t)e << 8));
+        } else {                               // sphere / cylinder obstacle: bounding spheres
+            const float orad = ob.brad;
+#pragma unroll 2
+            for (int e = e0; e < e1; ++e) NBX_ENV_PAIR(dot(dc, dc), orad)
         }
     }
+#undef NBX_ENV_PAIR
 #pragma unroll 2
     for (int e = 0; e < n_self; ++e) {
         const float4 rec = self4[e];
-        const uint32_t w1 = __float_as_uint(rec.y), w2 = __float_as_uint(rec.z);
-        const int slot_a = (int)(short)(w1 >> 16), slot_b = (int)(short)(w2 & 0xffffu);
-        const float* pa = my + (size_t)slot_a * NT;
-        const float* pb = my + (size_t)slot_b * NT;
+        const float* pa = reinterpret_cast<const float*>(myb + __float_as_int(rec.y));
+        const float* pb = reinterpret_cast<const float*>(myb + __float_as_int(rec.z));
         const V3 ca = mk(pa[0], pa[NT], pa[2 * NT]);
         const V3 cb = mk(pb[0], pb[NT], pb[2 * NT]);
         const V3 dc = cb - ca;
@@ -462,7 +466,7 @@ __device__ __forceinline__ void phase1(const WCtx& C, bool valid, QF qf, int n_o
             const float reach = rec.w + cut0;
             surv = valid && cd2 <= reach * reach;
         }
-        if (surv && ((w1 >> 8) & 0xffu)) {
+        if (surv && (__float_as_uint(rec.x) >> 24)) {
             // thin links: capsule bound  d(cyl, cyl) >= d(axis segment, axis segment) - rA - rB
             const PairK pr = C.V.self_pairs[e];
             const PrimK& ka = C.V.prims[pr.a];

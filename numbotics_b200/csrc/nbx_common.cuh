@@ -100,16 +100,17 @@ struct ObsK {
 };
 
 // One allowed pair, 16 bytes so the broad phase reads it with a single LDS.128.
+#define NBX_WARP_TILE 32   // items per warp tile of the collision kernels: the pose scratch is [value][NBX_WARP_TILE]
 struct PairK {
-    int16_t a;        // link primitive (self pairs: the one with the smaller device index)
-    int16_t b;        // link primitive (self) or obstacle (env)
+    uint8_t a;        // link primitive (self pairs: the one with the smaller device index)
+    uint8_t b;        // link primitive (self) or obstacle (env)
     uint8_t sharp;    // 1 = ignore margins (box-box under the Bullet model)
     uint8_t both_cyl; // self pairs: both primitives are cylinders -> capsule bound available
-    int16_t slot_a;   // float offset of a's world core in the per-item pose scratch
-    int16_t slot_b;   // same for b (self pairs only)
-    int16_t pad;
+    int32_t off_a;    // BYTE offset of a's world core in the warp's pose scratch (slot * NBX_WARP_TILE * 4)
+    int32_t off_b;    // same for b (self pairs only)
     float rsum;       // self: bounding radius a + bounding radius b ; env: bounding radius of the link primitive
 };
+static_assert(sizeof(PairK) == 16, "PairK must stay one 16-byte record");
 
 // Whole-tree walk used by the collision kernels.  Lives in global memory; blocks stage it in
 // shared memory once (it is read with uniform addresses -> LDS broadcast).
