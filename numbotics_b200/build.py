@@ -29,6 +29,10 @@ NVCC_FLAGS = [
 ]
 
 
+# extra nvcc flags for tuning experiments (e.g. NBX_NVCC_EXTRA="-DNBX_DENSE_MINB=6"); part of the build digest
+NVCC_FLAGS += [f for f in os.environ.get("NBX_NVCC_EXTRA", "").split() if f]
+
+
 def _nvcc():
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):

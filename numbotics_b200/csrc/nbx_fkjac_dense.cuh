@@ -9,6 +9,10 @@
 #include <algorithm>
 #include <cstdlib>
 
+#ifndef NBX_DENSE_MINB
+#define NBX_DENSE_MINB 5   // float kernels: <= 96 registers, 5 CTAs of 128 threads per SM
+#endif
+
 namespace nbxd {
 using namespace nbxj;
 
@@ -95,7 +99,7 @@ __device__ __forceinline__ void load_q_tile(T* sq, const T* __restrict__ q, int6
 // still draining through the TMA engine.
 // =============================================================================================
 template <typename T, int NJ, int TILE, int ALLZ, int KT, int CAP>
-__global__ void __launch_bounds__(TILE, (sizeof(T) == 4 && TILE == 128) ? 5 : 1)   // float: <= 96 registers, 5 CTAs per SM
+__global__ void __launch_bounds__(TILE, (sizeof(T) == 4 && TILE == 128) ? NBX_DENSE_MINB : 1)   // float: <= 96 registers, 5 CTAs per SM
 fkjac_dense_kernel(const __grid_constant__ PathK<T, CAP> P, const T* __restrict__ q, int64_t B,
                    const T* __restrict__ lp, int64_t lps, const T* __restrict__ gp, int64_t gps,
                    T* __restrict__ T_out, T* __restrict__ J_out, int vec_ok, int64_t ntiles) {
