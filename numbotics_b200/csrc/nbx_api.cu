@@ -47,6 +47,13 @@ float bounding_radius(int type, const double* dims) {
     return (float)std::sqrt(dims[0] * dims[0] + dims[1] * dims[1]);
 }
 
+// inscribed-sphere radius of the full primitive about its centre
+float inscribed_radius(int type, const double* dims) {
+    if (type == NBX_PRIM_SPHERE) return (float)dims[0];
+    if (type == NBX_PRIM_BOX) return (float)std::min(dims[0], std::min(dims[1], dims[2]));
+    return (float)std::min(dims[0], dims[1]);
+}
+
 int prim_pose_floats(int type) { return type == NBX_PRIM_SPHERE ? 3 : (type == NBX_PRIM_CYLINDER ? 6 : 12); }
 
 // core dims = full dims shrunk by the rounding margin (Bullet keeps "implicit shape dimensions" the same way)
@@ -164,6 +171,7 @@ int nbx_chain_create(const nbx_chain_desc* d, int device, nbx_chain** out) {
         pk.slot = ch->pose_floats;
         ch->pose_floats += prim_pose_floats(pk.type);
         pk.brad = bounding_radius(pk.type, &ch->prim_dims[3 * p]) * 1.000001f;
+        pk.rin = inscribed_radius(pk.type, &ch->prim_dims[3 * p]) * 0.999999f;
         pk.desc = p;
         pk.anc = 0ull;
         if (ch->n_mov <= 64)
@@ -250,6 +258,10 @@ int nbx_scene_create(const nbx_chain* ch, const nbx_scene_desc* d, nbx_scene** o
         int rc = core_dims(ok.type, &d->obs_dims[3 * o], d->obs_margin[o], ok.dims, &ok.margin);
         if (rc != NBX_OK) return rc;
         ok.brad = bounding_radius(ok.type, &d->obs_dims[3 * o]) * 1.000001f;
+        {
+            const float rin = inscribed_radius(ok.type, &d->obs_dims[3 * o]) * 0.999999f;
+            std::memcpy(&ok.pad[1], &rin, sizeof(float));
+        }
         // axis-aligned (rotation exactly the identity): the broad phase skips the rotation into the obstacle frame
         ok.pad[0] = (P[0] == 1.0 && P[5] == 1.0 && P[10] == 1.0 && P[1] == 0.0 && P[2] == 0.0 && P[4] == 0.0 && P[6] == 0.0 &&
                      P[8] == 0.0 && P[9] == 0.0) ? 1 : 0;

@@ -85,6 +85,7 @@ struct PrimK {
     int mov;        // owning movable joint (-1 = base)
     int slot;       // float offset of the stored world pose in the per-thread scratch, -1 = not stored
     float brad;     // bounding-sphere radius of the FULL primitive (core + margin) about its centre
+    float rin;      // inscribed-sphere radius of the FULL primitive about its centre (upper bounds of distance queries)
     int desc;       // index of this primitive in the chain descriptor (device order is sorted by owning joint)
     unsigned long long anc;   // bit j: movable joint j is on the path root -> this primitive (chains of <= 64 movable joints)
 };
@@ -96,7 +97,7 @@ struct ObsK {
     float margin;
     int type;
     float brad;     // bounding-sphere radius of the full obstacle
-    int pad[2];
+    int pad[2];     // pad[0]: 1 = axis-aligned (rotation exactly the identity); pad[1]: inscribed radius (float bits)
 };
 
 // One allowed pair, 16 bytes so the broad phase reads it with a single LDS.128.

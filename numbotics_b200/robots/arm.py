@@ -59,15 +59,38 @@ class Proximity:
 
 @dataclass
 class Proximities:
-    """Struct-of-arrays form of `Proximity` for a batch of configurations."""
-    subject: np.ndarray
-    target: np.ndarray
+    """Struct-of-arrays form of `Proximity` for a batch of configurations.
+
+    `subject_index` / `target_index` (int32, device-resident for CUDA inputs) index `links` (link primitives in
+    descriptor order) and, where `target_is_obstacle`, `obstacles`; `.subject` / `.target` materialise the object
+    arrays on demand (a host round trip)."""
     position_on_subject: object
     position_on_target: object
     normal_target_to_subject: object
     distance: object
     valid: object
+    subject_index: object
+    target_index: object
+    target_is_obstacle: object
+    links: np.ndarray
+    obstacles: np.ndarray
     gradient: object = None
+
+    @staticmethod
+    def _host(x):
+        return x.cpu().numpy() if _is_torch(x) else np.asarray(x)
+
+    @property
+    def subject(self):
+        i = self._host(self.subject_index).astype(np.int64)
+        return self.links[np.where(i >= 0, i, len(self.links) - 1)]
+
+    @property
+    def target(self):
+        i = self._host(self.target_index).astype(np.int64)
+        env = self._host(self.target_is_obstacle).astype(bool)
+        none_l, none_o = len(self.links) - 1, len(self.obstacles) - 1
+        return np.where(env, self.obstacles[np.where(env & (i >= 0), i, none_o)], self.links[np.where(~env & (i >= 0), i, none_l)])
 
 
 class Arm:
@@ -564,30 +587,37 @@ class Arm:
                                             ps.data_ptr(), pt.data_ptr(), nrm.data_ptr(), sub.data_ptr(), tgt.data_ptr(),
                                             ok.data_ptr(), grad.data_ptr() if gradient else None, _cuda_stream_ptr(dev_index)))
         del base_keep
-        link_of_prim = {p: l for l, p in self._arrays["prim_of_link"].items()}
+        # subject / target as indices (kept on the device for CUDA inputs) + lookup tables; object arrays on demand
+        prim_of_link = self._arrays["prim_of_link"]
+        n_prims = max(prim_of_link.values()) + 1 if prim_of_link else 0
         obstacles = arrays["obstacles"]
-        sub_h, tgt_h = sub.cpu().numpy(), tgt.cpu().numpy()
-        subjects = np.empty(B, dtype=object)
-        targets = np.empty(B, dtype=object)
-        for i in range(B):
-            subjects[i] = link_of_prim.get(int(sub_h[i]))
-            t = int(tgt_h[i])
-            targets[i] = None if t < 0 else (obstacles[t & 0x3fffffff] if t & 0x40000000 else link_of_prim.get(t))
+        link_tab = np.empty(n_prims + 1, dtype=object)            # last entry: None (no pair)
+        for l, p in prim_of_link.items():
+            link_tab[p] = l
+        obs_tab = np.empty(len(obstacles) + 1, dtype=object)
+        for i, o in enumerate(obstacles):
+            obs_tab[i] = o
+        is_env = (tgt >= 0) & ((tgt & 0x40000000) != 0)
+        tgt_idx = torch.where(tgt >= 0, tgt & 0x3fffffff, tgt)
         if in_torch:
             conv = lambda x: x.to(q.device)
         else:
             out_dt = q.dtype if getattr(q, "dtype", None) in (np.float32, np.float64) else np.float64
-            conv = lambda x: x.cpu().numpy().astype(out_dt if x.dtype == torch.float32 else bool, copy=False)
+            conv = lambda x: x.cpu().numpy().astype(out_dt, copy=False) if x.dtype == torch.float32 else x.cpu().numpy()
         shape = q_shape[:-1]
         rec = Proximities(
-            subject=subjects.reshape(shape), target=targets.reshape(shape),
             position_on_subject=conv(ps).reshape(*shape, 3), position_on_target=conv(pt).reshape(*shape, 3),
             normal_target_to_subject=conv(nrm).reshape(*shape, 3), distance=conv(dist).reshape(shape),
-            valid=conv(ok.to(torch.bool)).reshape(shape), gradient=conv(grad).reshape(*shape, self.dof) if gradient else None)
-        if single:
-            return Proximity(subject=subjects[0], target=targets[0], position_on_subject=rec.position_on_subject,
-                             position_on_target=rec.position_on_target, normal_target_to_subject=rec.normal_target_to_subject,
-                             distance=float(rec.distance)) if not gradient else rec
+            valid=conv(ok.to(torch.bool)).reshape(shape), subject_index=conv(sub).reshape(shape),
+            target_index=conv(tgt_idx).reshape(shape), target_is_obstacle=conv(is_env).reshape(shape),
+            links=link_tab, obstacles=obs_tab,
+            gradient=conv(grad).reshape(*shape, self.dof) if gradient else None)
+        if single and not gradient:
+            si, ti, env = int(sub[0]), int(tgt_idx[0]), bool(is_env[0])
+            return Proximity(subject=link_tab[si if si >= 0 else n_prims],
+                             target=(obs_tab if env else link_tab)[ti if ti >= 0 else -1],
+                             position_on_subject=rec.position_on_subject, position_on_target=rec.position_on_target,
+                             normal_target_to_subject=rec.normal_target_to_subject, distance=float(rec.distance))
         return rec
 
     def jacobian_proximity_closest(self, q):

@@ -100,7 +100,7 @@ def test_single_configuration_and_types(scene, cuda):
     assert batch.distance.dtype == np.float64
     assert abs(one.distance - batch.distance[0]) < 1e-6 and one.subject is batch.subject[0] and one.target is batch.target[0]
     t = arm.closest_to(torch.as_tensor(q, dtype=torch.float32, device=cuda).reshape(8, 8, 7), gradient=True)
-    assert t.distance.is_cuda and t.distance.shape == (8, 8) and t.gradient.shape == (8, 8, 7) and t.subject.shape == (8, 8)
+    assert t.distance.is_cuda and t.distance.shape == (8, 8) and t.gradient.shape == (8, 8, 7) and t.subject.shape == (8, 8) and t.subject_index.is_cuda
     assert np.abs(t.distance.cpu().numpy().reshape(-1) - batch.distance).max() < 1e-6
     # consistent with the distance query
     assert np.abs(arm.min_distance(q.astype(np.float32)) - batch.distance.astype(np.float32))[batch.valid].max() < 2e-5
