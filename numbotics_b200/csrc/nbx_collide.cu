@@ -287,7 +287,9 @@ template <int MODE>
 __device__ __forceinline__ void eval_cand(const WCtx& C, const Cand& K) {
     if (MODE == kDist) {
         const float best = entry_dist(((volatile unsigned long long*)C.flag)[K.fi]);
-        const GjkOut g = gjk_distance<kGjkItersDist>(K.A, K.B, best + K.m, -FLT_MAX);
+        // distance values are stated to 1e-4 m: stop when the bracket [lb, ub] is below half of that;
+        // curved cores (cylinders) converge only linearly, so the tolerance is a large part of the cost of this query
+        const GjkOut g = gjk_distance<kGjkItersDist>(K.A, K.B, best + K.m, -FLT_MAX, 2e-5f, 4e-5f);
         // overlapping cores: depth beyond the margins is not computed (clamp)
         const float d = g.overlap ? (-K.m - 1e-3f) : (g.contact ? (-K.m - 1e-6f) : (g.d - K.m));
         if (!g.pruned) atomicMin(&C.flag[K.fi], dist_entry(d, K.pc));

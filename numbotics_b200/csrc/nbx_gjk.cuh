@@ -110,7 +110,8 @@ struct GjkOut {
 };
 
 template <int MAX_ITER>
-__device__ GjkOut gjk_distance(const ShapeW& A, const ShapeW& B, float stop_above, float stop_below) {
+__device__ GjkOut gjk_distance(const ShapeW& A, const ShapeW& B, float stop_above, float stop_below,
+                                float conv_abs = 1e-6f, float conv_rel = 1e-5f) {
     GjkOut out;
     out.overlap = false;
     out.contact = false;
@@ -130,7 +131,7 @@ __device__ GjkOut gjk_distance(const ShapeW& A, const ShapeW& B, float stop_abov
         if (vw > 0.f) {
             const float lb = vw * rsqrtf(vv);
             if (lb > stop_above) { out.d = lb; out.pruned = true; return out; }
-            if (have_ub && ub - lb <= 1e-6f + 1e-5f * ub) break;   // converged
+            if (have_ub && ub - lb <= conv_abs + conv_rel * ub) break;   // converged: the distance lies in [lb, ub]
         }
         if (have_ub && vv - vw <= 1e-7f * vv) break;               // no progress possible
         // closest point of conv(simplex + w) to the origin
