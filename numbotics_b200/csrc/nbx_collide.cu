@@ -148,7 +148,7 @@ __device__ __forceinline__ void unround(ShapeW& S, float margin) {
 constexpr int kWarps = 4;            // autonomous warps per CTA (they only share the staged scene)
 constexpr int kWT = NBX_WARP_TILE;   // items per tile
 constexpr int kQCap = 48;            // materialised candidates per warp
-constexpr int kPendCap = 64;         // survivors of one tile awaiting materialisation
+constexpr int kPendCap = 128;        // survivors of one tile awaiting materialisation
 constexpr int kEW = 34;              // words per queue entry
 constexpr int kMaxRange = 256;       // units a warp owns (flags kept in shared memory until the range is done)
 constexpr uint32_t kEnvFlag = 0x80000000u;
@@ -327,7 +327,7 @@ __device__ __forceinline__ float seg_seg_distance(V3 ca, V3 ua, float ha, V3 cb,
 }
 
 // append the surviving lanes' codes to the pending list: one ballot, no atomics (npend is warp-uniform).  A full list
-// (> 64 survivors in a tile of 32 items: pathological scenes) only raises `npend` past the capacity; the tile is then
+// (> 128 survivors in a tile of 32 items: pathological scenes) only raises `npend` past the capacity; the tile is then
 // evaluated exhaustively after the culls (tile_exhaustive_cold) -- no call inside the cull loops, whose loop invariants
 // would otherwise be spilled around it.
 __device__ __forceinline__ void push_pending(const WCtx& C, int& npend, bool surv, uint32_t code) {
@@ -348,6 +348,9 @@ __device__ __noinline__ void tile_exhaustive_cold(const WCtx& C, bool valid, int
     for (int e = 0; e < n_self; ++e) eval_now_cold<MODE>(C, ((uint32_t)e << 8) | lane);
 }
 
+template <int MODE>
+__device__ __forceinline__ void materialise(const WCtx& C, int& npend, int& qn);
+
 // phase 1 for this lane's item.  `valid` = the lane has an item; invalid lanes still take part in the ballots.
 //   1a  walk the tree, park every primitive's world core in the warp's scratch;
 //   1b  broad phase.  Obstacle-major for the environment pairs (one obstacle's frame stays in registers while the
@@ -355,7 +358,7 @@ __device__ __noinline__ void tile_exhaustive_cold(const WCtx& C, bool valid, int
 //       compared squared -- no square root -- and without the rotation for axis-aligned boxes), then the self pairs
 //       (bounding spheres, refined by the capsule bound for cylinder-cylinder pairs that survive).
 template <int MODE, typename QF>
-__device__ __forceinline__ void phase1(const WCtx& C, bool valid, QF qf, int n_obs, int n_self, int& npend) {
+__device__ __forceinline__ void phase1(const WCtx& C, bool valid, QF qf, int n_obs, int n_self, int& npend, int& qn) {
     constexpr bool WANT_DIST = MODE == kDist;
     constexpr int NT = kWT;
     const int lane = threadIdx.x & 31;
@@ -451,6 +454,8 @@ __device__ __forceinline__ void phase1(const WCtx& C, bool valid, QF qf, int n_o
             surv = valid && l2 <= reach * reach;                                                         \
         }                                                                                                \
         push_pending(C, npend, surv, kEnvFlag | ((uint32_t)e << 8));                                     \
+        /* distance queries keep several pairs per item: empty the list into the queue before it can overflow */ \
+        if (WANT_DIST && npend > kPendCap - 32) materialise<MODE>(C, npend, qn);                         \
     }
 #pragma unroll 1
     for (int o = 0; o < n_obs; ++o) {
@@ -512,6 +517,7 @@ __device__ __forceinline__ void phase1(const WCtx& C, bool valid, QF qf, int n_o
             surv = d <= cut;
         }
         push_pending(C, npend, surv, (uint32_t)e << 8);
+        if (WANT_DIST && npend > kPendCap - 32) materialise<MODE>(C, npend, qn);
     }
     if (npend > kPendCap) {          // warp-uniform
         tile_exhaustive_cold<MODE>(C, valid, C.V.env_begin[n_obs], n_self);
@@ -659,7 +665,7 @@ in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict_
         C.item_fi[lane] = (MODE == kDist) ? t0 + lane : (int)(range0 + t0 + lane);
         __syncwarp();
         const float* myq = sq + lane * dof;
-        phase1<MODE>(C, lane < nv, [myq](int col) { return myq[col]; }, S.n_obs, S.n_self, npend);
+        phase1<MODE>(C, lane < nv, [myq](int col) { return myq[col]; }, S.n_obs, S.n_self, npend, qn);
         materialise<MODE>(C, npend, qn);
     }
     if (MODE == kDist) {
@@ -778,7 +784,7 @@ edges_valid_kernel(const __grid_constant__ SceneDev S, const float* __restrict__
             __syncwarp();
             const float* a = s_start + e * dof;
             const float* g = s_goal + e * dof;
-            phase1<kSplit>(C, have, [a, g, t](int col) { return fmaf(t, g[col], fmaf(-t, a[col], a[col])); }, S.n_obs, S.n_self, npend);
+            phase1<kSplit>(C, have, [a, g, t](int col) { return fmaf(t, g[col], fmaf(-t, a[col], a[col])); }, S.n_obs, S.n_self, npend, qn);
             materialise<kSplit>(C, npend, qn);
         }
     }
