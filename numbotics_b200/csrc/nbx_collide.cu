@@ -148,7 +148,7 @@ __device__ __forceinline__ void unround(ShapeW& S, float margin) {
 constexpr int kWarps = 4;            // autonomous warps per CTA (they only share the staged scene)
 constexpr int kWT = NBX_WARP_TILE;   // items per tile
 constexpr int kQCap = 48;            // materialised candidates per warp
-constexpr int kPendCap = 128;        // survivors of one tile awaiting materialisation
+constexpr int kPendCap = 256;        // survivors of one tile awaiting materialisation
 constexpr int kEW = 34;              // words per queue entry
 constexpr int kMaxRange = 256;       // units a warp owns (flags kept in shared memory until the range is done)
 constexpr uint32_t kEnvFlag = 0x80000000u;
@@ -327,7 +327,7 @@ __device__ __forceinline__ float seg_seg_distance(V3 ca, V3 ua, float ha, V3 cb,
 }
 
 // append the surviving lanes' codes to the pending list: one ballot, no atomics (npend is warp-uniform).  A full list
-// (> 128 survivors in a tile of 32 items: pathological scenes) only raises `npend` past the capacity; the tile is then
+// (> 256 survivors in a tile of 32 items: every lane deep inside several contacts) only raises `npend` past the capacity; the tile is then
 // evaluated exhaustively after the culls (tile_exhaustive_cold) -- no call inside the cull loops, whose loop invariants
 // would otherwise be spilled around it.
 __device__ __forceinline__ void push_pending(const WCtx& C, int& npend, bool surv, uint32_t code) {
@@ -1034,8 +1034,9 @@ struct SplitWs {
         cudaMemPool_t pool = nullptr;
         int rc = workspace_pool(device, &pool);
         if (rc != NBX_OK) return rc;
-        // ~0.3 candidates per item on the PRM scene; what does not fit is evaluated in place by the broad kernel
-        int64_t half = std::max<int64_t>(4096, std::min<int64_t>(n_items / 2, 1 << 20));
+        // ~0.3 candidates per item on random PRM configurations, ~3 on contact-seeking workloads (IRIS bisection rounds);
+        // what does not fit is evaluated in place by the broad kernel (correct, but several times slower)
+        int64_t half = std::max<int64_t>(4096, std::min<int64_t>(2 * n_items, 1 << 21));
         half = (half + 31) & ~(int64_t)31;
         const size_t bytes = 256 + sizeof(float) * (size_t)kEW * 2 * (size_t)half;
         NBX_CUDA_OK(cudaMallocFromPoolAsync(&p, bytes, pool, stream));
