@@ -663,6 +663,12 @@ in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict_
             for (int i = lane; i < n; i += 32) sq[i] = src[i];
         }
         C.item_fi[lane] = (MODE == kDist) ? t0 + lane : (int)(range0 + t0 + lane);
+        if (t0 + kWT < rangeN) {
+            // pull the next tile's q into L2 while this tile is evaluated (its load above is then an L2 hit)
+            const char* nq = reinterpret_cast<const char*>(src + kWT * dof);
+            const int nbytes = min(kWT, rangeN - t0 - kWT) * dof * (int)sizeof(float);
+            for (int o = lane * 128; o < nbytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nq + o));
+        }
         __syncwarp();
         const float* myq = sq + lane * dof;
         phase1<MODE>(C, lane < nv, [myq](int col) { return myq[col]; }, S.n_obs, S.n_self, npend, qn);
