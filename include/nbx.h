@@ -209,6 +209,18 @@ NBX_API int nbx_closest_f32(const nbx_chain* chain, const nbx_scene* scene, cons
                     int32_t* subject_prim, int32_t* target, uint8_t* valid, float* gradient, void* stream);
 
 /*
+ * Batched Arm.collisions (numbotics/robots/arm.py:555-580): one Proximity per ALLOWED PAIR and configuration.
+ * Outputs are indexed [b][p] with p the pair's index in the scene descriptor, self pairs first
+ * (p < n_self_pairs: self_pairs[p]; else env_pairs[p - n_self_pairs]); subject = the pair's first entry.
+ *   distance (B, P); position_on_subject / position_on_target / normal_target_to_subject (B, P, 3), nullable;
+ *   valid (B, P) u8, nullable: 0 where the two cores overlap (clamped distance, centres as points; no EPA).
+ * The scene must be unpruned.  Arm.distance_to(q, obj, link) (arm.py:607-618) is a column of this result.
+ */
+NBX_API int nbx_pair_distances_f32(const nbx_chain* chain, const nbx_scene* scene, const float* q, int64_t B,
+                           const double* base_pose, float* distance, float* position_on_subject,
+                           float* position_on_target, float* normal_target_to_subject, uint8_t* valid, void* stream);
+
+/*
  * Batched bisection towards the collision boundary: the zero-order-hold counter-example search of IRIS
  * (numbotics/planning/safe_sets.py:124-134, IrisSolver.counter_ex_search_bisection; its caller maps it over the
  * colliding samples with a thread pool, safe_sets.py:198-199).  Per sample b the interval [inside, outside[b]]

@@ -283,7 +283,17 @@ int nbx_scene_create(const nbx_chain* ch, const nbx_scene_desc* d, nbx_scene** o
         pr.off_a = pa.slot * NBX_WARP_TILE * 4; pr.off_b = pb.slot * NBX_WARP_TILE * 4;
         pr.rsum = pa.brad + pb.brad;
     }
-    std::stable_sort(self.begin(), self.end(), [](const PairK& x, const PairK& y) { return x.b != y.b ? x.b < y.b : x.a < y.a; });
+    // device order (sorted) -> descriptor order, for the queries that report per pair (nbx_pair_distances_f32)
+    auto sorted_with_origin = [](std::vector<PairK>& v, std::vector<int>& origin, int base) {
+        std::vector<int> idx(v.size());
+        for (size_t i = 0; i < idx.size(); ++i) idx[i] = (int)i;
+        std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return v[x].b != v[y].b ? v[x].b < v[y].b : v[x].a < v[y].a; });
+        std::vector<PairK> out(v.size());
+        for (size_t i = 0; i < idx.size(); ++i) { out[i] = v[idx[i]]; origin.push_back(base + idx[i]); }
+        v.swap(out);
+    };
+    sc->h_self_begin.clear();            // (name kept) [n_self + n_env]: descriptor pair index of each device pair
+    sorted_with_origin(self, sc->h_self_begin, 0);
     std::vector<PairK> env(d->n_env_pairs);
     for (int i = 0; i < d->n_env_pairs; ++i) {
         const int a = d->env_pairs[2 * i], o = d->env_pairs[2 * i + 1];
@@ -297,10 +307,9 @@ int nbx_scene_create(const nbx_chain* ch, const nbx_scene_desc* d, nbx_scene** o
         pr.rsum = pa.brad;
     }
     // obstacle-major: the broad phase keeps one obstacle in registers and streams the primitives past it
-    std::stable_sort(env.begin(), env.end(), [](const PairK& x, const PairK& y) { return x.b != y.b ? x.b < y.b : x.a < y.a; });
+    sorted_with_origin(env, sc->h_self_begin, d->n_self_pairs);
     sc->h_self = self;
     sc->h_env = env;
-    sc->h_self_begin.assign(1, 0);
     sc->h_env_begin.assign(d->n_obs + 1, 0);
     for (const PairK& p : env) sc->h_env_begin[p.b + 1]++;
     for (int i = 0; i < d->n_obs; ++i) sc->h_env_begin[i + 1] += sc->h_env_begin[i];

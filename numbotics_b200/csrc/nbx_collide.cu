@@ -948,6 +948,115 @@ closest_witness_kernel(const __grid_constant__ SceneDev S, const float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
+// Every allowed pair of every configuration: the batched form of Arm.collisions (reference robots/arm.py:555-580, one
+// Proximity per allowed pair).  Warp-autonomous like phase 1: the warp walks a tile of 32 configurations, parks the world
+// cores in its scratch, then loops over the pairs with every lane running the witness GJK of its own configuration on the
+// same pair (no divergence in shape kinds).  Outputs are indexed [configuration][descriptor pair], self pairs first.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarps * 32)
+pair_distances_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ q, int64_t B, int dof,
+                      float* __restrict__ dist, float* __restrict__ p_subject, float* __restrict__ p_target,
+                      float* __restrict__ normal, uint8_t* __restrict__ valid_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WCtx C;
+    unsigned char* p = stage_scene(S, smem_raw, C.V);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    p += (size_t)wid * align16(sizeof(float) * (size_t)kWT * max(S.scratch_floats, 1));
+    C.poses = reinterpret_cast<float*>(p);
+    __syncthreads();
+    const int64_t b = ((int64_t)blockIdx.x * kWarps + wid) * kWT + lane;
+    const bool have = b < B;
+    const float* myq = q + (have ? b : 0) * dof;
+    float* my = C.poses + lane;
+    {
+        PoseF X;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            X.R[r * 3 + 0] = S.base[r * 4 + 0]; X.R[r * 3 + 1] = S.base[r * 4 + 1]; X.R[r * 3 + 2] = S.base[r * 4 + 2];
+            X.p[r] = S.base[r * 4 + 3];
+        }
+        PoseF saved[kMaxSave];
+        auto do_prims = [&](int p0, int p1) {
+            for (int pi = p0; pi < p1; ++pi) {
+                const PrimK& pk = C.V.prims[pi];
+                ShapeW Bs;
+                prim_world(X, pk, Bs);
+                pose_store(my + (size_t)pk.slot * kWT, kWT, Bs);
+            }
+        };
+        do_prims(0, S.n_base_prims);
+#pragma unroll 1
+        for (int j = 0; j < S.n_mov; ++j) {
+            const TreeJointK& jk = C.V.tree[j];
+            if (jk.load_slot == -2) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    X.R[r * 3 + 0] = S.base[r * 4 + 0]; X.R[r * 3 + 1] = S.base[r * 4 + 1]; X.R[r * 3 + 2] = S.base[r * 4 + 2];
+                    X.p[r] = S.base[r * 4 + 3];
+                }
+            } else if (jk.load_slot >= 0) {
+                X = saved[jk.load_slot];
+            }
+            nbxj::joint_step<float, TreeJointK>(X, jk, have ? myq[jk.qidx] : 0.f);
+            if (jk.save_slot >= 0) saved[jk.save_slot] = X;
+            do_prims(jk.prim_begin, jk.prim_end);
+        }
+    }
+    __syncwarp();
+    const int n_env = C.V.env_begin[S.n_obs];
+    const int n_pairs = S.n_self + n_env;
+    const int* pair_desc = S.self_begin;               // device pair -> descriptor pair (global memory, uniform reads)
+#pragma unroll 1
+    for (int k = 0; k < n_pairs; ++k) {
+        const bool env = k >= S.n_self;
+        const int e = env ? k - S.n_self : k;
+        const PairK pr = env ? C.V.env_pairs[e] : C.V.self_pairs[e];
+        const PrimK& pa = C.V.prims[pr.a];
+        ShapeW Ssub, Stgt;
+        float m_sub = pa.margin, m_tgt;
+        pose_load(my + (size_t)pa.slot * kWT, kWT, pa, Ssub);
+        if (env) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Stgt.ax[i] = 0.f;
+            obs_world(C.V.obs[pr.b], Stgt);
+            m_tgt = C.V.obs[pr.b].margin;
+        } else {
+            const PrimK& pb = C.V.prims[pr.b];
+            pose_load(my + (size_t)pb.slot * kWT, kWT, pb, Stgt);
+            m_tgt = pb.margin;
+        }
+        if (pr.sharp) {
+            unround(Ssub, m_sub);
+            unround(Stgt, m_tgt);
+            m_sub = Ssub.type == NBX_PRIM_SPHERE ? m_sub : 0.f;
+            m_tgt = Stgt.type == NBX_PRIM_SPHERE ? m_tgt : 0.f;
+        }
+        const GjkWit g = gjk_witness<96>(Ssub, Stgt);
+        if (!have) continue;
+        const int64_t o = b * n_pairs + pair_desc[env ? S.n_self + e : e];
+        V3 n, ps, pt;
+        float d;
+        if (g.overlap) {
+            const V3 dc = Ssub.c - Stgt.c;
+            const float l = sqrtf(dot(dc, dc));
+            n = l > 0.f ? (1.f / l) * dc : mk(0.f, 0.f, 1.f);
+            ps = Ssub.c; pt = Stgt.c;
+            d = -(m_sub + m_tgt) - 1e-3f;
+        } else {
+            n = (1.f / g.d) * (g.pa - g.pb);
+            ps = madd(g.pa, -m_sub, n);
+            pt = madd(g.pb, m_tgt, n);
+            d = g.d - m_sub - m_tgt;
+        }
+        dist[o] = d;
+        if (valid_out != nullptr) valid_out[o] = g.overlap ? 0 : 1;
+        if (p_subject != nullptr) { p_subject[o * 3 + 0] = ps.x; p_subject[o * 3 + 1] = ps.y; p_subject[o * 3 + 2] = ps.z; }
+        if (p_target != nullptr) { p_target[o * 3 + 0] = pt.x; p_target[o * 3 + 1] = pt.y; p_target[o * 3 + 2] = pt.z; }
+        if (normal != nullptr) { normal[o * 3 + 0] = n.x; normal[o * 3 + 1] = n.y; normal[o * 3 + 2] = n.z; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Bisection towards the collision boundary (IRIS "zero-order hold" counter-example search, reference
 // numbotics/planning/safe_sets.py:124-134): per sample an interval [lo, hi] in configuration space, lo free, hi
 // colliding; each round tests the midpoint and keeps the half that still straddles the boundary.  Interval
@@ -1159,6 +1268,27 @@ int launch_closest(const nbx_chain* ch, const nbx_scene* sc, const float* q, int
     return NBX_OK;
 }
 
+int launch_pair_distances(const nbx_chain* ch, const nbx_scene* sc, const float* q, int64_t B, const double* base_pose,
+                          float* dist, float* p_subject, float* p_target, float* normal, uint8_t* valid, cudaStream_t stream) {
+    SceneDev S;
+    int rc = fill_scene_dev(ch, sc, base_pose, S);
+    if (rc != NBX_OK) return rc;
+    NBX_REQUIRE(B >= 0, "negative batch size");
+    if (B == 0 || sc->n_self + sc->n_env == 0) return NBX_OK;
+    NBX_REQUIRE(q != nullptr && dist != nullptr, "q / distance is NULL");
+    NBX_CUDA_OK(cudaSetDevice(ch->device));
+    const size_t smem = scene_smem_bytes(S.n_mov, S.n_prims, S.n_obs, S.n_self, S.n_env) +
+                        kWarps * align16(sizeof(float) * (size_t)kWT * std::max(S.scratch_floats, 1));
+    NBX_REQUIRE(smem <= 220 * 1024, "scene too large for shared memory (%zu bytes)", smem);
+    NBX_CUDA_OK(cudaFuncSetAttribute(pair_distances_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t grid = (B + kWarps * kWT - 1) / (kWarps * kWT);
+    NBX_REQUIRE(grid <= 0x7fffffffLL, "batch too large for one launch");
+    pair_distances_kernel<<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, q, B, ch->dof, dist, p_subject, p_target, normal, valid);
+    nbx_count_launch();
+    NBX_CUDA_OK(cudaGetLastError());
+    return NBX_OK;
+}
+
 template <typename T>
 int launch_bisect(const nbx_chain* ch, const nbx_scene* sc, const T* inside, int64_t inside_stride, const T* outside, int64_t B,
                   const double* base_pose, int n_bisections, float thr, T* out, cudaStream_t stream) {
@@ -1250,6 +1380,13 @@ int nbx_closest_f32(const nbx_chain* chain, const nbx_scene* scene, const float*
                     int32_t* subject_prim, int32_t* target, uint8_t* valid, float* gradient, void* stream) {
     return launch_closest(chain, scene, q, B, base_pose, distance, position_on_subject, position_on_target, normal_target_to_subject,
                           subject_prim, target, valid, gradient, static_cast<cudaStream_t>(stream));
+}
+
+int nbx_pair_distances_f32(const nbx_chain* chain, const nbx_scene* scene, const float* q, int64_t B, const double* base_pose,
+                           float* distance, float* position_on_subject, float* position_on_target, float* normal_target_to_subject,
+                           uint8_t* valid, void* stream) {
+    return launch_pair_distances(chain, scene, q, B, base_pose, distance, position_on_subject, position_on_target,
+                                 normal_target_to_subject, valid, static_cast<cudaStream_t>(stream));
 }
 
 int nbx_bisect_f32(const nbx_chain* chain, const nbx_scene* scene, const float* inside, int64_t inside_stride, const float* outside,

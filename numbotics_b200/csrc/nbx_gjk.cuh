@@ -280,7 +280,14 @@ __device__ GjkWit gjk_witness(const ShapeW& A, const ShapeW& B) {
     for (int it = 0; it < MAX_ITER; ++it) {
         const V3 sa = support(A, -v);
         const V3 sw = sa - support(B, v);
-        if (best_vv < FLT_MAX && vv - dot(v, sw) <= 1e-7f * vv) break;      // no support point beyond the current plane
+        const float vw = dot(v, sw);
+        if (best_vv < FLT_MAX) {
+            if (vv - vw <= 1e-7f * vv) break;                                // no support point beyond the current plane
+            // bracket [v.w / |v|, |v|] closed: stop BEFORE the simplex degenerates (continuing past convergence is what
+            // produces flat tetrahedra and false overlaps)
+            const float ubd = sqrtf(vv);
+            if (vw > 0.f && ubd - vw / ubd <= 1e-6f + 1e-5f * ubd) break;
+        }
         // append the new vertex at index n (n <= 3 here)
 #pragma unroll
         for (int i = 0; i < 4; ++i) if (i == n) { w[i] = sw; a[i] = sa; }

@@ -553,6 +553,75 @@ class Arm:
             dist = dist.reshape(shape) if not single else dist.reshape(())
         return verdict, dist
 
+    # ------------------------------------------------------------------ every allowed pair
+    def pair_distances(self, q, points: bool = False):
+        """Batched `Arm.collisions` (reference arm.py:555-580): one proximity per allowed pair and configuration.
+
+        Returns `(pairs, distance)` with `pairs` the list of `(subject, target)` objects (self pairs first) and
+        `distance (..., P)`; with `points=True` a `Proximities`-like dict of arrays
+        `{distance, position_on_subject, position_on_target, normal_target_to_subject, valid}` of shape `(..., P[, 3])`.
+        """
+        self._check_q(q)
+        in_torch = _is_torch(q)
+        q_shape = tuple(q.shape)
+        single = len(q_shape) == 1
+        B = int(np.prod(q_shape[:-1])) if not single else 1
+        scene = self._scene(0.0, exact_distance=True)
+        arrays = self._scene_arrays
+        link_of_prim = {p: l for l, p in self._arrays["prim_of_link"].items()}
+        obstacles = arrays["obstacles"]
+        pairs = [(link_of_prim[int(a)], link_of_prim[int(b)]) for a, b in arrays["self_pairs"]]
+        pairs += [(link_of_prim[int(a)], obstacles[int(o)]) for a, o in arrays["env_pairs"]]
+        P = len(pairs)
+        if P == 0:
+            raise ValueError("min() arg is an empty sequence")
+        dev_index = self.device_index
+        base_keep, base_ptr = _cabi.base_pose_arg(self.base_pose)
+        qd = self._to_device(q, torch.float32).reshape(B, self.dof)
+        lib = _cabi.load()
+        with torch.cuda.device(dev_index):
+            f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=qd.device)
+            dist = f(B, P)
+            ps, pt, nrm = (f(B, P, 3), f(B, P, 3), f(B, P, 3)) if points else (None, None, None)
+            ok = torch.empty((B, P), dtype=torch.uint8, device=qd.device) if points else None
+            _cabi.check(lib.nbx_pair_distances_f32(
+                self._handle().ptr, scene.ptr, qd.data_ptr(), B, base_ptr, dist.data_ptr(),
+                ps.data_ptr() if points else None, pt.data_ptr() if points else None, nrm.data_ptr() if points else None,
+                ok.data_ptr() if points else None, _cuda_stream_ptr(dev_index)))
+        del base_keep
+        if in_torch:
+            conv = lambda x: x.to(q.device)
+        else:
+            out_dt = q.dtype if getattr(q, "dtype", None) in (np.float32, np.float64) else np.float64
+            conv = lambda x: x.cpu().numpy().astype(out_dt, copy=False) if x.dtype == torch.float32 else x.cpu().numpy()
+        shape = q_shape[:-1]
+        dist_o = conv(dist).reshape(*shape, P)
+        if not points:
+            return pairs, dist_o
+        return pairs, {"distance": dist_o, "position_on_subject": conv(ps).reshape(*shape, P, 3),
+                       "position_on_target": conv(pt).reshape(*shape, P, 3),
+                       "normal_target_to_subject": conv(nrm).reshape(*shape, P, 3), "valid": conv(ok.to(torch.bool)).reshape(*shape, P)}
+
+    def collisions(self, q):
+        """reference arm.py:555-580 for one configuration: the list of `Proximity` records of every allowed pair."""
+        if tuple(q.shape) != (self.dof,):
+            raise ValueError(f"q must be a 1D array with {self.dof} elements")
+        pairs, rec = self.pair_distances(q, points=True)
+        host = lambda x: x.cpu().numpy() if _is_torch(x) else x
+        d, ps, pt, n = (host(rec[k]) for k in ("distance", "position_on_subject", "position_on_target", "normal_target_to_subject"))
+        return [Proximity(subject=s_, target=t_, position_on_subject=ps[i], position_on_target=pt[i],
+                          normal_target_to_subject=n[i], distance=float(d[i])) for i, (s_, t_) in enumerate(pairs)]
+
+    def distance_to(self, q, obj, link=None):
+        """reference arm.py:607-618: the proximities between the arm (or one `link`) and `obj`, one configuration."""
+        prox = [p for p in self.collisions(q) if p.target is obj or p.subject is obj]
+        if link is None:
+            return prox
+        out = [p for p in prox if p.subject is link or p.target is link]
+        if not out:
+            raise ValueError(f"Collision pair ({link.name}, {obj.name}) not valid")
+        return out
+
     # ------------------------------------------------------------------ closest pair, witness points, distance gradient
     def closest_to(self, q, gradient: bool = False):
         """Batched `Arm.closest_to` (reference arm.py:599-600): the allowed pair with the smallest distance.

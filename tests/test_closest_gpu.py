@@ -106,3 +106,44 @@ def test_single_configuration_and_types(scene, cuda):
     assert np.abs(arm.min_distance(q.astype(np.float32)) - batch.distance.astype(np.float32))[batch.valid].max() < 2e-5
     with pytest.raises(ValueError, match="q must have 7 elements"):
         arm.closest_to(np.zeros((3, 6)))
+
+
+def test_pair_distances_every_allowed_pair(scene):
+    """Batched Arm.collisions: the (B, P) distance matrix against the oracle's, pair by pair, and the single-configuration
+    list of Proximity records (reference robots/arm.py:555-580)."""
+    arm, so = scene
+    q = workloads.random_configs_np(arm, 6000, seed=24).astype(np.float32)
+    pairs, d = arm.pair_distances(q)
+    pd = so.pair_distances(q.astype(np.float64))
+    assert d.shape == pd.shape == (6000, len(pairs)) and d.dtype == np.float32
+    # same pairs, possibly in another order: match columns by (subject, target) objects
+    link_index = {l: i for i, l in enumerate(so.links)}
+    obj_index = {o: so.n_link + i for i, o in enumerate(so.objs)}
+    col = {}
+    for c, (a, b) in enumerate(so.pairs):
+        col[(int(a), int(b))] = c
+        col[(int(b), int(a))] = c
+    order = [col[(link_index[s_], link_index[t_] if t_ in link_index else obj_index[t_])] for s_, t_ in pairs]
+    assert sorted(order) == list(range(len(pairs)))
+    ref = pd[:, order]
+    sep = ref > 1e-3
+    assert sep.mean() > 0.9
+    assert (np.abs(d[sep] - ref[sep]) / np.maximum(ref[sep], 1.0)).max() < 1e-4      # fp32: 1e-4 m, relative beyond 1 m
+    assert (d[ref < -0.02] < 0).all()
+    # the minimum over the pairs is the distance query; the arg-min is the closest pair
+    md = arm.min_distance(q)
+    assert np.abs(d.min(axis=1) - md)[md > 1e-3].max() < 1e-4
+    # one configuration -> list of Proximity, witness points consistent with the distances
+    prox = arm.collisions(q[0])
+    assert len(prox) == len(pairs) and all(isinstance(p, Proximity) for p in prox)
+    for p, (s_, t_), dd in zip(prox, pairs, d[0]):
+        assert p.subject is s_ and p.target is t_ and abs(p.distance - dd) < 1e-6
+        if dd > 1e-3:
+            assert abs(np.linalg.norm(p.position_on_subject - p.position_on_target) - dd) < 1e-4
+    cube = so.objs[0]
+    to_cube = arm.distance_to(q[0], cube)
+    assert len(to_cube) == sum(1 for _, t_ in pairs if t_ is cube) and all(p.target is cube for p in to_cube)
+    one = arm.distance_to(q[0], cube, link=to_cube[0].subject)
+    assert len(one) == 1 and one[0].distance == to_cube[0].distance
+    with pytest.raises(ValueError, match="q must be a 1D array with 7 elements"):
+        arm.collisions(q[:2])
