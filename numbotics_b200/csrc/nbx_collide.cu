@@ -1,21 +1,18 @@
-// nbx_collide.cu -- batched Arm.in_collision and DiscreteConnector edge validation for sm_100a.
+// nbx_collide.cu -- collision queries for sm_100a: batched Arm.in_collision, DiscreteConnector edge validation, minimum
+// distance, closest pair with witness points and distance gradient, all-pairs proximities, IRIS bisection.
 //
-// Replaces reference numbotics/robots/arm.py:555-604 (collisions / closest_to / in_collision:
-// one PyBullet state reset + getClosestPoints sweep per configuration) and
-// numbotics/planning/sampling_based/connectors.py:57-100 (connect / steer: a Python loop of
-// validity_checker calls along a linear trajectory).
+// Replaces reference numbotics/robots/arm.py:555-632 (collisions / closest_to / in_collision / distance_to /
+// jacobian_proximity: one PyBullet state reset + getClosestPoints sweep per configuration),
+// numbotics/planning/sampling_based/connectors.py:57-100 (connect / steer: a Python loop of validity_checker calls along a
+// linear trajectory) and numbotics/planning/safe_sets.py:124-134 (bisection towards the contact boundary).
 //
-// One thread evaluates one configuration: it walks the whole kinematic tree once (all link
-// frames, not just one path), turns each link primitive into a world-space core as soon as its
-// frame is known, and immediately tests it against the obstacles and the earlier primitives it
-// is paired with.  Primitive poses that later pairs need are parked in a per-thread shared-memory
-// scratch laid out [value][thread] (bank-conflict free).  The scene (tree, primitives,
-// obstacles, pair lists; a few KB) is staged in shared memory once per CTA and read with
-// warp-uniform addresses.  FP32-FMA bound; HBM traffic is 4*dof bytes in + 1 byte out.
-//
-// The edge kernel flattens the (edge, sample) space of a CTA's edges with a block prefix sum so
-// every lane always has an interpolation sample to evaluate (no idle lanes on short edges) and
-// edges that are already known invalid are skipped.
+// Common structure: a warp owns a contiguous range of units and works through it in tiles of 32
+// items, lane = item.  The lane walks the whole kinematic tree once (all link frames, not just one path), parks every link
+// primitive's world-space core in the warp's shared-memory scratch [value][lane] (bank-conflict free) and runs the cheap
+// conservative culls on every allowed pair; the scene (tree, primitives, obstacles, pair lists; a few KB) is staged in
+// shared memory once per CTA and read with warp-uniform addresses.  Survivors go through the GJK narrow phase -- in a
+// second kernel over a global queue for verdict queries, in the same warp for distance queries.  Issue-bound; HBM traffic
+// is 4*dof bytes in + 1 byte out per configuration plus the candidate queue.
 #include "nbx_common.cuh"
 #include "nbx_gjk.cuh"
 #include "nbx_joint.cuh"

@@ -4,7 +4,11 @@
 // nb_compute_transformation, nb_compute_jacobian) and the arithmetic around them in
 // numbotics/robots/arm.py:394-406, 451-457.
 //
-// Design:
+// This file: the dispatcher (dense <= 8 joints -> wide 9..32 joints -> deep -> legacy generic), the deep and legacy generic
+// kernels, the host-buffer pipeline and the C-ABI entry points.  The dense kernel lives in nbx_fkjac_dense.cuh, the wide
+// kernels in nbx_fkjac_wide.inc.
+//
+// Design of the dense kernel:
 //   * one thread per configuration, one CTA per tile of TILE consecutive configurations;
 //   * the path descriptor (pre-folded Rodrigues constants A, Bm, Cm, t per joint) is a
 //     __grid_constant__ kernel parameter: it sits in constant bank 0, so every joint constant
