@@ -236,6 +236,18 @@ NBX_API int nbx_bisect_f64(const nbx_chain* chain, const nbx_scene* scene, const
                    double* out, void* stream);
 
 /*
+ * Exact k nearest neighbours in L2 (float32, brute force): the faiss IndexFlatL2.search behind
+ * ApproximateNearestNeighborsIndex.query / k_nearest (numbotics/math/geometry/nearest_neighbors.py:55-85) as the PRM loop
+ * uses it (numbotics/planning/sampling_based/planners/prm.py:35-40).
+ *   refs (n_refs, dof), queries (n_queries, dof) device, dof <= 64, k <= 32;
+ *   causal != 0: queries and refs are the same vertex list and query i only sees refs j < i (incremental roadmap);
+ *   idx (n_queries, k) int64 sorted by distance (ties: lower index first), valid (n_queries, k) u8 nullable (0 where fewer
+ *   than k references exist), dist2 (n_queries, k) squared distances, nullable.
+ */
+NBX_API int nbx_knn_f32(const float* refs, int64_t n_refs, const float* queries, int64_t n_queries, int dof, int k,
+                int causal, int64_t* idx, uint8_t* valid, float* dist2, int device, void* stream);
+
+/*
  * Batched damped-least-squares inverse kinematics: the reference's whole iteration loop
  * (numbotics/robots/arm.py:464-552, Arm.inverse_kinematics) on the device, one problem per thread.
  *   target_pose (B,4,4) or (4,4) device; target_stride = 16 or 0 (broadcast)

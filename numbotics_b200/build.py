@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libnbx.so")
 STAMP = os.path.join(LIB_DIR, "libnbx.stamp")
-SOURCES = ["nbx_fkjac_wide_a.cu", "nbx_fkjac_wide_b.cu", "nbx_api.cu", "nbx_fkjac.cu", "nbx_collide.cu", "nbx_ik.cu"]
+SOURCES = ["nbx_fkjac_wide_a.cu", "nbx_fkjac_wide_b.cu", "nbx_api.cu", "nbx_fkjac.cu", "nbx_collide.cu", "nbx_ik.cu", "nbx_knn.cu"]
 HEADERS = ["nbx_common.cuh", "nbx_gjk.cuh", "nbx_joint.cuh", "nbx_fkjac_dense.cuh", "nbx_fkjac_wide.inc"]
 
 NVCC_FLAGS = [

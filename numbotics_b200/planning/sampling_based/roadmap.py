@@ -61,24 +61,22 @@ class Roadmap:
 
 
 def knn_earlier(nodes, k: int, chunk: int = 4096):
-    """For every vertex i > 0 its (up to) k nearest vertices among 0..i-1 (the reference's incremental kNN).
-    Returns (idx (N,k) int64, valid (N,k) bool)."""
-    N = nodes.shape[0]
-    idx = torch.zeros((N, k), dtype=torch.long, device=nodes.device)
-    ok = torch.zeros((N, k), dtype=torch.bool, device=nodes.device)
-    sq = (nodes * nodes).sum(-1)
-    cols = torch.arange(N, device=nodes.device)
-    for s in range(0, N, chunk):
-        e = min(s + chunk, N)
-        hi = e                                       # rows s..e-1 only look at columns < e
-        d2 = sq[s:e, None] - 2.0 * nodes[s:e] @ nodes[:hi].T + sq[None, :hi]
-        rows = torch.arange(s, e, device=nodes.device)
-        d2 = torch.where(cols[None, :hi] < rows[:, None], d2, torch.full_like(d2, float("inf")))
-        kk = min(k, hi)
-        val, ind = torch.topk(d2, kk, dim=1, largest=False)
-        idx[s:e, :kk] = ind
-        ok[s:e, :kk] = torch.isfinite(val)
-    return idx, ok
+    """For every vertex i > 0 its (up to) k nearest vertices among 0..i-1 (the reference's incremental kNN:
+    `ApproximateNearestNeighborsIndex.k_nearest` before `add_point`, planners/prm.py:35-40), exact L2, one kernel launch
+    (`nbx_knn_f32`, causal mode).  Returns (idx (N,k) int64 sorted by distance, valid (N,k) bool).  `chunk` is ignored
+    (kept for the signature of the earlier torch implementation)."""
+    from ... import _cabi
+    if not nodes.is_cuda:
+        raise ValueError("knn_earlier needs a CUDA tensor: numbotics_b200 has no CPU path")
+    x = nodes.to(torch.float32).contiguous()
+    N, dof = x.shape
+    idx = torch.empty((N, k), dtype=torch.long, device=x.device)
+    ok = torch.empty((N, k), dtype=torch.uint8, device=x.device)
+    lib = _cabi.load()
+    with torch.cuda.device(x.device):
+        _cabi.check(lib.nbx_knn_f32(x.data_ptr(), N, x.data_ptr(), N, dof, int(k), 1, idx.data_ptr(), ok.data_ptr(), None,
+                                    x.device.index, torch.cuda.current_stream(x.device).cuda_stream))
+    return idx, ok.to(torch.bool)
 
 
 class BatchedPRM:

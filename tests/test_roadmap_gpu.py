@@ -9,19 +9,58 @@ from oracle import collision
 pytestmark = pytest.mark.gpu
 
 
-def test_knn_earlier_matches_bruteforce(cuda):
+@pytest.mark.parametrize("N,dof,k", [(700, 7, 5), (1500, 7, 10), (900, 3, 16), (600, 30, 20), (400, 64, 32), (5, 7, 10)])
+def test_knn_earlier_matches_bruteforce(cuda, N, dof, k):
+    """Exact L2 kNN among the EARLIER vertices (the reference's incremental index): every row against NumPy."""
     import torch
-    x = torch.rand((700, 7), device=cuda)
-    idx, ok = knn_earlier(x, 5, chunk=256)
+    g = torch.Generator(device=cuda); g.manual_seed(N + dof)
+    x = torch.rand((N, dof), device=cuda, generator=g)
+    idx, ok = knn_earlier(x, k)
+    assert idx.shape == (N, k) and idx.dtype == torch.long and ok.dtype == torch.bool
     xn = x.cpu().numpy().astype(np.float64)
-    for i in (0, 1, 3, 5, 6, 100, 699):
-        if i == 0:
-            assert not ok[0].any()
-            continue
+    idx_h, ok_h = idx.cpu().numpy(), ok.cpu().numpy()
+    assert not ok_h[0].any()
+    for i in range(1, N):
         d = np.linalg.norm(xn[:i] - xn[i], axis=1)
-        want = set(np.argsort(d)[: min(5, i)].tolist())
-        got = set(idx[i][ok[i]].cpu().numpy().tolist())
-        assert got == want and int(ok[i].sum()) == min(5, i)
+        n = min(k, i)
+        assert int(ok_h[i].sum()) == n and ok_h[i, :n].all()
+        got = idx_h[i, :n]
+        assert len(set(got.tolist())) == n and got.max() < i
+        # same distances as the true k smallest (sets can differ only between fp32-equal distances), ascending order
+        assert np.allclose(np.sort(d)[:n], d[got], rtol=0, atol=1e-6)
+        assert np.all(np.diff(d[got]) >= -1e-6)
+
+
+def test_nearest_neighbors_index_mirror(cuda):
+    """`ApproximateNearestNeighborsIndex` (reference math/geometry/nearest_neighbors.py:6-85): ids, removal, shapes."""
+    from numbotics_b200.math.geometry import ApproximateNearestNeighborsIndex
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(-1, 1, size=(500, 7))
+    index = ApproximateNearestNeighborsIndex(7)
+    assert len(index) == 0
+    ids = index.add_points(pts[:400])
+    assert ids == list(range(400)) and index.add_point(pts[400]) == 400 and len(index) == 401
+    q = rng.uniform(-1, 1, size=7)
+    d = np.linalg.norm(pts[:401] - q, axis=1)
+    item, label = index.nearest(q, return_labels=True)
+    assert label == int(np.argmin(d)) and np.array_equal(item, pts[label]) and item.shape == (7,)
+    items, labels = index.k_nearest(q, 6, return_labels=True)
+    assert labels.tolist() == np.argsort(d)[:6].tolist() and items.shape == (6, 7)
+    index.remove_points(labels[:3].tolist())
+    assert len(index) == 398
+    items2, labels2 = index.k_nearest(q, 3, return_labels=True)
+    assert labels2.tolist() == np.argsort(d)[3:6].tolist()          # ids survive the removal
+    lab, d2 = index.query_batch(pts[450:470], 4)
+    assert lab.shape == (20, 4) and d2.shape == (20, 4) and np.all(np.diff(d2, axis=1) >= 0)
+    with pytest.raises(ValueError, match="does not match index dimension"):
+        index.add_points(np.zeros((2, 6)))
+    with pytest.raises(ValueError, match="Query dimension 6 does not match index dimension 7"):
+        index.query(np.zeros(6))
+    with pytest.raises(ValueError, match="Point should be a 1D array"):
+        index.add_point(np.zeros((2, 7)))
+    small = ApproximateNearestNeighborsIndex(7)
+    small.add_points(pts[:2])
+    assert small.k_nearest(q, 5).shape == (2, 7)                     # k is clipped to the number of points
 
 
 def test_roadmap_equals_sequential_prm_loop(cuda):
