@@ -9,7 +9,7 @@
 // shared-memory loads per 8 dimensions plus 2 flops per dimension.  A candidate enters the list only if it beats the current
 // worst entry (after the first few hundred candidates that is rare: ~k ln(N/k) insertions per query), by a branch-free
 // bubble pass over the statically indexed list.  `causal` restricts query i to references j < i (the incremental roadmap);
-// CTAs are launched heaviest first.  FP32-issue bound: N^2/2 * ~20 instructions for the roadmap of N vertices.
+// the triangular work is balanced by pairing heavy and light query blocks in one CTA.  FP32-issue bound: N^2/2 * ~20 instructions for the roadmap of N vertices.
 #include "nbx_common.cuh"
 #include <float.h>
 
@@ -24,8 +24,17 @@ knn_kernel(const float* __restrict__ refs, int64_t n_refs, const float* __restri
            int causal, int64_t* __restrict__ idx_out, uint8_t* __restrict__ valid_out, float* __restrict__ d2_out) {
     constexpr int kKnnTile = kKnnTileFloats / D;
     __shared__ __align__(16) float tile[kKnnTile * D];
-    const int64_t nblocks = gridDim.x;
-    const int64_t qb = (nblocks - 1 - (int64_t)blockIdx.x) * kKnnThreads;     // heaviest (latest) queries first
+    // Causal mode is triangular (query i scans i references): a CTA takes the query blocks b and nblocks - 1 - b, one after
+    // the other, so that every CTA scans the same number of references (one wave of CTAs, all of the same length).
+    const int64_t nblocks = (n_q + kKnnThreads - 1) / kKnnThreads;
+    const int passes = causal ? 2 : 1;
+    for (int pass = 0; pass < passes; ++pass) {
+    int64_t blk = (int64_t)blockIdx.x;
+    if (causal) {
+        blk = pass == 0 ? nblocks - 1 - (int64_t)blockIdx.x : (int64_t)blockIdx.x;
+        if (pass == 1 && blk >= nblocks - 1 - (int64_t)blockIdx.x) break;     // odd count: the middle block was pass 0
+    }
+    const int64_t qb = blk * kKnnThreads;
     const int64_t qi = qb + threadIdx.x;
     const bool have = qi < n_q;
     float qv[D];
@@ -49,16 +58,17 @@ knn_kernel(const float* __restrict__ refs, int64_t n_refs, const float* __restri
         __syncthreads();
         if (!have) continue;
         const int lim = (int)max((int64_t)0, min((int64_t)nt, my_end - r0));
-#pragma unroll 2
+#pragma unroll 4
         for (int r = 0; r < lim; ++r) {
             const float4* t4 = reinterpret_cast<const float4*>(tile + r * D);
-            float d2 = 0.f;
+            float da = 0.f, db = 0.f;          // two partial sums: half the dependent FFMA chain
 #pragma unroll
             for (int d = 0; d < D / 4; ++d) {
                 const float4 c = t4[d];
                 const float e0 = qv[4 * d] - c.x, e1 = qv[4 * d + 1] - c.y, e2 = qv[4 * d + 2] - c.z, e3 = qv[4 * d + 3] - c.w;
-                d2 = fmaf(e0, e0, d2); d2 = fmaf(e1, e1, d2); d2 = fmaf(e2, e2, d2); d2 = fmaf(e3, e3, d2);
+                da = fmaf(e0, e0, da); db = fmaf(e1, e1, db); da = fmaf(e2, e2, da); db = fmaf(e3, e3, db);
             }
+            const float d2 = da + db;
             if (d2 < worst) {
                 float cd = d2;
                 int ci = (int)(r0 + r);
@@ -78,22 +88,25 @@ knn_kernel(const float* __restrict__ refs, int64_t n_refs, const float* __restri
             }
         }
     }
-    if (!have) return;
+    if (have) {
 #pragma unroll
-    for (int s = 0; s < K; ++s) {
-        if (s < k) {
-            const bool ok = bi[s] >= 0;
-            idx_out[qi * k + s] = ok ? (int64_t)bi[s] : 0;
-            if (valid_out != nullptr) valid_out[qi * k + s] = ok ? 1 : 0;
-            if (d2_out != nullptr) d2_out[qi * k + s] = ok ? bd[s] : INFINITY;
+        for (int s = 0; s < K; ++s) {
+            if (s < k) {
+                const bool ok = bi[s] >= 0;
+                idx_out[qi * k + s] = ok ? (int64_t)bi[s] : 0;
+                if (valid_out != nullptr) valid_out[qi * k + s] = ok ? 1 : 0;
+                if (d2_out != nullptr) d2_out[qi * k + s] = ok ? bd[s] : INFINITY;
+            }
         }
     }
+    }   // pass
 }
 
 template <int D>
 int launch_knn_d(const float* refs, int64_t n_refs, const float* queries, int64_t n_q, int dof, int k, int causal,
                  int64_t* idx, uint8_t* valid, float* d2, cudaStream_t stream) {
-    const int64_t grid = (n_q + kKnnThreads - 1) / kKnnThreads;
+    const int64_t nblocks = (n_q + kKnnThreads - 1) / kKnnThreads;
+    const int64_t grid = causal ? (nblocks + 1) / 2 : nblocks;      // causal: two query blocks per CTA (see the kernel)
     NBX_REQUIRE(grid <= 0x7fffffffLL, "too many queries for one launch");
     if (k <= 16) knn_kernel<D, 16><<<(unsigned)grid, kKnnThreads, 0, stream>>>(refs, n_refs, queries, n_q, dof, k, causal, idx, valid, d2);
     else knn_kernel<D, 32><<<(unsigned)grid, kKnnThreads, 0, stream>>>(refs, n_refs, queries, n_q, dof, k, causal, idx, valid, d2);
