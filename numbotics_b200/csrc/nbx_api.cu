@@ -6,6 +6,7 @@
 #include <cstring>
 #include <cmath>
 #include <algorithm>
+#include <mutex>
 #include <new>
 
 namespace {
@@ -21,6 +22,31 @@ void nbx_set_error(const char* fmt, ...) {
 }
 
 void nbx_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// The library's own memory pool per device, with an unbounded release threshold: the default pool hands its memory
+// back to the driver at every synchronisation, which turned each call's 100+ MB workspace into a ~10 ms allocation.
+int nbx_workspace_pool(int device, cudaMemPool_t* out) {
+    static std::mutex mu;
+    static cudaMemPool_t pools[64] = {};
+    NBX_REQUIRE(device >= 0 && device < 64, "device index out of range");
+    std::lock_guard<std::mutex> lock(mu);
+    if (pools[device] == nullptr) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaMemPool_t pool = nullptr;
+        NBX_CUDA_OK(cudaMemPoolCreate(&pool, &props));
+        uint64_t keep = ~0ull;
+        NBX_CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        pools[device] = pool;
+    }
+    *out = pools[device];
+    return NBX_OK;
+}
+
+
 
 namespace {
 

@@ -1113,29 +1113,6 @@ int units_per_warp(int64_t n_units, int sm_count, int warps_per_sm, int waves = 
     return (int)u * kWT;
 }
 
-// The library's own memory pool per device, with an unbounded release threshold: the default pool hands its memory
-// back to the driver at every synchronisation, which turned each call's 100+ MB workspace into a ~10 ms allocation.
-int workspace_pool(int device, cudaMemPool_t* out) {
-    static std::mutex mu;
-    static cudaMemPool_t pools[64] = {};
-    NBX_REQUIRE(device >= 0 && device < 64, "device index out of range");
-    std::lock_guard<std::mutex> lock(mu);
-    if (pools[device] == nullptr) {
-        cudaMemPoolProps props = {};
-        props.allocType = cudaMemAllocationTypePinned;
-        props.handleTypes = cudaMemHandleTypeNone;
-        props.location.type = cudaMemLocationTypeDevice;
-        props.location.id = device;
-        cudaMemPool_t pool = nullptr;
-        NBX_CUDA_OK(cudaMemPoolCreate(&pool, &props));
-        uint64_t keep = ~0ull;
-        NBX_CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-        pools[device] = pool;
-    }
-    *out = pools[device];
-    return NBX_OK;
-}
-
 // stream-ordered workspace of a verdict query: the global queue and its two counters
 struct SplitWs {
     void* p = nullptr;
@@ -1144,7 +1121,7 @@ struct SplitWs {
     int alloc(int device, int64_t n_items, cudaStream_t stream) {
         st = stream;
         cudaMemPool_t pool = nullptr;
-        int rc = workspace_pool(device, &pool);
+        int rc = nbx_workspace_pool(device, &pool);
         if (rc != NBX_OK) return rc;
         // ~0.3 candidates per item on random PRM configurations, ~3 on contact-seeking workloads (IRIS bisection rounds);
         // what does not fit is evaluated in place by the broad kernel (correct, but several times slower)
@@ -1241,7 +1218,7 @@ int launch_closest(const nbx_chain* ch, const nbx_scene* sc, const float* q, int
     NBX_REQUIRE(grad == nullptr || ch->n_mov <= 64, "distance gradients support chains of at most 64 movable joints");
     NBX_CUDA_OK(cudaSetDevice(ch->device));
     cudaMemPool_t pool = nullptr;
-    int rc = workspace_pool(ch->device, &pool);
+    int rc = nbx_workspace_pool(ch->device, &pool);
     if (rc != NBX_OK) return rc;
     struct Tmp { void* p = nullptr; cudaStream_t st = nullptr; ~Tmp() { if (p) cudaFreeAsync(p, st); } } tmp;
     tmp.st = stream;
@@ -1301,7 +1278,7 @@ int launch_bisect(const nbx_chain* ch, const nbx_scene* sc, const T* inside, int
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t bytes = 2 * up(sizeof(double) * n) + up(sizeof(float) * n) + up((size_t)B);
     cudaMemPool_t pool = nullptr;
-    int rc = workspace_pool(ch->device, &pool);
+    int rc = nbx_workspace_pool(ch->device, &pool);
     if (rc != NBX_OK) return rc;
     struct Tmp { void* p = nullptr; cudaStream_t st = nullptr; ~Tmp() { if (p) cudaFreeAsync(p, st); } } tmp;
     tmp.st = stream;
@@ -1331,7 +1308,7 @@ struct HostStage {
     cudaStream_t st = nullptr;
     int open(int device, size_t bytes) {
         cudaMemPool_t pool = nullptr;
-        int rc = workspace_pool(device, &pool);
+        int rc = nbx_workspace_pool(device, &pool);
         if (rc != NBX_OK) return rc;
         NBX_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         NBX_CUDA_OK(cudaMallocFromPoolAsync(&p, bytes, pool, st));

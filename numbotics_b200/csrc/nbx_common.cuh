@@ -11,6 +11,8 @@
 // ---------------------------------------------------------------------------------------------
 void nbx_set_error(const char* fmt, ...);
 void nbx_count_launch(int n = 1);
+// library-owned stream-ordered memory pool of a device (unbounded release threshold); see nbx_api.cu
+int nbx_workspace_pool(int device, cudaMemPool_t* out);
 
 #define NBX_CUDA_OK(expr)                                                                    \
     do {                                                                                     \

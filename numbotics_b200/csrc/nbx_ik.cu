@@ -13,7 +13,8 @@
 //         worse = |diff'| > |diff| ; lambda *= worse ? 1.2 : 0.5               arm.py:539-542
 //         failures = worse ? failures + 1 : 0                                  arm.py:544-545
 //
-// Registers stay O(1) in the chain depth: the Jacobian is never stored.  Each iteration walks the path
+// Lanes are persistent: a finished problem is retired and the next one fetched, so every trip through the loop is one
+// uniform iteration for all lanes (see the kernel).  Registers stay O(1) in the chain depth: the Jacobian is never stored.  Each iteration walks the path
 // twice: walk A accumulates the 21 entries of J J^T column by column (column i needs only p_e of the
 // current q, known from the previous walk); walk B re-derives column i, applies dq_i = col_i . x, and
 // advances a second pose with the UPDATED q_i, so it ends with FK(q_new) -- which is exactly what the
@@ -22,6 +23,7 @@
 #include "nbx_common.cuh"
 #include "nbx_joint.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 using namespace nbxj;
 
@@ -113,105 +115,138 @@ __device__ __forceinline__ void chol_solve6(T* L, const T* b, T* x) {
 #undef LI
 }
 
+// Persistent lanes.  Problems need 1..max_iter iterations (mean ~10 on the Kinova), so "one thread runs its problem to the
+// end" left a warp waiting for its slowest lane (~40 % lane utilisation).  Here a lane that finishes retires its problem and
+// fetches the next one from a global counter (one warp-aggregated atomic), and every trip through the loop is ONE uniform
+// iteration for all lanes whatever their iteration number.  A freshly loaded problem spends its first trip as a degenerate
+// iteration with x = 0: walk B then leaves q untouched and returns FK(q0), the error the reference computes before its
+// loop -- so loading costs no divergent code beyond the copies themselves.  Results do not depend on the schedule.
 template <typename T>
 __global__ void __launch_bounds__(kIkTile)
 ik_dls_kernel(const __grid_constant__ PathK<T, NBX_MAX_PATH> P, const __grid_constant__ IkParams<T> K,
               const T* __restrict__ target, int64_t target_stride, const T* __restrict__ q0, int64_t B,
-              T* __restrict__ q_out, uint8_t* __restrict__ success, int32_t* __restrict__ iters_out) {
+              T* __restrict__ q_out, uint8_t* __restrict__ success, int32_t* __restrict__ iters_out,
+              unsigned long long* __restrict__ next) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* sq = reinterpret_cast<T*>(smem_raw);          // [kIkTile][dof]
     const int dof = P.dof, n = P.n;
-    const int64_t tile0 = (int64_t)blockIdx.x * kIkTile;
-    const int nvalid = (int)min((int64_t)kIkTile, B - tile0);
-    const int tid = threadIdx.x;
-    for (int i = tid; i < nvalid * dof; i += kIkTile) sq[i] = q0[tile0 * dof + i];
-    __syncthreads();
-
-    int it = 0;
-    bool ok = false;
-    if (tid < nvalid) {
-        T* myq = sq + tid * dof;
-        const T* tg = target + (tile0 + tid) * target_stride;
-        T Rt[9], pt[3];
+    const int lane = threadIdx.x & 31;
+    T* myq = reinterpret_cast<T*>(smem_raw) + (size_t)threadIdx.x * dof;     // this lane's configuration
+    auto reset = [&](Pose<T>& X) {
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            Rt[r * 3 + 0] = tg[r * 4 + 0]; Rt[r * 3 + 1] = tg[r * 4 + 1]; Rt[r * 3 + 2] = tg[r * 4 + 2];
-            pt[r] = tg[r * 4 + 3];
+            X.R[r * 3 + 0] = P.base[r * 4 + 0]; X.R[r * 3 + 1] = P.base[r * 4 + 1]; X.R[r * 3 + 2] = P.base[r * 4 + 2];
+            X.p[r] = P.base[r * 4 + 3];
         }
-        auto reset = [&](Pose<T>& X) {
+    };
+    int64_t b = -1;                 // current problem (-1: none)
+    bool exhausted = false, fresh = false;
+    int it = 0, fails = 0;
+    T Rt[9], pt[3], diff[6], pe[3] = {T(0), T(0), T(0)};
+    T norm = T(0), lambda = T(0.1);
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                X.R[r * 3 + 0] = P.base[r * 4 + 0]; X.R[r * 3 + 1] = P.base[r * 4 + 1]; X.R[r * 3 + 2] = P.base[r * 4 + 2];
-                X.p[r] = P.base[r * 4 + 3];
+    for (int k = 0; k < 9; ++k) Rt[k] = T(0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pt[k] = T(0);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) diff[k] = T(0);
+
+#pragma unroll 1
+    while (true) {
+        // ---- retire (reference loop condition, arm.py:516-519) -----------------------------------------
+        if (b >= 0 && !fresh && (!(norm > K.tol) || fails >= K.max_failures || it >= K.max_iter)) {
+            for (int c = 0; c < dof; ++c) q_out[b * dof + c] = myq[c];
+            success[b] = norm < K.tol ? 1 : 0;
+            if (iters_out != nullptr) iters_out[b] = it;
+            b = -1;
+        }
+        // ---- refill: one atomic for all the idle lanes of the warp ----------------------------------
+        const bool want = b < 0 && !exhausted;
+        const unsigned wm = __ballot_sync(0xffffffffu, want);
+        if (wm != 0) {
+            unsigned long long base = 0;
+            const int leader = __ffs(wm) - 1;
+            if (lane == leader) base = atomicAdd(next, (unsigned long long)__popc(wm));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (want) {
+                const int64_t nb = (int64_t)base + __popc(wm & ((1u << lane) - 1u));
+                if (nb >= B) {
+                    exhausted = true;
+                } else {
+                    b = nb;
+                    for (int c = 0; c < dof; ++c) myq[c] = q0[b * dof + c];
+                    const T* tg = target + b * target_stride;
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        Rt[r * 3 + 0] = tg[r * 4 + 0]; Rt[r * 3 + 1] = tg[r * 4 + 1]; Rt[r * 3 + 2] = tg[r * 4 + 2];
+                        pt[r] = tg[r * 4 + 3];
+                    }
+                    fresh = true; it = 0; fails = 0; lambda = T(0.1); norm = T(0);
+                    pe[0] = pe[1] = pe[2] = T(0);
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) diff[k] = T(0);
+                }
             }
-        };
-        // FK at q0
+        }
+        if (__all_sync(0xffffffffu, b < 0)) break;
+        if (b < 0) continue;          // idle lane at the tail of the run
+
+        // ---- one iteration --------------------------------------------------------------------------
+        // walk A: A = J J^T + lambda I (lower triangle); a fresh problem computes it on p_e = 0 and discards the result
         Pose<T> X;
+        T A[21];
+#pragma unroll
+        for (int k = 0; k < 21; ++k) A[k] = T(0);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) A[k * (k + 1) / 2 + k] = lambda;
         reset(X);
 #pragma unroll 1
-        for (int i = 0; i < n; ++i) joint_step<T, JointK<T>>(X, P.j[i], myq[P.j[i].qidx]);
-        pose_mul_const<T>(X, P.tail);
-        T diff[6];
-        T norm = pose_error<T>(X, Rt, pt, diff);
-        T pe[3] = {X.p[0], X.p[1], X.p[2]};
-        T lambda = T(0.1);
-        int fails = 0;
+        for (int i = 0; i < n; ++i) {
+            joint_step<T, JointK<T>>(X, P.j[i], myq[P.j[i].qidx]);
+            T col[6];
+            joint_column<T>(X, P.j[i], pe, col);
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int c = 0; c <= r; ++c) A[r * (r + 1) / 2 + c] = fma_t<T>(col[r], col[c], A[r * (r + 1) / 2 + c]);
+        }
+        T x[6];
+        chol_solve6<T>(A, diff, x);
+        if (fresh) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) x[k] = T(0);
+        }
+        // walk B: q_i += col_i . x, and FK of the updated configuration in the same pass
+        Pose<T> Xn;
+        reset(X);
+        reset(Xn);
 #pragma unroll 1
-        for (; it < K.max_iter; ++it) {
-            if (!(norm > K.tol) || fails >= K.max_failures) break;
-            // ---- walk A: A = J J^T + lambda I (lower triangle) ------------------------------------
-            T A[21];
+        for (int i = 0; i < n; ++i) {
+            const int col_q = P.j[i].qidx;
+            const T qi = myq[col_q];
+            joint_step<T, JointK<T>>(X, P.j[i], qi);
+            T col[6];
+            joint_column<T>(X, P.j[i], pe, col);
+            T dq = T(0);
 #pragma unroll
-            for (int k = 0; k < 21; ++k) A[k] = T(0);
-#pragma unroll
-            for (int k = 0; k < 6; ++k) A[k * (k + 1) / 2 + k] = lambda;
-            reset(X);
-#pragma unroll 1
-            for (int i = 0; i < n; ++i) {
-                joint_step<T, JointK<T>>(X, P.j[i], myq[P.j[i].qidx]);
-                T col[6];
-                joint_column<T>(X, P.j[i], pe, col);
-#pragma unroll
-                for (int r = 0; r < 6; ++r)
-#pragma unroll
-                    for (int c = 0; c <= r; ++c) A[r * (r + 1) / 2 + c] = fma_t<T>(col[r], col[c], A[r * (r + 1) / 2 + c]);
-            }
-            T x[6];
-            chol_solve6<T>(A, diff, x);
-            // ---- walk B: q_i += col_i . x, and FK of the updated configuration in the same pass -------
-            Pose<T> Xn;
-            reset(X);
-            reset(Xn);
-#pragma unroll 1
-            for (int i = 0; i < n; ++i) {
-                const int col_q = P.j[i].qidx;
-                const T qi = myq[col_q];
-                joint_step<T, JointK<T>>(X, P.j[i], qi);
-                T col[6];
-                joint_column<T>(X, P.j[i], pe, col);
-                T dq = T(0);
-#pragma unroll
-                for (int k = 0; k < 6; ++k) dq = fma_t<T>(col[k], x[k], dq);
-                T qn = qi + dq;
-                if (K.use_limits) qn = qn < K.lower[i] ? K.lower[i] : (qn > K.upper[i] ? K.upper[i] : qn);
-                myq[col_q] = qn;
-                joint_step<T, JointK<T>>(Xn, P.j[i], qn);
-            }
-            pose_mul_const<T>(Xn, P.tail);
-            const T new_norm = pose_error<T>(Xn, Rt, pt, diff);
-            pe[0] = Xn.p[0]; pe[1] = Xn.p[1]; pe[2] = Xn.p[2];
+            for (int k = 0; k < 6; ++k) dq = fma_t<T>(col[k], x[k], dq);
+            T qn = qi + dq;
+            if (K.use_limits && !fresh) qn = qn < K.lower[i] ? K.lower[i] : (qn > K.upper[i] ? K.upper[i] : qn);
+            if (fresh) qn = qi;        // (0 * col is 0 for finite columns; be exact regardless)
+            myq[col_q] = qn;
+            joint_step<T, JointK<T>>(Xn, P.j[i], qn);
+        }
+        pose_mul_const<T>(Xn, P.tail);
+        const T new_norm = pose_error<T>(Xn, Rt, pt, diff);
+        pe[0] = Xn.p[0]; pe[1] = Xn.p[1]; pe[2] = Xn.p[2];
+        if (fresh) {
+            fresh = false;            // this was FK(q0): the error before the reference's loop (arm.py:507-511)
+        } else {
             const bool worse = new_norm > norm;
             lambda *= worse ? T(1.2) : T(0.5);
             fails = worse ? fails + 1 : 0;
-            norm = new_norm;
+            ++it;
         }
-        ok = norm < K.tol;
-    }
-    __syncthreads();
-    for (int i = tid; i < nvalid * dof; i += kIkTile) q_out[tile0 * dof + i] = sq[i];
-    if (tid < nvalid) {
-        success[tile0 + tid] = ok ? 1 : 0;
-        if (iters_out != nullptr) iters_out[tile0 + tid] = it;
+        norm = new_norm;
     }
 }
 
@@ -254,11 +289,23 @@ int launch_ik(const nbx_chain* ch, int frame, const T* target, int64_t target_st
     NBX_REQUIRE(smem <= 200 * 1024, "dof %d too large for the IK kernel", ch->dof);
     auto kern = ik_dls_kernel<T>;
     NBX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t grid = (B + kIkTile - 1) / kIkTile;
-    NBX_REQUIRE(grid <= 0x7fffffffLL, "batch too large for one launch");
-    kern<<<(unsigned)grid, kIkTile, smem, stream>>>(P, K, target, target_stride, q0, B, q_out, success, iters_out);
+    // persistent lanes: enough CTAs to fill the machine a few times over, never more than the problems need
+    static const int cps_env = std::getenv("NBX_IK_CTAS_PER_SM") ? std::atoi(std::getenv("NBX_IK_CTAS_PER_SM")) : 0;   // tuning only
+    const int cps = cps_env > 0 ? cps_env : 16;
+    const int64_t grid = std::min<int64_t>((B + kIkTile - 1) / kIkTile, (int64_t)ch->sm_count * cps);
+    unsigned long long* next = nullptr;
+    cudaMemPool_t pool = nullptr;
+    {
+        const int prc = nbx_workspace_pool(ch->device, &pool);
+        if (prc != NBX_OK) return prc;
+    }
+    NBX_CUDA_OK(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&next), sizeof(unsigned long long), pool, stream));
+    NBX_CUDA_OK(cudaMemsetAsync(next, 0, sizeof(unsigned long long), stream));
+    kern<<<(unsigned)grid, kIkTile, smem, stream>>>(P, K, target, target_stride, q0, B, q_out, success, iters_out, next);
     nbx_count_launch();
-    NBX_CUDA_OK(cudaGetLastError());
+    const cudaError_t launch_err = cudaGetLastError();
+    NBX_CUDA_OK(cudaFreeAsync(next, stream));
+    NBX_CUDA_OK(launch_err);
     return NBX_OK;
 }
 
