@@ -112,12 +112,15 @@ class BatchedPRM:
         N = nodes.shape[0]
         node_valid = ~self.arm.in_collision(nodes, self.connector._params.validity_checker.threshold)
         idx, ok = knn_earlier(nodes, self.k)
-        later = torch.arange(N, device=dev)[:, None].expand(N, self.k)
-        u = idx[ok]
-        v = later[ok]
-        starts = nodes[u].contiguous()      # connect(neighbor.state, new_node.state)
-        ends = nodes[v].contiguous()
-        valid = self.connector.connect_batch(starts, ends)
+        # every (vertex, neighbour slot) goes through the edge kernel -- the few empty slots of the first k vertices are
+        # masked afterwards -- so that the only host round trip of the build is the final compaction of the edge list
+        u = idx.reshape(-1)
+        v = torch.arange(N, device=dev).repeat_interleave(self.k)
+        okf = ok.reshape(-1)
+        starts = nodes[u]                   # connect(neighbor.state, new_node.state)
+        ends = nodes[v]
+        valid = self.connector.connect_batch(starts, ends) & okf
         edges = torch.stack([u[valid], v[valid]], dim=1)
         weights = (nodes[edges[:, 0]] - nodes[edges[:, 1]]).norm(dim=1)
-        return Roadmap(nodes=nodes, edges=edges, weights=weights, candidates=int(u.shape[0]), node_valid=node_valid)
+        n_candidates = int(min(N, self.k + 1) * (min(N, self.k + 1) - 1) // 2 + max(0, N - self.k - 1) * self.k)
+        return Roadmap(nodes=nodes, edges=edges, weights=weights, candidates=n_candidates, node_valid=node_valid)
