@@ -287,3 +287,40 @@ def test_host_buffer_entry_points_and_concurrent_threads(scene):
     [t.start() for t in threads]
     [t.join() for t in threads]
     assert all(results)
+
+
+def test_crowded_scene_overflow_paths(cuda):
+    """A workspace crowded with obstacles: dozens of candidate pairs per configuration, so a tile of 32 configurations
+    overflows the warp's pending list (-> exhaustive evaluation of the tile) and the batch overflows the global candidate
+    queue (-> in-place evaluation).  Those are the cold paths of csrc/nbx_collide.cu; verdicts, distances and edge verdicts
+    must still equal the oracle's."""
+    w = workloads.fresh_world("crowded")
+    arm = workloads.kinova_arm(w, device=0)
+    workloads.apply_rrt_pair_removals(arm)
+    rng = np.random.default_rng(11)
+    obs = []
+    for i in range(36):                          # small cubes scattered through the reachable volume
+        c = Cube(half_extent=float(rng.uniform(0.04, 0.09)), mass=1.0, world_name=w.name)
+        r, th, z = rng.uniform(0.25, 0.8), rng.uniform(-np.pi, np.pi), rng.uniform(0.1, 1.0)
+        c.position = np.array([r * np.cos(th), r * np.sin(th), z])
+        obs.append(c)
+    so = collision.SceneOracle(arm)
+    q = workloads.random_configs_np(arm, 3000, seed=12).astype(np.float32)
+    d = so.min_distance(q.astype(np.float64))
+    hit = arm.in_collision(q)
+    assert hit.mean() > 0.5                      # nearly everything touches something
+    check_verdicts(hit, d)
+    # a threshold that makes (almost) every pair a candidate
+    hit2 = arm.in_collision(q, 0.3)
+    clear = np.abs(d - 0.3) > EPS
+    assert np.array_equal(hit2[clear], (d < 0.3)[clear]) and hit2.mean() > 0.95
+    dist = arm.min_distance(q[:1000])
+    sep = d[:1000] > 0
+    assert np.abs(dist[sep] - d[:1000][sep]).max() < 1e-4
+    # edges through the clutter
+    s, g = q[:300], q[300:600].copy()
+    g[:150] = s[:150] + 0.1 * (g[:150] - s[:150])
+    valid = arm.edges_valid(s, g, 0.1)
+    ov, _, md = so.edges_valid(s.astype(np.float64), g.astype(np.float64), 0.1, return_detail=True)
+    check_edges(valid, ov, md)
+    del obs
