@@ -267,7 +267,7 @@ int nbx_scene_create(const nbx_chain* ch, const nbx_scene_desc* d, nbx_scene** o
     sc->chain = ch;
     sc->n_obs = d->n_obs; sc->n_self = d->n_self_pairs; sc->n_env = d->n_env_pairs;
     sc->d_prims = nullptr; sc->d_obs = nullptr; sc->d_self = nullptr; sc->d_env = nullptr;
-    sc->d_self_begin = nullptr; sc->d_env_begin = nullptr;
+    sc->d_pair_desc = nullptr; sc->d_env_begin = nullptr;
     sc->h_prims = ch->h_prims;
 
     sc->h_obs.resize(d->n_obs);
@@ -318,8 +318,8 @@ int nbx_scene_create(const nbx_chain* ch, const nbx_scene_desc* d, nbx_scene** o
         for (size_t i = 0; i < idx.size(); ++i) { out[i] = v[idx[i]]; origin.push_back(base + idx[i]); }
         v.swap(out);
     };
-    sc->h_self_begin.clear();            // (name kept) [n_self + n_env]: descriptor pair index of each device pair
-    sorted_with_origin(self, sc->h_self_begin, 0);
+    sc->h_pair_desc.clear();            // [n_self + n_env]: descriptor pair index of each device pair
+    sorted_with_origin(self, sc->h_pair_desc, 0);
     std::vector<PairK> env(d->n_env_pairs);
     for (int i = 0; i < d->n_env_pairs; ++i) {
         const int a = d->env_pairs[2 * i], o = d->env_pairs[2 * i + 1];
@@ -333,7 +333,7 @@ int nbx_scene_create(const nbx_chain* ch, const nbx_scene_desc* d, nbx_scene** o
         pr.rsum = pa.brad;
     }
     // obstacle-major: the broad phase keeps one obstacle in registers and streams the primitives past it
-    sorted_with_origin(env, sc->h_self_begin, d->n_self_pairs);
+    sorted_with_origin(env, sc->h_pair_desc, d->n_self_pairs);
     sc->h_self = self;
     sc->h_env = env;
     sc->h_env_begin.assign(d->n_obs + 1, 0);
@@ -346,7 +346,7 @@ int nbx_scene_create(const nbx_chain* ch, const nbx_scene_desc* d, nbx_scene** o
     if ((rc = upload(sc->h_obs, &sc->d_obs)) != NBX_OK) return rc;
     if ((rc = upload(sc->h_self, &sc->d_self)) != NBX_OK) return rc;
     if ((rc = upload(sc->h_env, &sc->d_env)) != NBX_OK) return rc;
-    if ((rc = upload(sc->h_self_begin, &sc->d_self_begin)) != NBX_OK) return rc;
+    if ((rc = upload(sc->h_pair_desc, &sc->d_pair_desc)) != NBX_OK) return rc;
     if ((rc = upload(sc->h_env_begin, &sc->d_env_begin)) != NBX_OK) return rc;
     guard.s = nullptr;
     *out = sc;
@@ -360,7 +360,7 @@ void nbx_scene_destroy(nbx_scene* sc) {
     if (sc->d_obs) cudaFree(sc->d_obs);
     if (sc->d_self) cudaFree(sc->d_self);
     if (sc->d_env) cudaFree(sc->d_env);
-    if (sc->d_self_begin) cudaFree(sc->d_self_begin);
+    if (sc->d_pair_desc) cudaFree(sc->d_pair_desc);
     if (sc->d_env_begin) cudaFree(sc->d_env_begin);
     delete sc;
 }

@@ -34,7 +34,7 @@ struct SceneDev {
     const ObsK* obs;
     const PairK* self_pairs;
     const PairK* env_pairs;
-    const int* self_begin;
+    const int* pair_desc;
     const int* env_begin;
     int n_mov, n_prims, n_base_prims, n_obs, n_self, n_env, scratch_floats;
     float base[12];
@@ -47,7 +47,7 @@ struct SceneSm {
     const ObsK* obs;
     const PairK* self_pairs;
     const PairK* env_pairs;
-    const int* self_begin;
+    const int* pair_desc;
     const int* env_begin;
 };
 
@@ -73,7 +73,7 @@ __device__ __forceinline__ unsigned char* stage_scene(const SceneDev& S, unsigne
     V.self_pairs = reinterpret_cast<const PairK*>(p); copy_words(p, S.self_pairs, sizeof(PairK) * S.n_self); p += align16(sizeof(PairK) * S.n_self);
     V.env_pairs = reinterpret_cast<const PairK*>(p);  copy_words(p, S.env_pairs, sizeof(PairK) * S.n_env);   p += align16(sizeof(PairK) * S.n_env);
     V.env_begin = reinterpret_cast<const int*>(p);    copy_words(p, S.env_begin, sizeof(int) * (S.n_obs + 1));    p += align16(sizeof(int) * (S.n_obs + 1));
-    V.self_begin = nullptr;
+    V.pair_desc = nullptr;
     return p;
 }
 
@@ -1002,7 +1002,7 @@ pair_distances_kernel(const __grid_constant__ SceneDev S, const float* __restric
     __syncwarp();
     const int n_env = C.V.env_begin[S.n_obs];
     const int n_pairs = S.n_self + n_env;
-    const int* pair_desc = S.self_begin;               // device pair -> descriptor pair (global memory, uniform reads)
+    const int* pair_desc = S.pair_desc;               // device pair -> descriptor pair (global memory, uniform reads)
 #pragma unroll 1
     for (int k = 0; k < n_pairs; ++k) {
         const bool env = k >= S.n_self;
@@ -1090,7 +1090,7 @@ int fill_scene_dev(const nbx_chain* ch, const nbx_scene* sc, const double* base_
     S.obs = sc->d_obs;
     S.self_pairs = sc->d_self;
     S.env_pairs = sc->d_env;
-    S.self_begin = sc->d_self_begin;
+    S.pair_desc = sc->d_pair_desc;
     S.env_begin = sc->d_env_begin;
     S.n_mov = ch->n_mov;
     S.n_prims = ch->n_prims;

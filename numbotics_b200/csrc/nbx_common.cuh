@@ -160,13 +160,13 @@ struct nbx_scene {
     std::vector<PrimK> h_prims;      // chain prims with `slot` resolved for this pair set
     std::vector<ObsK> h_obs;
     std::vector<PairK> h_self, h_env;   // self: sorted by (b, a); env: sorted by (obstacle, primitive)
-    std::vector<int> h_self_begin, h_env_begin;   // h_env_begin: [n_obs+1] ranges per obstacle; h_self_begin: [n_self + n_env]
+    std::vector<int> h_pair_desc, h_env_begin;   // h_env_begin: [n_obs+1] ranges per obstacle; h_pair_desc: [n_self + n_env]
                                                   // descriptor pair index of each device (sorted) pair, self pairs first
     PrimK* d_prims;
     ObsK* d_obs;
     PairK* d_self;
     PairK* d_env;
-    int* d_self_begin;
+    int* d_pair_desc;
     int* d_env_begin;
 };
 
