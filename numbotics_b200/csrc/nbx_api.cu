@@ -204,6 +204,7 @@ int nbx_chain_create(const nbx_chain_desc* d, int device, nbx_chain** out) {
             for (int j = pk.mov; j >= 0; j = ch->mov_parent[j]) pk.anc |= 1ull << j;
         if (pk.mov < 0) ch->n_base_prims++;
     }
+    ch->fast_walk = ch->n_mov > 0 ? 1 : 0;
     ch->h_tree.resize(ch->n_mov);
     std::vector<int> save_slot(ch->n_mov, -1);
     int n_save = 0;
@@ -224,6 +225,8 @@ int nbx_chain_create(const nbx_chain_desc* d, int device, nbx_chain** out) {
         tj.qidx = jk.qidx;
         tj.kind = jk.kind;
         tj.sgn = jk.sgn;
+        tj.okind = jk.okind; tj.oc = jk.oc; tj.os = jk.os;
+        if (jk.kind != NBX_KIND_Z || jk.okind == 0) ch->fast_walk = 0;
         const int pj = ch->mov_parent[j];
         tj.load_slot = (pj == j - 1) ? -1 : (pj < 0 ? -2 : save_slot[pj]);
         tj.save_slot = save_slot[j];

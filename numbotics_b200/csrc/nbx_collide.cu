@@ -354,7 +354,7 @@ __device__ __forceinline__ void materialise(const WCtx& C, int& npend, int& qn);
 //       primitives paired with it stream past: exact point-to-box distance against the primitive's bounding radius,
 //       compared squared -- no square root -- and without the rotation for axis-aligned boxes), then the self pairs
 //       (bounding spheres, refined by the capsule bound for cylinder-cylinder pairs that survive).
-template <int MODE, typename QF>
+template <int MODE, bool FAST, typename QF>
 __device__ __forceinline__ void phase1(const WCtx& C, bool valid, QF qf, int n_obs, int n_self, int& npend, int& qn) {
     constexpr bool WANT_DIST = MODE == kDist;
     constexpr int NT = kWT;
@@ -389,7 +389,15 @@ __device__ __forceinline__ void phase1(const WCtx& C, bool valid, QF qf, int n_o
             } else if (jk.load_slot >= 0) {
                 X = saved[jk.load_slot];
             }
-            nbxj::joint_step<float, TreeJointK>(X, jk, valid ? qf(jk.qidx) : 0.f);
+            if (FAST) {
+                // DH-style arm (every joint a revolute about its own z, roll-only offsets: ch->fast_walk): no kind switch,
+                // the offset rotation is a plane rotation of two columns
+                float sn, cs;
+                nbxj::sincos_t<float>(valid ? qf(jk.qidx) : 0.f, &sn, &cs);
+                nbxj::joint_step_zx<float, TreeJointK>(X, jk, sn, cs);
+            } else {
+                nbxj::joint_step<float, TreeJointK>(X, jk, valid ? qf(jk.qidx) : 0.f);
+            }
             if (jk.save_slot >= 0) saved[jk.save_slot] = X;
             do_prims(jk.prim_begin, jk.prim_end);
         }
@@ -618,7 +626,7 @@ struct SplitArgs {
 // ---------------------------------------------------------------------------------------------
 // in_collision.  MODE kSplit: broad kernel of the verdict query (verdict[b] = 0 here, the narrow kernel raises it);
 // MODE kDist: fused distance query (min_dist[b] and the verdict at the end of the warp's range).
-template <int MODE>
+template <int MODE, bool FAST>
 __global__ void __launch_bounds__(kWarps * 32, MODE == kSplit ? 5 : 1)
 in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ q, int64_t B, int dof, float thr,
                     uint8_t* __restrict__ verdict, float* __restrict__ min_dist, uint32_t* __restrict__ pair_code, int upw,
@@ -668,7 +676,7 @@ in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict_
         }
         __syncwarp();
         const float* myq = sq + lane * dof;
-        phase1<MODE>(C, lane < nv, [myq](int col) { return myq[col]; }, S.n_obs, S.n_self, npend, qn);
+        phase1<MODE, FAST>(C, lane < nv, [myq](int col) { return myq[col]; }, S.n_obs, S.n_self, npend, qn);
         materialise<MODE>(C, npend, qn);
     }
     if (MODE == kDist) {
@@ -694,6 +702,7 @@ in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict_
 // samples go through phase 1 with the configuration interpolated on the fly.  valid[e] starts as 1 (0 for an edge
 // shorter than float32 eps) and the narrow kernel clears it when one of the edge's candidates collides.
 // ---------------------------------------------------------------------------------------------
+template <bool FAST>
 __global__ void __launch_bounds__(kWarps * 32, 4)
 edges_valid_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ starts, const float* __restrict__ goals,
                    int64_t E, int dof, double resolution, double max_distance, float thr,
@@ -787,7 +796,7 @@ edges_valid_kernel(const __grid_constant__ SceneDev S, const float* __restrict__
             __syncwarp();
             const float* a = s_start + e * dof;
             const float* g = s_goal + e * dof;
-            phase1<kSplit>(C, have, [a, g, t](int col) { return fmaf(t, g[col], fmaf(-t, a[col], a[col])); }, S.n_obs, S.n_self, npend, qn);
+            phase1<kSplit, FAST>(C, have, [a, g, t](int col) { return fmaf(t, g[col], fmaf(-t, a[col], a[col])); }, S.n_obs, S.n_self, npend, qn);
             materialise<kSplit>(C, npend, qn);
         }
     }
@@ -1162,16 +1171,17 @@ int launch_in_collision(const nbx_chain* ch, const nbx_scene* sc, const float* q
     const int upw = units_per_warp(B, ch->sm_count, mode == kDist ? 12 : 20);
     const int64_t grid = (B + (int64_t)kWarps * upw - 1) / ((int64_t)kWarps * upw);
     if (mode == kDist) {
-        NBX_CUDA_OK(cudaFuncSetAttribute(in_collision_kernel<kDist>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        in_collision_kernel<kDist><<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, q, B, ch->dof, thr, verdict, min_dist, pair_code, upw, SplitArgs{nullptr, nullptr, 0});
+        NBX_CUDA_OK(cudaFuncSetAttribute(in_collision_kernel<kDist, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        in_collision_kernel<kDist, false><<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, q, B, ch->dof, thr, verdict, min_dist, pair_code, upw, SplitArgs{nullptr, nullptr, 0});
         nbx_count_launch();
         NBX_CUDA_OK(cudaGetLastError());
         return NBX_OK;
     }
     SplitWs ws;
     if ((rc = ws.alloc(ch->device, B, stream)) != NBX_OK) return rc;
-    NBX_CUDA_OK(cudaFuncSetAttribute(in_collision_kernel<kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    in_collision_kernel<kSplit><<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, q, B, ch->dof, thr, verdict, nullptr, nullptr, upw, ws.args);
+    auto kern = ch->fast_walk ? in_collision_kernel<kSplit, true> : in_collision_kernel<kSplit, false>;
+    NBX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, q, B, ch->dof, thr, verdict, nullptr, nullptr, upw, ws.args);
     nbx_count_launch();
     NBX_CUDA_OK(cudaGetLastError());
     return launch_narrow(ch, ws.args, thr, verdict, 1, stream);
@@ -1196,12 +1206,13 @@ int launch_edges(const nbx_chain* ch, const nbx_scene* sc, const float* starts, 
     NBX_REQUIRE(smem <= 220 * 1024, "scene too large for shared memory (%zu bytes)", smem);
     SplitWs ws;
     if ((rc = ws.alloc(ch->device, E * 8, stream)) != NBX_OK) return rc;
-    NBX_CUDA_OK(cudaFuncSetAttribute(edges_valid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = ch->fast_walk ? edges_valid_kernel<true> : edges_valid_kernel<false>;
+    NBX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // an edge is ~13 tiles of work for its warp, so the per-CTA prologue is already amortised by one tile of edges; what
     // matters is the tail: 10^6 edges in ranges of 256 were 977 CTAs = 1.65 waves of the 592 resident ones (ncu: +7 %)
     const int upw = units_per_warp(E, ch->sm_count, 16, 8);
     const int64_t grid = (E + (int64_t)kWarps * upw - 1) / ((int64_t)kWarps * upw);
-    edges_valid_kernel<<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, starts, goals, E, dof, resolution, max_distance, thr, valid, n_samples, upw, ws.args);
+    kern<<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, starts, goals, E, dof, resolution, max_distance, thr, valid, n_samples, upw, ws.args);
     nbx_count_launch();
     NBX_CUDA_OK(cudaGetLastError());
     return launch_narrow(ch, ws.args, thr, valid, 0, stream);

@@ -127,6 +127,8 @@ struct TreeJointK {
     int kind;        // NBX_KIND_*
     float sgn;
     float ax[3];     // joint axis in the joint frame (world axis = R_after * ax)
+    int okind;       // structure of the offset rotation (JointK::okind): 0 general, 1 roll about x, 2 identity
+    float oc, os;    // cos / sin of the roll
 };
 
 struct nbx_chain {
@@ -142,6 +144,7 @@ struct nbx_chain {
     std::vector<double> prim_dims, prim_offset, prim_margin;
     std::vector<std::vector<int>> frame_path;   // movable joints root->frame
     // collision walk
+    int fast_walk;                   // 1: every movable joint is a revolute about its own z with a roll-only offset
     int n_save_slots;
     int n_base_prims;                // primitives attached to the base (sorted first)
     int pose_floats;                 // per-item floats needed to park every primitive's world core
