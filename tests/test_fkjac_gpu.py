@@ -249,3 +249,37 @@ def test_cabi_rejects_bad_arguments(kinova, cuda):
     assert lib.nbx_fk_jac_f32(None, 0, q.data_ptr(), 4, base, 0, None, 0, None, 0, T.data_ptr(), None, None) == -1
     with pytest.raises(_cabi.NbxError, match="frame id"):
         _cabi.check(lib.nbx_fk_jac_f32(h.ptr, -3, q.data_ptr(), 4, base, 0, None, 0, None, 0, T.data_ptr(), None, None))
+
+
+def test_concurrent_host_threads(kinova):
+    """Handles are immutable and the host-buffer pipeline is guarded: several host threads calling at once (NumPy in,
+    NumPy out, and device tensors on their own streams) get the bits of a serial call."""
+    import threading
+    import torch
+    q = workloads.random_configs_np(kinova, 40000, seed=17).astype(np.float32)
+    T0, J0 = kinova.fk_jacobian(q, "tool_frame")
+    qd = torch.as_tensor(q, device="cuda:0")
+    ok = [False] * 6
+
+    def host_worker(i):
+        good = True
+        for _ in range(4):
+            T, J = kinova.fk_jacobian(q[i::3], "tool_frame")
+            good = good and np.array_equal(T, T0[i::3]) and np.array_equal(J, J0[i::3])
+        ok[i] = good
+
+    def device_worker(i):
+        good = True
+        with torch.cuda.stream(torch.cuda.Stream(device="cuda:0")):
+            for _ in range(4):
+                T, J = kinova.fk_jacobian(qd[(i - 3)::3].contiguous(), "end_effector_link" if i == 5 else "tool_frame")
+                torch.cuda.current_stream().synchronize()
+                if i != 5:
+                    good = good and np.array_equal(T.cpu().numpy(), T0[(i - 3)::3]) and np.array_equal(J.cpu().numpy(), J0[(i - 3)::3])
+        ok[i] = good
+
+    threads = [threading.Thread(target=host_worker, args=(i,)) for i in range(3)] + \
+              [threading.Thread(target=device_worker, args=(i,)) for i in range(3, 6)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert all(ok), ok
