@@ -471,14 +471,14 @@ __device__ __forceinline__ void phase1(const WCtx& C, bool valid, QF qf, int n_o
         if (ob.type == NBX_PRIM_BOX) {
             const float hx = ob.dims[0] + ob.margin, hy = ob.dims[1] + ob.margin, hz = ob.dims[2] + ob.margin;
             if (ob.pad[0] != 0) {              // axis-aligned box: exact point-to-box distance without the rotation
-#pragma unroll 2
+#pragma unroll 4
                 for (int e = e0; e < e1; ++e)
                     NBX_ENV_PAIR(sq3(fmaxf(fabsf(dc.x) - hx, 0.f), fmaxf(fabsf(dc.y) - hy, 0.f), fmaxf(fabsf(dc.z) - hz, 0.f)), 0.f)
             } else {
                 float R[9];
 #pragma unroll
                 for (int k = 0; k < 9; ++k) R[k] = ob.R[k];
-#pragma unroll 2
+#pragma unroll 4
                 for (int e = e0; e < e1; ++e)
                     NBX_ENV_PAIR(sq3(fmaxf(fabsf(fmaf(R[0], dc.x, fmaf(R[3], dc.y, R[6] * dc.z))) - hx, 0.f),
                                      fmaxf(fabsf(fmaf(R[1], dc.x, fmaf(R[4], dc.y, R[7] * dc.z))) - hy, 0.f),
@@ -486,12 +486,12 @@ __device__ __forceinline__ void phase1(const WCtx& C, bool valid, QF qf, int n_o
             }
         } else {                               // sphere / cylinder obstacle: bounding spheres
             const float orad = ob.brad;
-#pragma unroll 2
+#pragma unroll 4
             for (int e = e0; e < e1; ++e) NBX_ENV_PAIR(dot(dc, dc), orad)
         }
     }
 #undef NBX_ENV_PAIR
-#pragma unroll 2
+#pragma unroll 4
     for (int e = 0; e < n_self; ++e) {
         const float4 rec = self4[e];
         const float* pa = reinterpret_cast<const float*>(myb + __float_as_int(rec.y));
