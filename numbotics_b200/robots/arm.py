@@ -612,6 +612,11 @@ class Arm:
         return [Proximity(subject=s_, target=t_, position_on_subject=ps[i], position_on_target=pt[i],
                           normal_target_to_subject=n[i], distance=float(d[i])) for i, (s_, t_) in enumerate(pairs)]
 
+    def self_collisions(self, q):
+        """reference arm.py:583-596: the proximities of the allowed link-link pairs, one configuration."""
+        links = set(self._arrays["prim_of_link"].keys())
+        return [p for p in self.collisions(q) if p.target in links]
+
     def distance_to(self, q, obj, link=None):
         """reference arm.py:607-618: the proximities between the arm (or one `link`) and `obj`, one configuration."""
         prox = [p for p in self.collisions(q) if p.target is obj or p.subject is obj]

@@ -140,6 +140,8 @@ def test_pair_distances_every_allowed_pair(scene):
         assert p.subject is s_ and p.target is t_ and abs(p.distance - dd) < 1e-6
         if dd > 1e-3:
             assert abs(np.linalg.norm(p.position_on_subject - p.position_on_target) - dd) < 1e-4
+    selfp = arm.self_collisions(q[0])
+    assert len(selfp) == sum(1 for _, t_ in pairs if t_ in link_index) and all(p.target in link_index for p in selfp)
     cube = so.objs[0]
     to_cube = arm.distance_to(q[0], cube)
     assert len(to_cube) == sum(1 for _, t_ in pairs if t_ is cube) and all(p.target is cube for p in to_cube)
