@@ -419,6 +419,24 @@ def secondary_measurements(arm, q, dev, rank, world, clocks_mhz):
                                 "valid_fraction_rank0": float(v.float().mean()), "mean_samples_per_edge_rank0": float(ns.float().mean()),
                                 "samples_per_sec": float(ns.sum()) * world / ms * 1e3,
                                 "workload": "BASELINE configs[3]: 100k nodes x 10-NN = 1M edges, resolution 0.1, contiguous E/G slices"}
+    if world == 1:
+        # CPU figures for configs[2] and [3]: the float64 C/OpenMP restatement (the reference's PyBullet path cannot run
+        # here at all) on bounded samples, all host threads -- "restated oracle, not reference" 
+        import time as _time
+        import numpy as _np
+        from oracle import collision as _oc
+        _oc.set_threads(host_threads())
+        desc = _oc.CDesc(arm._arrays, arm.scene_arrays(None))
+        qn = qc[: 1 << 17].cpu().numpy().astype(_np.float64)
+        t0 = _time.perf_counter(); hit_cpu = _oc.c_in_collision(desc, qn, arm.base_pose); dt = _time.perf_counter() - t0
+        out["in_collision_configs_per_sec"]["cpu_port"] = {
+            "value": qn.shape[0] / dt, "unit": "configs/s", "cores": _oc.num_threads(), "kind": "restated oracle, not reference",
+            "sample": f"{qn.shape[0]} of the same configurations", "hit_fraction": float(hit_cpu.mean())}
+        sn, gn = s[: 1 << 14].cpu().numpy().astype(_np.float64), g[: 1 << 14].cpu().numpy().astype(_np.float64)
+        t0 = _time.perf_counter(); v_cpu, _, _ = _oc.c_edges_valid(desc, sn, gn, arm.base_pose, 0.1); dt = _time.perf_counter() - t0
+        out["prm_edges_per_sec"]["cpu_port"] = {
+            "value": sn.shape[0] / dt, "unit": "edges/s", "cores": _oc.num_threads(), "kind": "restated oracle, not reference",
+            "sample": f"{sn.shape[0]} of the same edges", "valid_fraction": float(v_cpu.mean())}
     del s_all, g_all, s, g, nodes
     # configs[4]: 2^25 configurations of the 30-DoF chain per GPU (2^28 over 8 GPUs), J alone is 24 GB per GPU
     arm30 = workloads.serial_arm(30, device=dev.index)
