@@ -293,7 +293,11 @@ def main():
                 "traffic": recorded_traffic(), "kernel": "fkjac_dense_kernel<float, 7, 128, ALLZ=true, KT=2>",
                 "algorithmic_bytes_per_launch": BYTES_PER_CFG * B, "avg_launch_ms": avg_launch_ms,
                 "best_launch_ms": per_step[0], "median_launch_ms": per_step[len(per_step) // 2],
-                "peak_source": peak_src, "fp32_tflops": FLOPS_PER_CFG * B / (avg_launch_ms * 1e-3) / 1e12}
+                "peak_source": peak_src,
+                "peak_note": "the denominator is the measured COPY bandwidth (half reads, half writes); this kernel's stream is 89 % "
+                             "writes in 8 KB + 21 KB bulk stores per tile, which DRAM sustains slightly better, so frac can exceed 1. "
+                             "ncu: dram__bytes.sum 6.6 TB/s = 81 % of the 8.18 TB/s pin rate (profiles/r01_ncu_full_summary_final.csv)",
+                "fp32_tflops": FLOPS_PER_CFG * B / (avg_launch_ms * 1e-3) / 1e12}
 
     # ---- CPU baseline (oracle port) + parity gate, rank 0, N = 1 only ------------------------------------------
     cpu_baseline = None
