@@ -451,6 +451,29 @@ int launch_generic(const PathK<T, NBX_MAX_PATH>& P, const T* q, int64_t B, const
     return launch_generic_t<T, TILE, false>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, smem, stream);
 }
 
+// Paths of joints about their own +-z with roll-only offsets (mode 2).  Rz(-q) = Rx(pi) Rz(q) Rx(pi): a joint about its
+// own -z is one about +z whose offset roll is turned by pi; the trailing half turn goes into the next joint's offset
+// ([Rx(pi) | 0] [Rx(a) | t] = [Rx(a + pi) | (t_x, -t_y, -t_z)]) or, after the last joint, into the tail.  Only signs
+// change, so the result is the same to the bit; the kernel then never multiplies by sgn (joint_step_zxp, joint_screw_zp).
+template <typename T, int MAXJ>
+void fold_axis_signs(PathK<T, MAXJ>& P) {
+    bool half_turn = false;                  // a pending Rx(pi) on the left of the next constant pose
+    for (int i = 0; i < P.n; ++i) {
+        JointK<T>& jk = P.j[i];
+        const bool neg = jk.sgn < (T)0;
+        if (half_turn) { jk.t[1] = -jk.t[1]; jk.t[2] = -jk.t[2]; }
+        if (half_turn != neg) { jk.oc = -jk.oc; jk.os = -jk.os; }
+        jk.A[0] = (T)1; jk.A[1] = jk.A[2] = jk.A[3] = jk.A[6] = (T)0;
+        jk.A[4] = jk.oc; jk.A[5] = -jk.os; jk.A[7] = jk.os; jk.A[8] = jk.oc;
+        jk.ax[0] = jk.ax[1] = (T)0; jk.ax[2] = (T)1;
+        jk.sgn = (T)1;
+        if (jk.okind == 2 && (jk.oc != (T)1 || jk.os != (T)0)) jk.okind = 1;
+        half_turn = neg;
+    }
+    if (half_turn)
+        for (int k = 4; k < 12; ++k) P.tail[k] = -P.tail[k];
+}
+
 template <typename T>
 int launch_fkjac(const nbx_chain* ch, int frame, const T* q, int64_t B, const double* base_pose, int use_com,
                  const T* lp, int64_t lps, const T* gp, int64_t gps, T* T_out, T* J_out, cudaStream_t stream) {
@@ -498,6 +521,7 @@ int launch_fkjac(const nbx_chain* ch, int frame, const T* q, int64_t B, const do
                 for (int i = 0; i < P.n; ++i) { allz_b = allz_b && P.j[i].kind == NBX_KIND_Z; roll = roll && P.j[i].okind != 0; }
                 static const bool no_roll = std::getenv("NBX_NO_ROLL_FASTPATH") != nullptr;   // A/B measurements and tests only
                 const int allz = allz_b ? ((roll && !no_roll) ? 2 : 1) : 0;
+                if (allz == 2) fold_axis_signs(P);
                 return n <= NBX_WIDE_SPLIT ? nbx_launch_wide_a_f32(P, allz, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, ch->sm_count, stream)
                                            : nbx_launch_wide_b_f32(P, allz, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, ch->sm_count, stream);
             }

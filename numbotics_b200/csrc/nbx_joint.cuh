@@ -23,13 +23,9 @@ static __device__ __noinline__ float2 sincos_huge(float x) {
     return make_float2(s, c);
 }
 
-__device__ __forceinline__ void sincos_fast(float x, float* sp, float* cp) {
-    if (fabsf(x) > 1.0e5f) {   // cold, kept out of line
-        const float2 r = sincos_huge(x);
-        *sp = r.x;
-        *cp = r.y;
-        return;
-    }
+// the fast path alone: valid for |x| <= 1e5 (callers that screen their arguments once per tile use it directly:
+// no compare / branch / reconvergence per joint)
+__device__ __forceinline__ void sincos_core(float x, float* sp, float* cp) {
     // round-to-nearest via the 1.5 * 2^23 magic constant: FFMA / FADD only (no FRND / F2I on the XU pipe),
     // the integer part sits in the low mantissa bits of `t`
     const float t = fmaf(x, 0.636619747f, 12582912.0f);
@@ -53,6 +49,29 @@ __device__ __forceinline__ void sincos_fast(float x, float* sp, float* cp) {
     co = __int_as_float(__float_as_int(co) ^ (((i + 1) & 2) << 30));    // quadrants 1, 2: cos < 0
     *sp = so;
     *cp = co;
+}
+
+__device__ __forceinline__ void sincos_fast(float x, float* sp, float* cp) {
+    if (fabsf(x) > 1.0e5f) {   // cold, kept out of line
+        const float2 r = sincos_huge(x);
+        *sp = r.x;
+        *cp = r.y;
+        return;
+    }
+    sincos_core(x, sp, cp);
+}
+
+// Cold companion of sincos_core: replace every |x| > 1e5 of a row by the equivalent angle in [-pi, pi]
+// (double-precision sine / cosine of the exact float, then atan2: half an ulp of the reduced angle).
+static __device__ __noinline__ void reduce_huge_angles(float* row, int n) {
+    for (int i = 0; i < n; ++i) {
+        const float x = row[i];
+        if (fabsf(x) > 1.0e5f) {
+            double s, c;
+            sincos((double)x, &s, &c);
+            row[i] = (float)atan2(s, c);      // NaN / inf stay NaN
+        }
+    }
 }
 
 template <typename T> __device__ __forceinline__ void sincos_t(T x, T* s, T* c);
@@ -170,6 +189,25 @@ __device__ __forceinline__ void joint_step_zx(Pose<T>& X, const JK& jk, T s, T c
     rot_cols<T, 1, 2>(X, (T)jk.oc, (T)jk.os);
     s *= (T)jk.sgn;
     rot_cols<T, 0, 1>(X, c, s);
+}
+
+// joint_step_zx / joint_screw_z for paths whose axis signs were folded into the offsets on the host
+// (fold_axis_signs, nbx_fkjac.cu): every joint turns about its own +z, no multiplication by sgn.
+template <typename T, typename JK>
+__device__ __forceinline__ void joint_step_zxp(Pose<T>& X, const JK& jk, T s, T c) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+        X.p[r] = fma_t<T>(X.R[r * 3 + 0], (T)jk.t[0], fma_t<T>(X.R[r * 3 + 1], (T)jk.t[1], fma_t<T>(X.R[r * 3 + 2], (T)jk.t[2], X.p[r])));
+    rot_cols<T, 1, 2>(X, (T)jk.oc, (T)jk.os);
+    rot_cols<T, 0, 1>(X, c, s);
+}
+
+template <typename T>
+__device__ __forceinline__ void joint_screw_zp(const Pose<T>& X, T* w, T* m) {
+    w[0] = X.R[2]; w[1] = X.R[5]; w[2] = X.R[8];
+    m[0] = fma_t<T>(w[1], X.p[2], -w[2] * X.p[1]);
+    m[1] = fma_t<T>(w[2], X.p[0], -w[0] * X.p[2]);
+    m[2] = fma_t<T>(w[0], X.p[1], -w[1] * X.p[0]);
 }
 
 template <typename T, typename JK>

@@ -114,6 +114,72 @@ def test_allz_serial_chains(cuda, n):
     _check_arm(_mixed_serial_arm(n, seed=1000 + n, allz=True), n, seed=n, tol32=1e-5 if n <= 16 else 3e-5)
 
 
+def _dh_serial_arm(n, seed, device=0):
+    """DH-style serial chain: every joint about its own +z or -z, link offsets with a roll-only rotation (angles
+    including 0, pi and +-pi/2) and a full translation -- the compile-time `ALLZ == 2` variants, whose axis signs the
+    host folds into the offsets (fold_axis_signs, csrc/nbx_fkjac.cu)."""
+    import networkx as nx
+    from numbotics_b200.math import trans_mat
+    from numbotics_b200.physics import GraphChain, Joint, Constraint, DummyLink
+    from numbotics_b200.robots import Arm
+    rng = np.random.default_rng(seed)
+    w = workloads.fresh_world(f"dh{n}_{seed}")
+    G = nx.DiGraph()
+    G.add_node("l0", link=DummyLink(1.0, trans_mat(pos=rng.normal(size=3) * 0.02), name="l0"))
+    special = [0.0, np.pi, np.pi / 2, -np.pi / 2]
+    prev = "l0"
+    for i in range(n):
+        roll = special[int(rng.integers(0, 4))] if rng.random() < 0.5 else float(rng.uniform(-np.pi, np.pi))
+        c, s_ = np.cos(roll), np.sin(roll)
+        if roll == 0.0:
+            c, s_ = 1.0, 0.0
+        R = np.array([[1.0, 0.0, 0.0], [0.0, c, -s_], [0.0, s_, c]])
+        off = trans_mat(pos=rng.normal(size=3) * 0.08, orn=R)
+        ax = np.array([0.0, 0.0, 1.0 if rng.random() < 0.5 else -1.0])
+        name = f"l{i + 1}"
+        G.add_node(name, link=DummyLink(1.0, trans_mat(pos=rng.normal(size=3) * 0.01), name=name))
+        G.add_edge(prev, name, joint=Joint(off, ax, Constraint.REVOLUTE, name=f"j{i + 1}", lower_limit=-np.pi, upper_limit=np.pi))
+        prev = name
+    G.add_node("tool", link=DummyLink(0.1, np.eye(4), name="tool"))
+    G.add_edge(prev, "tool", joint=Joint(trans_mat(pos=np.array([0.05, 0.01, -0.02])), np.zeros(3), Constraint.FIXED, name="tool_joint"))
+    return Arm(GraphChain(G, world_name=w.name), device=device)
+
+
+# 7: dense kernel; 9, 30, 31 (odd row length), 32: wide kernels with folded axis signs; 40: deep kernel
+@pytest.mark.parametrize("n", [7, 9, 30, 31, 32, 40])
+def test_dh_chains_with_negative_axes(cuda, n):
+    arm = _dh_serial_arm(n, seed=2000 + n)
+    _check_arm(arm, n, seed=n, tol32=1e-5 if n <= 16 else 3e-5)
+
+
+@pytest.mark.parametrize("n", [9, 30, 31])
+def test_wide_kernel_huge_angles(cuda, n):
+    """|q| > 1e5 leaves the fast sine / cosine range: the wide kernels screen each q tile once and reduce the offenders
+    out of line.  float32 q is exact in float64, so the oracle sees the same angles."""
+    arm = _dh_serial_arm(n, seed=3000 + n)
+    com = {nm: l._offset for nm, l in arm._links_from_nodes.items()}
+    ora = fkjac.ArmOracle(arm._link_joint_sequence, arm.dof, arm.base_pose, com)
+    rng = np.random.default_rng(n)
+    B = 32 * 9 + 5                                     # several tiles per warp + a ragged one
+    q = workloads.random_configs_np(arm, B, seed=n).astype(np.float32)
+    q[3, 1] = 2.5e5
+    q[40, n - 1] = -7.7e8                              # first tile clean, later tiles not
+    q[100:108, :] = (rng.uniform(-1, 1, size=(8, n)) * 1e6).astype(np.float32)
+    q[B - 1, 0] = 3.0e30                               # ragged last tile
+    q64 = q.astype(np.float64)
+    T32, J32 = arm.fk_jacobian(q, "tool")
+    assert rel_err(T32, ora.forward_kinematics(q64, "tool")) <= 3e-5
+    assert rel_err(J32, ora.jacobian(q64, "tool")) <= 3e-5
+    # non-finite angles poison only their own configuration
+    q[7, 2] = np.inf
+    q[8, 0] = np.nan
+    T32b, J32b = arm.fk_jacobian(q, "tool")
+    assert np.isnan(T32b[7]).any() and np.isnan(T32b[8]).any()
+    keep = np.ones(B, bool)
+    keep[[7, 8]] = False
+    assert np.array_equal(T32b[keep], T32[keep]) and np.array_equal(J32b[keep], J32[keep])
+
+
 def test_too_long_path_is_rejected(cuda):
     from numbotics_b200 import _cabi
     arm = _mixed_serial_arm(65, seed=65)
@@ -134,6 +200,6 @@ def test_other_kernel_families_in_subprocess(cuda, env):
     if env == "NBX_GENERIC_LEGACY":
         e["NBX_NO_WIDE"] = "1"
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k",
-                        "mixed_serial_chains or allz_serial_chains"], env=e, capture_output=True, text=True, timeout=900,
+                        "mixed_serial_chains or allz_serial_chains or dh_chains"], env=e, capture_output=True, text=True, timeout=900,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
