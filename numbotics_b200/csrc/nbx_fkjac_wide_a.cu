@@ -2,7 +2,4 @@
 #define NBX_WIDE_LO 9
 #define NBX_WIDE_HI 22
 #define NBX_WIDE_FN nbx_launch_wide_a_f32
-#ifndef NBX_WIDE_WARPS
-#define NBX_WIDE_WARPS 1
-#endif
 #include "nbx_fkjac_wide.inc"

@@ -2,7 +2,4 @@
 #define NBX_WIDE_LO 23
 #define NBX_WIDE_HI 32
 #define NBX_WIDE_FN nbx_launch_wide_b_f32
-#ifndef NBX_WIDE_WARPS
-#define NBX_WIDE_WARPS 1
-#endif
 #include "nbx_fkjac_wide.inc"
