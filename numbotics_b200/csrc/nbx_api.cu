@@ -226,7 +226,7 @@ int nbx_chain_create(const nbx_chain_desc* d, int device, nbx_chain** out) {
         tj.kind = jk.kind;
         tj.sgn = jk.sgn;
         tj.okind = jk.okind; tj.oc = jk.oc; tj.os = jk.os;
-        if (jk.kind != NBX_KIND_Z || jk.okind == 0) ch->fast_walk = 0;
+        if (jk.kind != NBX_KIND_Z || jk.okind == 0 || ch->mov_parent[j] != j - 1) ch->fast_walk = 0;
         const int pj = ch->mov_parent[j];
         tj.load_slot = (pj == j - 1) ? -1 : (pj < 0 ? -2 : save_slot[pj]);
         tj.save_slot = save_slot[j];

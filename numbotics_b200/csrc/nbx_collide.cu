@@ -380,7 +380,10 @@ __device__ __forceinline__ void phase1(const WCtx& C, bool valid, QF qf, int n_o
 #pragma unroll 1
         for (int j = 0; j < C.n_mov; ++j) {
             const TreeJointK& jk = C.V.tree[j];
-            if (jk.load_slot == -2) {
+            if (FAST) {
+                // serial chain: the frame just reached is the parent of the next joint, nothing to save or restore
+                // (a `saved[]` slot picked at run time would live in local memory)
+            } else if (jk.load_slot == -2) {
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
                     X.R[r * 3 + 0] = C.base[r * 4 + 0]; X.R[r * 3 + 1] = C.base[r * 4 + 1]; X.R[r * 3 + 2] = C.base[r * 4 + 2];
@@ -390,7 +393,7 @@ __device__ __forceinline__ void phase1(const WCtx& C, bool valid, QF qf, int n_o
                 X = saved[jk.load_slot];
             }
             if (FAST) {
-                // DH-style arm (every joint a revolute about its own z, roll-only offsets: ch->fast_walk): no kind switch,
+                // serial DH-style arm (every joint a revolute about its own z, roll-only offsets: ch->fast_walk): no kind switch,
                 // the offset rotation is a plane rotation of two columns
                 float sn, cs;
                 nbxj::sincos_t<float>(valid ? qf(jk.qidx) : 0.f, &sn, &cs);
@@ -398,7 +401,7 @@ __device__ __forceinline__ void phase1(const WCtx& C, bool valid, QF qf, int n_o
             } else {
                 nbxj::joint_step<float, TreeJointK>(X, jk, valid ? qf(jk.qidx) : 0.f);
             }
-            if (jk.save_slot >= 0) saved[jk.save_slot] = X;
+            if (!FAST && jk.save_slot >= 0) saved[jk.save_slot] = X;
             do_prims(jk.prim_begin, jk.prim_end);
         }
     }

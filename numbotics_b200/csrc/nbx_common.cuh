@@ -144,7 +144,7 @@ struct nbx_chain {
     std::vector<double> prim_dims, prim_offset, prim_margin;
     std::vector<std::vector<int>> frame_path;   // movable joints root->frame
     // collision walk
-    int fast_walk;                   // 1: every movable joint is a revolute about its own z with a roll-only offset
+    int fast_walk;                   // 1: serial chain, every movable joint a revolute about its own z with a roll-only offset
     int n_save_slots;
     int n_base_prims;                // primitives attached to the base (sorted first)
     int pose_floats;                 // per-item floats needed to park every primitive's world core
