@@ -58,12 +58,27 @@ __host__ __device__ inline size_t scene_smem_bytes(int n_mov, int n_prims, int n
            align16(sizeof(PairK) * n_self) + align16(sizeof(PairK) * n_env) + align16(sizeof(int) * (n_obs + 1));
 }
 
+// Asynchronous global -> shared copies (cp.async).  The scene arrays and the q tiles are staged with these so that all
+// of a CTA's staging loads are in flight together (ncu, source page: six dependent load -> store round trips of the
+// prologue and the per-tile q load were 11 % of the broad kernel's warp samples, all long_scoreboard).
+__device__ __forceinline__ void cp_async4(void* sdst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ void copy_words(void* dst, const void* src, size_t bytes) {
     const int n = (int)(bytes / 4);
     const int* s = static_cast<const int*>(src);
     int* d = static_cast<int*>(dst);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) cp_async4(d + i, s + i);
 }
+
+// Every thread waits for its own staging copies; the caller's __syncthreads() then publishes the scene to the CTA.
+__device__ __forceinline__ void stage_wait() { cp_async_commit(); cp_async_wait_all(); }
 
 __device__ __forceinline__ unsigned char* stage_scene(const SceneDev& S, unsigned char* sm, SceneSm& V) {
     unsigned char* p = sm;
@@ -74,7 +89,7 @@ __device__ __forceinline__ unsigned char* stage_scene(const SceneDev& S, unsigne
     V.env_pairs = reinterpret_cast<const PairK*>(p);  copy_words(p, S.env_pairs, sizeof(PairK) * S.n_env);   p += align16(sizeof(PairK) * S.n_env);
     V.env_begin = reinterpret_cast<const int*>(p);    copy_words(p, S.env_begin, sizeof(int) * (S.n_obs + 1));    p += align16(sizeof(int) * (S.n_obs + 1));
     V.pair_desc = nullptr;
-    return p;
+    return p;                                            // copies still in flight: stage_wait() + __syncthreads() before use
 }
 
 using PoseF = nbxj::Pose<float>;
@@ -354,8 +369,12 @@ __device__ __forceinline__ void materialise(const WCtx& C, int& npend, int& qn);
 //       primitives paired with it stream past: exact point-to-box distance against the primitive's bounding radius,
 //       compared squared -- no square root -- and without the rotation for axis-aligned boxes), then the self pairs
 //       (bounding spheres, refined by the capsule bound for cylinder-cylinder pairs that survive).
-template <int MODE, bool FAST, typename QF>
-__device__ __forceinline__ void phase1(const WCtx& C, bool valid, QF qf, int n_obs, int n_self, int& npend, int& qn) {
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+
+// `after_walk` runs once the whole warp has finished reading its configurations (between 1a and 1b): in_collision uses
+// it to request the NEXT tile's q into the same staging tile, so that the load has the whole broad phase to land.
+template <int MODE, bool FAST, typename QF, typename AW = NoHook>
+__device__ __forceinline__ void phase1(const WCtx& C, bool valid, QF qf, int n_obs, int n_self, int& npend, int& qn, AW after_walk = AW()) {
     constexpr bool WANT_DIST = MODE == kDist;
     constexpr int NT = kWT;
     const int lane = threadIdx.x & 31;
@@ -406,6 +425,7 @@ __device__ __forceinline__ void phase1(const WCtx& C, bool valid, QF qf, int n_o
         }
     }
     __syncwarp();
+    after_walk();
 
     const float4* env4 = reinterpret_cast<const float4*>(C.V.env_pairs);
     const float4* self4 = reinterpret_cast<const float4*>(C.V.self_pairs);
@@ -646,40 +666,43 @@ in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict_
     C.thr = thr;
     C.gq = G.gq; C.gq_count = G.gq_count; C.gq_half = G.gq_half;
     C.gflag = verdict; C.hit_value = 1;
-    __syncthreads();                                     // the staged scene is the only thing the warps share
 
     const int64_t range0 = ((int64_t)blockIdx.x * kWarps + wid) * upw;
     const int rangeN = (int)max((int64_t)0, min((int64_t)upw, B - range0));
+    const bool vec = (reinterpret_cast<uintptr_t>(q) & 15u) == 0;
+    // request the q tile that starts at item t0 of the warp's range into the staging tile (asynchronous)
+    auto request_q = [&](int t0) {
+        const int nv = min(kWT, rangeN - t0);
+        const float* src = q + (range0 + t0) * dof;
+        const int n = nv * dof;
+        if (nv == kWT && vec && (((range0 + t0) * dof) & 3) == 0) {
+            const float4* s16 = reinterpret_cast<const float4*>(src);
+            float4* d16 = reinterpret_cast<float4*>(sq);
+            for (int i = lane; i < n / 4; i += 32) cp_async16(d16 + i, s16 + i);
+        } else {
+            for (int i = lane; i < n; i += 32) cp_async4(sq + i, src + i);
+        }
+        cp_async_commit();
+    };
+    if (rangeN > 0) request_q(0);                        // travels together with the scene
+    stage_wait();
+    __syncthreads();                                     // the staged scene is the only thing the warps share
     if (rangeN == 0) return;
     for (int i = lane; i < rangeN; i += 32) {
         if (MODE == kDist) C.flag[i] = dist_entry(FLT_MAX, 0xffffffffu);
         else verdict[range0 + i] = 0;
     }
     int npend = 0, qn = 0;
-    const bool vec = (reinterpret_cast<uintptr_t>(q) & 15u) == 0;
 #pragma unroll 1
     for (int t0 = 0; t0 < rangeN; t0 += kWT) {
         const int nv = min(kWT, rangeN - t0);
-        const float* src = q + (range0 + t0) * dof;
-        const int n = nv * dof;
-        __syncwarp();
-        if (nv == kWT && vec && (((range0 + t0) * dof) & 3) == 0) {
-            const float4* s16 = reinterpret_cast<const float4*>(src);
-            float4* d16 = reinterpret_cast<float4*>(sq);
-            for (int i = lane; i < n / 4; i += 32) d16[i] = __ldg(s16 + i);
-        } else {
-            for (int i = lane; i < n; i += 32) sq[i] = src[i];
-        }
+        cp_async_wait_all();                             // this tile's q (requested during the previous tile's broad phase)
+        __syncwarp();                                    // the previous tile's materialise has read item_fi
         C.item_fi[lane] = (MODE == kDist) ? t0 + lane : (int)(range0 + t0 + lane);
-        if (t0 + kWT < rangeN) {
-            // pull the next tile's q into L2 while this tile is evaluated (its load above is then an L2 hit)
-            const char* nq = reinterpret_cast<const char*>(src + kWT * dof);
-            const int nbytes = min(kWT, rangeN - t0 - kWT) * dof * (int)sizeof(float);
-            for (int o = lane * 128; o < nbytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nq + o));
-        }
         __syncwarp();
         const float* myq = sq + lane * dof;
-        phase1<MODE, FAST>(C, lane < nv, [myq](int col) { return myq[col]; }, S.n_obs, S.n_self, npend, qn);
+        phase1<MODE, FAST>(C, lane < nv, [myq](int col) { return myq[col]; }, S.n_obs, S.n_self, npend, qn,
+                           [&]() { if (t0 + kWT < rangeN) request_q(t0 + kWT); });
         materialise<MODE>(C, npend, qn);
     }
     if (MODE == kDist) {
@@ -727,6 +750,7 @@ edges_valid_kernel(const __grid_constant__ SceneDev S, const float* __restrict__
     C.thr = thr;
     C.gq = G.gq; C.gq_count = G.gq_count; C.gq_half = G.gq_half;
     C.gflag = valid; C.hit_value = 0;
+    stage_wait();
     __syncthreads();
 
     const int64_t range0 = ((int64_t)blockIdx.x * kWarps + wid) * upw;
@@ -847,6 +871,7 @@ closest_witness_kernel(const __grid_constant__ SceneDev S, const float* __restri
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SceneSm V;
     stage_scene(S, smem_raw, V);
+    stage_wait();
     __syncthreads();
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
@@ -972,6 +997,7 @@ pair_distances_kernel(const __grid_constant__ SceneDev S, const float* __restric
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     p += (size_t)wid * align16(sizeof(float) * (size_t)kWT * max(S.scratch_floats, 1));
     C.poses = reinterpret_cast<float*>(p);
+    stage_wait();
     __syncthreads();
     const int64_t b = ((int64_t)blockIdx.x * kWarps + wid) * kWT + lane;
     const bool have = b < B;
