@@ -73,6 +73,7 @@ class ClockSampler:
         self.samples, self.reasons = [], set()
         self.max_mhz = None
         self._stop = threading.Event()
+        self._rec = threading.Event()
         self._thread = None
         self._h = None
         try:
@@ -88,7 +89,11 @@ class ClockSampler:
         nv = self._nv
         while not self._stop.is_set():
             try:
-                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                mhz = float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                if not self._rec.is_set():         # polling before the timed region keeps NVML warm (its first calls can
+                    time.sleep(0.001)              # take longer than a whole short timed region); nothing is recorded
+                    continue
+                self.samples.append(mhz)
                 r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
                     else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
                 for bit, name in self.REASONS.items():
@@ -98,10 +103,16 @@ class ClockSampler:
                 break
             time.sleep(0.001)
 
-    def start(self):
-        if self._h is not None:
+    def warm(self):
+        """Start polling without recording (call before the warm-up steps)."""
+        if self._h is not None and self._thread is None:
             self._thread = threading.Thread(target=self._run, daemon=True)
             self._thread.start()
+
+    def start(self):
+        """Record from here on: called right before the timed region."""
+        self.warm()
+        self._rec.set()
 
     def stop(self):
         self._stop.set()
@@ -222,10 +233,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    clocks = ClockSampler(local_rank)
+    clocks.warm()
     for _ in range(args.warmup):
         step()
     barrier()
-    clocks = ClockSampler(local_rank)
     launches0 = _cabi.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     clocks.start()
