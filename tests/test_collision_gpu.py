@@ -324,3 +324,29 @@ def test_crowded_scene_overflow_paths(cuda):
     ov, _, md = so.edges_valid(s.astype(np.float64), g.astype(np.float64), 0.1, return_detail=True)
     check_edges(valid, ov, md)
     del obs
+
+
+def test_multi_tile_ranges_partial_tiles_and_unaligned_q(scene, cuda):
+    """Ranges of several tiles per warp (the next q tile is requested with cp.async while the current one is culled),
+    a partial last tile, and a q buffer that is only 4-byte aligned (the 4-byte cp.async path): same verdicts and
+    distances as single-tile calls on the same rows, and as the oracle on a sub-sample."""
+    import torch
+    arm, cubes, so = scene
+    B = 1_250_000 + 19                      # > 2 tiles per warp with the default range length, ragged end
+    q = workloads.random_configs_cuda(arm, B, seed=11)
+    hit = arm.in_collision(q)
+    dist = arm.min_distance(q[:200_003])
+    # (a) chunks small enough for one tile per warp
+    ref = torch.cat([arm.in_collision(q[i:i + 4096]) for i in range(0, B, 4096)])
+    assert torch.equal(hit, ref)
+    # (b) only 4-byte aligned
+    store = torch.empty(B * arm.dof + 1, dtype=torch.float32, device=q.device)
+    qu = store[1:].view(B, arm.dof)
+    qu.copy_(q)
+    assert qu.data_ptr() % 16 == 4
+    assert torch.equal(arm.in_collision(qu), hit)
+    assert torch.equal(arm.min_distance(qu[:200_003]), dist)
+    # (c) oracle on a strided sub-sample
+    idx = torch.arange(0, B, 97, device=q.device)
+    d = so.min_distance(q[idx].cpu().numpy().astype(np.float64))
+    check_verdicts(hit[idx].cpu().numpy(), d)
