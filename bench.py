@@ -10,9 +10,14 @@ fp32 Kinova-7 configurations per GPU (T (B,4,4) and J (B,6,7) both written).  We
 rank owns its own 2^24 configurations (seed 0 + rank), no data-path collective.  Rank 0 prints ONE
 JSON line; see README / DESIGN.md section 7 for every key.
 
-`--impl reference` times the reference's algorithm on the host cores instead: the float64 C/OpenMP
-restatement under oracle/ (the reference itself is Python + numba + PyBullet and cannot travel to the
-GPU box), same metric and workload, each step a bounded sample.
+`--impl reference` times the reference's CPU implementation of the same path on the host cores instead:
+the reference's OWN numba kernels (numbotics/robots/helpers.py:91-187, staged unmodified under oracle/_ref/
+by __graft_entry__.build()) in one process per host core when numba imports, else the float64 C/OpenMP
+restatement under oracle/ (`cpu_baseline.kind` says which); same metric, same `config`, each step a bounded
+sample of the workload.
+
+Exit status: non-zero when a parity gate of the line fails (`parity.ok`, the host-path bit check, or an
+extra's `parity.mismatches_outside_band`); the JSON line is still printed.
 """
 import argparse
 import json
@@ -29,6 +34,7 @@ CONFIGS_PER_GPU = 1 << 24          # BASELINE configs[1]: 16M configurations on 
 DOF = 7
 BYTES_PER_CFG = 4 * DOF + 64 + 24 * DOF     # q in + T out + J out, fp32 = 260
 FLOPS_PER_CFG = 7 * 137 + 72                # SURVEY.md section 8d accounting = 1031
+BAND = 1e-4                                 # stated contact band, metres
 METRIC = "fk_jacobian_configs_per_sec"
 UNIT = "configs/s"
 WORKLOAD = "kinova7_fk_jacobian_2^24_fp32_per_gpu (BASELINE configs[1])"
@@ -131,9 +137,17 @@ def host_threads() -> int:
 
 
 # -------------------------------------------------------------------------------------------------
+def bench_config(world: int) -> dict:
+    """The `config` of the line -- the same dict in both arms (the reference arm's bounded sample is described in its
+    `cpu_baseline.sample`)."""
+    return {"workload": WORKLOAD, "configs_per_gpu": CONFIGS_PER_GPU, "frame": "tool_frame",
+            "outputs": "T (B,4,4) and J (B,6,7)",
+            "l2_policy": "inputs larger than L2: each step streams 4.36 GB per GPU (126 MB L2)",
+            "parallelism": f"batch sharded over {world} GPU(s), no data-path collective"}
+
+
 def cpu_port_rate(arm, n_cfg: int, threads: int | None = None, repeats: int = 1):
     """configs/s of the float64 C/OpenMP restatement (FK + Jacobian, tool_frame) on `n_cfg` configs."""
-    import numpy as np
     from numbotics_b200 import workloads
     from oracle import collision
     # torchrun exports OMP_NUM_THREADS=1 to its workers: ask for every core this process may run on instead
@@ -150,42 +164,148 @@ def cpu_port_rate(arm, n_cfg: int, threads: int | None = None, repeats: int = 1)
     return n_cfg / best, collision.num_threads(), q, out
 
 
+def reference_numba_available() -> bool:
+    try:
+        from oracle import ref_loader
+        return ref_loader.available()
+    except Exception:
+        return False
+
+
 def run_reference(args, rank):
-    """`--impl reference`: the CPU restatement of the reference's algorithm, all host threads."""
+    """`--impl reference`: the reference's CPU implementation of the path on the host cores (rank 0 only)."""
     if rank != 0:
         return
     from numbotics_b200 import workloads
     arm = workloads.kinova_arm(device=0)       # no device call is made on this arm
-    import numpy as np
     from oracle import collision
-    sample = 1 << 21
-    # inputs, descriptor and thread pool are prepared OUTSIDE the timed region (the GPU arm's inputs are resident too);
-    # a step is one call of the port on the sample, outputs allocated by the call as in the reference's API
-    collision.set_threads(host_threads())      # torchrun exports OMP_NUM_THREADS=1: ask for every core we may run on
+    cores = host_threads()
+    line_extra = {}
+    kind = "port"
+    value = ms = None
+    if reference_numba_available():
+        pool = None
+        try:
+            from oracle import ref_bench
+            pool = ref_bench.RefPool(arm, cores)          # spawns the workers; each JIT-compiles / loads its cache here
+            batches = 2
+            for _ in range(args.warmup):
+                pool.step(batches)
+            n_tot, t_tot = 0, 0.0
+            for _ in range(args.steps):
+                n, dt = pool.step(batches)
+                n_tot += n
+                t_tot += dt
+            value, ms = n_tot / t_tot, t_tot / args.steps * 1e3
+            kind = "reference"
+            sample = (f"{cores} processes x {batches} batches x {ref_bench.B_REF} uniformly sampled Kinova-7 configurations per step "
+                      f"(= {cores * batches * ref_bench.B_REF} configs/step, float64), the reference's own numba kernels "
+                      "nb_compute_transformation + nb_compute_jacobian (numbotics/robots/helpers.py:91-187, staged unmodified in "
+                      "oracle/_ref/) through the restated Arm wrappers (arm.py:369-461), batch size 4096 = BASELINE configs[0]; "
+                      "the helpers are serial, so one process per host core, independent slices")
+        except Exception as exc:                           # numba present but the pool failed: fall back to the port
+            line_extra["reference_numba_error"] = f"{type(exc).__name__}: {exc}"[:300]
+            value = None
+        finally:
+            if pool is not None:
+                pool.close()
+    # the C/OpenMP port, all host threads: the fallback arm, and context next to the numba figure
+    n_port = 1 << 21
+    collision.set_threads(cores)               # torchrun exports OMP_NUM_THREADS=1: ask for every core we may run on
     desc = collision.CDesc(arm._arrays)
     fid = arm._arrays["frame_id"]["tool_frame"]
-    q = workloads.random_configs_np(arm, sample, seed=0)
+    q = workloads.random_configs_np(arm, n_port, seed=0)
     base = arm.base_pose
-    for _ in range(max(args.warmup, 1)):
+    port_steps = args.steps if value is None else min(args.steps, 3)
+    for _ in range(args.warmup if value is None else 1):
         collision.c_fk_jac(desc, fid, q, base)
-    cores = collision.num_threads()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(port_steps):
         collision.c_fk_jac(desc, fid, q, base)
     dt = time.perf_counter() - t0
-    value = args.steps * sample / dt
+    port_value = port_steps * n_port / dt
+    port = {"value": port_value, "unit": UNIT, "cores": collision.num_threads(), "kind": "port",
+            "sample": f"{n_port} configurations per step, float64 C/OpenMP restatement (oracle/nbx_oracle.c)"}
+    if value is None:
+        value, ms = port_value, dt / port_steps * 1e3
+        sample = (f"{n_port} uniformly sampled Kinova-7 configurations per step, float64 C/OpenMP restatement of "
+                  "numbotics/robots/helpers.py:91-187 (numba not importable here, so the reference's own kernels could not run)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_configs_per_step": sample, "frame": "tool_frame"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} uniformly sampled Kinova-7 configurations per step, float64 C/OpenMP restatement "
-                                   "of numbotics/robots/helpers.py:91-187 (the reference's numba kernels cannot travel to the GPU box)"},
+        "config": bench_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "port": port},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    line.update(line_extra)
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_block(arm, dev):
+    """Rank 0, N = 1: the reference's numba kernels (when they can run here) and the C/OpenMP port, on the host cores,
+    + the FK/J parity gates against both."""
+    import numpy as np
+    import torch
+    from oracle import collision as _oc
+    fid = arm._arrays["frame_id"]["tool_frame"]
+    cores = host_threads()
+    rate0, _, _, _ = cpu_port_rate(arm, 1 << 17)
+    sample = int(min(1 << 24, max(1 << 18, 2 ** int(np.log2(max(rate0 * 8.0, 1.0))))))   # about 8 s of CPU work
+    rate, pcores, qs, (To, Jo) = cpu_port_rate(arm, sample)
+    rate1, _, _, _ = cpu_port_rate(arm, 1 << 17, threads=1)
+    _oc.set_threads(cores)
+    port = {"value": rate, "unit": UNIT, "cores": pcores, "kind": "port", "single_thread_value": rate1,
+            "sample": f"{sample} uniformly sampled Kinova-7 configurations (seed 0), float64 C/OpenMP restatement of "
+                      "numbotics/robots/helpers.py:91-187, FK + Jacobian of tool_frame"}
+    # parity gate 1: fp32 kernel vs the float64 port on the first 4096 rows of that sample (q rounded to fp32 on both sides)
+    n = 4096
+    Tg, Jg = arm.fk_jacobian(torch.as_tensor(qs[:n], dtype=torch.float32, device=dev), "tool_frame")
+    qs32 = qs[:n].astype(np.float32).astype(np.float64)
+    To32, Jo32 = _oc.c_fk_jac(_oc.CDesc(arm._arrays), fid, qs32, arm.base_pose)
+    eT = float(np.abs(Tg.cpu().numpy() - To32).max())
+    eJ = float(np.abs(Jg.cpu().numpy() - Jo32).max())
+    rel = lambda G, O: float((np.abs(G - O).reshape(n, -1).max(1) / np.maximum(np.abs(O).reshape(n, -1).max(1), 1.0)).max())
+    parity = {"checked_rows": n, "max_abs_err_T": eT, "max_abs_err_J": eJ,
+              "max_rel_err_T": rel(Tg.cpu().numpy(), To32), "max_rel_err_J": rel(Jg.cpu().numpy(), Jo32),
+              "tolerance": 1e-5, "ok": bool(eT < 1e-5 and eJ < 1e-5)}
+    baseline = dict(port)
+    baseline["port"] = port
+    if reference_numba_available():
+        pool = None
+        try:
+            from oracle import ref_bench
+            q_ref = qs[:ref_bench.B_REF]
+            r1, Tr, Jr = ref_bench.single_core_rate(arm, q_ref)          # BASELINE configs[0]: B = 4096, float64, one core
+            pool = ref_bench.RefPool(arm, cores)
+            n_tot, t_tot = 0, 0.0
+            for i in range(6):
+                nn, dt = pool.step(2)
+                if i >= 1:
+                    n_tot += nn
+                    t_tot += dt
+            agg = n_tot / t_tot
+            baseline = {"value": agg, "unit": UNIT, "cores": cores, "kind": "reference",
+                        "sample": f"BASELINE configs[0]: batches of {ref_bench.B_REF} uniformly sampled Kinova-7 configurations, float64, the "
+                                  "reference's own numba kernels (numbotics/robots/helpers.py:91-187 staged in oracle/_ref/) through the "
+                                  f"restated Arm wrappers; aggregate of {cores} processes x 2 batches x 5 steps; single_core_value = best of 5 "
+                                  "on one core",
+                        "single_core_value": r1, "procs": cores, "port": port}
+            # parity gate 2: the float64 kernels (the drop-in caller's default dtype) against the reference's numba output
+            Tg64, Jg64 = arm.fk_jacobian(np.ascontiguousarray(q_ref), "tool_frame")
+            e64T, e64J = float(np.abs(Tg64 - Tr).max()), float(np.abs(Jg64 - Jr).max())
+            parity["vs_reference_numba_f64"] = {"rows": int(q_ref.shape[0]), "max_abs_err_T": e64T, "max_abs_err_J": e64J,
+                                                "tolerance": 1e-9}
+            parity["ok"] = bool(parity["ok"] and e64T < 1e-9 and e64J < 1e-9)
+        except Exception as exc:
+            baseline["reference_numba_error"] = f"{type(exc).__name__}: {exc}"[:300]
+        finally:
+            if pool is not None:
+                pool.close()
+    else:
+        baseline["reference_numba_error"] = "numba or oracle/_ref/ref_helpers.py not present on this box"
+    return baseline, parity
 
 
 # -------------------------------------------------------------------------------------------------
@@ -197,7 +317,8 @@ def main():
     ap.add_argument("--impl", default="nbx", choices=["nbx", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary collision / edge / 30-DoF measurements")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
+    if args.warmup < 3:
+        raise SystemExit("bench.py: --warmup must be >= 3 (timing rules)")
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -294,11 +415,38 @@ def main():
     e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
     e2e_value = world * B * e2e_steps / e2e_s
     e2e_ok = bool(torch.equal(Th[:4096], T[:4096].cpu()) and torch.equal(Jh[-4096:], J[-4096:].cpu()))
+    e2e_ok_all = max_over_ranks(0.0 if e2e_ok else 1.0, dev) == 0.0
+
+    # ---- the host link's own ceiling for that step: the same three transfers (q up; T, J down) as plain pinned
+    # cudaMemcpyAsync on two streams, no kernel, all ranks at once -- the roofline of the end-to-end number
+    s_up, s_dn = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    ceil_s = float("inf")
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s_up):
+            q.copy_(qh, non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            Th.copy_(T, non_blocking=True)
+            Jh.copy_(J, non_blocking=True)
+        s_up.synchronize()
+        s_dn.synchronize()
+        barrier()
+        ceil_s = min(ceil_s, max_over_ranks(time.perf_counter() - t0, dev))
+    step_bytes = BYTES_PER_CFG * B
+    e2e_roofline = {"bound": "host link (PCIe + host memory)", "unit": "GB/s",
+                    "achieved": world * step_bytes * e2e_steps / e2e_s / 1e9,
+                    "peak": world * step_bytes / ceil_s / 1e9,
+                    "frac": (world * step_bytes * e2e_steps / e2e_s) / (world * step_bytes / ceil_s),
+                    "peak_source": f"measured in this run: the step's three transfers ({4 * DOF * B} B up, {(64 + 24 * DOF) * B} B down per GPU) as "
+                                   f"plain pinned cudaMemcpyAsync on two streams, no kernels, {world} rank(s) concurrently, best of 3, max over ranks",
+                    "ceiling_configs_per_sec": world * B / ceil_s}
 
     extras = None
+    extras_ok = True
     if not args.no_extras:
         del qh, Th, Jh
-        extras = secondary_measurements(arm, q, dev, rank, world, float(clock_info.get("sm_mhz") or 1965.0))
+        extras, extras_ok = secondary_measurements(arm, q, dev, rank, world, float(clock_info.get("sm_mhz") or 1965.0))
 
     if rank != 0:
         if world > 1:
@@ -320,44 +468,27 @@ def main():
                              "ncu: dram__bytes.sum 6.6 TB/s = 81 % of the 8.18 TB/s pin rate (profiles/r01_ncu_full_summary_final.csv)",
                 "fp32_tflops": FLOPS_PER_CFG * B / (avg_launch_ms * 1e-3) / 1e12}
 
-    # ---- CPU baseline (oracle port) + parity gate, rank 0, N = 1 only ------------------------------------------
+    # ---- CPU baseline (reference numba kernels / oracle port) + parity gates, rank 0, N = 1 only ------------------
     cpu_baseline = None
     parity = None
     if world == 1:
-        rate0, cores, _, _ = cpu_port_rate(arm, 1 << 17)
-        sample = int(min(1 << 24, max(1 << 18, 2 ** int(np.log2(max(rate0 * 10.0, 1.0))))))   # about 10 s of CPU work
-        rate, cores, qs, (To, Jo) = cpu_port_rate(arm, sample)
-        rate1, _, _, _ = cpu_port_rate(arm, 1 << 17, threads=1)
-        from oracle import collision as _oc
-        _oc.set_threads(host_threads())
-        cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"{sample} uniformly sampled Kinova-7 configurations (seed 0), float64 C/OpenMP restatement of "
-                                  "numbotics/robots/helpers.py:91-187, FK + Jacobian of tool_frame",
-                        "single_thread_value": rate1,
-                        "reference_numba_survey_value": 4.0e4,
-                        "note": "the reference's own numba kernels measured 4.0e4 cfg/s on one core at survey time (BASELINE.md section 2); "
-                                "they cannot run on the GPU box"}
-        # parity gate on the first 4096 rows of that sample (fp32 kernel vs float64 oracle)
-        n = 4096
-        Tg, Jg = arm.fk_jacobian(torch.as_tensor(qs[:n], dtype=torch.float32, device=dev), "tool_frame")
-        qs32 = qs[:n].astype(np.float32).astype(np.float64)
-        To32, Jo32 = _oc.c_fk_jac(_oc.CDesc(arm._arrays), fid, qs32, arm.base_pose)
-        eT = float(np.abs(Tg.cpu().numpy() - To32).max())
-        eJ = float(np.abs(Jg.cpu().numpy() - Jo32).max())
-        parity = {"checked_rows": n, "max_abs_err_T": eT, "max_abs_err_J": eJ, "tolerance": 1e-5, "ok": bool(eT < 1e-5 and eJ < 1e-5),
-                  "e2e_host_path_bitwise_equal_to_device_path": e2e_ok}
+        cpu_baseline, parity = cpu_baseline_block(arm, dev)
+        parity["e2e_host_path_bitwise_equal_to_device_path"] = e2e_ok_all
+        parity["ok"] = bool(parity["ok"] and e2e_ok_all and extras_ok)
+    else:
+        parity = {"e2e_host_path_bitwise_equal_to_device_path": e2e_ok_all, "ok": bool(e2e_ok_all and extras_ok),
+                  "note": "the oracle comparisons run at N = 1 only"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "configs_per_gpu": B, "frame": "tool_frame", "outputs": "T (B,4,4) and J (B,6,7)",
-                   "l2_policy": "inputs larger than L2: each step streams 4.36 GB per GPU (126 MB L2)",
-                   "parallelism": f"batch sharded over {world} GPU(s), no data-path collective"},
+        "config": bench_config(world),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * DOF * B, "d2h_bytes_per_step": (64 + 24 * DOF) * B,
-                "steps": e2e_steps, "api": "nbx_fk_jac_host_f32 (pinned host buffers, 3-slot H2D/kernel/D2H pipeline)", "cpu_affinity": numa},
+                "steps": e2e_steps, "api": "nbx_fk_jac_host_f32 (pinned host buffers, 3-slot H2D/kernel/D2H pipeline)", "cpu_affinity": numa,
+                "roofline": e2e_roofline},
         "gpu_launches": int(gpu_launches),
         "clocks": clock_info,
         "parity": parity,
@@ -367,6 +498,8 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if not parity["ok"]:
+        raise SystemExit(1)
 
 
 def fp32_convention_flops_per_config(arm):
@@ -386,12 +519,16 @@ def fp32_convention_flops_per_config(arm):
 
 
 def secondary_measurements(arm, q, dev, rank, world, clocks_mhz):
-    """BASELINE configs 3-5 (not the headline; reported for the roofline table in DESIGN.md).  Every rank runs its
-    shard; times are the max over ranks between two barriers, values are whole-job aggregates."""
+    """BASELINE configs 3-5 and the float64 / gather / end-to-end figures around them (not the headline).  Every rank runs
+    its shard; times are the max over ranks between two barriers, values are whole-job aggregates.  Returns
+    (extras, ok): ok is False when a parity gate failed on some rank."""
+    import numpy as np
     import torch
     import torch.distributed as dist
-    from numbotics_b200 import workloads
-    from numbotics_b200.dist import max_over_ranks, shard_bounds
+    from numbotics_b200 import _cabi, workloads
+    from numbotics_b200.dist import max_over_ranks, shard_bounds, gather_shards
+
+    lib = _cabi.load()
 
     def barrier():
         if world > 1:
@@ -410,8 +547,24 @@ def secondary_measurements(arm, q, dev, rank, world, clocks_mhz):
             ts.append(max_over_ranks(a.elapsed_time(b), dev))
         return min(ts)
 
+    def best_wall_s(fn, n=4, warm=1):
+        """host-buffer calls return when the results are in host memory: wall clock between barriers, max over ranks"""
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(n):
+            barrier()
+            t0 = time.perf_counter()
+            fn()
+            dt = time.perf_counter() - t0
+            ts.append(max_over_ranks(dt, dev))
+        return min(ts)
+
+    ok_all = True
     out = {}
-    # configs[2]: 4 Mi configurations per GPU (weak)
+    base_keep, base_ptr = _cabi.base_pose_arg(arm.base_pose)
+    h = arm._handle()
+    # ---- configs[2]: 4 Mi configurations per GPU (weak) -------------------------------------------------
     Bc = 1 << 22
     qc = q[:Bc]
     ms = best_ms(lambda: arm.in_collision(qc))
@@ -419,64 +572,174 @@ def secondary_measurements(arm, q, dev, rank, world, clocks_mhz):
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     fp32_peak = sms * 128 * 2 * clocks_mhz * 1e6 / 1e12
     rate = world * Bc / ms * 1e3
+    hit_gpu = arm.in_collision(qc)
     out["in_collision_configs_per_sec"] = {
         "value": rate, "configs_per_gpu": Bc, "best_ms": ms, "scaling": "weak",
-        "hit_fraction": float(arm.in_collision(qc).float().mean()),
+        "hit_fraction": float(hit_gpu.float().mean()),
         "workload": "BASELINE configs[2]: Kinova-7 + 3 cubes, self + env pairs, 2^22 configurations per GPU",
         "kernels": "in_collision_kernel<split> (tree walk + broad phase) + narrow_kernel (GJK over the candidate queue)",
-        "roofline": {"bound": "issue (fp32 pipe)", "convention_flops_per_config": flops, "n_prims": n_prims, "self_pairs": n_self, "env_pairs": n_env,
-                     "convention_tflops": flops * rate / world / 1e12, "fp32_peak_tflops": fp32_peak,
-                     "convention_frac_of_fp32_peak": flops * rate / world / 1e12 / fp32_peak,
-                     "ncu": recorded_traffic("in_collision_ncu"),
-                     "note": "SURVEY 8(d) accounting convention: 256 flop charged per ALLOWED pair, whereas a culled pair executes ~20 -- "
-                             "the convention figure is a throughput in the survey's units, not a bound (it can exceed 1). The measured "
-                             "limiter is instruction issue: see the ncu entry (issue-slot utilisation, executed FP32 flop per configuration) "
-                             "and profiles/README.md"}}
-    # configs[3]: 1 M candidate edges in total, sharded over the GPUs (strong)
+        "roofline": {"bound": "issue (fp32 pipe)", "ncu": recorded_traffic("in_collision_ncu"),
+                     "fp32_peak_tflops": fp32_peak,
+                     "survey_convention": {"flops_per_config": flops, "n_prims": n_prims, "self_pairs": n_self, "env_pairs": n_env,
+                                           "tflops": flops * rate / world / 1e12,
+                                           "note": "SURVEY 8(d) charges 256 flop per ALLOWED pair whereas a culled pair executes ~20: a throughput in "
+                                                   "the survey's units, NOT a roofline fraction; the limiter is instruction issue (ncu entry)"}}}
+    # end to end through nbx_in_collision_host_f32: pinned q in, verdict bytes out, copies inside the timed region
+    scene = arm._scene(0.0)
+    qch = torch.empty((Bc, DOF), dtype=torch.float32).pin_memory()
+    qch.copy_(qc)
+    vh = torch.empty((Bc,), dtype=torch.uint8).pin_memory()
+    wall = best_wall_s(lambda: _cabi.check(lib.nbx_in_collision_host_f32(h.ptr, scene.ptr, qch.data_ptr(), Bc, base_ptr, 0.0, vh.data_ptr())))
+    same = bool(torch.equal(vh.to(torch.bool), hit_gpu.cpu()))
+    ok_all &= same
+    out["in_collision_configs_per_sec"]["e2e"] = {
+        "value": world * Bc / wall, "unit": "configs/s", "h2d_bytes_per_step": 4 * DOF * Bc, "d2h_bytes_per_step": Bc,
+        "api": "nbx_in_collision_host_f32 (pinned host buffers; 2^19-configuration chunks alternate between two pooled streams)",
+        "host_link_GBps": world * (4 * DOF + 1) * Bc / wall / 1e9, "equal_to_device_path": same}
+    del qch, vh
+
+    # ---- configs[3]: 1 M candidate edges in total, sharded over the GPUs (strong) ------------------------------
     nodes = workloads.random_configs_cuda(arm, 100000, seed=0)
     s_all, g_all = workloads.knn_edges_cuda(nodes, 10)
-    lo, hi = shard_bounds(s_all.shape[0], rank, world)
+    E_total = int(s_all.shape[0])
+    lo, hi = shard_bounds(E_total, rank, world)
     s, g = s_all[lo:hi].contiguous(), g_all[lo:hi].contiguous()
     ms = best_ms(lambda: arm.edges_valid(s, g, 0.1))
     v, ns = arm.edges_valid(s, g, 0.1, return_samples=True)
-    out["prm_edges_per_sec"] = {"value": s_all.shape[0] / ms * 1e3, "edges_total": int(s_all.shape[0]), "edges_this_rank": int(hi - lo),
+    out["prm_edges_per_sec"] = {"value": E_total / ms * 1e3, "edges_total": E_total, "edges_this_rank": int(hi - lo),
                                 "best_ms": ms, "scaling": "strong",
                                 "valid_fraction_rank0": float(v.float().mean()), "mean_samples_per_edge_rank0": float(ns.float().mean()),
-                                "samples_per_sec": float(ns.sum()) * world / ms * 1e3,
+                                "issued_samples_per_sec": float(ns.sum()) * world / ms * 1e3,
                                 "workload": "BASELINE configs[3]: 100k nodes x 10-NN = 1M edges, resolution 0.1, contiguous E/G slices"}
+    En = int(hi - lo)
+    sh, gh = torch.empty((En, DOF), dtype=torch.float32).pin_memory(), torch.empty((En, DOF), dtype=torch.float32).pin_memory()
+    sh.copy_(s); gh.copy_(g)
+    veh = torch.empty((En,), dtype=torch.uint8).pin_memory()
+    wall = best_wall_s(lambda: _cabi.check(lib.nbx_edges_valid_host_f32(h.ptr, scene.ptr, sh.data_ptr(), gh.data_ptr(), En, base_ptr,
+                                                                         0.1, 0.0, 0.0, veh.data_ptr())))
+    same = bool(torch.equal(veh.to(torch.bool), v.cpu()))
+    ok_all &= same
+    out["prm_edges_per_sec"]["e2e"] = {
+        "value": E_total / wall, "unit": "edges/s", "h2d_bytes_per_step": 8 * DOF * En, "d2h_bytes_per_step": En,
+        "api": "nbx_edges_valid_host_f32 (pinned host buffers; 2^17-edge chunks alternate between two pooled streams)",
+        "equal_to_device_path": same}
+    del sh, gh, veh
+    if world > 1:
+        # north_star: NCCL only gathers verdicts / poses where a caller wants them in one place -- timed separately
+        gather_ms = best_ms(lambda: gather_shards(v.to(torch.uint8), E_total, dst=0))
+        Bp = 1 << 20
+        plo, phi = shard_bounds(Bp, rank, world)
+        poses = arm.forward_kinematics(q[: phi - plo], "tool_frame")
+        gather_pose_ms = best_ms(lambda: gather_shards(poses, Bp, dst=0))
+        full = gather_shards(v.to(torch.uint8), E_total, dst=0)
+        out["nccl_gather"] = {"edge_verdicts": {"bytes_total": E_total, "best_ms": gather_ms},
+                              "poses": {"rows_total": Bp, "bytes_total": Bp * 64, "best_ms": gather_pose_ms,
+                                        "GBps": Bp * 64 / gather_pose_ms / 1e6},
+                              "api": "numbotics_b200.dist.gather_shards(dst=0) over NCCL (pad to the largest shard, gather, trim)",
+                              "rank0_got_all_rows": bool(rank != 0 or (full is not None and full.shape[0] == E_total))}
+        del poses, full
     if world == 1:
         # CPU figures for configs[2] and [3]: the float64 C/OpenMP restatement (the reference's PyBullet path cannot run
-        # here at all) on bounded samples, all host threads -- "restated oracle, not reference" 
-        import time as _time
-        import numpy as _np
+        # here at all) on bounded samples of the SAME rows, all host threads -- "restated oracle, not reference" 
+        # -- and the parity gates of SURVEY 8(d): verdicts identical outside the stated contact band
         from oracle import collision as _oc
         _oc.set_threads(host_threads())
         desc = _oc.CDesc(arm._arrays, arm.scene_arrays(None))
-        qn = qc[: 1 << 17].cpu().numpy().astype(_np.float64)
-        t0 = _time.perf_counter(); hit_cpu = _oc.c_in_collision(desc, qn, arm.base_pose); dt = _time.perf_counter() - t0
+        n_c = 1 << 17
+        qn = qc[:n_c].cpu().numpy().astype(np.float64)
+        t0 = time.perf_counter(); hit_cpu = _oc.c_in_collision(desc, qn, arm.base_pose); dt = time.perf_counter() - t0
+        _, d_cpu = _oc.c_in_collision(desc, qn, arm.base_pose, want_dist=True)
+        band = np.abs(d_cpu) <= BAND
+        g_hit = hit_gpu[:n_c].cpu().numpy()
+        mism = int(np.sum((g_hit != (d_cpu < 0.0)) & ~band))
+        ok_all &= mism == 0
         out["in_collision_configs_per_sec"]["cpu_port"] = {
-            "value": qn.shape[0] / dt, "unit": "configs/s", "cores": _oc.num_threads(), "kind": "restated oracle, not reference",
-            "sample": f"{qn.shape[0]} of the same configurations", "hit_fraction": float(hit_cpu.mean())}
-        sn, gn = s[: 1 << 14].cpu().numpy().astype(_np.float64), g[: 1 << 14].cpu().numpy().astype(_np.float64)
-        t0 = _time.perf_counter(); v_cpu, _, _ = _oc.c_edges_valid(desc, sn, gn, arm.base_pose, 0.1); dt = _time.perf_counter() - t0
+            "value": n_c / dt, "unit": "configs/s", "cores": _oc.num_threads(), "kind": "restated oracle, not reference",
+            "sample": f"the first {n_c} of the same configurations", "hit_fraction": float(hit_cpu.mean())}
+        out["in_collision_configs_per_sec"]["parity"] = {
+            "rows": n_c, "band_m": BAND, "mismatches_outside_band": mism, "in_band_fraction": float(band.mean()),
+            "in_band_rows": int(band.sum()), "gpu_hit_fraction_same_rows": float(g_hit.mean()),
+            "against": "oracle/nbx_oracle.c min distance (float64) on the same rows; parity UNPINNED against Bullet (DESIGN.md section 4)"}
+        n_e = 1 << 14
+        sn, gn = s[:n_e].cpu().numpy().astype(np.float64), g[:n_e].cpu().numpy().astype(np.float64)
+        t0 = time.perf_counter(); v_cpu, ns_cpu, nu_cpu = _oc.c_edges_valid(desc, sn, gn, arm.base_pose, 0.1); dt = time.perf_counter() - t0
+        _, _, _, md = _oc.c_edges_valid(desc, sn, gn, arm.base_pose, 0.1, want_min_d=True)
+        band_e = np.abs(md) <= BAND
+        g_v = v[:n_e].cpu().numpy()
+        mism_e = int(np.sum((g_v != v_cpu) & ~band_e))
+        cnt_bad = int(np.sum(ns[:n_e].cpu().numpy() != ns_cpu))
+        ok_all &= mism_e == 0 and cnt_bad == 0
         out["prm_edges_per_sec"]["cpu_port"] = {
-            "value": sn.shape[0] / dt, "unit": "edges/s", "cores": _oc.num_threads(), "kind": "restated oracle, not reference",
-            "sample": f"{sn.shape[0]} of the same edges", "valid_fraction": float(v_cpu.mean())}
+            "value": n_e / dt, "unit": "edges/s", "cores": _oc.num_threads(), "kind": "restated oracle, not reference",
+            "sample": f"the first {n_e} of the same edges", "valid_fraction": float(v_cpu.mean())}
+        out["prm_edges_per_sec"]["parity"] = {
+            "rows": n_e, "band_m": BAND, "mismatches_outside_band": mism_e, "in_band_fraction": float(band_e.mean()),
+            "sample_count_mismatches": cnt_bad,
+            "against": "oracle/nbx_oracle.c, sequential connectors.py:57-100 semantics, on the same edges (an edge is in the band when its "
+                       "smallest sample distance is within band_m of the threshold)"}
+        useful_frac = float(nu_cpu.sum()) / float(ns_cpu.sum())
+        out["prm_edges_per_sec"]["useful_vs_issued"] = {
+            "issued_samples_per_edge": float(ns_cpu.mean()), "useful_samples_per_edge": float(nu_cpu.mean()), "useful_fraction": useful_frac,
+            "useful_samples_per_sec_estimate": out["prm_edges_per_sec"]["issued_samples_per_sec"] * useful_frac,
+            "note": f"useful = samples up to and including the first invalid one (what the sequential reference evaluates, connectors.py:71-73), "
+                    f"counted by the oracle on the first {n_e} edges; the kernel evaluates every sample of every edge (issued)"}
     del s_all, g_all, s, g, nodes
-    # configs[4]: 2^25 configurations of the 30-DoF chain per GPU (2^28 over 8 GPUs), J alone is 24 GB per GPU
+
+    # ---- float64 path (the drop-in caller's default dtype): device-resident and through host buffers ---------------
+    peak, _ = measured_hbm_peak()
+    B64 = 1 << 24
+    q64 = q.double()
+    T64 = torch.empty((B64, 4, 4), dtype=torch.float64, device=dev)
+    J64 = torch.empty((B64, 6, DOF), dtype=torch.float64, device=dev)
+    fid = arm._arrays["frame_id"]["tool_frame"]
+    st = torch.cuda.current_stream(dev)
+    ms = best_ms(lambda: _cabi.check(lib.nbx_fk_jac_f64(h.ptr, fid, q64.data_ptr(), B64, base_ptr, 0, None, 0, None, 0,
+                                                        T64.data_ptr(), J64.data_ptr(), st.cuda_stream)), n=5, warm=3)
+    out["fk_jacobian_f64_configs_per_sec"] = {
+        "value": world * B64 / ms * 1e3, "configs_per_gpu": B64, "best_ms": ms, "scaling": "weak", "dtype": "f64",
+        "workload": "BASELINE configs[1] in float64 (the reference API's dtype): Kinova-7, T (B,4,4) and J (B,6,7), 2^24 configurations per GPU",
+        "roofline": {"bound": "hbm", "achieved": 2 * BYTES_PER_CFG * B64 / ms / 1e6, "peak": peak, "unit": "GB/s",
+                     "frac": 2 * BYTES_PER_CFG * B64 / ms / 1e6 / peak, "algorithmic_bytes_per_config": 2 * BYTES_PER_CFG}}
+    del T64, J64
+    Bh = 1 << 22
+    qh64 = torch.empty((Bh, DOF), dtype=torch.float64).pin_memory()
+    qh64.copy_(q64[:Bh])
+    Th64 = torch.empty((Bh, 4, 4), dtype=torch.float64).pin_memory()
+    Jh64 = torch.empty((Bh, 6, DOF), dtype=torch.float64).pin_memory()
+    del q64
+    wall = best_wall_s(lambda: _cabi.check(lib.nbx_fk_jac_host_f64(h.ptr, fid, qh64.data_ptr(), Bh, base_ptr, 0, Th64.data_ptr(), Jh64.data_ptr())), n=3)
+    out["fk_jacobian_f64_configs_per_sec"]["e2e"] = {
+        "value": world * Bh / wall, "unit": "configs/s", "configs_per_gpu": Bh, "h2d_bytes_per_step": 8 * DOF * Bh,
+        "d2h_bytes_per_step": (128 + 48 * DOF) * Bh, "host_link_GBps": world * 2 * BYTES_PER_CFG * Bh / wall / 1e9,
+        "api": "nbx_fk_jac_host_f64 (pinned host buffers)"}
+    del qh64, Th64, Jh64
+
+    # ---- configs[4]: 2^25 configurations of the 30-DoF chain per GPU (2^28 over 8 GPUs), J alone is 24 GB per GPU ------
     arm30 = workloads.serial_arm(30, device=dev.index)
     B30 = 1 << 25
     q30 = workloads.random_configs_cuda(arm30, B30, seed=1 + rank)
     ms = best_ms(lambda: arm30.fk_jacobian(q30, "tool"), n=3, warm=2)
-    peak, _ = measured_hbm_peak()
     out["serial30_fk_jacobian_configs_per_sec"] = {
         "value": world * B30 / ms * 1e3, "configs_per_gpu": B30, "best_ms": ms, "scaling": "weak",
         "workload": "BASELINE configs[4]: programmatic 30-DoF serial chain, 2^25 configurations per GPU (2^28 on 8)",
         "kernel": "fkjac_wide_kernel<30, ALLZ>",
         "roofline": {"bound": "hbm", "achieved": 904 * B30 / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": 904 * B30 / ms / 1e6 / peak,
                      "algorithmic_bytes_per_config": 904}}
+    if world == 1:
+        from oracle import collision as _oc
+        n30 = 1 << 14
+        q30s = q30[:n30].contiguous()
+        T30, J30 = arm30.fk_jacobian(q30s, "tool")
+        To, Jo = _oc.c_fk_jac(_oc.CDesc(arm30._arrays), arm30._arrays["frame_id"]["tool"], q30s.cpu().numpy().astype(np.float64), arm30.base_pose)
+        relm = lambda G, O: float((np.abs(G - O).reshape(n30, -1).max(1) / np.maximum(np.abs(O).reshape(n30, -1).max(1), 1.0)).max())
+        eT, eJ = relm(T30.cpu().numpy(), To), relm(J30.cpu().numpy(), Jo)
+        ok_all &= eT < 1e-5 and eJ < 1e-5
+        out["serial30_fk_jacobian_configs_per_sec"]["parity"] = {
+            "rows": n30, "max_rel_err_T": eT, "max_rel_err_J": eJ, "tolerance": 1e-5,
+            "definition": "max over rows of max|gpu - oracle| / max(max|oracle|, 1) per matrix (SURVEY 8d), fp32 kernel vs float64 oracle on the same fp32 q"}
     del q30
-    return out
+    ok = max_over_ranks(0.0 if ok_all else 1.0, dev) == 0.0
+    return out, ok
 
 
 if __name__ == "__main__":

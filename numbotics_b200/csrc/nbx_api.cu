@@ -46,6 +46,53 @@ int nbx_workspace_pool(int device, cudaMemPool_t* out) {
     return NBX_OK;
 }
 
+// Dynamic shared-memory limit of a kernel: raised once per (kernel, device) instead of a cudaFuncSetAttribute driver
+// call in front of every launch (round 1 paid it on each of the ~45 launches of a bisection).
+int nbx_func_smem(const void* func, int device, size_t bytes) {
+    struct Entry { const void* f; int bytes[64]; };
+    static std::mutex mu;
+    static std::vector<Entry> table;
+    if (device < 0) NBX_CUDA_OK(cudaGetDevice(&device));     // the caller has already selected the chain's device
+    NBX_REQUIRE(device >= 0 && device < 64, "device index out of range");
+    std::lock_guard<std::mutex> lock(mu);
+    Entry* e = nullptr;
+    for (Entry& t : table)
+        if (t.f == func) { e = &t; break; }
+    if (e == nullptr) {
+        table.push_back(Entry{func, {}});
+        e = &table.back();
+    }
+    if ((int)bytes <= e->bytes[device]) return NBX_OK;
+    NBX_CUDA_OK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    e->bytes[device] = (int)bytes;
+    return NBX_OK;
+}
+
+// Library-owned non-blocking streams for the *_host_* entry points: a caller borrows one for the duration of the call
+// and hands it back, so concurrent host threads each get their own stream and nothing is created or destroyed per call.
+namespace {
+std::mutex g_stream_mu;
+std::vector<cudaStream_t> g_stream_free[64];
+}  // namespace
+
+int nbx_stream_acquire(int device, cudaStream_t* out) {
+    NBX_REQUIRE(device >= 0 && device < 64, "device index out of range");
+    {
+        std::lock_guard<std::mutex> lock(g_stream_mu);
+        std::vector<cudaStream_t>& f = g_stream_free[device];
+        if (!f.empty()) { *out = f.back(); f.pop_back(); return NBX_OK; }
+    }
+    NBX_CUDA_OK(cudaSetDevice(device));
+    NBX_CUDA_OK(cudaStreamCreateWithFlags(out, cudaStreamNonBlocking));
+    return NBX_OK;
+}
+
+void nbx_stream_release(int device, cudaStream_t st) {
+    if (st == nullptr || device < 0 || device >= 64) return;
+    std::lock_guard<std::mutex> lock(g_stream_mu);
+    g_stream_free[device].push_back(st);
+}
+
 
 
 namespace {

@@ -184,6 +184,7 @@ struct WCtx {
     int gq_half;
     uint8_t* gflag;           // per unit: verdict (hit_value 1) or edge validity (hit_value 0)
     int hit_value;
+    int gjk_iters;            // iteration cap of the verdict GJK (kGjkIters; NBX_GJK_ITERS overrides it for the tests)
 };
 
 __device__ __forceinline__ int float_key(float f) {            // order-preserving float -> int
@@ -308,9 +309,12 @@ __device__ __forceinline__ void eval_cand(const WCtx& C, const Cand& K) {
     } else {
         volatile uint8_t* f = C.gflag + K.fi;
         if (*f == (uint8_t)C.hit_value) return;              // this unit is already decided
-        const GjkOut g = gjk_distance<kGjkIters>(K.A, K.B, C.thr + K.m, C.thr + K.m);
-        const float d = g.overlap ? (-K.m - 1e-3f) : (g.contact ? (-K.m - 1e-6f) : (g.d - K.m));
-        if (d < C.thr) *f = (uint8_t)C.hit_value;
+        const GjkOut g = gjk_distance<kGjkIters>(K.A, K.B, C.thr + K.m, C.thr + K.m, 1e-6f, 1e-5f, C.gjk_iters);
+        // Verdict: a pair is FREE only on proof -- a separating plane beyond the threshold (`pruned`).  Overlap, contact and
+        // an upper bound below the threshold are hits; so is a bracket [lb, ub] that still straddles the threshold when the
+        // iteration stops (converged to its tolerance, stalled, or out of iterations: rounded cylinders converge only
+        // linearly).  The unsafe direction for in_collision / edges_valid / bisect would be to call such a pair free.
+        if (!g.pruned) *f = (uint8_t)C.hit_value;
     }
 }
 
@@ -664,6 +668,7 @@ struct SplitArgs {
     float* gq;
     int* gq_count;
     int gq_half;
+    int gjk_iters;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -685,7 +690,7 @@ in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict_
     C.n_mov = S.n_mov; C.n_prims = S.n_prims; C.n_base_prims = S.n_base_prims;
     C.thr = thr;
     C.gq = G.gq; C.gq_count = G.gq_count; C.gq_half = G.gq_half;
-    C.gflag = verdict; C.hit_value = 1;
+    C.gflag = verdict; C.hit_value = 1; C.gjk_iters = G.gjk_iters;
 
     const int64_t range0 = ((int64_t)blockIdx.x * kWarps + wid) * upw;
     const int rangeN = (int)max((int64_t)0, min((int64_t)upw, B - range0));
@@ -769,7 +774,7 @@ edges_valid_kernel(const __grid_constant__ SceneDev S, const float* __restrict__
     C.n_mov = S.n_mov; C.n_prims = S.n_prims; C.n_base_prims = S.n_base_prims;
     C.thr = thr;
     C.gq = G.gq; C.gq_count = G.gq_count; C.gq_half = G.gq_half;
-    C.gflag = valid; C.hit_value = 0;
+    C.gflag = valid; C.hit_value = 0; C.gjk_iters = G.gjk_iters;
     stage_wait();
     __syncthreads();
 
@@ -854,11 +859,12 @@ edges_valid_kernel(const __grid_constant__ SceneDev S, const float* __restrict__
 // the self pairs (a warp works on one kind of pair).  The entry count lives on the device: no host round trip.
 __global__ void __launch_bounds__(128)
 narrow_kernel(const float* __restrict__ gq, const int* __restrict__ gq_count, int gq_half, float thr,
-              uint8_t* __restrict__ gflag, int hit_value) {
+              uint8_t* __restrict__ gflag, int hit_value, int gjk_iters) {
     WCtx C;
     C.thr = thr;
     C.gflag = gflag;
     C.hit_value = hit_value;
+    C.gjk_iters = gjk_iters;
     const int n_env = min(gq_count[0], gq_half), n_self = min(gq_count[1], gq_half);
     const int stride = gridDim.x * blockDim.x;
     const int first = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1120,8 +1126,9 @@ pair_distances_kernel(const __grid_constant__ SceneDev S, const float* __restric
 template <typename T>
 __global__ void bisect_step_kernel(double* __restrict__ lo, double* __restrict__ hi, const T* __restrict__ inside, int64_t inside_stride,
                                    const T* __restrict__ outside, const uint8_t* __restrict__ verdict, float* __restrict__ mid32,
-                                   T* __restrict__ out, int64_t B, int dof, int round, int last) {
+                                   T* __restrict__ out, int64_t B, int dof, int round, int last, int* __restrict__ gq_count) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { gq_count[0] = 0; gq_count[1] = 0; }      // the previous round's narrow kernel is done (stream order)
     if (i >= B * dof) return;
     const int64_t b = i / dof;
     double l, h;
@@ -1175,7 +1182,7 @@ int units_per_warp(int64_t n_units, int sm_count, int warps_per_sm, int waves = 
 struct SplitWs {
     void* p = nullptr;
     cudaStream_t st = nullptr;
-    SplitArgs args{nullptr, nullptr, 0};
+    SplitArgs args{nullptr, nullptr, 0, kGjkIters};
     int alloc(int device, int64_t n_items, cudaStream_t stream) {
         st = stream;
         cudaMemPool_t pool = nullptr;
@@ -1191,20 +1198,25 @@ struct SplitWs {
         args.gq_count = static_cast<int*>(p);
         args.gq = reinterpret_cast<float*>(static_cast<unsigned char*>(p) + 256);
         args.gq_half = (int)half;
+        static const int iters_env = std::getenv("NBX_GJK_ITERS") ? std::atoi(std::getenv("NBX_GJK_ITERS")) : 0;   // tests only
+        args.gjk_iters = iters_env > 0 ? iters_env : kGjkIters;
         return NBX_OK;
     }
     ~SplitWs() { if (p) cudaFreeAsync(p, st); }
 };
 
 int launch_narrow(const nbx_chain* ch, const SplitArgs& G, float thr, uint8_t* gflag, int hit_value, cudaStream_t stream) {
-    narrow_kernel<<<(unsigned)(ch->sm_count * 8), 128, 0, stream>>>(G.gq, G.gq_count, G.gq_half, thr, gflag, hit_value);
+    narrow_kernel<<<(unsigned)(ch->sm_count * 8), 128, 0, stream>>>(G.gq, G.gq_count, G.gq_half, thr, gflag, hit_value, G.gjk_iters);
     nbx_count_launch();
     NBX_CUDA_OK(cudaGetLastError());
     return NBX_OK;
 }
 
+// `shared`: workspace owned by the caller, counters already zero on `stream` (the bisection keeps ONE workspace for all of
+// its rounds and resets the counters inside its own step kernel: no allocation, memset or free per round).
 int launch_in_collision(const nbx_chain* ch, const nbx_scene* sc, const float* q, int64_t B, const double* base_pose,
-                        float thr, uint8_t* verdict, float* min_dist, cudaStream_t stream, uint32_t* pair_code = nullptr) {
+                        float thr, uint8_t* verdict, float* min_dist, cudaStream_t stream, uint32_t* pair_code = nullptr,
+                        const SplitArgs* shared = nullptr) {
     SceneDev S;
     int rc = fill_scene_dev(ch, sc, base_pose, S);
     if (rc != NBX_OK) return rc;
@@ -1220,20 +1232,21 @@ int launch_in_collision(const nbx_chain* ch, const nbx_scene* sc, const float* q
     const int upw = units_per_warp(B, ch->sm_count, mode == kDist ? 12 : 20);
     const int64_t grid = (B + (int64_t)kWarps * upw - 1) / ((int64_t)kWarps * upw);
     if (mode == kDist) {
-        NBX_CUDA_OK(cudaFuncSetAttribute(in_collision_kernel<kDist, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        in_collision_kernel<kDist, false><<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, q, B, ch->dof, thr, verdict, min_dist, pair_code, upw, SplitArgs{nullptr, nullptr, 0});
+        NBX_SMEM_LIMIT((in_collision_kernel<kDist, false>), smem);
+        in_collision_kernel<kDist, false><<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, q, B, ch->dof, thr, verdict, min_dist, pair_code, upw, SplitArgs{nullptr, nullptr, 0, kGjkIters});
         nbx_count_launch();
         NBX_CUDA_OK(cudaGetLastError());
         return NBX_OK;
     }
     SplitWs ws;
-    if ((rc = ws.alloc(ch->device, B, stream)) != NBX_OK) return rc;
+    if (shared == nullptr && (rc = ws.alloc(ch->device, B, stream)) != NBX_OK) return rc;
+    const SplitArgs& G = shared != nullptr ? *shared : ws.args;
     auto kern = ch->fast_walk ? in_collision_kernel<kSplit, true> : in_collision_kernel<kSplit, false>;
-    NBX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, q, B, ch->dof, thr, verdict, nullptr, nullptr, upw, ws.args);
+    NBX_SMEM_LIMIT(kern, smem);
+    kern<<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, q, B, ch->dof, thr, verdict, nullptr, nullptr, upw, G);
     nbx_count_launch();
     NBX_CUDA_OK(cudaGetLastError());
-    return launch_narrow(ch, ws.args, thr, verdict, 1, stream);
+    return launch_narrow(ch, G, thr, verdict, 1, stream);
 }
 
 int launch_edges(const nbx_chain* ch, const nbx_scene* sc, const float* starts, const float* goals, int64_t E,
@@ -1256,7 +1269,7 @@ int launch_edges(const nbx_chain* ch, const nbx_scene* sc, const float* starts, 
     SplitWs ws;
     if ((rc = ws.alloc(ch->device, E * 8, stream)) != NBX_OK) return rc;
     auto kern = ch->fast_walk ? edges_valid_kernel<true> : edges_valid_kernel<false>;
-    NBX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NBX_SMEM_LIMIT(kern, smem);
     // an edge is ~13 tiles of work for its warp, so the per-CTA prologue is already amortised by one tile of edges; what
     // matters is the tail: 10^6 edges in ranges of 256 were 977 CTAs = 1.65 waves of the 592 resident ones (ncu: +7 %)
     const int upw = units_per_warp(E, ch->sm_count, 16, 8);
@@ -1294,7 +1307,7 @@ int launch_closest(const nbx_chain* ch, const nbx_scene* sc, const float* q, int
     if (rc != NBX_OK) return rc;
     const size_t smem = scene_smem_bytes(S.n_mov, S.n_prims, S.n_obs, S.n_self, S.n_env);
     NBX_REQUIRE(smem <= 220 * 1024, "scene too large for shared memory (%zu bytes)", smem);
-    NBX_CUDA_OK(cudaFuncSetAttribute(closest_witness_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NBX_SMEM_LIMIT(closest_witness_kernel, smem);
     closest_witness_kernel<<<(unsigned)((B + 127) / 128), 128, smem, stream>>>(S, q, B, ch->dof, code, dist, p_subject, p_target, normal,
                                                                               subject, target, valid, grad);
     nbx_count_launch();
@@ -1314,7 +1327,7 @@ int launch_pair_distances(const nbx_chain* ch, const nbx_scene* sc, const float*
     const size_t smem = scene_smem_bytes(S.n_mov, S.n_prims, S.n_obs, S.n_self, S.n_env) +
                         kWarps * align16(sizeof(float) * (size_t)kWT * std::max(S.scratch_floats, 1));
     NBX_REQUIRE(smem <= 220 * 1024, "scene too large for shared memory (%zu bytes)", smem);
-    NBX_CUDA_OK(cudaFuncSetAttribute(pair_distances_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NBX_SMEM_LIMIT(pair_distances_kernel, smem);
     const int64_t grid = (B + kWarps * kWT - 1) / (kWarps * kWT);
     NBX_REQUIRE(grid <= 0x7fffffffLL, "batch too large for one launch");
     pair_distances_kernel<<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, q, B, ch->dof, dist, p_subject, p_target, normal, valid);
@@ -1349,36 +1362,56 @@ int launch_bisect(const nbx_chain* ch, const nbx_scene* sc, const T* inside, int
     float* mid = reinterpret_cast<float*>(w + 2 * up(sizeof(double) * n));
     uint8_t* verdict = w + 2 * up(sizeof(double) * n) + up(sizeof(float) * n);
     const unsigned grid = (unsigned)((n + 255) / 256);
+    SplitWs ws;                          // one candidate queue for all rounds; the step kernel resets its counters
+    if ((rc = ws.alloc(ch->device, B, stream)) != NBX_OK) return rc;
     for (int r = 0; r <= n_bisections; ++r) {
         const int last = r == n_bisections;
-        bisect_step_kernel<T><<<grid, 256, 0, stream>>>(lo, hi, inside, inside_stride, outside, verdict, mid, out, B, dof, r, last);
+        bisect_step_kernel<T><<<grid, 256, 0, stream>>>(lo, hi, inside, inside_stride, outside, verdict, mid, out, B, dof, r, last, ws.args.gq_count);
         nbx_count_launch();
         NBX_CUDA_OK(cudaGetLastError());
         if (last) break;
-        rc = launch_in_collision(ch, sc, mid, B, base_pose, thr, verdict, nullptr, stream);
+        rc = launch_in_collision(ch, sc, mid, B, base_pose, thr, verdict, nullptr, stream, nullptr, &ws.args);
         if (rc != NBX_OK) return rc;
     }
     return NBX_OK;
 }
 
-// host-buffer variants: stream-ordered staging buffers from the library's pool (no cudaMalloc per call), one private
-// stream per call so that concurrent host threads overlap.
-struct HostStage {
-    void* p = nullptr;
-    cudaStream_t st = nullptr;
-    int open(int device, size_t bytes) {
-        cudaMemPool_t pool = nullptr;
+// host-buffer variants: the batch is cut into chunks that alternate between two streams borrowed from the library's
+// stream pool (nothing is created or destroyed per call), each chunk = stream-ordered staging buffer from the library's
+// memory pool -> H2D -> kernels -> D2H of the verdict bytes -> free; chunk k+1's upload overlaps chunk k's kernels.
+// Concurrent host threads borrow different streams and overlap.
+struct HostLanes {
+    static constexpr int kLanes = 2;
+    int device;
+    cudaStream_t st[kLanes] = {nullptr, nullptr};
+    cudaMemPool_t pool = nullptr;
+    explicit HostLanes(int dev) : device(dev) {}
+    int open() {
         int rc = nbx_workspace_pool(device, &pool);
         if (rc != NBX_OK) return rc;
-        NBX_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        NBX_CUDA_OK(cudaMallocFromPoolAsync(&p, bytes, pool, st));
+        for (int i = 0; i < kLanes; ++i)
+            if ((rc = nbx_stream_acquire(device, &st[i])) != NBX_OK) return rc;
         return NBX_OK;
     }
-    ~HostStage() {
-        if (p) cudaFreeAsync(p, st);
-        if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    int finish(int rc) {
+        for (int i = 0; i < kLanes; ++i) {
+            if (st[i] == nullptr) continue;
+            const cudaError_t e = cudaStreamSynchronize(st[i]);
+            if (e != cudaSuccess && rc == NBX_OK) { nbx_set_error("cudaStreamSynchronize failed: %s", cudaGetErrorString(e)); rc = NBX_ERR_CUDA; }
+            nbx_stream_release(device, st[i]);
+            st[i] = nullptr;
+        }
+        return rc;
     }
+    ~HostLanes() { finish(NBX_OK); }
 };
+
+int64_t host_chunk(int64_t n, int64_t dflt) {
+    static const int64_t env = std::getenv("NBX_HOST_CHUNK") ? std::atoll(std::getenv("NBX_HOST_CHUNK")) : 0;   // tuning only
+    int64_t chunk = env > 0 ? env : dflt;
+    if (n < 2 * chunk) chunk = std::max<int64_t>(4096, ((n + 1) / 2 + 127) & ~(int64_t)127);
+    return chunk;
+}
 
 }  // namespace
 
@@ -1395,18 +1428,29 @@ int nbx_in_collision_host_f32(const nbx_chain* chain, const nbx_scene* scene, co
     if (B <= 0) return NBX_OK;
     NBX_REQUIRE(q != nullptr && verdict != nullptr, "q / verdict is NULL");
     NBX_CUDA_OK(cudaSetDevice(chain->device));
-    const size_t qb = (sizeof(float) * (size_t)B * chain->dof + 255) & ~(size_t)255;
-    HostStage hs;
-    int rc = hs.open(chain->device, qb + (size_t)B);
+    const int dof = chain->dof;
+    const int64_t chunk = host_chunk(B, (int64_t)1 << 19);
+    const size_t qb = (sizeof(float) * (size_t)chunk * dof + 255) & ~(size_t)255;
+    HostLanes hl(chain->device);
+    int rc = hl.open();
     if (rc != NBX_OK) return rc;
-    float* dq = static_cast<float*>(hs.p);
-    uint8_t* dv = static_cast<unsigned char*>(hs.p) + qb;
-    NBX_CUDA_OK(cudaMemcpyAsync(dq, q, sizeof(float) * (size_t)B * chain->dof, cudaMemcpyHostToDevice, hs.st));
-    rc = launch_in_collision(chain, scene, dq, B, base_pose, threshold, dv, nullptr, hs.st);
-    if (rc != NBX_OK) return rc;
-    NBX_CUDA_OK(cudaMemcpyAsync(verdict, dv, (size_t)B, cudaMemcpyDeviceToHost, hs.st));
-    NBX_CUDA_OK(cudaStreamSynchronize(hs.st));
-    return NBX_OK;
+    int lane = 0;
+    for (int64_t off = 0; off < B && rc == NBX_OK; off += chunk, lane ^= 1) {
+        const int64_t n = std::min(chunk, B - off);
+        cudaStream_t st = hl.st[lane];
+        void* p = nullptr;
+        NBX_CUDA_OK(cudaMallocFromPoolAsync(&p, qb + (size_t)chunk, hl.pool, st));
+        float* dq = static_cast<float*>(p);
+        uint8_t* dv = static_cast<unsigned char*>(p) + qb;
+        cudaError_t e = cudaMemcpyAsync(dq, q + off * dof, sizeof(float) * (size_t)n * dof, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) {
+            rc = launch_in_collision(chain, scene, dq, n, base_pose, threshold, dv, nullptr, st);
+            if (rc == NBX_OK) e = cudaMemcpyAsync(verdict + off, dv, (size_t)n, cudaMemcpyDeviceToHost, st);
+        }
+        cudaFreeAsync(p, st);
+        if (e != cudaSuccess) { nbx_set_error("cudaMemcpyAsync failed: %s", cudaGetErrorString(e)); rc = NBX_ERR_CUDA; }
+    }
+    return hl.finish(rc);
 }
 
 int nbx_closest_f32(const nbx_chain* chain, const nbx_scene* scene, const float* q, int64_t B, const double* base_pose,
@@ -1448,21 +1492,32 @@ int nbx_edges_valid_host_f32(const nbx_chain* chain, const nbx_scene* scene, con
     if (E <= 0) return NBX_OK;
     NBX_REQUIRE(starts != nullptr && goals != nullptr && valid != nullptr, "starts / goals / valid is NULL");
     NBX_CUDA_OK(cudaSetDevice(chain->device));
-    const size_t raw = sizeof(float) * (size_t)E * chain->dof;
-    const size_t qb = (raw + 255) & ~(size_t)255;
-    HostStage hs;
-    int rc = hs.open(chain->device, 2 * qb + (size_t)E);
+    const int dof = chain->dof;
+    const int64_t chunk = host_chunk(E, (int64_t)1 << 17);
+    const size_t qb = (sizeof(float) * (size_t)chunk * dof + 255) & ~(size_t)255;
+    HostLanes hl(chain->device);
+    int rc = hl.open();
     if (rc != NBX_OK) return rc;
-    float* ds = static_cast<float*>(hs.p);
-    float* dg = reinterpret_cast<float*>(static_cast<unsigned char*>(hs.p) + qb);
-    uint8_t* dv = static_cast<unsigned char*>(hs.p) + 2 * qb;
-    NBX_CUDA_OK(cudaMemcpyAsync(ds, starts, raw, cudaMemcpyHostToDevice, hs.st));
-    NBX_CUDA_OK(cudaMemcpyAsync(dg, goals, raw, cudaMemcpyHostToDevice, hs.st));
-    rc = launch_edges(chain, scene, ds, dg, E, base_pose, resolution, max_distance, threshold, dv, nullptr, hs.st);
-    if (rc != NBX_OK) return rc;
-    NBX_CUDA_OK(cudaMemcpyAsync(valid, dv, (size_t)E, cudaMemcpyDeviceToHost, hs.st));
-    NBX_CUDA_OK(cudaStreamSynchronize(hs.st));
-    return NBX_OK;
+    int lane = 0;
+    for (int64_t off = 0; off < E && rc == NBX_OK; off += chunk, lane ^= 1) {
+        const int64_t n = std::min(chunk, E - off);
+        cudaStream_t st = hl.st[lane];
+        void* p = nullptr;
+        NBX_CUDA_OK(cudaMallocFromPoolAsync(&p, 2 * qb + (size_t)chunk, hl.pool, st));
+        float* ds = static_cast<float*>(p);
+        float* dg = reinterpret_cast<float*>(static_cast<unsigned char*>(p) + qb);
+        uint8_t* dv = static_cast<unsigned char*>(p) + 2 * qb;
+        const size_t raw = sizeof(float) * (size_t)n * dof;
+        cudaError_t e = cudaMemcpyAsync(ds, starts + off * dof, raw, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dg, goals + off * dof, raw, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) {
+            rc = launch_edges(chain, scene, ds, dg, n, base_pose, resolution, max_distance, threshold, dv, nullptr, st);
+            if (rc == NBX_OK) e = cudaMemcpyAsync(valid + off, dv, (size_t)n, cudaMemcpyDeviceToHost, st);
+        }
+        cudaFreeAsync(p, st);
+        if (e != cudaSuccess) { nbx_set_error("cudaMemcpyAsync failed: %s", cudaGetErrorString(e)); rc = NBX_ERR_CUDA; }
+    }
+    return hl.finish(rc);
 }
 
 }  // extern "C"

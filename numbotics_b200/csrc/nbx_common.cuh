@@ -13,6 +13,16 @@ void nbx_set_error(const char* fmt, ...);
 void nbx_count_launch(int n = 1);
 // library-owned stream-ordered memory pool of a device (unbounded release threshold); see nbx_api.cu
 int nbx_workspace_pool(int device, cudaMemPool_t* out);
+// raise a kernel's dynamic shared-memory limit once per (kernel, device); see nbx_api.cu
+int nbx_func_smem(const void* func, int device, size_t bytes);
+#define NBX_SMEM_LIMIT(kern, bytes)                                                       \
+    do {                                                                                  \
+        const int _rc = nbx_func_smem(reinterpret_cast<const void*>(kern), -1, (bytes)); \
+        if (_rc != NBX_OK) return _rc;                                                    \
+    } while (0)
+// borrow / return one of the library's non-blocking streams (the *_host_* entry points)
+int nbx_stream_acquire(int device, cudaStream_t* out);
+void nbx_stream_release(int device, cudaStream_t st);
 
 #define NBX_CUDA_OK(expr)                                                                    \
     do {                                                                                     \

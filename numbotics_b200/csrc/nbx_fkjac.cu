@@ -427,7 +427,7 @@ template <typename T, int TILE, bool ALLZ>
 int launch_generic_t(const PathK<T, NBX_MAX_PATH>& P, const T* q, int64_t B, const T* lp, int64_t lps, const T* gp, int64_t gps,
                      T* T_out, T* J_out, int vec_ok, size_t smem, cudaStream_t stream) {
     auto kern = fkjac_generic_kernel<T, TILE, ALLZ>;
-    NBX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NBX_SMEM_LIMIT(kern, smem);
     const int64_t grid = (B + TILE - 1) / TILE;
     NBX_REQUIRE(grid <= 0x7fffffffLL, "batch too large for one launch");
     kern<<<(unsigned)grid, TILE, smem, stream>>>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok);
@@ -550,7 +550,7 @@ int launch_fkjac(const nbx_chain* ch, int frame, const T* q, int64_t B, const do
         const int64_t grid = (B + 127) / 128;
         NBX_REQUIRE(grid <= 0x7fffffffLL, "batch too large for one launch");
         auto kern = allz ? fkjac_deep_kernel<T, true> : fkjac_deep_kernel<T, false>;
-        NBX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NBX_SMEM_LIMIT(kern, smem);
         kern<<<(unsigned)grid, 128, smem, stream>>>(P, q, B, lp, lps, gp, gps, T_out, J_out, vec_ok, K, slab(K));
         nbx_count_launch();
         NBX_CUDA_OK(cudaGetLastError());
@@ -570,15 +570,34 @@ int launch_fkjac(const nbx_chain* ch, int frame, const T* q, int64_t B, const do
 }
 
 // ---- host-buffer pipeline ------------------------------------------------------------------
+// A pipe = kSlots device staging slots, each with its own stream (H2D -> kernel -> D2H in stream order; consecutive
+// chunks go to consecutive slots, so chunk k+1's upload and kernel overlap chunk k's download).  Pipes are pooled per
+// device: a call borrows one (creating it on first use) and returns it, so concurrent host threads -- the IRIS
+// thread-pool caller of numbotics/utils/threading.py:33-37 -- run side by side instead of queueing on one mutex.
 struct HostPipe {
     static constexpr int kSlots = 3;
     int device = -1;
     size_t cap[kSlots] = {0, 0, 0};
     void* buf[kSlots] = {nullptr, nullptr, nullptr};
     cudaStream_t st[kSlots] = {nullptr, nullptr, nullptr};
-    std::mutex mu;
 };
-HostPipe g_pipe[16];
+std::mutex g_pipe_mu;
+std::vector<HostPipe*> g_pipe_free[64];
+
+struct PipeLease {
+    HostPipe* hp = nullptr;
+    int device;
+    explicit PipeLease(int dev) : device(dev) {
+        std::lock_guard<std::mutex> lock(g_pipe_mu);
+        std::vector<HostPipe*>& f = g_pipe_free[dev];
+        if (!f.empty()) { hp = f.back(); f.pop_back(); }
+        else hp = new HostPipe();
+    }
+    ~PipeLease() {
+        std::lock_guard<std::mutex> lock(g_pipe_mu);
+        g_pipe_free[device].push_back(hp);
+    }
+};
 
 int pipe_prepare(HostPipe& hp, int device, size_t bytes_per_slot) {
     NBX_CUDA_OK(cudaSetDevice(device));
@@ -601,17 +620,20 @@ int fkjac_host(const nbx_chain* ch, int frame, const T* q, int64_t B, const doub
     NBX_REQUIRE(ch != nullptr, "chain handle is NULL");
     NBX_REQUIRE(B >= 0, "negative batch size");
     if (B == 0 || (T_out == nullptr && J_out == nullptr)) return NBX_OK;
-    NBX_REQUIRE(ch->device >= 0 && ch->device < 16, "device index out of range");
+    NBX_REQUIRE(ch->device >= 0 && ch->device < 64, "device index out of range");
     const int dof = ch->dof;
-    // chunk so that three slots stay well inside HBM and the copies are long enough to saturate PCIe
-    const int64_t chunk = 1 << 19;
+    // chunk so that three slots stay well inside HBM and the copies are long enough to saturate PCIe; small batches
+    // are cut into kSlots pieces so that their upload, kernel and download still overlap
+    static const int64_t chunk_env = std::getenv("NBX_HOST_CHUNK") ? std::atoll(std::getenv("NBX_HOST_CHUNK")) : 0;   // tuning only
+    int64_t chunk = chunk_env > 0 ? chunk_env : (int64_t)1 << 19;
+    if (B < chunk * HostPipe::kSlots) chunk = std::max<int64_t>(4096, ((B + HostPipe::kSlots - 1) / HostPipe::kSlots + 127) & ~(int64_t)127);
     const size_t q_bytes = sizeof(T) * (size_t)chunk * dof;
     const size_t t_bytes = T_out ? sizeof(T) * (size_t)chunk * 16 : 0;
     const size_t j_bytes = J_out ? sizeof(T) * (size_t)chunk * 6 * dof : 0;
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t slot_bytes = up(q_bytes) + up(t_bytes) + up(j_bytes);
-    HostPipe& hp = g_pipe[ch->device];
-    std::lock_guard<std::mutex> lock(hp.mu);
+    PipeLease lease(ch->device);
+    HostPipe& hp = *lease.hp;
     int rc = pipe_prepare(hp, ch->device, slot_bytes);
     if (rc != NBX_OK) return rc;
     int slot = 0;
@@ -625,12 +647,16 @@ int fkjac_host(const nbx_chain* ch, int frame, const T* q, int64_t B, const doub
         // stream order guarantees the slot's previous D2H finished before this H2D overwrites it
         NBX_CUDA_OK(cudaMemcpyAsync(dq, q + off * dof, sizeof(T) * (size_t)n * dof, cudaMemcpyHostToDevice, st));
         rc = launch_fkjac<T>(ch, frame, dq, n, base_pose, use_com, nullptr, 0, nullptr, 0, dT, dJ, st);
-        if (rc != NBX_OK) return rc;
+        if (rc != NBX_OK) break;
         if (T_out) NBX_CUDA_OK(cudaMemcpyAsync(T_out + off * 16, dT, sizeof(T) * (size_t)n * 16, cudaMemcpyDeviceToHost, st));
         if (J_out) NBX_CUDA_OK(cudaMemcpyAsync(J_out + off * 6 * dof, dJ, sizeof(T) * (size_t)n * 6 * dof, cudaMemcpyDeviceToHost, st));
     }
-    for (int s = 0; s < HostPipe::kSlots; ++s) NBX_CUDA_OK(cudaStreamSynchronize(hp.st[s]));
-    return NBX_OK;
+    // always drain before the pipe goes back to the pool (also on the error path)
+    for (int s = 0; s < HostPipe::kSlots; ++s) {
+        const cudaError_t e = cudaStreamSynchronize(hp.st[s]);
+        if (e != cudaSuccess && rc == NBX_OK) { nbx_set_error("cudaStreamSynchronize failed: %s", cudaGetErrorString(e)); rc = NBX_ERR_CUDA; }
+    }
+    return rc;
 }
 
 }  // namespace

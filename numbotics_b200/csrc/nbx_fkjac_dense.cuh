@@ -249,7 +249,7 @@ int launch_dense_kt(const PathK<T, CAP>& P, const T* q, int64_t B, const T* lp, 
                     int64_t gps, T* T_out, T* J_out, int vec_ok, cudaStream_t stream) {
     const size_t smem = sizeof(T) * (size_t)TILE * (6 * NJ + 16 + KT * NJ);
     auto kern = fkjac_dense_kernel<T, NJ, TILE, ALLZ, KT, CAP>;
-    NBX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NBX_SMEM_LIMIT(kern, smem);
     const int64_t ntiles = (B + TILE - 1) / TILE;
     const int64_t grid = (ntiles + KT - 1) / KT;
     NBX_REQUIRE(grid <= 0x7fffffffLL, "batch too large for one launch");

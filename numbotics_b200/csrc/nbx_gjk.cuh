@@ -104,6 +104,7 @@ __device__ __forceinline__ V3 closest_tri(V3 a, V3 b, V3 c, int* mask) {
 //          below stop_below or converged.  Overlapping cores report d = 0 and overlap = true.
 struct GjkOut {
     float d;
+    float lb;       // best separating-plane LOWER bound seen (0 if none): the distance lies in [lb, d] when !pruned
     bool overlap;   // proven: the simplex encloses the origin
     bool contact;   // |v| fell below the fp32 contact resolution (grazing or shallow penetration)
     bool pruned;
@@ -111,8 +112,9 @@ struct GjkOut {
 
 template <int MAX_ITER>
 __device__ GjkOut gjk_distance(const ShapeW& A, const ShapeW& B, float stop_above, float stop_below,
-                                float conv_abs = 1e-6f, float conv_rel = 1e-5f) {
+                                float conv_abs = 1e-6f, float conv_rel = 1e-5f, int max_iter = MAX_ITER) {
     GjkOut out;
+    out.lb = 0.f;
     out.overlap = false;
     out.contact = false;
     out.pruned = false;
@@ -124,12 +126,13 @@ __device__ GjkOut gjk_distance(const ShapeW& A, const ShapeW& B, float stop_abov
     bool have_ub = false;   // v is a point of the difference only after the first support call
     float ub = FLT_MAX;
 #pragma unroll 1
-    for (int it = 0; it < MAX_ITER; ++it) {
+    for (int it = 0; it < max_iter; ++it) {
         const V3 w = support(A, -v) - support(B, v);
         const float vw = dot(v, w);
         // separating-plane lower bound: the difference lies in the half space {x : x.v >= v.w}
         if (vw > 0.f) {
             const float lb = vw * rsqrtf(vv);
+            out.lb = fmaxf(out.lb, lb);
             if (lb > stop_above) { out.d = lb; out.pruned = true; return out; }
             if (have_ub && ub - lb <= conv_abs + conv_rel * ub) break;   // converged: the distance lies in [lb, ub]
         }

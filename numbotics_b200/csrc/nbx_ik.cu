@@ -21,6 +21,7 @@
 // next iteration needs.  q lives in a shared-memory tile ([config][dof], the global layout).
 // Compute-bound (no HBM traffic inside the loop); fp64 by default because the reference's tol is 1e-6.
 #include "nbx_common.cuh"
+#include <limits>
 #include "nbx_joint.cuh"
 #include <algorithm>
 #include <cstdlib>
@@ -86,7 +87,7 @@ __device__ __forceinline__ void chol_solve6(T* L, const T* b, T* x) {
         T d = L[LI(j, j)];
 #pragma unroll
         for (int k = 0; k < j; ++k) d = fma_t<T>(-L[LI(j, k)], L[LI(j, k)], d);
-        d = sqrt_t<T>(d > T(0) ? d : T(1e-300));
+        d = sqrt_t<T>(d > T(0) ? d : std::numeric_limits<T>::min());   // type-appropriate pivot floor (1e-300 is 0 in float)
         L[LI(j, j)] = d;
         const T inv = T(1) / d;
 #pragma unroll
@@ -288,7 +289,7 @@ int launch_ik(const nbx_chain* ch, int frame, const T* target, int64_t target_st
     const size_t smem = sizeof(T) * (size_t)kIkTile * std::max(ch->dof, 1);
     NBX_REQUIRE(smem <= 200 * 1024, "dof %d too large for the IK kernel", ch->dof);
     auto kern = ik_dls_kernel<T>;
-    NBX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NBX_SMEM_LIMIT(kern, smem);
     // persistent lanes: enough CTAs to fill the machine a few times over, never more than the problems need
     static const int cps_env = std::getenv("NBX_IK_CTAS_PER_SM") ? std::atoi(std::getenv("NBX_IK_CTAS_PER_SM")) : 0;   // tuning only
     const int cps = cps_env > 0 ? cps_env : 16;

@@ -143,7 +143,9 @@ def flatten_chain(chain, margin_model: str = "bullet") -> dict:
 def primitive_reach(chain_arrays: dict, joint_limits) -> np.ndarray:
     """Upper bound, per link primitive, on the distance of ANY of its points from the base-frame origin,
     over every configuration: sum of the translation norms along the path (rotations preserve norms;
-    a prismatic joint adds its largest travel) + the primitive's own offset + its bounding radius."""
+    anything behind a prismatic joint is unbounded) + the primitive's own offset + its bounding radius.
+    `joint_limits` is accepted for signature stability and not used: verdicts must not depend on limits that
+    q is never checked against."""
     A = chain_arrays
     n_mov = len(A["mov_type"])
     off = np.asarray(A["mov_offset"]).reshape(n_mov, 12)
@@ -153,8 +155,9 @@ def primitive_reach(chain_arrays: dict, joint_limits) -> np.ndarray:
         par = int(A["mov_parent"][j])
         r = (reach_j[par] if par >= 0 else 0.0) + np.linalg.norm(off[j, [3, 7, 11]])
         if int(A["mov_type"][j]) == _cabi.NBX_JOINT_PRISMATIC:
-            lo, hi = joint_limits[int(A["mov_qidx"][j])]
-            r += max(abs(lo), abs(hi)) * np.linalg.norm(axis[j])      # inf for an unlimited slider: never pruned
+            # q is never clamped to the joint limits (the reference does not clamp either), so a slider's travel is
+            # unbounded as far as pruning is concerned: nothing downstream of a prismatic joint is ever pruned
+            r = np.inf
         reach_j[j] = r
     tail = np.asarray(A["frame_tail"]).reshape(-1, 12)
     poff = np.asarray(A["prim_offset"]).reshape(-1, 12)

@@ -125,18 +125,21 @@ def c_in_collision(desc: CDesc, q, base_pose, threshold=0.0, want_dist=False):
     return (v.astype(bool), d) if want_dist else v.astype(bool)
 
 
-def c_edges_valid(desc: CDesc, starts, goals, base_pose, resolution, max_distance=None, threshold=0.0):
+def c_edges_valid(desc: CDesc, starts, goals, base_pose, resolution, max_distance=None, threshold=0.0, want_min_d=False):
+    """(valid, n_samples, n_useful[, min_d]); `want_min_d` evaluates every sample of every edge (no early exit) and adds
+    the smallest min-distance over the edge's samples (what decides whether an edge is inside the contact band)."""
     s = np.ascontiguousarray(starts, dtype=np.float64).reshape(-1, desc.dof)
     g = np.ascontiguousarray(goals, dtype=np.float64).reshape(-1, desc.dof)
     E = s.shape[0]
     base = np.ascontiguousarray(base_pose, dtype=np.float64)
     v = np.empty(E, np.uint8); ns = np.empty(E, np.int32); nu = np.empty(E, np.int32)
-    rc = lib().oracle_edges_valid(C.byref(desc.chain), C.byref(desc.scene), _p(s, C.c_double), _p(g, C.c_double), C.c_int64(E),
-                                  _p(base, C.c_double), C.c_double(resolution),
-                                  C.c_double(0.0 if max_distance is None else max_distance), C.c_double(threshold),
-                                  _p(v, C.c_uint8), _p(ns, C.c_int32), _p(nu, C.c_int32))
+    md = np.empty(E, np.float64) if want_min_d else None
+    rc = lib().oracle_edges_valid_ex(C.byref(desc.chain), C.byref(desc.scene), _p(s, C.c_double), _p(g, C.c_double), C.c_int64(E),
+                                     _p(base, C.c_double), C.c_double(resolution),
+                                     C.c_double(0.0 if max_distance is None else max_distance), C.c_double(threshold),
+                                     _p(v, C.c_uint8), _p(ns, C.c_int32), _p(nu, C.c_int32), _p(md, C.c_double) if want_min_d else None)
     assert rc == 0
-    return v.astype(bool), ns, nu
+    return (v.astype(bool), ns, nu, md) if want_min_d else (v.astype(bool), ns, nu)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -402,10 +402,12 @@ int oracle_in_collision(const ochain* ch, const oscene* sc, const double* q, int
 }
 
 /* connectors.py:57-100.  valid[e] = 1 iff the reference would return a state.  n_samples / n_useful nullable:
- * samples of the edge, and samples the sequential reference evaluates (up to and including the first invalid). */
-int oracle_edges_valid(const ochain* ch, const oscene* sc, const double* starts, const double* goals, int64_t E,
-                       const double* base16, double resolution, double max_distance, double threshold, uint8_t* valid,
-                       int32_t* n_samples, int32_t* n_useful) {
+ * samples of the edge, and samples the sequential reference evaluates (up to and including the first invalid).
+ * min_d nullable: the smallest min-distance over ALL samples of the edge (no early exit then; checker use: an edge
+ * is "borderline" iff |min_d - threshold| is inside the contact band). */
+int oracle_edges_valid_ex(const ochain* ch, const oscene* sc, const double* starts, const double* goals, int64_t E,
+                          const double* base16, double resolution, double max_distance, double threshold, uint8_t* valid,
+                          int32_t* n_samples, int32_t* n_useful, double* min_d) {
     if (ch->n_prims > 64 || ch->n_mov > 256 || ch->dof > 256) return -1;
     const int dof = ch->dof;
 #pragma omp parallel for schedule(dynamic, 16)
@@ -416,6 +418,7 @@ int oracle_edges_valid(const ochain* ch, const oscene* sc, const double* starts,
         for (int k = 0; k < dof; ++k) ss += (s[k] - g[k]) * (s[k] - g[k]);
         const double dist = sqrt(ss);
         int ok = 1, cnt = 0, used = 0;
+        double md = INFINITY;
         if (dist <= 1.1920928955078125e-07) {
             ok = 0;
         } else {
@@ -425,18 +428,28 @@ int oracle_edges_valid(const ochain* ch, const oscene* sc, const double* starts,
             const int len = (int)ceil(tf / step);   /* numpy.arange length rule */
             cnt = len + 1;
             double qv[256];
-            for (int k = 0; k <= len && ok; ++k) {
+            for (int k = 0; k <= len && (ok || min_d); ++k) {
                 const double t = k == len ? tf : k * step;
                 for (int c = 0; c < dof; ++c) qv[c] = (1.0 - t) * s[c] + t * g[c];
-                ++used;
-                if (config_min_distance(ch, sc, qv, base16, threshold) < threshold) ok = 0;
+                if (ok) ++used;
+                const double d = config_min_distance(ch, sc, qv, base16, min_d ? -INFINITY : threshold);
+                if (d < md) md = d;
+                if (d < threshold) ok = 0;
             }
         }
         valid[e] = (uint8_t)ok;
         if (n_samples) n_samples[e] = cnt;
         if (n_useful) n_useful[e] = used;
+        if (min_d) min_d[e] = md;
     }
     return 0;
+}
+
+int oracle_edges_valid(const ochain* ch, const oscene* sc, const double* starts, const double* goals, int64_t E,
+                       const double* base16, double resolution, double max_distance, double threshold, uint8_t* valid,
+                       int32_t* n_samples, int32_t* n_useful) {
+    return oracle_edges_valid_ex(ch, sc, starts, goals, E, base16, resolution, max_distance, threshold, valid, n_samples,
+                                 n_useful, NULL);
 }
 
 int oracle_num_threads(void) {

@@ -1,5 +1,6 @@
-"""bench.py contract, CPU side: the reference arm (`--impl reference`) runs without a GPU (it times the oracle port on
-the host cores) and prints one JSON line with the keys the driver reads; under a 2-rank launch only rank 0 prints."""
+"""bench.py contract, CPU side: the reference arm (`--impl reference`) runs without a GPU (it times the reference's own
+numba kernels staged under oracle/_ref/ -- or the oracle port when numba is missing -- on the host cores) and prints one
+JSON line with the keys the driver reads; under a 2-rank launch only rank 0 prints."""
 import json
 import os
 import subprocess
@@ -24,8 +25,14 @@ def test_reference_arm_line():
     assert KEYS <= set(d)
     assert d["impl"] == "reference" and d["metric"] == "fk_jacobian_configs_per_sec" and d["unit"] == "configs/s"
     assert d["steps"] == 2 and d["warmup"] >= 3 and d["higher_is_better"] is True
-    assert d["value"] > 1e5 and abs(d["ms_per_step"] * 1e-3 * d["value"] - d["config"]["sample_configs_per_step"]) < 1.0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["value"] > 1e4
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert cb["port"]["kind"] == "port" and cb["port"]["value"] > 1e5
+    # the config is the GPU arm's own (the driver compares the two dicts): the bounded sample lives in cpu_baseline.sample
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.bench_config(1)
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and "workload" in d["config"]
 

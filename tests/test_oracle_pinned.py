@@ -114,3 +114,14 @@ def test_oracle_matches_live_reference_kernels():
             continue   # the reference cannot unpack the root's empty sequence (arm.py:395)
         assert np.abs(ref.forward_kinematics(q, frame) - ora.forward_kinematics(q, frame)).max() < TOL, frame
         assert np.abs(ref.jacobian(q, frame) - ora.jacobian(q, frame)).max() < TOL, frame
+
+
+def test_staged_reference_helpers_are_the_reference_file():
+    """oracle/_ref/ref_helpers.py (what bench.py's reference-numba leg times on the GPU box) is the reference's
+    numbotics/robots/helpers.py byte for byte -- staged by ref_loader.stage(), never edited."""
+    import os
+    if not os.path.exists(ref_loader.LIVE_PATH):
+        pytest.skip("reference checkout not visible (GPU box)")
+    staged = ref_loader.stage()
+    assert staged == ref_loader.STAGED_PATH
+    assert open(staged, "rb").read() == open(ref_loader.LIVE_PATH, "rb").read()
