@@ -605,11 +605,24 @@ def secondary_measurements(arm, q, dev, rank, world, clocks_mhz):
     lo, hi = shard_bounds(E_total, rank, world)
     s, g = s_all[lo:hi].contiguous(), g_all[lo:hi].contiguous()
     ms = best_ms(lambda: arm.edges_valid(s, g, 0.1))
-    v, ns = arm.edges_valid(s, g, 0.1, return_samples=True)
+    v, ns, nu = arm.edges_valid(s, g, 0.1, return_samples=True, return_useful=True)
+    v_plain = arm.edges_valid(s, g, 0.1)
+    ok_all &= bool(torch.equal(v, v_plain))
+    from numbotics_b200.dist import sum_over_ranks
+    issued_total = sum_over_ranks(float(ns.sum()), dev)
+    useful_total = sum_over_ranks(float(nu.sum()), dev)
     out["prm_edges_per_sec"] = {"value": E_total / ms * 1e3, "edges_total": E_total, "edges_this_rank": int(hi - lo),
                                 "best_ms": ms, "scaling": "strong",
                                 "valid_fraction_rank0": float(v.float().mean()), "mean_samples_per_edge_rank0": float(ns.float().mean()),
-                                "issued_samples_per_sec": float(ns.sum()) * world / ms * 1e3,
+                                "issued_samples_per_sec": issued_total / ms * 1e3,
+                                "useful_samples_per_sec": useful_total / ms * 1e3,
+                                "useful_vs_issued": {
+                                    "issued_samples": issued_total, "useful_samples": useful_total, "useful_fraction": useful_total / max(issued_total, 1.0),
+                                    "note": "useful = samples up to and including the first invalid one of each edge (what the sequential reference "
+                                            "evaluates, connectors.py:71-73; the roofline numerator of SURVEY 8d), from nbx_edges_valid_detail_f32's "
+                                            "first_invalid output; issued = every sample of every edge (what the kernel evaluates)"},
+                                "kernels": "edge_prepare + 2-level scan + edges_flat_kernel (persistent grid, dynamic 32-sample tiles over the flat "
+                                           "(edge, sample) space) + narrow_kernel",
                                 "workload": "BASELINE configs[3]: 100k nodes x 10-NN = 1M edges, resolution 0.1, contiguous E/G slices"}
     En = int(hi - lo)
     sh, gh = torch.empty((En, DOF), dtype=torch.float32).pin_memory(), torch.empty((En, DOF), dtype=torch.float32).pin_memory()
@@ -668,21 +681,16 @@ def secondary_measurements(arm, q, dev, rank, world, clocks_mhz):
         g_v = v[:n_e].cpu().numpy()
         mism_e = int(np.sum((g_v != v_cpu) & ~band_e))
         cnt_bad = int(np.sum(ns[:n_e].cpu().numpy() != ns_cpu))
+        useful_bad = int(np.sum((nu[:n_e].cpu().numpy() != nu_cpu) & ~band_e))
         ok_all &= mism_e == 0 and cnt_bad == 0
         out["prm_edges_per_sec"]["cpu_port"] = {
             "value": n_e / dt, "unit": "edges/s", "cores": _oc.num_threads(), "kind": "restated oracle, not reference",
             "sample": f"the first {n_e} of the same edges", "valid_fraction": float(v_cpu.mean())}
         out["prm_edges_per_sec"]["parity"] = {
             "rows": n_e, "band_m": BAND, "mismatches_outside_band": mism_e, "in_band_fraction": float(band_e.mean()),
-            "sample_count_mismatches": cnt_bad,
+            "sample_count_mismatches": cnt_bad, "useful_count_mismatches_outside_band": useful_bad,
             "against": "oracle/nbx_oracle.c, sequential connectors.py:57-100 semantics, on the same edges (an edge is in the band when its "
                        "smallest sample distance is within band_m of the threshold)"}
-        useful_frac = float(nu_cpu.sum()) / float(ns_cpu.sum())
-        out["prm_edges_per_sec"]["useful_vs_issued"] = {
-            "issued_samples_per_edge": float(ns_cpu.mean()), "useful_samples_per_edge": float(nu_cpu.mean()), "useful_fraction": useful_frac,
-            "useful_samples_per_sec_estimate": out["prm_edges_per_sec"]["issued_samples_per_sec"] * useful_frac,
-            "note": f"useful = samples up to and including the first invalid one (what the sequential reference evaluates, connectors.py:71-73), "
-                    f"counted by the oracle on the first {n_e} edges; the kernel evaluates every sample of every edge (issued)"}
     del s_all, g_all, s, g, nodes
 
     # ---- float64 path (the drop-in caller's default dtype): device-resident and through host buffers ---------------

@@ -186,6 +186,17 @@ NBX_API int nbx_edges_valid_f32(const nbx_chain* chain, const nbx_scene* scene,
                         const float* starts, const float* goals, int64_t E,
                         const double* base_pose, double resolution, double max_distance,
                         float threshold, uint8_t* valid, int32_t* n_samples, void* stream);
+/*
+ * Same query with per-edge detail.  first_invalid (nullable, int32[E]) receives the index of the FIRST colliding
+ * interpolation sample of the edge (0x7fffffff when the edge is valid): the sequential reference stops there
+ * (connectors.py:71-73), so  useful samples = first_invalid + 1  for an invalid edge and n_samples for a valid one --
+ * the "useful vs issued" accounting of the edge benchmark.  (With first_invalid the narrow phase evaluates every
+ * candidate that precedes the current minimum instead of stopping at the edge's first hit.)
+ */
+NBX_API int nbx_edges_valid_detail_f32(const nbx_chain* chain, const nbx_scene* scene,
+                               const float* starts, const float* goals, int64_t E,
+                               const double* base_pose, double resolution, double max_distance,
+                               float threshold, uint8_t* valid, int32_t* n_samples, int32_t* first_invalid, void* stream);
 NBX_API int nbx_edges_valid_host_f32(const nbx_chain* chain, const nbx_scene* scene,
                              const float* starts, const float* goals, int64_t E,
                              const double* base_pose, double resolution, double max_distance,

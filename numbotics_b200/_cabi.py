@@ -66,6 +66,7 @@ SIGNATURES = {
     "nbx_in_collision_f32": (C.c_int, [_vp, _vp, _vp, _i64, _f64p, C.c_float, _vp, _vp, _vp]),
     "nbx_in_collision_host_f32": (C.c_int, [_vp, _vp, _vp, _i64, _f64p, C.c_float, _vp]),
     "nbx_edges_valid_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f64p, C.c_double, C.c_double, C.c_float, _vp, _vp, _vp]),
+    "nbx_edges_valid_detail_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f64p, C.c_double, C.c_double, C.c_float, _vp, _vp, _vp, _vp]),
     "nbx_edges_valid_host_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f64p, C.c_double, C.c_double, C.c_float, _vp]),
     "nbx_closest_f32": (C.c_int, [_vp, _vp, _vp, _i64, _f64p, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nbx_pair_distances_f32": (C.c_int, [_vp, _vp, _vp, _i64, _f64p, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -176,6 +176,8 @@ struct WCtx {
     uint32_t* pend;           // [kPendCap] survivor codes: env flag | pair << 8 | item lane
     unsigned long long* flag; // kDist: [kMaxRange] running minimum: (ordered key of the distance) << 32 | pair code
     int* item_fi;             // [32] item lane -> flag index (kDist: within the warp's range; kSplit: global unit index)
+    int* item_aux;            // [32] edges only (else nullptr): the item's sample index on its edge, carried in the entry's pair-code word
+    int* first_bad;           // edges only, nullable: per edge the smallest colliding sample index (atomicMin by the narrow phase)
     int n_mov, n_prims, n_base_prims;
     float thr;
     // kSplit
@@ -235,7 +237,7 @@ __device__ __forceinline__ void build_cand(const WCtx& C, uint32_t code, Cand& K
     const int item = (int)(code & 0xffu);
     const int e = (int)((code & ~kEnvFlag) >> 8);
     K.fi = C.item_fi[item];
-    K.pc = (code & kEnvFlag) | (uint32_t)e;
+    K.pc = C.item_aux != nullptr ? (uint32_t)C.item_aux[item] : ((code & kEnvFlag) | (uint32_t)e);
     float mA, mB;
     bool sharp;
     if (code & kEnvFlag) {
@@ -303,18 +305,40 @@ __device__ __forceinline__ void eval_cand(const WCtx& C, const Cand& K) {
         // distance values are stated to 1e-4 m: stop when the bracket [lb, ub] is below half of that;
         // curved cores (cylinders) converge only linearly, so the tolerance is a large part of the cost of this query
         const GjkOut g = gjk_distance<kGjkItersDist>(K.A, K.B, best + K.m, -FLT_MAX, 2e-5f, 4e-5f);
-        // overlapping cores: depth beyond the margins is not computed (clamp)
-        const float d = g.overlap ? (-K.m - 1e-3f) : (g.contact ? (-K.m - 1e-6f) : (g.d - K.m));
-        if (!g.pruned) atomicMin(&C.flag[K.fi], dist_entry(d, K.pc));
+        if (g.pruned) return;
+        // overlapping cores: the signed distance continues below -(mA + mB) by the cores' penetration depth (EPA, out of line)
+        float d;
+        if (g.overlap) d = -K.m - core_penetration(K.A, K.B).depth;
+        else d = g.contact ? (-K.m - 1e-6f) : (g.d - K.m);
+        atomicMin(&C.flag[K.fi], dist_entry(d, K.pc));
     } else {
         volatile uint8_t* f = C.gflag + K.fi;
-        if (*f == (uint8_t)C.hit_value) return;              // this unit is already decided
-        const GjkOut g = gjk_distance<kGjkIters>(K.A, K.B, C.thr + K.m, C.thr + K.m, 1e-6f, 1e-5f, C.gjk_iters);
-        // Verdict: a pair is FREE only on proof -- a separating plane beyond the threshold (`pruned`).  Overlap, contact and
-        // an upper bound below the threshold are hits; so is a bracket [lb, ub] that still straddles the threshold when the
-        // iteration stops (converged to its tolerance, stalled, or out of iterations: rounded cylinders converge only
-        // linearly).  The unsafe direction for in_collision / edges_valid / bisect would be to call such a pair free.
-        if (!g.pruned) *f = (uint8_t)C.hit_value;
+        if (C.first_bad == nullptr) {
+            if (*f == (uint8_t)C.hit_value) return;          // this unit is already decided
+        } else if (((volatile int*)C.first_bad)[K.fi] <= (int)K.pc) {
+            return;                                          // an earlier sample of this edge already collides
+        }
+        const float lim = C.thr + K.m;                       // the pair collides iff  core distance < lim
+        bool hit;
+        if (lim > 0.f) {
+            // the bracket only has to close to a fraction of the stated 1e-4 m contact band: a pair whose [lb, ub] still straddles
+            // the threshold at 2e-5 is inside the band whichever way it is called (round 1 iterated on to 1e-6: the narrow kernel
+            // of a bisection round, where every candidate sits on the contact boundary, took 85 us instead of ~45)
+            const GjkOut g = gjk_distance<kGjkIters>(K.A, K.B, lim, lim, 2e-5f, 1e-5f, C.gjk_iters);
+            // Verdict: a pair is FREE only on proof -- a separating plane beyond the threshold (`pruned`).  Overlap, contact and
+            // an upper bound below the threshold are hits; so is a bracket [lb, ub] that still straddles the threshold when the
+            // iteration stops (converged to its tolerance, stalled, or out of iterations: rounded cylinders converge only
+            // linearly).  The unsafe direction for in_collision / edges_valid / bisect would be to call such a pair free.
+            hit = !g.pruned;
+        } else {
+            // negative threshold beyond this pair's margins: only cores that interpenetrate by more than -lim collide
+            const GjkOut g = gjk_distance<kGjkIters>(K.A, K.B, 1e-6f, -1.f, 2e-5f, 1e-5f, C.gjk_iters);
+            hit = g.overlap && core_penetration(K.A, K.B).depth > -lim;
+        }
+        if (hit) {
+            *f = (uint8_t)C.hit_value;
+            if (C.first_bad != nullptr) atomicMin(&C.first_bad[K.fi], (int)K.pc);
+        }
     }
 }
 
@@ -472,7 +496,7 @@ __device__ __forceinline__ void phase1(const WCtx& C, bool valid, QF qf, int n_o
         cut0 = ub + 1e-5f;       // the bound is conservative up to rounding; equal lower bounds must survive
     }
     // one environment pair: squared distance l2 from the primitive's centre to the obstacle, against the reach
-#define NBX_ENV_SURV(E, SURV, L2_EXPR, ORAD)                                                             \
+#define NBX_ENV_SURV(E, SURV, L2_EXPR, ORAD, INSIDE_EXPR)                                                           \
     bool SURV;                                                                                           \
     {                                                                                                    \
         const float4 rec = env4[E];        /* {a|b|sharp|both_cyl, off_a, off_b, rsum} */                \
@@ -480,7 +504,10 @@ __device__ __forceinline__ void phase1(const WCtx& C, bool valid, QF qf, int n_o
         const V3 dc = mk(pc[0], pc[NT], pc[2 * NT]) - oc;                                                \
         const float l2 = (L2_EXPR);                                                                      \
         if (WANT_DIST) {                                                                                 \
-            SURV = valid && sqrtf(l2) - rec.w - (ORAD) <= cut0;                                          \
+            /* centre inside the obstacle (l2 == 0): the signed distance can be far below -radius, so the lower bound */ \
+            /* continues inwards with the (negative) distance to the nearest face (INSIDE_EXPR) */        \
+            const float cdist = l2 > 0.f ? sqrtf(l2) : fminf((INSIDE_EXPR), 0.f);                        \
+            SURV = valid && cdist - rec.w - (ORAD) <= cut0;                                              \
         } else {                                                                                         \
             const float reach = rec.w + (ORAD) + cut0;     /* >= 0: thresholds are non-negative */       \
             SURV = valid && l2 <= reach * reach;                                                         \
@@ -495,20 +522,20 @@ __device__ __forceinline__ void phase1(const WCtx& C, bool valid, QF qf, int n_o
     // The pairs of one obstacle in groups of four: the four culls are independent straight-line code and ONE vote decides
     // whether any lane kept any of them (survivors are rare: 0.28 per configuration out of 58 pairs), instead of a ballot
     // and a branch behind every pair (ncu: 4.6 % of the warp samples waited on those branches).
-#define NBX_ENV_LOOP(L2_EXPR, ORAD)                                                                      \
+#define NBX_ENV_LOOP(L2_EXPR, ORAD, INSIDE_EXPR)                                                                    \
     {                                                                                                    \
         int e = e0;                                                                                      \
         _Pragma("unroll 1") for (; e + 4 <= e1; e += 4) {                                                \
-            NBX_ENV_SURV(e, s0, L2_EXPR, ORAD)                                                           \
-            NBX_ENV_SURV(e + 1, s1, L2_EXPR, ORAD)                                                       \
-            NBX_ENV_SURV(e + 2, s2, L2_EXPR, ORAD)                                                       \
-            NBX_ENV_SURV(e + 3, s3, L2_EXPR, ORAD)                                                       \
+            NBX_ENV_SURV(e, s0, L2_EXPR, ORAD, INSIDE_EXPR)                                                           \
+            NBX_ENV_SURV(e + 1, s1, L2_EXPR, ORAD, INSIDE_EXPR)                                                       \
+            NBX_ENV_SURV(e + 2, s2, L2_EXPR, ORAD, INSIDE_EXPR)                                                       \
+            NBX_ENV_SURV(e + 3, s3, L2_EXPR, ORAD, INSIDE_EXPR)                                                       \
             if (__any_sync(0xffffffffu, s0 | s1 | s2 | s3)) {                                            \
                 NBX_ENV_PUSH(e, s0) NBX_ENV_PUSH(e + 1, s1) NBX_ENV_PUSH(e + 2, s2) NBX_ENV_PUSH(e + 3, s3) \
             }                                                                                            \
         }                                                                                                \
         _Pragma("unroll 1") for (; e < e1; ++e) {                                                        \
-            NBX_ENV_SURV(e, s0, L2_EXPR, ORAD)                                                           \
+            NBX_ENV_SURV(e, s0, L2_EXPR, ORAD, INSIDE_EXPR)                                                           \
             NBX_ENV_PUSH(e, s0)                                                                          \
         }                                                                                                \
     }
@@ -521,18 +548,22 @@ __device__ __forceinline__ void phase1(const WCtx& C, bool valid, QF qf, int n_o
         if (ob.type == NBX_PRIM_BOX) {
             const float hx = ob.dims[0] + ob.margin, hy = ob.dims[1] + ob.margin, hz = ob.dims[2] + ob.margin;
             if (ob.pad[0] != 0) {              // axis-aligned box: exact point-to-box distance without the rotation
-                NBX_ENV_LOOP(sq3(fmaxf(fabsf(dc.x) - hx, 0.f), fmaxf(fabsf(dc.y) - hy, 0.f), fmaxf(fabsf(dc.z) - hz, 0.f)), 0.f)
+                NBX_ENV_LOOP(sq3(fmaxf(fabsf(dc.x) - hx, 0.f), fmaxf(fabsf(dc.y) - hy, 0.f), fmaxf(fabsf(dc.z) - hz, 0.f)), 0.f,
+                             fmaxf(fabsf(dc.x) - hx, fmaxf(fabsf(dc.y) - hy, fabsf(dc.z) - hz)))
             } else {
                 float R[9];
 #pragma unroll
                 for (int k = 0; k < 9; ++k) R[k] = ob.R[k];
                 NBX_ENV_LOOP(sq3(fmaxf(fabsf(fmaf(R[0], dc.x, fmaf(R[3], dc.y, R[6] * dc.z))) - hx, 0.f),
                                  fmaxf(fabsf(fmaf(R[1], dc.x, fmaf(R[4], dc.y, R[7] * dc.z))) - hy, 0.f),
-                                 fmaxf(fabsf(fmaf(R[2], dc.x, fmaf(R[5], dc.y, R[8] * dc.z))) - hz, 0.f)), 0.f)
+                                 fmaxf(fabsf(fmaf(R[2], dc.x, fmaf(R[5], dc.y, R[8] * dc.z))) - hz, 0.f)), 0.f,
+                             fmaxf(fabsf(fmaf(R[0], dc.x, fmaf(R[3], dc.y, R[6] * dc.z))) - hx,
+                                   fmaxf(fabsf(fmaf(R[1], dc.x, fmaf(R[4], dc.y, R[7] * dc.z))) - hy,
+                                         fabsf(fmaf(R[2], dc.x, fmaf(R[5], dc.y, R[8] * dc.z))) - hz)))
             }
         } else {                               // sphere / cylinder obstacle: bounding spheres
             const float orad = ob.brad;
-            NBX_ENV_LOOP(dot(dc, dc), orad)
+            NBX_ENV_LOOP(dot(dc, dc), orad, 0.f)
         }
     }
 #undef NBX_ENV_LOOP
@@ -647,7 +678,7 @@ __device__ __forceinline__ void materialise(const WCtx& C, int& npend, int& qn) 
 __host__ __device__ inline size_t warp_smem_bytes(int mode, int pose_floats, int extra_floats) {
     return align16(sizeof(float) * (size_t)kWT * (pose_floats > 0 ? pose_floats : 1)) +
            (mode == kDist ? align16(sizeof(float) * (size_t)kEW * kQCap) + align16(sizeof(unsigned long long) * kMaxRange) : 0) +
-           align16(sizeof(uint32_t) * kPendCap) + align16(sizeof(int) * kWT) + align16(sizeof(float) * (size_t)extra_floats);
+           align16(sizeof(uint32_t) * kPendCap) + 2 * align16(sizeof(int) * kWT) + align16(sizeof(float) * (size_t)extra_floats);
 }
 
 template <int MODE>
@@ -661,6 +692,9 @@ __device__ __forceinline__ unsigned char* carve_warp(WCtx& C, unsigned char* p, 
     }
     C.pend = reinterpret_cast<uint32_t*>(p);    p += align16(sizeof(uint32_t) * kPendCap);
     C.item_fi = reinterpret_cast<int*>(p);      p += align16(sizeof(int) * kWT);
+    C.item_aux = nullptr;                       // edges point it at the next kWT ints
+    C.first_bad = nullptr;
+    p += align16(sizeof(int) * kWT);
     return p;
 }
 
@@ -669,6 +703,7 @@ struct SplitArgs {
     int* gq_count;
     int gq_half;
     int gjk_iters;
+    int* first_bad;           // edges only, nullable
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -744,112 +779,221 @@ in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
-// Edge validation, broad kernel.  Per edge (all float64, bit-for-bit the reference's NumPy arithmetic,
-// connectors.py:62-69 / :84-93):
+// Edge validation (reference DiscreteConnector.connect / steer, connectors.py:57-100), flattened over the GRID.
+//
+// Per edge, all float64 and bit for bit the reference's NumPy arithmetic (connectors.py:62-69 / :84-93):
 //   distance = ||goal - start||_2 ; distance <= float32 eps -> invalid
 //   step = resolution / distance ; T_f = 1 (connect) or min(1, max_distance / distance) (steer)
 //   samples: t_k = k * step for k < ceil(T_f / step)  (numpy.arange length rule), then t = T_f.
-// A warp prefix sum flattens the (edge, sample) space of 32 edges, so every lane always has a sample; rounds of 32
-// samples go through phase 1 with the configuration interpolated on the fly.  valid[e] starts as 1 (0 for an edge
-// shorter than float32 eps) and the narrow kernel clears it when one of the edge's candidates collides.
+//
+// Round 1 gave every warp 32 edges; at 125 k edges per GPU that was 1.65 waves of ragged CTAs (strong scaling 0.56 on 8
+// GPUs).  Now:  (1) edge_prepare_kernel  -- one thread per edge: sample count, {step, T_f}, valid[e] = 1 (0 for an edge
+// shorter than float32 eps) and per-block sums;  (2) + (3) a two-level exclusive scan turns the counts into int64 offsets
+// of ONE flat sample space;  (4) edges_flat_kernel -- a persistent grid whose warps draw chunks of consecutive 32-sample
+// tiles from an atomic counter (dynamic: edge lengths vary and a static split leaves a ragged last wave).  A lane finds
+// its (edge, sample) through a 34-entry window of the offset array that the warp stages in shared memory, interpolates its
+// own configuration into the warp's q tile, and the tile goes through phase 1 like a tile of in_collision.  The narrow
+// kernel clears valid[e] when a candidate of the edge collides (and keeps the smallest colliding sample index when the
+// caller asks for it: that is how "useful" samples -- the ones the sequential reference evaluates -- are counted).
 // ---------------------------------------------------------------------------------------------
+struct EdgeMeta { double step, tf; };
+constexpr int kPrepBlock = 256;
+
+__global__ void __launch_bounds__(kPrepBlock)
+edge_prepare_kernel(const float* __restrict__ starts, const float* __restrict__ goals, int64_t E, int dof, double resolution,
+                    double max_distance, uint8_t* __restrict__ valid, int32_t* __restrict__ n_samples, int* __restrict__ first_bad,
+                    EdgeMeta* __restrict__ meta, long long* __restrict__ offs /* [E + 1]: offs[e + 1] = count */,
+                    long long* __restrict__ block_sums) {
+    const int64_t e = (int64_t)blockIdx.x * kPrepBlock + threadIdx.x;
+    int cnt = 0;
+    if (e < E) {
+        int dead = 1;            // edges shorter than float32 eps have no samples and are invalid
+        double ss = 0.0;
+        const float* a = starts + e * dof;
+        const float* g = goals + e * dof;
+        for (int k = 0; k < dof; ++k) {
+            const double dlt = (double)a[k] - (double)g[k];
+            ss = fma(dlt, dlt, ss);
+        }
+        const double dist = sqrt(ss);
+        EdgeMeta m{0.0, 0.0};
+        if (dist > (double)1.1920928955078125e-07f) {
+            m.step = resolution / dist;
+            m.tf = 1.0;
+            if (max_distance > 0.0 && dist > max_distance) m.tf = max_distance / dist;
+            const double len = ceil(m.tf / m.step);
+            cnt = (int)fmin(len, 1.0e9) + 1;
+            dead = 0;
+        }
+        meta[e] = m;
+        if (n_samples != nullptr) n_samples[e] = cnt;
+        if (first_bad != nullptr) first_bad[e] = 0x7fffffff;
+        valid[e] = (uint8_t)(dead ? 0 : 1);
+        offs[e + 1] = cnt;
+    }
+    // block sum of the counts (int64: 2^31 edges of up to 10^9 samples)
+    __shared__ long long wsum[kPrepBlock / 32];
+    long long x = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int i = 0; i < kPrepBlock / 32; ++i) t += wsum[i];
+        block_sums[blockIdx.x] = t;
+        if (blockIdx.x == 0) offs[0] = 0;
+    }
+}
+
+// exclusive scan of the block sums by ONE block (n_blocks = E / 256: 3907 for 10^6 edges); also resets the tile counter
+__global__ void __launch_bounds__(1024)
+edge_scan_blocks_kernel(long long* __restrict__ block_sums, int n_blocks, int* __restrict__ tile_counter) {
+    __shared__ long long part[1024];
+    const int per = (n_blocks + 1023) / 1024;
+    const int b0 = threadIdx.x * per, b1 = min(n_blocks, b0 + per);
+    long long t = 0;
+    for (int i = b0; i < b1; ++i) t += block_sums[i];
+    part[threadIdx.x] = t;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {          // Hillis-Steele inclusive scan of the 1024 partial sums
+        const long long y = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+        __syncthreads();
+        part[threadIdx.x] += y;
+        __syncthreads();
+    }
+    long long run = part[threadIdx.x] - t;        // exclusive
+    for (int i = b0; i < b1; ++i) { const long long c = block_sums[i]; block_sums[i] = run; run += c; }
+    if (threadIdx.x == 0) *tile_counter = 0;
+}
+
+// offs[e + 1] (count) -> inclusive prefix, i.e. offs[e] = first flat sample of edge e and offs[E] = total
+__global__ void __launch_bounds__(kPrepBlock)
+edge_offsets_kernel(long long* __restrict__ offs, int64_t E, const long long* __restrict__ block_sums) {
+    const int64_t e = (int64_t)blockIdx.x * kPrepBlock + threadIdx.x;
+    long long c = e < E ? offs[e + 1] : 0;
+    long long x = c;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    __shared__ long long wsum[kPrepBlock / 32];
+    if (lane == 31) wsum[wid] = x;
+    __syncthreads();
+    long long base = block_sums[blockIdx.x];
+    for (int i = 0; i < wid; ++i) base += wsum[i];
+    if (e < E) offs[e + 1] = base + x;
+}
+
+constexpr int kEdgeWin = 34;           // offsets of the tile's first edge .. +33 (>= 1 sample per live edge: a tile spans <= 32 live edges)
+
 template <bool FAST>
 __global__ void __launch_bounds__(kWarps * 32, 4)
-edges_valid_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ starts, const float* __restrict__ goals,
-                   int64_t E, int dof, double resolution, double max_distance, float thr,
-                   uint8_t* __restrict__ valid, int32_t* __restrict__ n_samples, int upw, const SplitArgs G) {
+edges_flat_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ starts, const float* __restrict__ goals,
+                  int64_t E, int dof, float thr, uint8_t* __restrict__ valid, const EdgeMeta* __restrict__ meta,
+                  const long long* __restrict__ offs, int* __restrict__ tile_counter, const SplitArgs G) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WCtx C;
     unsigned char* p = stage_scene(S, smem_raw, C.V);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int extra = 2 * kWT * dof + 4 * kWT + (kWT + 4);       // start/goal tiles, step/tf (double), sample offsets
+    const int extra = kWT * dof + 2 * (kEdgeWin + 2);      // the tile's configurations [32][dof], the offset window (int)
     const size_t wbytes = warp_smem_bytes(kSplit, S.scratch_floats, extra);
     p = carve_warp<kSplit>(C, p + (size_t)wid * wbytes, S.scratch_floats);
-    double* s_step = reinterpret_cast<double*>(p);       // [32]   (16-byte aligned: first in the extra area)
-    double* s_tf = s_step + kWT;                         // [32]
-    float* s_start = reinterpret_cast<float*>(s_tf + kWT);   // [32][dof]
-    float* s_goal = s_start + (size_t)kWT * dof;         // [32][dof]
-    int* s_off = reinterpret_cast<int*>(s_goal + (size_t)kWT * dof);   // [33] exclusive prefix of sample counts
+    C.item_aux = C.item_fi + kWT;                           // carve_warp reserves 2 x kWT ints
+    float* sq = reinterpret_cast<float*>(p);               // [32][dof]
+    int* s_win = reinterpret_cast<int*>(sq + (size_t)kWT * dof);   // [kEdgeWin] offsets relative to the tile's first sample
     C.base = S.base;
     C.n_mov = S.n_mov; C.n_prims = S.n_prims; C.n_base_prims = S.n_base_prims;
     C.thr = thr;
     C.gq = G.gq; C.gq_count = G.gq_count; C.gq_half = G.gq_half;
     C.gflag = valid; C.hit_value = 0; C.gjk_iters = G.gjk_iters;
+    C.first_bad = G.first_bad;
     stage_wait();
     __syncthreads();
 
-    const int64_t range0 = ((int64_t)blockIdx.x * kWarps + wid) * upw;
-    const int rangeN = (int)max((int64_t)0, min((int64_t)upw, E - range0));
-    if (rangeN == 0) return;
+    const long long total = offs[E];
+    const long long n_tiles = (total + kWT - 1) / kWT;
+    // tiles per draw: enough draws per warp to even out the tail, few enough that the binary search per draw stays small
+    const long long warps = (long long)gridDim.x * kWarps;
+    const int tpc = (int)max(1LL, min(8LL, n_tiles / (warps * 8)));
     int npend = 0, qn = 0;
 #pragma unroll 1
-    for (int t0 = 0; t0 < rangeN; t0 += kWT) {
-        const int nv = min(kWT, rangeN - t0);
-        __syncwarp();
-        for (int i = lane; i < nv * dof; i += 32) {
-            s_start[i] = starts[(range0 + t0) * dof + i];
-            s_goal[i] = goals[(range0 + t0) * dof + i];
-        }
-        __syncwarp();
-        int cnt = 0;
-        if (lane < nv) {
-            int dead = 1;            // edges shorter than float32 eps have no samples and are invalid
-            double ss = 0.0;
-            for (int k = 0; k < dof; ++k) {
-                const double dlt = (double)s_start[lane * dof + k] - (double)s_goal[lane * dof + k];
-                ss = fma(dlt, dlt, ss);
+    for (;;) {
+        int c = 0;
+        if (lane == 0) c = atomicAdd(tile_counter, 1);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        const long long t_begin = (long long)c * tpc;
+        if (t_begin >= n_tiles) break;
+        const long long t_end = min(n_tiles, t_begin + tpc);
+        // first edge of the draw: the LAST e with offs[e] <= first sample (edges without samples share their successor's offset)
+        long long e_cur;
+        {
+            const long long s_first = t_begin * kWT;
+            long long lo = 0, hi = E - 1;
+            while (lo < hi) {
+                const long long mid = (lo + hi + 1) >> 1;
+                if (offs[mid] <= s_first) lo = mid; else hi = mid - 1;
             }
-            const double dist = sqrt(ss);
-            if (dist > (double)1.1920928955078125e-07f) {
-                const double step = resolution / dist;
-                double tf = 1.0;
-                if (max_distance > 0.0 && dist > max_distance) tf = max_distance / dist;
-                const double len = ceil(tf / step);
-                cnt = (int)fmin(len, 1.0e9) + 1;
-                s_step[lane] = step;
-                s_tf[lane] = tf;
-                dead = 0;
-            }
-            if (n_samples != nullptr) n_samples[range0 + t0 + lane] = cnt;
-            valid[range0 + t0 + lane] = (uint8_t)(dead ? 0 : 1);
+            e_cur = lo;
         }
-        // warp exclusive scan of cnt
-        int x = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        s_off[lane] = x - cnt;
-        if (lane == 31) s_off[32] = x;
-        __syncwarp();
-        const int total = s_off[32];
-
 #pragma unroll 1
-        for (int round0 = 0; round0 < total; round0 += kWT) {
-            const int s = round0 + lane;
+        for (long long tile = t_begin; tile < t_end; ++tile) {
+            const long long s0 = tile * kWT;
+            const long long s = s0 + lane;
             const bool have = s < total;
-            int e = 0;
-            float t = 0.f;
-            if (have) {
-                // owning edge: last e with s_off[e] <= s
-                int lo = 0, hi = kWT - 1;
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (s_off[mid] <= s) lo = mid; else hi = mid - 1;
-                }
-                e = lo;
-                const int k = s - s_off[e];
-                const int last = s_off[e + 1] - s_off[e] - 1;
-                t = (float)((k == last) ? s_tf[e] : (double)k * s_step[e]);
+            __syncwarp();                                   // the previous tile's materialise has read item_fi / item_aux
+            // stage the window: offsets of edges e_cur .. e_cur + 33 relative to s0, clamped into int range
+            for (int i = lane; i < kEdgeWin; i += 32) {
+                const long long ei = min(e_cur + i, (long long)E);
+                s_win[i] = (int)max(-0x40000000LL, min(0x40000000LL, offs[ei] - s0));
             }
             __syncwarp();
-            C.item_fi[lane] = (int)(range0 + t0 + e);
+            long long e = e_cur;
+            int k = 0, last = 0;
+            if (have) {
+                int j;
+                if (lane >= s_win[kEdgeWin - 2] && e_cur + kEdgeWin - 2 < E) {
+                    // more than 32 edges inside one tile: only possible with edges that have no samples at all
+                    long long lo = e_cur, hi = E - 1;
+                    while (lo < hi) {
+                        const long long mid = (lo + hi + 1) >> 1;
+                        if (offs[mid] <= s) lo = mid; else hi = mid - 1;
+                    }
+                    e = lo;
+                    k = (int)(s - offs[e]);
+                    last = (int)(offs[e + 1] - offs[e]) - 1;
+                } else {
+                    int lo = 0, hi = kEdgeWin - 2;          // last j with s_win[j] <= lane
+                    while (lo < hi) {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if (s_win[mid] <= lane) lo = mid; else hi = mid - 1;
+                    }
+                    j = lo;
+                    e = e_cur + j;
+                    k = lane - s_win[j];
+                    last = s_win[j + 1] - s_win[j] - 1;
+                }
+                const EdgeMeta m = meta[e];
+                const float t = (float)((k == last) ? m.tf : (double)k * m.step);
+                const float* a = starts + e * dof;
+                const float* g = goals + e * dof;
+                float* mq = sq + lane * dof;
+                for (int col = 0; col < dof; ++col) {
+                    const float av = __ldg(a + col);
+                    mq[col] = fmaf(t, __ldg(g + col), fmaf(-t, av, av));
+                }
+            }
+            C.item_fi[lane] = (int)e;
+            C.item_aux[lane] = k;
             __syncwarp();
-            const float* a = s_start + e * dof;
-            const float* g = s_goal + e * dof;
-            phase1<kSplit, FAST>(C, have, [a, g, t](int col) { return fmaf(t, g[col], fmaf(-t, a[col], a[col])); }, S.n_obs, S.n_self, npend, qn);
+            const float* myq = sq + lane * dof;
+            phase1<kSplit, FAST>(C, have, [myq](int col) { return myq[col]; }, S.n_obs, S.n_self, npend, qn);
             materialise<kSplit>(C, npend, qn);
+            // the next tile starts at, or after, the edge of this tile's last sample
+            e_cur = __shfl_sync(0xffffffffu, e, 31);
+            if (!__shfl_sync(0xffffffffu, (int)have, 31)) break;      // ragged last tile of the whole sample space
         }
     }
 }
@@ -859,8 +1003,10 @@ edges_valid_kernel(const __grid_constant__ SceneDev S, const float* __restrict__
 // the self pairs (a warp works on one kind of pair).  The entry count lives on the device: no host round trip.
 __global__ void __launch_bounds__(128)
 narrow_kernel(const float* __restrict__ gq, const int* __restrict__ gq_count, int gq_half, float thr,
-              uint8_t* __restrict__ gflag, int hit_value, int gjk_iters) {
+              uint8_t* __restrict__ gflag, int hit_value, int gjk_iters, int* __restrict__ first_bad) {
     WCtx C;
+    C.first_bad = first_bad;
+    C.item_aux = nullptr;
     C.thr = thr;
     C.gflag = gflag;
     C.hit_value = hit_value;
@@ -967,14 +1113,13 @@ closest_witness_kernel(const __grid_constant__ SceneDev S, const float* __restri
     target[b] = env ? ((int)pr.b | 0x40000000) : V.prims[ib].desc;
     V3 n, ps, pt;
     if (g.overlap) {
-        // cores overlap: depth beyond the margins needs EPA; the distance is the clamp that
-        // min_distance reports, the points are the centres and the normal joins them
-        const V3 dc = Ssub.c - Stgt.c;
-        const float l = sqrtf(dot(dc, dc));
-        n = l > 0.f ? (1.f / l) * dc : mk(0.f, 0.f, 1.f);
-        ps = Ssub.c; pt = Stgt.c;
-        dist[b] = -(m_sub + m_tgt) - 1e-3f;
-        valid[b] = 0;
+        // cores overlap: penetration depth, push-out normal and witness points from the EPA (out of line)
+        const EpaOut ep = core_penetration(Ssub, Stgt);
+        n = ep.n;
+        ps = madd(ep.pa, -m_sub, n);
+        pt = madd(ep.pb, m_tgt, n);
+        dist[b] = -ep.depth - m_sub - m_tgt;
+        valid[b] = 1;
     } else {
         n = (1.f / g.d) * (g.pa - g.pb);            // target -> subject
         ps = madd(g.pa, -m_sub, n);
@@ -1098,11 +1243,11 @@ pair_distances_kernel(const __grid_constant__ SceneDev S, const float* __restric
         V3 n, ps, pt;
         float d;
         if (g.overlap) {
-            const V3 dc = Ssub.c - Stgt.c;
-            const float l = sqrtf(dot(dc, dc));
-            n = l > 0.f ? (1.f / l) * dc : mk(0.f, 0.f, 1.f);
-            ps = Ssub.c; pt = Stgt.c;
-            d = -(m_sub + m_tgt) - 1e-3f;
+            const EpaOut ep = core_penetration(Ssub, Stgt);
+            n = ep.n;
+            ps = madd(ep.pa, -m_sub, n);
+            pt = madd(ep.pb, m_tgt, n);
+            d = -ep.depth - m_sub - m_tgt;
         } else {
             n = (1.f / g.d) * (g.pa - g.pb);
             ps = madd(g.pa, -m_sub, n);
@@ -1110,7 +1255,7 @@ pair_distances_kernel(const __grid_constant__ SceneDev S, const float* __restric
             d = g.d - m_sub - m_tgt;
         }
         dist[o] = d;
-        if (valid_out != nullptr) valid_out[o] = g.overlap ? 0 : 1;
+        if (valid_out != nullptr) valid_out[o] = 1;
         if (p_subject != nullptr) { p_subject[o * 3 + 0] = ps.x; p_subject[o * 3 + 1] = ps.y; p_subject[o * 3 + 2] = ps.z; }
         if (p_target != nullptr) { p_target[o * 3 + 0] = pt.x; p_target[o * 3 + 1] = pt.y; p_target[o * 3 + 2] = pt.z; }
         if (normal != nullptr) { normal[o * 3 + 0] = n.x; normal[o * 3 + 1] = n.y; normal[o * 3 + 2] = n.z; }
@@ -1182,7 +1327,7 @@ int units_per_warp(int64_t n_units, int sm_count, int warps_per_sm, int waves = 
 struct SplitWs {
     void* p = nullptr;
     cudaStream_t st = nullptr;
-    SplitArgs args{nullptr, nullptr, 0, kGjkIters};
+    SplitArgs args{nullptr, nullptr, 0, kGjkIters, nullptr};
     int alloc(int device, int64_t n_items, cudaStream_t stream) {
         st = stream;
         cudaMemPool_t pool = nullptr;
@@ -1206,7 +1351,7 @@ struct SplitWs {
 };
 
 int launch_narrow(const nbx_chain* ch, const SplitArgs& G, float thr, uint8_t* gflag, int hit_value, cudaStream_t stream) {
-    narrow_kernel<<<(unsigned)(ch->sm_count * 8), 128, 0, stream>>>(G.gq, G.gq_count, G.gq_half, thr, gflag, hit_value, G.gjk_iters);
+    narrow_kernel<<<(unsigned)(ch->sm_count * 8), 128, 0, stream>>>(G.gq, G.gq_count, G.gq_half, thr, gflag, hit_value, G.gjk_iters, G.first_bad);
     nbx_count_launch();
     NBX_CUDA_OK(cudaGetLastError());
     return NBX_OK;
@@ -1223,7 +1368,6 @@ int launch_in_collision(const nbx_chain* ch, const nbx_scene* sc, const float* q
     NBX_REQUIRE(B >= 0, "negative batch size");
     if (B == 0) return NBX_OK;
     NBX_REQUIRE(q != nullptr && verdict != nullptr, "q / verdict is NULL");
-    NBX_REQUIRE(thr >= 0.f, "negative thresholds need penetration depth, which this path does not compute");
     NBX_REQUIRE(B <= 0x7fffffffLL, "batch too large for one launch");
     NBX_CUDA_OK(cudaSetDevice(ch->device));
     const int mode = min_dist != nullptr ? kDist : kSplit;
@@ -1233,7 +1377,7 @@ int launch_in_collision(const nbx_chain* ch, const nbx_scene* sc, const float* q
     const int64_t grid = (B + (int64_t)kWarps * upw - 1) / ((int64_t)kWarps * upw);
     if (mode == kDist) {
         NBX_SMEM_LIMIT((in_collision_kernel<kDist, false>), smem);
-        in_collision_kernel<kDist, false><<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, q, B, ch->dof, thr, verdict, min_dist, pair_code, upw, SplitArgs{nullptr, nullptr, 0, kGjkIters});
+        in_collision_kernel<kDist, false><<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, q, B, ch->dof, thr, verdict, min_dist, pair_code, upw, SplitArgs{nullptr, nullptr, 0, kGjkIters, nullptr});
         nbx_count_launch();
         NBX_CUDA_OK(cudaGetLastError());
         return NBX_OK;
@@ -1249,9 +1393,15 @@ int launch_in_collision(const nbx_chain* ch, const nbx_scene* sc, const float* q
     return launch_narrow(ch, G, thr, verdict, 1, stream);
 }
 
+// persistent grid of the flattened edge kernel: what the launch bounds make resident
+int edges_grid(const nbx_chain* ch) {
+    static const int env = std::getenv("NBX_EDGE_CTAS_PER_SM") ? std::atoi(std::getenv("NBX_EDGE_CTAS_PER_SM")) : 0;   // tuning only
+    return ch->sm_count * (env > 0 ? env : 4);
+}
+
 int launch_edges(const nbx_chain* ch, const nbx_scene* sc, const float* starts, const float* goals, int64_t E,
                  const double* base_pose, double resolution, double max_distance, float thr, uint8_t* valid,
-                 int32_t* n_samples, cudaStream_t stream) {
+                 int32_t* n_samples, int32_t* first_invalid, cudaStream_t stream) {
     SceneDev S;
     int rc = fill_scene_dev(ch, sc, base_pose, S);
     if (rc != NBX_OK) return rc;
@@ -1259,22 +1409,39 @@ int launch_edges(const nbx_chain* ch, const nbx_scene* sc, const float* starts, 
     if (E == 0) return NBX_OK;
     NBX_REQUIRE(starts != nullptr && goals != nullptr && valid != nullptr, "starts / goals / valid is NULL");
     NBX_REQUIRE(resolution > 0.0, "Resolution must be positive");
-    NBX_REQUIRE(thr >= 0.f, "negative thresholds need penetration depth, which this path does not compute");
     NBX_REQUIRE(E <= 0x7fffffffLL, "too many edges for one launch");
     NBX_CUDA_OK(cudaSetDevice(ch->device));
     const int dof = ch->dof;
     const size_t smem = scene_smem_bytes(S.n_mov, S.n_prims, S.n_obs, S.n_self, S.n_env) +
-                        kWarps * warp_smem_bytes(kSplit, S.scratch_floats, 2 * kWT * dof + 4 * kWT + (kWT + 4));
+                        kWarps * warp_smem_bytes(kSplit, S.scratch_floats, kWT * dof + 2 * (kEdgeWin + 2));
     NBX_REQUIRE(smem <= 220 * 1024, "scene too large for shared memory (%zu bytes)", smem);
     SplitWs ws;
     if ((rc = ws.alloc(ch->device, E * 8, stream)) != NBX_OK) return rc;
-    auto kern = ch->fast_walk ? edges_valid_kernel<true> : edges_valid_kernel<false>;
+    ws.args.first_bad = first_invalid;
+    // per-call workspace: offsets (int64 [E + 1]), {step, T_f} per edge, block sums, the tile counter
+    const int n_blocks = (int)((E + kPrepBlock - 1) / kPrepBlock);
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t b_offs = up(sizeof(long long) * (size_t)(E + 1)), b_meta = up(sizeof(EdgeMeta) * (size_t)E),
+                 b_sums = up(sizeof(long long) * (size_t)n_blocks);
+    cudaMemPool_t pool = nullptr;
+    if ((rc = nbx_workspace_pool(ch->device, &pool)) != NBX_OK) return rc;
+    struct Tmp { void* p = nullptr; cudaStream_t st = nullptr; ~Tmp() { if (p) cudaFreeAsync(p, st); } } tmp;
+    tmp.st = stream;
+    NBX_CUDA_OK(cudaMallocFromPoolAsync(&tmp.p, b_offs + b_meta + b_sums + 256, pool, stream));
+    unsigned char* w = static_cast<unsigned char*>(tmp.p);
+    long long* offs = reinterpret_cast<long long*>(w);
+    EdgeMeta* meta = reinterpret_cast<EdgeMeta*>(w + b_offs);
+    long long* sums = reinterpret_cast<long long*>(w + b_offs + b_meta);
+    int* counter = reinterpret_cast<int*>(w + b_offs + b_meta + b_sums);
+    edge_prepare_kernel<<<(unsigned)n_blocks, kPrepBlock, 0, stream>>>(starts, goals, E, dof, resolution, max_distance, valid, n_samples,
+                                                                        first_invalid, meta, offs, sums);
+    edge_scan_blocks_kernel<<<1, 1024, 0, stream>>>(sums, n_blocks, counter);
+    edge_offsets_kernel<<<(unsigned)n_blocks, kPrepBlock, 0, stream>>>(offs, E, sums);
+    nbx_count_launch(3);
+    NBX_CUDA_OK(cudaGetLastError());
+    auto kern = ch->fast_walk ? edges_flat_kernel<true> : edges_flat_kernel<false>;
     NBX_SMEM_LIMIT(kern, smem);
-    // an edge is ~13 tiles of work for its warp, so the per-CTA prologue is already amortised by one tile of edges; what
-    // matters is the tail: 10^6 edges in ranges of 256 were 977 CTAs = 1.65 waves of the 592 resident ones (ncu: +7 %)
-    const int upw = units_per_warp(E, ch->sm_count, 16, 8);
-    const int64_t grid = (E + (int64_t)kWarps * upw - 1) / ((int64_t)kWarps * upw);
-    kern<<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, starts, goals, E, dof, resolution, max_distance, thr, valid, n_samples, upw, ws.args);
+    kern<<<(unsigned)edges_grid(ch), kWarps * 32, smem, stream>>>(S, starts, goals, E, dof, thr, valid, meta, offs, counter, ws.args);
     nbx_count_launch();
     NBX_CUDA_OK(cudaGetLastError());
     return launch_narrow(ch, ws.args, thr, valid, 0, stream);
@@ -1363,7 +1530,8 @@ int launch_bisect(const nbx_chain* ch, const nbx_scene* sc, const T* inside, int
     uint8_t* verdict = w + 2 * up(sizeof(double) * n) + up(sizeof(float) * n);
     const unsigned grid = (unsigned)((n + 255) / 256);
     SplitWs ws;                          // one candidate queue for all rounds; the step kernel resets its counters
-    if ((rc = ws.alloc(ch->device, B, stream)) != NBX_OK) return rc;
+    // late rounds sit on the contact boundary: ~3 candidates per sample, nearly all of one kind -> 8 entries per sample and kind
+    if ((rc = ws.alloc(ch->device, 4 * B, stream)) != NBX_OK) return rc;
     for (int r = 0; r <= n_bisections; ++r) {
         const int last = r == n_bisections;
         bisect_step_kernel<T><<<grid, 256, 0, stream>>>(lo, hi, inside, inside_stride, outside, verdict, mid, out, B, dof, r, last, ws.args.gq_count);
@@ -1482,7 +1650,14 @@ int nbx_bisect_f64(const nbx_chain* chain, const nbx_scene* scene, const double*
 int nbx_edges_valid_f32(const nbx_chain* chain, const nbx_scene* scene, const float* starts, const float* goals, int64_t E,
                         const double* base_pose, double resolution, double max_distance, float threshold, uint8_t* valid,
                         int32_t* n_samples, void* stream) {
-    return launch_edges(chain, scene, starts, goals, E, base_pose, resolution, max_distance, threshold, valid, n_samples,
+    return launch_edges(chain, scene, starts, goals, E, base_pose, resolution, max_distance, threshold, valid, n_samples, nullptr,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int nbx_edges_valid_detail_f32(const nbx_chain* chain, const nbx_scene* scene, const float* starts, const float* goals, int64_t E,
+                               const double* base_pose, double resolution, double max_distance, float threshold, uint8_t* valid,
+                               int32_t* n_samples, int32_t* first_invalid, void* stream) {
+    return launch_edges(chain, scene, starts, goals, E, base_pose, resolution, max_distance, threshold, valid, n_samples, first_invalid,
                         static_cast<cudaStream_t>(stream));
 }
 
@@ -1511,7 +1686,7 @@ int nbx_edges_valid_host_f32(const nbx_chain* chain, const nbx_scene* scene, con
         cudaError_t e = cudaMemcpyAsync(ds, starts + off * dof, raw, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(dg, goals + off * dof, raw, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) {
-            rc = launch_edges(chain, scene, ds, dg, n, base_pose, resolution, max_distance, threshold, dv, nullptr, st);
+            rc = launch_edges(chain, scene, ds, dg, n, base_pose, resolution, max_distance, threshold, dv, nullptr, nullptr, st);
             if (rc == NBX_OK) e = cudaMemcpyAsync(valid + off, dv, (size_t)n, cudaMemcpyDeviceToHost, st);
         }
         cudaFreeAsync(p, st);

@@ -237,6 +237,8 @@ struct GjkWit {
     float d;        // distance between the cores (0 when they overlap)
     V3 pa, pb;      // closest points on core A / core B
     bool overlap;
+    bool enclosed;  // overlap proven by a tetrahedron around the origin: tw / ta hold it (the seed of the EPA below)
+    V3 tw[4], ta[4];
 };
 
 // barycentric coordinates of the point of triangle (a,b,c) closest to the origin (Ericson 5.1.5)
@@ -266,9 +268,10 @@ __device__ __forceinline__ void closest_tri_bary(V3 a, V3 b, V3 c, float* la, fl
 }
 
 template <int MAX_ITER>
-__device__ GjkWit gjk_witness(const ShapeW& A, const ShapeW& B) {
+__device__ GjkWit gjk_witness(const ShapeW& A, const ShapeW& B, bool generic_start = false) {
     GjkWit out;
     out.overlap = false;
+    out.enclosed = false;
     V3 w[4], a[4];
     float lam[4];
 #pragma unroll
@@ -277,6 +280,7 @@ __device__ GjkWit gjk_witness(const ShapeW& A, const ShapeW& B) {
     V3 v = A.c - B.c;
     float vv = dot(v, v);
     if (vv < 1e-20f) { v = mk(1.f, 0.f, 0.f); vv = 1.f; }
+    if (generic_start) { v = mk(-0.3034f, 0.2939f, -0.9065f); vv = dot(v, v); }   // retries of core_penetration: break symmetry
     V3 best_pa = A.c, best_v = v;
     float best_vv = FLT_MAX;
 #pragma unroll 1
@@ -331,7 +335,7 @@ __device__ GjkWit gjk_witness(const ShapeW& A, const ShapeW& B) {
             NBX_WFACE(0, 2, 3, 1)
             NBX_WFACE(1, 2, 3, 0)
 #undef NBX_WFACE
-            if (!outside_any) { out.overlap = true; break; }
+            if (!outside_any) { out.overlap = true; out.enclosed = true; break; }
         }
         V3 nv = mk(0, 0, 0), pa = mk(0, 0, 0);
 #pragma unroll
@@ -352,17 +356,172 @@ __device__ GjkWit gjk_witness(const ShapeW& A, const ShapeW& B) {
                     lam[i] = lam[i + 1]; lam[i + 1] = 0.f;
                 }
         n = (lam[0] > 0.f) + (lam[1] > 0.f) + (lam[2] > 0.f) + (lam[3] > 0.f);
-        if (n == 4) { out.overlap = true; break; }
+        if (n == 4) { out.overlap = true; out.enclosed = true; break; }
     }
     if (out.overlap || best_vv == FLT_MAX) {
         out.overlap = true;
         out.d = 0.f;
         out.pa = A.c; out.pb = B.c;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { out.tw[i] = w[i]; out.ta[i] = a[i]; }
         return out;
     }
     out.d = sqrtf(best_vv);
     out.pa = best_pa;
     out.pb = best_pa - best_v;
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// EPA: penetration depth of two OVERLAPPING cores = distance from the origin to the boundary of the Minkowski difference
+// D = A - B = min over unit n of h_D(n), h_D(n) = n . (s_A(n) - s_B(-n)) (van den Bergen's expanding polytope; what Bullet
+// runs behind getClosestPoints once its GJK reports an intersection, reference numbotics/physics/chain.py:944-951).  The
+// signed distance of the rounded-core model continues below -(mA + mB) as  -(mA + mB) - depth(cores)  (DESIGN.md section 4).
+// Rare path (only pairs whose cores interpenetrate reach it): out of line, the polytope lives in local memory --
+// kEpaV vertices, 2 kEpaV - 4 faces -- and the iteration count is bounded by the vertex budget.
+// Result: depth >= 0, n = unit normal from B (target) to A (subject), witness points with  pa - pb = -depth * n.
+// ---------------------------------------------------------------------------------------------
+constexpr int kEpaV = 36;
+constexpr int kEpaF = 2 * kEpaV;
+
+struct EpaOut {
+    float depth;
+    V3 n, pa, pb;
+    bool ok;
+};
+
+struct EpaFace {
+    unsigned char v0, v1, v2, alive;
+    float nx, ny, nz, d;
+};
+
+__device__ __forceinline__ bool epa_make_face(EpaFace& f, const V3* W, int i0, int i1, int i2, V3 inside) {
+    V3 n = cross(W[i1] - W[i0], W[i2] - W[i0]);
+    const float l2 = dot(n, n);
+    if (!(l2 > 1e-30f)) return false;
+    n = rsqrtf(l2) * n;
+    f.v0 = (unsigned char)i0; f.v1 = (unsigned char)i1; f.v2 = (unsigned char)i2;
+    if (dot(n, W[i0] - inside) < 0.f) { f.v1 = (unsigned char)i2; f.v2 = (unsigned char)i1; n = -n; }
+    f.nx = n.x; f.ny = n.y; f.nz = n.z;
+    f.d = dot(n, W[i0]);
+    f.alive = 1;
+    return true;
+}
+
+__device__ __noinline__ EpaOut epa_penetration(const ShapeW& A, const ShapeW& B, const V3* sw, const V3* sa) {
+    EpaOut out;
+    out.ok = false;
+    out.depth = 0.f;
+    out.n = mk(0.f, 0.f, 1.f);
+    out.pa = A.c; out.pb = B.c;
+    V3 W[kEpaV], PA[kEpaV];
+    EpaFace F[kEpaF];
+    unsigned char E0[3 * 24], E1[3 * 24];         // horizon candidates: edges of the faces that see the new vertex
+    int nv = 4, nf = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { W[i] = sw[i]; PA[i] = sa[i]; }
+    const V3 inside = 0.25f * (W[0] + W[1] + W[2] + W[3]);
+    if (!epa_make_face(F[nf++], W, 0, 1, 2, inside)) return out;
+    if (!epa_make_face(F[nf++], W, 0, 1, 3, inside)) return out;
+    if (!epa_make_face(F[nf++], W, 0, 2, 3, inside)) return out;
+    if (!epa_make_face(F[nf++], W, 1, 2, 3, inside)) return out;
+    float best_h = FLT_MAX, lower = 0.f;
+    EpaFace bf = F[0];
+#pragma unroll 1
+    for (int it = 0; it < kEpaV; ++it) {
+        int f = -1;
+        float fd = FLT_MAX;
+        for (int i = 0; i < nf; ++i)
+            if (F[i].alive && F[i].d < fd) { fd = F[i].d; f = i; }
+        if (f < 0) break;
+        const V3 n = mk(F[f].nx, F[f].ny, F[f].nz);
+        const V3 a = support(A, n);
+        const V3 w = a - support(B, -n);
+        const float h = dot(n, w);
+        lower = fd;
+        if (h < best_h) { best_h = h; bf = F[f]; }
+        if (h - fd <= 2e-6f + 2e-5f * fabsf(h) || nv >= kEpaV) break;
+        W[nv] = w; PA[nv] = a;
+        int ne = 0, nvis = 0;
+        const float eps = 1e-6f * (1.f + fabsf(h));
+        for (int i = 0; i < nf; ++i) {
+            if (!F[i].alive) continue;
+            if (dot(mk(F[i].nx, F[i].ny, F[i].nz), w - W[F[i].v0]) > eps) {
+                if (ne + 3 > 3 * 24) { ne = -1; break; }       // absurdly large visible region: stop with the bracket found so far
+                F[i].alive = 0; ++nvis;
+                E0[ne] = F[i].v0; E1[ne] = F[i].v1; ++ne;
+                E0[ne] = F[i].v1; E1[ne] = F[i].v2; ++ne;
+                E0[ne] = F[i].v2; E1[ne] = F[i].v0; ++ne;
+            }
+        }
+        if (ne <= 0 || nvis == 0) break;
+        int added = 0;
+        for (int i = 0; i < ne; ++i) {
+            bool twin = false;
+            for (int j = 0; j < ne; ++j) twin = twin || (E0[j] == E1[i] && E1[j] == E0[i]);
+            if (twin) continue;
+            // reuse the slot of a dead face if the array is full
+            int slot = nf < kEpaF ? nf : -1;
+            if (slot < 0)
+                for (int k = 0; k < nf; ++k)
+                    if (!F[k].alive) { slot = k; break; }
+            if (slot < 0) break;
+            if (epa_make_face(F[slot], W, E0[i], E1[i], nv, inside)) { if (slot == nf) ++nf; ++added; }
+        }
+        ++nv;
+        if (added < 3) break;
+    }
+    if (best_h == FLT_MAX) return out;
+    const V3 n = mk(bf.nx, bf.ny, bf.nz);
+    const float d = 0.5f * (fmaxf(fminf(lower, best_h), 0.f) + fmaxf(best_h, 0.f));
+    float l0, l1, l2;
+    {
+        // barycentric coordinates of the projection of the origin on the best face (in the face's own frame: shift by -proj)
+        const V3 proj = bf.d * n;
+        closest_tri_bary(W[bf.v0] - proj, W[bf.v1] - proj, W[bf.v2] - proj, &l0, &l1, &l2);
+    }
+    out.pa = madd(madd(l0 * PA[bf.v0], l1, PA[bf.v1]), l2, PA[bf.v2]);
+    out.n = -n;
+    out.pb = madd(out.pa, -d, n);
+    out.depth = d;
+    out.ok = true;
+    return out;
+}
+
+// Penetration of two cores known (or suspected) to overlap: seed GJK with witness bookkeeping, then the EPA.  A seed that
+// degenerates -- the origin on a vertex / edge / face of the simplex, which symmetric scenes produce exactly and which
+// the contact regime of the GJK reports as grazing -- is retried with A shifted by a generic 2e-5 m and a generic first
+// search direction (depth changes by at most the shift; half of the stated 1e-4 m band with the contact regime's 5e-5).
+__device__ __noinline__ EpaOut core_penetration(const ShapeW& A, const ShapeW& B) {
+    EpaOut out;
+    out.ok = false; out.depth = 0.f; out.n = mk(0.f, 0.f, 1.f); out.pa = A.c; out.pb = B.c;
+    ShapeW As = A;
+#pragma unroll 1
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        const GjkWit g = gjk_witness<64>(As, B, attempt > 0);
+        if (!g.overlap) {
+            // separated after all (grazing contact, or the shift pulled it apart): depth below the resolution of this path
+            const float l = g.d > 0.f ? g.d : 1.f;
+            out.n = (1.f / l) * (g.pa - g.pb);
+            out.pa = g.pa; out.pb = g.pb; out.depth = 0.f; out.ok = true;
+            return out;
+        }
+        if (g.enclosed) {
+            out = epa_penetration(As, B, g.tw, g.ta);
+            if (out.ok) {
+                out.pa = out.pa - (As.c - A.c);
+                out.pb = madd(out.pa, out.depth, out.n);      // pa - pb = -depth * n
+                return out;
+            }
+        }
+        const float sh = attempt == 0 ? 2e-5f : 2e-4f;
+        As.c = A.c + sh * mk(0.5377f, -0.8311f, 0.1418f);
+    }
+    // no usable seed: report contact along the line of centres
+    const V3 dc = A.c - B.c;
+    const float l = sqrtf(dot(dc, dc));
+    out.n = l > 0.f ? (1.f / l) * dc : mk(0.f, 0.f, 1.f);
+    out.ok = true;
     return out;
 }
 

@@ -514,13 +514,12 @@ class Arm:
         return verdict
 
     def min_distance(self, q, threshold: float = 0.0):
-        """Minimum distance over the allowed pairs (clamped at overlap)."""
+        """Signed minimum distance over the allowed pairs: negative = penetration depth (EPA), as the reference's
+        `closest_to(q).distance` (arm.py:599-604)."""
         return self._collide(q, threshold, want_dist=True)[1]
 
     def _collide(self, q, threshold, want_dist):
         self._check_q(q)
-        if threshold < 0:
-            raise NotImplementedError("negative thresholds need penetration depth (EPA), which this path does not compute")
         in_torch = _is_torch(q)
         q_shape = tuple(q.shape)
         single = len(q_shape) == 1
@@ -634,7 +633,8 @@ class Arm:
         `q (dof,)` -> one `Proximity` (the reference's record: subject, target, position_on_subject,
         position_on_target, normal_target_to_subject, distance); `q (..., dof)` -> a `Proximities` record whose
         fields are arrays with the batch dimensions of q (`subject` / `target` are object arrays of Link /
-        PhysicsObject, `valid` is False where the two cores overlap: no EPA).
+        PhysicsObject, `valid` is False only where no allowed pair exists; overlapping pairs report the signed
+        penetration distance, push-out normal and witness points of the EPA).
         `gradient=True` adds `.gradient (..., dof)`: d distance / d q, i.e. `jacobian_proximity` of the closest pair.
         """
         self._check_q(q)
@@ -711,8 +711,6 @@ class Arm:
         self._check_q(inside, "inside")
         if num_bisections < 1:
             raise ValueError("num_bisections must be greater than 0")
-        if threshold < 0:
-            raise NotImplementedError("negative thresholds need penetration depth (EPA), which this path does not compute")
         in_torch = _is_torch(outside)
         o_shape = tuple(outside.shape)
         i_shape = tuple(inside.shape)
@@ -751,10 +749,12 @@ class Arm:
 
     # ------------------------------------------------------------------ edge validation
     def edges_valid(self, starts, goals, resolution: float, max_distance: float | None = None,
-                    threshold: float = 0.0, return_samples: bool = False):
+                    threshold: float = 0.0, return_samples: bool = False, return_useful: bool = False):
         """Batched DiscreteConnector verdicts for edges start[e] -> goal[e] (see planning.sampling_based).
 
         `max_distance=None` = `connect` semantics, otherwise `steer` semantics.
+        `return_samples` adds the number of interpolation samples per edge; `return_useful` adds the number of samples
+        the sequential reference would have evaluated (up to and including the first invalid one, connectors.py:71-73).
         """
         self._check_q(starts, "start")
         self._check_q(goals, "goal")
@@ -762,8 +762,6 @@ class Arm:
             raise ValueError("starts and goals must have the same shape")
         if resolution <= 0:
             raise ValueError("Resolution must be positive")
-        if threshold < 0:
-            raise NotImplementedError("negative thresholds need penetration depth (EPA), which this path does not compute")
         in_torch = _is_torch(starts)
         shape = tuple(starts.shape[:-1])
         E = int(np.prod(shape)) if len(shape) else 1
@@ -777,18 +775,30 @@ class Arm:
         lib = _cabi.load()
         with torch.cuda.device(dev_index):
             vd = torch.empty((E,), dtype=torch.uint8, device=sd.device)
-            nd = torch.empty((E,), dtype=torch.int32, device=sd.device) if return_samples else None
-            _cabi.check(lib.nbx_edges_valid_f32(
-                self._handle().ptr, scene.ptr, sd.data_ptr(), gd.data_ptr(), E, base_ptr,
-                float(resolution), float(max_distance) if max_distance is not None else 0.0,
-                float(threshold), vd.data_ptr(), nd.data_ptr() if return_samples else None,
-                _cuda_stream_ptr(dev_index)))
+            want_n = return_samples or return_useful
+            nd = torch.empty((E,), dtype=torch.int32, device=sd.device) if want_n else None
+            fd = torch.empty((E,), dtype=torch.int32, device=sd.device) if return_useful else None
+            if return_useful:
+                _cabi.check(lib.nbx_edges_valid_detail_f32(
+                    self._handle().ptr, scene.ptr, sd.data_ptr(), gd.data_ptr(), E, base_ptr,
+                    float(resolution), float(max_distance) if max_distance is not None else 0.0,
+                    float(threshold), vd.data_ptr(), nd.data_ptr(), fd.data_ptr(), _cuda_stream_ptr(dev_index)))
+            else:
+                _cabi.check(lib.nbx_edges_valid_f32(
+                    self._handle().ptr, scene.ptr, sd.data_ptr(), gd.data_ptr(), E, base_ptr,
+                    float(resolution), float(max_distance) if max_distance is not None else 0.0,
+                    float(threshold), vd.data_ptr(), nd.data_ptr() if want_n else None,
+                    _cuda_stream_ptr(dev_index)))
         del base_keep
         valid = vd.to(torch.bool)
+        useful = torch.where(valid, nd, torch.clamp(fd, max=0x7ffffffe) + 1) if return_useful else None
         if in_torch:
-            valid = valid.to(starts.device).reshape(shape)
-            ns = nd.to(starts.device).reshape(shape) if return_samples else None
+            conv = lambda x: x.to(starts.device).reshape(shape)
         else:
-            valid = valid.cpu().numpy().reshape(shape)
-            ns = nd.cpu().numpy().reshape(shape) if return_samples else None
-        return (valid, ns) if return_samples else valid
+            conv = lambda x: x.cpu().numpy().reshape(shape)
+        out = [conv(valid)]
+        if return_samples:
+            out.append(conv(nd))
+        if return_useful:
+            out.append(conv(useful))
+        return tuple(out) if len(out) > 1 else out[0]

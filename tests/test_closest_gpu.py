@@ -30,12 +30,12 @@ def test_closest_pair_distance_points_normal(scene):
     ok = rec.valid & (d_or > 1e-3)                  # clearly separated surfaces
     assert ok.mean() > 0.9
     assert np.abs(rec.distance[ok] - d_or[ok]).max() < 1e-4
-    # overlapping cores are flagged and carry the documented clamp
+    # overlapping cores: signed penetration distance from the EPA (oracle: float64 EPA), every record valid
     am = pd.argmin(axis=1)
     msum = so.margins[so.pairs[am, 0]] + so.margins[so.pairs[am, 1]]
-    deep = d_or <= -msum - 0.9e-3                    # the oracle's clamp for cores that interpenetrate beyond the band
-    assert deep.any() and not rec.valid[deep].any()
-    assert np.abs(rec.distance[deep] - d_or[deep]).max() < 1.1e-3      # both are clamps: -(margins) - {1e-6 grazing | 1e-3 deep}
+    deep = d_or <= -msum - 1e-3                      # cores interpenetrate
+    assert deep.sum() > 10 and rec.valid.all()
+    assert np.abs(rec.distance[deep] - d_or[deep]).max() < 2e-4
     # witness points are |distance| apart along the normal, which is a unit vector from target to subject
     ps, pt, n = rec.position_on_subject[ok], rec.position_on_target[ok], rec.normal_target_to_subject[ok]
     assert np.abs(np.linalg.norm(n, axis=1) - 1).max() < 1e-5
@@ -129,7 +129,8 @@ def test_pair_distances_every_allowed_pair(scene):
     sep = ref > 1e-3
     assert sep.mean() > 0.9
     assert (np.abs(d[sep] - ref[sep]) / np.maximum(ref[sep], 1.0)).max() < 1e-4      # fp32: 1e-4 m, relative beyond 1 m
-    assert (d[ref < -0.02] < 0).all()
+    pen = ref < -1e-3
+    assert pen.sum() > 50 and np.abs(d[pen] - ref[pen]).max() < 2e-4                  # signed: EPA depth on both sides
     # the minimum over the pairs is the distance query; the arg-min is the closest pair
     md = arm.min_distance(q)
     assert np.abs(d.min(axis=1) - md)[md > 1e-3].max() < 1e-4

@@ -36,6 +36,16 @@ def test_in_collision_matches_oracle(cuda, margin_model):
     check_verdicts(hit, d)
 
 
+def _dense_contact_configs(n, seed):
+    rng = np.random.default_rng(seed)
+    sgn = lambda k: rng.choice([-1.0, 1.0], k)
+    q = rng.normal(scale=0.5, size=(n, 7))
+    q[:, 1] = rng.uniform(1.2, 2.41, n) * sgn(n)     # shoulder down
+    q[:, 3] = rng.uniform(2.2, 2.66, n) * sgn(n)     # elbow folded
+    q[:, 5] = rng.uniform(1.5, 2.23, n) * sgn(n)     # wrist folded
+    return q.astype(np.float32)
+
+
 def test_in_collision_dense_contacts(scene):
     """Configurations concentrated where contacts happen: arm folded on itself / reaching into the cubes."""
     arm, cubes, so = scene
@@ -60,7 +70,10 @@ def test_min_distance_matches_oracle(scene):
     sep = d > 0
     err = np.abs(dist[sep] - d[sep])
     assert err.max() < 1e-4, (err.max(), np.argmax(err), dist[sep][np.argmax(err)], d[sep][np.argmax(err)])
-    assert np.all(dist[~sep] < 0)
+    # penetration: signed distance from the EPA on both sides (float32 kernel / float64 oracle)
+    assert (~sep).sum() > 30
+    errn = np.abs(dist[~sep] - d[~sep])
+    assert errn.max() < 2e-4, (errn.max(), dist[~sep][np.argmax(errn)], d[~sep][np.argmax(errn)])
 
 
 def test_threshold_and_single_config_api(scene):
@@ -75,8 +88,15 @@ def test_threshold_and_single_config_api(scene):
     assert arm.in_collision(q3).shape == (2, 3, 4)
     with pytest.raises(ValueError, match="q must have 7 elements"):
         arm.in_collision(np.zeros(6))
-    with pytest.raises(NotImplementedError):
-        arm.in_collision(q[0], threshold=-0.01)
+    # negative thresholds (reference arm.py:603-604 compares Bullet's signed distance): inside the margins, and beyond them
+    # where only interpenetrating cores count
+    qd = np.concatenate([q, _dense_contact_configs(3000, seed=9)])
+    dd = so.min_distance(qd.astype(np.float64))
+    for thr in (-0.003, -0.02, -0.06):
+        hit = arm.in_collision(qd, thr)
+        clear = np.abs(dd - thr) > 2 * EPS
+        assert (dd < thr).sum() > 20
+        assert np.array_equal(hit[clear], (dd < thr)[clear]), thr
 
 
 def test_torch_in_torch_out(scene, cuda):
@@ -317,6 +337,7 @@ def test_crowded_scene_overflow_paths(cuda):
     dist = arm.min_distance(q[:1000])
     sep = d[:1000] > 0
     assert np.abs(dist[sep] - d[:1000][sep]).max() < 1e-4
+    assert np.abs(dist[~sep] - d[:1000][~sep]).max() < 3e-4       # penetration depth into the small cubes (EPA both sides)
     # edges through the clutter
     s, g = q[:300], q[300:600].copy()
     g[:150] = s[:150] + 0.1 * (g[:150] - s[:150])
