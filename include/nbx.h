@@ -161,10 +161,10 @@ NBX_API int nbx_fk_jac_host_f64(const nbx_chain* chain, int frame, const double*
 
 /*
  * Batched Arm.in_collision (numbotics/robots/arm.py:555-604): verdict[b] = 1 iff the
- * minimum distance over the allowed pairs is < threshold.  Optional min_dist[b]
- * (nullable) receives a clamped minimum distance: exact while the cores are apart
- * (distance >= -(margin_a + margin_b)), and -(margin_a + margin_b) - 1e-3 when the cores
- * overlap (no EPA: depth beyond the margins is not computed).
+ * minimum distance over the allowed pairs is < threshold (any sign: the reference compares
+ * Bullet's signed distance).  Optional min_dist[b] (nullable) receives the SIGNED minimum
+ * distance: core distance minus the two margins while the cores are apart, and
+ * -(margin_a + margin_b) - penetration depth of the cores (EPA) once they overlap; see DESIGN.md section 4.
  */
 NBX_API int nbx_in_collision_f32(const nbx_chain* chain, const nbx_scene* scene, const float* q, int64_t B,
                          const double* base_pose, float threshold,
@@ -211,8 +211,8 @@ NBX_API int nbx_edges_valid_host_f32(const nbx_chain* chain, const nbx_scene* sc
  *   subject_prim (B,) index of the link primitive in the chain descriptor,
  *   target (B,): obstacle index in the scene descriptor when the pair is (link, obstacle) -- then is_env bit 30 is
  *   set: target = obstacle | 0x40000000 -- else the chain-descriptor index of the other link primitive,
- *   valid (B,) u8: 0 when the two cores overlap (no EPA: distance is the clamp of nbx_in_collision_f32's min_dist,
- *   points are the centres), gradient (nullable, (B,dof)).
+ *   valid (B,) u8: 0 only when no allowed pair exists; overlapping pairs carry the signed penetration distance, the
+ *   push-out normal and the witness points of the EPA.  gradient (nullable, (B,dof)).
  * The scene must be unpruned (every allowed pair present).
  */
 NBX_API int nbx_closest_f32(const nbx_chain* chain, const nbx_scene* scene, const float* q, int64_t B, const double* base_pose,
@@ -224,12 +224,23 @@ NBX_API int nbx_closest_f32(const nbx_chain* chain, const nbx_scene* scene, cons
  * Outputs are indexed [b][p] with p the pair's index in the scene descriptor, self pairs first
  * (p < n_self_pairs: self_pairs[p]; else env_pairs[p - n_self_pairs]); subject = the pair's first entry.
  *   distance (B, P); position_on_subject / position_on_target / normal_target_to_subject (B, P, 3), nullable;
- *   valid (B, P) u8, nullable: 0 where the two cores overlap (clamped distance, centres as points; no EPA).
+ *   valid (B, P) u8, nullable: always 1 (kept for ABI stability; overlapping pairs report signed EPA distances).
  * The scene must be unpruned.  Arm.distance_to(q, obj, link) (arm.py:607-618) is a column of this result.
  */
 NBX_API int nbx_pair_distances_f32(const nbx_chain* chain, const nbx_scene* scene, const float* q, int64_t B,
                            const double* base_pose, float* distance, float* position_on_subject,
                            float* position_on_target, float* normal_target_to_subject, uint8_t* valid, void* stream);
+
+/*
+ * Same, plus the gradient of every pair's distance with respect to q: the batched form of Arm.jacobian_proximity(q, obj, link)
+ * (numbotics/robots/arm.py:621-632) for EVERY allowed pair,
+ *   gradient[b][p][:] = n . J_v(subject, position_on_subject) - n . J_v(target, position_on_target)   (B, P, dof), nullable
+ * (the second term only when the target is a link of this chain).  Chains of at most 64 movable joints.
+ */
+NBX_API int nbx_pair_distances_grad_f32(const nbx_chain* chain, const nbx_scene* scene, const float* q, int64_t B,
+                                const double* base_pose, float* distance, float* position_on_subject,
+                                float* position_on_target, float* normal_target_to_subject, uint8_t* valid,
+                                float* gradient, void* stream);
 
 /*
  * Batched bisection towards the collision boundary: the zero-order-hold counter-example search of IRIS

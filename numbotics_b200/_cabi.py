@@ -70,6 +70,7 @@ SIGNATURES = {
     "nbx_edges_valid_host_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f64p, C.c_double, C.c_double, C.c_float, _vp]),
     "nbx_closest_f32": (C.c_int, [_vp, _vp, _vp, _i64, _f64p, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nbx_pair_distances_f32": (C.c_int, [_vp, _vp, _vp, _i64, _f64p, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nbx_pair_distances_grad_f32": (C.c_int, [_vp, _vp, _vp, _i64, _f64p, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nbx_knn_f32": (C.c_int, [_vp, _i64, _vp, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp]),
     "nbx_bisect_f32": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _f64p, C.c_int, C.c_float, _vp, _vp]),
     "nbx_bisect_f64": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _f64p, C.c_int, C.c_float, _vp, _vp]),

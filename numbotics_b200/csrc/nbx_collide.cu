@@ -1161,13 +1161,17 @@ closest_witness_kernel(const __grid_constant__ SceneDev S, const float* __restri
 __global__ void __launch_bounds__(kWarps * 32)
 pair_distances_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ q, int64_t B, int dof,
                       float* __restrict__ dist, float* __restrict__ p_subject, float* __restrict__ p_target,
-                      float* __restrict__ normal, uint8_t* __restrict__ valid_out) {
+                      float* __restrict__ normal, uint8_t* __restrict__ valid_out, float* __restrict__ grad) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WCtx C;
     unsigned char* p = stage_scene(S, smem_raw, C.V);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    p += (size_t)wid * align16(sizeof(float) * (size_t)kWT * max(S.scratch_floats, 1));
+    // per warp: the primitives' world cores, and (gradient only) every joint's world axis and origin [6 n_mov][32]
+    const size_t pose_bytes = align16(sizeof(float) * (size_t)kWT * max(S.scratch_floats, 1));
+    const size_t jscr_bytes = grad != nullptr ? align16(sizeof(float) * (size_t)kWT * 6 * max(S.n_mov, 1)) : 0;
+    p += (size_t)wid * (pose_bytes + jscr_bytes);
     C.poses = reinterpret_cast<float*>(p);
+    float* jscr = reinterpret_cast<float*>(p + pose_bytes) + (threadIdx.x & 31);
     stage_wait();
     __syncthreads();
     const int64_t b = ((int64_t)blockIdx.x * kWarps + wid) * kWT + lane;
@@ -1205,6 +1209,19 @@ pair_distances_kernel(const __grid_constant__ SceneDev S, const float* __restric
             }
             nbxj::joint_step<float, TreeJointK>(X, jk, have ? myq[jk.qidx] : 0.f);
             if (jk.save_slot >= 0) saved[jk.save_slot] = X;
+            if (grad != nullptr) {
+                // world axis and origin of joint j: what d(point)/dq_j needs (w x (p - p_j) revolute, w prismatic)
+                V3 w;
+                if (jk.kind == NBX_KIND_X) w = jk.sgn * mk(X.R[0], X.R[3], X.R[6]);
+                else if (jk.kind == NBX_KIND_Y) w = jk.sgn * mk(X.R[1], X.R[4], X.R[7]);
+                else if (jk.kind == NBX_KIND_Z) w = jk.sgn * mk(X.R[2], X.R[5], X.R[8]);
+                else w = mk(fmaf(X.R[0], jk.ax[0], fmaf(X.R[1], jk.ax[1], X.R[2] * jk.ax[2])),
+                            fmaf(X.R[3], jk.ax[0], fmaf(X.R[4], jk.ax[1], X.R[5] * jk.ax[2])),
+                            fmaf(X.R[6], jk.ax[0], fmaf(X.R[7], jk.ax[1], X.R[8] * jk.ax[2])));
+                float* js = jscr + (size_t)j * 6 * kWT;
+                js[0] = w.x; js[kWT] = w.y; js[2 * kWT] = w.z;
+                js[3 * kWT] = X.p[0]; js[4 * kWT] = X.p[1]; js[5 * kWT] = X.p[2];
+            }
             do_prims(jk.prim_begin, jk.prim_end);
         }
     }
@@ -1259,6 +1276,30 @@ pair_distances_kernel(const __grid_constant__ SceneDev S, const float* __restric
         if (p_subject != nullptr) { p_subject[o * 3 + 0] = ps.x; p_subject[o * 3 + 1] = ps.y; p_subject[o * 3 + 2] = ps.z; }
         if (p_target != nullptr) { p_target[o * 3 + 0] = pt.x; p_target[o * 3 + 1] = pt.y; p_target[o * 3 + 2] = pt.z; }
         if (normal != nullptr) { normal[o * 3 + 0] = n.x; normal[o * 3 + 1] = n.y; normal[o * 3 + 2] = n.z; }
+        if (grad != nullptr) {
+            // d distance / d q = n . J_v(subject, p_subject) - n . J_v(target, p_target)  (reference robots/arm.py:621-632):
+            // joints above exactly one of the two bodies contribute, joints above both cancel
+            const unsigned long long anc_s = pa.anc, anc_t = env ? 0ull : C.V.prims[pr.b].anc;
+            float* go = grad + o * dof;
+#pragma unroll 1
+            for (int j = 0; j < S.n_mov; ++j) {
+                const TreeJointK& jk = C.V.tree[j];
+                const bool on_s = (anc_s >> j) & 1ull, on_t = (anc_t >> j) & 1ull;
+                float gj = 0.f;
+                if (on_s != on_t) {
+                    const float* js = jscr + (size_t)j * 6 * kWT;
+                    const V3 w = mk(js[0], js[kWT], js[2 * kWT]);
+                    if (jk.type == NBX_JOINT_REVOLUTE) {
+                        const V3 pj = mk(js[3 * kWT], js[4 * kWT], js[5 * kWT]);
+                        gj = dot(n, cross(w, (on_s ? ps : pt) - pj));
+                    } else {
+                        gj = dot(n, w);
+                    }
+                    if (!on_s) gj = -gj;
+                }
+                go[jk.qidx] = gj;
+            }
+        }
     }
 }
 
@@ -1483,7 +1524,8 @@ int launch_closest(const nbx_chain* ch, const nbx_scene* sc, const float* q, int
 }
 
 int launch_pair_distances(const nbx_chain* ch, const nbx_scene* sc, const float* q, int64_t B, const double* base_pose,
-                          float* dist, float* p_subject, float* p_target, float* normal, uint8_t* valid, cudaStream_t stream) {
+                          float* dist, float* p_subject, float* p_target, float* normal, uint8_t* valid, float* grad,
+                          cudaStream_t stream) {
     SceneDev S;
     int rc = fill_scene_dev(ch, sc, base_pose, S);
     if (rc != NBX_OK) return rc;
@@ -1491,13 +1533,15 @@ int launch_pair_distances(const nbx_chain* ch, const nbx_scene* sc, const float*
     if (B == 0 || sc->n_self + sc->n_env == 0) return NBX_OK;
     NBX_REQUIRE(q != nullptr && dist != nullptr, "q / distance is NULL");
     NBX_CUDA_OK(cudaSetDevice(ch->device));
+    NBX_REQUIRE(grad == nullptr || ch->n_mov <= 64, "distance gradients support chains of at most 64 movable joints");
     const size_t smem = scene_smem_bytes(S.n_mov, S.n_prims, S.n_obs, S.n_self, S.n_env) +
-                        kWarps * align16(sizeof(float) * (size_t)kWT * std::max(S.scratch_floats, 1));
+                        kWarps * (align16(sizeof(float) * (size_t)kWT * std::max(S.scratch_floats, 1)) +
+                                  (grad != nullptr ? align16(sizeof(float) * (size_t)kWT * 6 * std::max(S.n_mov, 1)) : 0));
     NBX_REQUIRE(smem <= 220 * 1024, "scene too large for shared memory (%zu bytes)", smem);
     NBX_SMEM_LIMIT(pair_distances_kernel, smem);
     const int64_t grid = (B + kWarps * kWT - 1) / (kWarps * kWT);
     NBX_REQUIRE(grid <= 0x7fffffffLL, "batch too large for one launch");
-    pair_distances_kernel<<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, q, B, ch->dof, dist, p_subject, p_target, normal, valid);
+    pair_distances_kernel<<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, q, B, ch->dof, dist, p_subject, p_target, normal, valid, grad);
     nbx_count_launch();
     NBX_CUDA_OK(cudaGetLastError());
     return NBX_OK;
@@ -1632,7 +1676,14 @@ int nbx_pair_distances_f32(const nbx_chain* chain, const nbx_scene* scene, const
                            float* distance, float* position_on_subject, float* position_on_target, float* normal_target_to_subject,
                            uint8_t* valid, void* stream) {
     return launch_pair_distances(chain, scene, q, B, base_pose, distance, position_on_subject, position_on_target,
-                                 normal_target_to_subject, valid, static_cast<cudaStream_t>(stream));
+                                 normal_target_to_subject, valid, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int nbx_pair_distances_grad_f32(const nbx_chain* chain, const nbx_scene* scene, const float* q, int64_t B, const double* base_pose,
+                                float* distance, float* position_on_subject, float* position_on_target,
+                                float* normal_target_to_subject, uint8_t* valid, float* gradient, void* stream) {
+    return launch_pair_distances(chain, scene, q, B, base_pose, distance, position_on_subject, position_on_target,
+                                 normal_target_to_subject, valid, gradient, static_cast<cudaStream_t>(stream));
 }
 
 int nbx_bisect_f32(const nbx_chain* chain, const nbx_scene* scene, const float* inside, int64_t inside_stride, const float* outside,
