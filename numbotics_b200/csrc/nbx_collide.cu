@@ -166,6 +166,10 @@ constexpr int kMaxRange = 256;       // units a warp owns (flags kept in shared 
 constexpr uint32_t kEnvFlag = 0x80000000u;
 
 constexpr int kSplit = 0;            // verdict query, global queue + narrow kernel
+constexpr int kSplitNeg = 2;         // the same for NEGATIVE thresholds: pairs whose margins the threshold exceeds need the cores'
+                                     // penetration depth (EPA).  A separate instantiation so that the usual verdict kernels carry
+                                     // neither its stack frame nor its registers (ptxas: 3.2 KB of stack and twice the spills when
+                                     // the EPA call was reachable from them; in_collision 0.70 -> 0.97 ms)
 constexpr int kDist = 1;             // distance query, fused
 
 struct WCtx {
@@ -320,7 +324,7 @@ __device__ __forceinline__ void eval_cand(const WCtx& C, const Cand& K) {
         }
         const float lim = C.thr + K.m;                       // the pair collides iff  core distance < lim
         bool hit;
-        if (lim > 0.f) {
+        if (MODE != kSplitNeg || lim > 0.f) {
             // the bracket only has to close to a fraction of the stated 1e-4 m contact band: a pair whose [lb, ub] still straddles
             // the threshold at 2e-5 is inside the band whichever way it is called (round 1 iterated on to 1e-6: the narrow kernel
             // of a bisection round, where every candidate sits on the contact boundary, took 85 us instead of ~45)
@@ -330,7 +334,7 @@ __device__ __forceinline__ void eval_cand(const WCtx& C, const Cand& K) {
             // iteration stops (converged to its tolerance, stalled, or out of iterations: rounded cylinders converge only
             // linearly).  The unsafe direction for in_collision / edges_valid / bisect would be to call such a pair free.
             hit = !g.pruned;
-        } else {
+        } else if (MODE == kSplitNeg) {
             // negative threshold beyond this pair's margins: only cores that interpenetrate by more than -lim collide
             const GjkOut g = gjk_distance<kGjkIters>(K.A, K.B, 1e-6f, -1.f, 2e-5f, 1e-5f, C.gjk_iters);
             hit = g.overlap && core_penetration(K.A, K.B).depth > -lim;
@@ -710,7 +714,7 @@ struct SplitArgs {
 // in_collision.  MODE kSplit: broad kernel of the verdict query (verdict[b] = 0 here, the narrow kernel raises it);
 // MODE kDist: fused distance query (min_dist[b] and the verdict at the end of the warp's range).
 template <int MODE, bool FAST>
-__global__ void __launch_bounds__(kWarps * 32, MODE == kSplit ? 5 : 1)
+__global__ void __launch_bounds__(kWarps * 32, MODE == kSplit ? 5 : (MODE == kSplitNeg ? 4 : 1))
 in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ q, int64_t B, int dof, float thr,
                     uint8_t* __restrict__ verdict, float* __restrict__ min_dist, uint32_t* __restrict__ pair_code, int upw,
                     const SplitArgs G) {
@@ -889,7 +893,7 @@ edge_offsets_kernel(long long* __restrict__ offs, int64_t E, const long long* __
 
 constexpr int kEdgeWin = 34;           // offsets of the tile's first edge .. +33 (>= 1 sample per live edge: a tile spans <= 32 live edges)
 
-template <bool FAST>
+template <bool FAST, int MODE>
 __global__ void __launch_bounds__(kWarps * 32, 4)
 edges_flat_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ starts, const float* __restrict__ goals,
                   int64_t E, int dof, float thr, uint8_t* __restrict__ valid, const EdgeMeta* __restrict__ meta,
@@ -900,7 +904,7 @@ edges_flat_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int extra = kWT * dof + 2 * (kEdgeWin + 2);      // the tile's configurations [32][dof], the offset window (int)
     const size_t wbytes = warp_smem_bytes(kSplit, S.scratch_floats, extra);
-    p = carve_warp<kSplit>(C, p + (size_t)wid * wbytes, S.scratch_floats);
+    p = carve_warp<MODE>(C, p + (size_t)wid * wbytes, S.scratch_floats);
     C.item_aux = C.item_fi + kWT;                           // carve_warp reserves 2 x kWT ints
     float* sq = reinterpret_cast<float*>(p);               // [32][dof]
     int* s_win = reinterpret_cast<int*>(sq + (size_t)kWT * dof);   // [kEdgeWin] offsets relative to the tile's first sample
@@ -989,8 +993,8 @@ edges_flat_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ 
             C.item_aux[lane] = k;
             __syncwarp();
             const float* myq = sq + lane * dof;
-            phase1<kSplit, FAST>(C, have, [myq](int col) { return myq[col]; }, S.n_obs, S.n_self, npend, qn);
-            materialise<kSplit>(C, npend, qn);
+            phase1<MODE, FAST>(C, have, [myq](int col) { return myq[col]; }, S.n_obs, S.n_self, npend, qn);
+            materialise<MODE>(C, npend, qn);
             // the next tile starts at, or after, the edge of this tile's last sample
             e_cur = __shfl_sync(0xffffffffu, e, 31);
             if (!__shfl_sync(0xffffffffu, (int)have, 31)) break;      // ragged last tile of the whole sample space
@@ -1001,6 +1005,7 @@ edges_flat_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 // Narrow kernel of the verdict queries: one thread per queue entry, grid-stride, first the environment pairs, then
 // the self pairs (a warp works on one kind of pair).  The entry count lives on the device: no host round trip.
+template <int MODE>
 __global__ void __launch_bounds__(128)
 narrow_kernel(const float* __restrict__ gq, const int* __restrict__ gq_count, int gq_half, float thr,
               uint8_t* __restrict__ gflag, int hit_value, int gjk_iters, int* __restrict__ first_bad) {
@@ -1020,7 +1025,7 @@ narrow_kernel(const float* __restrict__ gq, const int* __restrict__ gq_count, in
         for (int i = first; i < n; i += stride) {
             Cand K;
             load_cand(gq, off + i, K, 2 * gq_half);
-            eval_cand<kSplit>(C, K);
+            eval_cand<MODE>(C, K);
         }
     }
 }
@@ -1392,7 +1397,10 @@ struct SplitWs {
 };
 
 int launch_narrow(const nbx_chain* ch, const SplitArgs& G, float thr, uint8_t* gflag, int hit_value, cudaStream_t stream) {
-    narrow_kernel<<<(unsigned)(ch->sm_count * 8), 128, 0, stream>>>(G.gq, G.gq_count, G.gq_half, thr, gflag, hit_value, G.gjk_iters, G.first_bad);
+    if (thr < 0.f)
+        narrow_kernel<kSplitNeg><<<(unsigned)(ch->sm_count * 8), 128, 0, stream>>>(G.gq, G.gq_count, G.gq_half, thr, gflag, hit_value, G.gjk_iters, G.first_bad);
+    else
+        narrow_kernel<kSplit><<<(unsigned)(ch->sm_count * 8), 128, 0, stream>>>(G.gq, G.gq_count, G.gq_half, thr, gflag, hit_value, G.gjk_iters, G.first_bad);
     nbx_count_launch();
     NBX_CUDA_OK(cudaGetLastError());
     return NBX_OK;
@@ -1426,7 +1434,8 @@ int launch_in_collision(const nbx_chain* ch, const nbx_scene* sc, const float* q
     SplitWs ws;
     if (shared == nullptr && (rc = ws.alloc(ch->device, B, stream)) != NBX_OK) return rc;
     const SplitArgs& G = shared != nullptr ? *shared : ws.args;
-    auto kern = ch->fast_walk ? in_collision_kernel<kSplit, true> : in_collision_kernel<kSplit, false>;
+    auto kern = thr < 0.f ? (ch->fast_walk ? in_collision_kernel<kSplitNeg, true> : in_collision_kernel<kSplitNeg, false>)
+                          : (ch->fast_walk ? in_collision_kernel<kSplit, true> : in_collision_kernel<kSplit, false>);
     NBX_SMEM_LIMIT(kern, smem);
     kern<<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, q, B, ch->dof, thr, verdict, nullptr, nullptr, upw, G);
     nbx_count_launch();
@@ -1480,7 +1489,8 @@ int launch_edges(const nbx_chain* ch, const nbx_scene* sc, const float* starts, 
     edge_offsets_kernel<<<(unsigned)n_blocks, kPrepBlock, 0, stream>>>(offs, E, sums);
     nbx_count_launch(3);
     NBX_CUDA_OK(cudaGetLastError());
-    auto kern = ch->fast_walk ? edges_flat_kernel<true> : edges_flat_kernel<false>;
+    auto kern = thr < 0.f ? (ch->fast_walk ? edges_flat_kernel<true, kSplitNeg> : edges_flat_kernel<false, kSplitNeg>)
+                          : (ch->fast_walk ? edges_flat_kernel<true, kSplit> : edges_flat_kernel<false, kSplit>);
     NBX_SMEM_LIMIT(kern, smem);
     kern<<<(unsigned)edges_grid(ch), kWarps * 32, smem, stream>>>(S, starts, goals, E, dof, thr, valid, meta, offs, counter, ws.args);
     nbx_count_launch();

@@ -238,6 +238,7 @@ struct GjkWit {
     V3 pa, pb;      // closest points on core A / core B
     bool overlap;
     bool enclosed;  // overlap proven by a tetrahedron around the origin: tw / ta hold it (the seed of the EPA below)
+    int n;          // !enclosed overlap (contact regime): the origin lies within 5e-5 of the hull of tw[0..n-1]
     V3 tw[4], ta[4];
 };
 
@@ -344,7 +345,6 @@ __device__ GjkWit gjk_witness(const ShapeW& A, const ShapeW& B, bool generic_sta
         if (nvv >= best_vv) break;                       // rounding stopped the descent: keep the best point so far
         best_vv = nvv; best_v = nv; best_pa = pa;
         v = nv; vv = nvv;
-        if (vv <= 2.5e-9f) { out.overlap = true; break; }   // contact regime (see gjk_distance)
         // drop the vertices that do not support the closest point (stable compaction, static indices)
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass)
@@ -357,7 +357,9 @@ __device__ GjkWit gjk_witness(const ShapeW& A, const ShapeW& B, bool generic_sta
                 }
         n = (lam[0] > 0.f) + (lam[1] > 0.f) + (lam[2] > 0.f) + (lam[3] > 0.f);
         if (n == 4) { out.overlap = true; out.enclosed = true; break; }
+        if (vv <= 2.5e-9f) { out.overlap = true; break; }   // contact regime (see gjk_distance): origin on the hull of w[0..n-1]
     }
+    out.n = n;
     if (out.overlap || best_vv == FLT_MAX) {
         out.overlap = true;
         out.d = 0.f;
@@ -381,8 +383,8 @@ __device__ GjkWit gjk_witness(const ShapeW& A, const ShapeW& B, bool generic_sta
 // kEpaV vertices, 2 kEpaV - 4 faces -- and the iteration count is bounded by the vertex budget.
 // Result: depth >= 0, n = unit normal from B (target) to A (subject), witness points with  pa - pb = -depth * n.
 // ---------------------------------------------------------------------------------------------
-constexpr int kEpaV = 36;
-constexpr int kEpaF = 2 * kEpaV;
+constexpr int kEpaV = 48;
+constexpr int kEpaF = 2 * kEpaV;          // a closed triangulated polytope of V vertices has 2V - 4 faces
 
 struct EpaOut {
     float depth;
@@ -440,7 +442,9 @@ __device__ __noinline__ EpaOut epa_penetration(const ShapeW& A, const ShapeW& B,
         const float h = dot(n, w);
         lower = fd;
         if (h < best_h) { best_h = h; bf = F[f]; }
-        if (h - fd <= 2e-6f + 2e-5f * fabsf(h) || nv >= kEpaV) break;
+        // the bracket [closest face, smallest h] is closed to a fraction of the stated 1e-4 m band: stop BEFORE the new vertex
+        // lands in the plane of its face (the slivers that come out of such an expansion have garbage normals)
+        if (h - fd <= 1e-5f + 5e-5f * fabsf(h) || nv >= kEpaV) break;
         W[nv] = w; PA[nv] = a;
         int ne = 0, nvis = 0;
         const float eps = 1e-6f * (1.f + fabsf(h));
@@ -454,26 +458,43 @@ __device__ __noinline__ EpaOut epa_penetration(const ShapeW& A, const ShapeW& B,
                 E0[ne] = F[i].v2; E1[ne] = F[i].v0; ++ne;
             }
         }
+#ifdef EPA_TRACE
+        printf("  it %d nv %d nf %d fd %.6f h %.6f nvis %d ne %d\n", it, nv, nf, fd, h, nvis, ne);
+#endif
         if (ne <= 0 || nvis == 0) break;
+        if (nf + ne > kEpaF) {                     // out of slots: squeeze the dead faces out (alive <= 2 nv - 4)
+            int k = 0;
+            for (int i = 0; i < nf; ++i)
+                if (F[i].alive) { if (k != i) F[k] = F[i]; ++k; }
+            nf = k;
+            if (nf + ne > kEpaF) break;
+        }
         int added = 0;
+        bool garbage = false;
         for (int i = 0; i < ne; ++i) {
             bool twin = false;
             for (int j = 0; j < ne; ++j) twin = twin || (E0[j] == E1[i] && E1[j] == E0[i]);
             if (twin) continue;
-            // reuse the slot of a dead face if the array is full
-            int slot = nf < kEpaF ? nf : -1;
-            if (slot < 0)
-                for (int k = 0; k < nf; ++k)
-                    if (!F[k].alive) { slot = k; break; }
-            if (slot < 0) break;
-            if (epa_make_face(F[slot], W, E0[i], E1[i], nv, inside)) { if (slot == nf) ++nf; ++added; }
+            if (epa_make_face(F[nf], W, E0[i], E1[i], nv, inside)) {
+                // a face of the grown (convex) polytope cannot be closer to the origin than the closest face before
+                garbage = garbage || F[nf].d < fd - (1e-5f + 1e-4f * fabsf(h));
+                ++nf; ++added;
+            }
         }
         ++nv;
-        if (added < 3) break;
+#ifdef EPA_TRACE
+        if (added < 3 || garbage) printf("  stop: added %d garbage %d\n", added, (int)garbage);
+#endif
+        if (added < 3 || garbage) break;
     }
     if (best_h == FLT_MAX) return out;
     const V3 n = mk(bf.nx, bf.ny, bf.nz);
-    const float d = 0.5f * (fmaxf(fminf(lower, best_h), 0.f) + fmaxf(best_h, 0.f));
+    // The depth lies in [lower, best_h]: closest face of the inscribed polytope / smallest support value seen.  best_h is
+    // reported: h_D(n) of an actual direction is attained exactly where the minimum sits on a flat feature or on a whole
+    // circle of normals (coaxial cylinders, a point on a cylinder's axis), where the polygonal lower bound of a 48-vertex
+    // polytope is still 0.5 % short; on generic curved contacts both ends are within 1e-5 at termination anyway.
+    (void)lower;
+    const float d = fmaxf(best_h, 0.f);
     float l0, l1, l2;
     {
         // barycentric coordinates of the projection of the origin on the best face (in the face's own frame: shift by -proj)
@@ -489,33 +510,153 @@ __device__ __noinline__ EpaOut epa_penetration(const ShapeW& A, const ShapeW& B,
 }
 
 // Penetration of two cores known (or suspected) to overlap: seed GJK with witness bookkeeping, then the EPA.  A seed that
-// degenerates -- the origin on a vertex / edge / face of the simplex, which symmetric scenes produce exactly and which
-// the contact regime of the GJK reports as grazing -- is retried with A shifted by a generic 2e-5 m and a generic first
-// search direction (depth changes by at most the shift; half of the stated 1e-4 m band with the contact regime's 5e-5).
+// degenerates -- the origin within the contact resolution of a vertex / edge / face of the GJK simplex: symmetric scenes
+// produce that exactly, and a triangle of three early support points passes within 5e-5 of the origin about once in 10^4
+// generic deep overlaps -- is retried with A shifted by a generic 1 mm (then 3 mm) and a generic first search direction.
+// The shift is taken out again at the end: with the face normal n found on the shifted problem the depth is re-evaluated
+// on the UNSHIFTED cores, depth = h_D(n) = n . (s_A(n) - s_B(-n)), which is exact for the same contact feature and off by
+// O(shift^2 / curvature radius) otherwise.
+// point core (sphere primitive) inside a box / cylinder core: closed form.  Returns the depth, `dir` = the unit direction
+// that takes the POINT out of the shape by the shortest way.
+__device__ __forceinline__ float point_in_core(V3 p, const ShapeW& S, V3* dir) {
+    const V3 r = p - S.c;
+    if (S.type == NBX_PRIM_BOX) {
+        float best = FLT_MAX;
+        V3 bd = mk(0.f, 0.f, 1.f);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const V3 a = mk(S.ax[k], S.ax[3 + k], S.ax[6 + k]);
+            const float x = dot(r, a);
+            const float g = S.d[k] - fabsf(x);
+            if (g < best) { best = g; bd = copysignf(1.f, x) * a; }
+        }
+        *dir = bd;
+        return fmaxf(best, 0.f);
+    }
+    const V3 u = mk(S.ax[0], S.ax[1], S.ax[2]);
+    const float z = dot(r, u);
+    const V3 rad = madd(r, -z, u);
+    const float rho = sqrtf(dot(rad, rad));
+    const float gr = S.d[0] - rho, gz = S.d[1] - fabsf(z);
+    if (gr <= gz) {
+        // on the axis every radial direction is equally short: pick one square to u
+        V3 e = fabsf(u.x) <= fabsf(u.y) && fabsf(u.x) <= fabsf(u.z) ? mk(1.f, 0.f, 0.f) : (fabsf(u.y) <= fabsf(u.z) ? mk(0.f, 1.f, 0.f) : mk(0.f, 0.f, 1.f));
+        e = cross(u, e);
+        *dir = rho > 1e-7f * S.d[0] ? (1.f / rho) * rad : rsqrtf(dot(e, e)) * e;
+        return fmaxf(gr, 0.f);
+    }
+    *dir = copysignf(1.f, z) * u;
+    return fmaxf(gz, 0.f);
+}
+
 __device__ __noinline__ EpaOut core_penetration(const ShapeW& A, const ShapeW& B) {
     EpaOut out;
     out.ok = false; out.depth = 0.f; out.n = mk(0.f, 0.f, 1.f); out.pa = A.c; out.pb = B.c;
+    if (A.type == NBX_PRIM_SPHERE || B.type == NBX_PRIM_SPHERE) {
+        // a point core in a box / cylinder core (two points never overlap): exact, no polytope
+        out.ok = true;
+        if (A.type == NBX_PRIM_SPHERE && B.type == NBX_PRIM_SPHERE) return out;
+        V3 dir;
+        if (A.type == NBX_PRIM_SPHERE) {
+            out.depth = point_in_core(A.c, B, &dir);
+            out.n = dir;                                   // A (the point) leaves B along dir
+            out.pa = A.c;
+            out.pb = madd(A.c, out.depth, dir);
+        } else {
+            out.depth = point_in_core(B.c, A, &dir);
+            out.n = -dir;                                  // A moves the other way
+            out.pb = B.c;
+            out.pa = madd(B.c, out.depth, dir);            // pa - pb = -depth * n
+        }
+        return out;
+    }
+    if (A.type == NBX_PRIM_CYLINDER && B.type == NBX_PRIM_CYLINDER) {
+        // parallel axes (to 1e-4 rad): A - B is itself a cylinder of radius rA + rB and half height hA + hB about cA - cB, and
+        // the minimum over the normals sits on a whole circle -- exact in closed form, a 0.1 % error for a 48-vertex polytope
+        const V3 ua = mk(A.ax[0], A.ax[1], A.ax[2]), ub = mk(B.ax[0], B.ax[1], B.ax[2]);
+        const V3 cx = cross(ua, ub);
+        if (dot(cx, cx) < 1e-8f) {
+            ShapeW D = B;
+            D.d[0] = A.d[0] + B.d[0]; D.d[1] = A.d[1] + B.d[1];
+            V3 dir;
+            out.depth = point_in_core(A.c, D, &dir);
+            out.n = dir;
+            out.ok = true;
+            const V3 r = A.c - B.c;
+            const float z = dot(r, ub);
+            const V3 rad = madd(r, -z, ub);
+            const float rho = sqrtf(dot(rad, rad));
+            if (fabsf(dot(dir, ub)) < 0.5f) {
+                // side contact: on A's side facing B's axis, half way along the axial overlap
+                const float zlo = fmaxf(z - A.d[1], -B.d[1]), zhi = fminf(z + A.d[1], B.d[1]);
+                out.pa = madd(madd(A.c, -A.d[0], dir), 0.5f * (zlo + zhi) - z, ub);
+            } else {
+                // cap contact: A's cap centre, pulled towards B's axis until it is over B's cap
+                const float t = fmaxf(rho - B.d[0], 0.f);
+                out.pa = madd(A.c, -A.d[1], dir);
+                if (rho > 0.f) out.pa = madd(out.pa, -t / rho, rad);
+            }
+            out.pb = madd(out.pa, out.depth, out.n);
+            return out;
+        }
+    }
     ShapeW As = A;
 #pragma unroll 1
     for (int attempt = 0; attempt < 3; ++attempt) {
         const GjkWit g = gjk_witness<64>(As, B, attempt > 0);
+#ifdef EPA_TRACE
+        printf(" attempt %d overlap %d enclosed %d d %.6g\n", attempt, (int)g.overlap, (int)g.enclosed, g.d);
+#endif
         if (!g.overlap) {
-            // separated after all (grazing contact, or the shift pulled it apart): depth below the resolution of this path
+            if (attempt > 0) break;                 // the shift pulled a shallow overlap apart: report contact (below)
+            // separated after all (grazing contact): depth below the resolution of this path
             const float l = g.d > 0.f ? g.d : 1.f;
             out.n = (1.f / l) * (g.pa - g.pb);
             out.pa = g.pa; out.pb = g.pb; out.depth = 0.f; out.ok = true;
             return out;
         }
-        if (g.enclosed) {
-            out = epa_penetration(As, B, g.tw, g.ta);
+        V3 tw[4], ta[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { tw[i] = g.tw[i]; ta[i] = g.ta[i]; }
+        bool seeded = g.enclosed;
+        if (!seeded && g.n >= 2) {
+            // The origin sits (to 5e-5) ON a segment or triangle of the seed simplex.  That is grazing contact only if the
+            // simplex is part of the boundary; for a deep overlap it is a chord through the interior (a triangle of three early
+            // support points of two big cylinders does that routinely).  Complete it to a tetrahedron: a support point square
+            // to the segment, then one beyond the triangle's plane on the origin's side.
+            if (g.n == 2) {
+                const V3 e = tw[1] - tw[0];
+                const V3 ax = fabsf(e.x) <= fabsf(e.y) && fabsf(e.x) <= fabsf(e.z) ? mk(1.f, 0.f, 0.f)
+                              : (fabsf(e.y) <= fabsf(e.z) ? mk(0.f, 1.f, 0.f) : mk(0.f, 0.f, 1.f));
+                const V3 d = cross(e, ax);
+                ta[2] = support(As, d);
+                tw[2] = ta[2] - support(B, -d);
+            }
+            V3 nrm = cross(tw[1] - tw[0], tw[2] - tw[0]);
+            const float l2 = dot(nrm, nrm);
+            if (l2 > 1e-20f) {
+                if (dot(nrm, tw[0]) > 0.f) nrm = -nrm;        // towards the side of the plane the origin is on
+                ta[3] = support(As, nrm);
+                tw[3] = ta[3] - support(B, -nrm);
+                // a real tetrahedron (the 4th point clear of the plane), and the origin not beyond it: else this IS the boundary
+                const float hgt = dot(nrm, tw[3] - tw[0]) * rsqrtf(l2);
+                seeded = hgt > 1e-4f;
+            }
+        }
+        if (seeded) {
+            out = epa_penetration(As, B, tw, ta);
             if (out.ok) {
-                out.pa = out.pa - (As.c - A.c);
+                if (attempt > 0) {
+                    const V3 nf = -out.n;           // outward normal of the face of A - B closest to the origin
+                    const V3 a = support(A, nf);
+                    out.depth = fmaxf(dot(nf, a - support(B, -nf)), 0.f);
+                    out.pa = out.pa - (As.c - A.c);
+                }
                 out.pb = madd(out.pa, out.depth, out.n);      // pa - pb = -depth * n
                 return out;
             }
         }
-        const float sh = attempt == 0 ? 2e-5f : 2e-4f;
-        As.c = A.c + sh * mk(0.5377f, -0.8311f, 0.1418f);
+        As.c = A.c + (attempt == 0 ? 1e-3f : 3e-3f) * (attempt == 0 ? mk(0.5377f, -0.8311f, 0.1418f) : mk(-0.6245f, -0.2171f, 0.7502f));
     }
     // no usable seed: report contact along the line of centres
     const V3 dc = A.c - B.c;

@@ -60,13 +60,20 @@ static void support(const oshape* S, const double* dir, double* out) {
         const double u[3] = {S->R[2], S->R[5], S->R[8]};
         const double du = dot3(dir, u);
         double perp[3] = {dir[0] - du * u[0], dir[1] - du * u[1], dir[2] - du * u[2]};
-        /* remove the rounding residue along the axis (dir almost parallel to u: cap contacts) */
-        const double pu = dot3(perp, u);
-        for (int i = 0; i < 3; ++i) perp[i] -= pu * u[i];
+        /* remove the rounding residue along the axis (dir almost parallel to u: cap contacts).  u comes from a rotation
+         * matrix that may have been rounded to float32 (|u|^2 - 1 ~ 6e-8), so one pass leaves a residue of that relative
+         * size along u: two passes, and a direction within 1e-9 rad of the axis is treated as the axis (every cap point is
+         * a support point then; the support VALUE changes by radius * 1e-9).  With a 1e-13 cut-off an EPA face lying
+         * exactly in the cap plane produced a "support point" 3 mm outside the cylinder (noise direction with a 1 %
+         * axial component times the radius), i.e. a polytope that was not inscribed and a depth 4 % too large. */
+        for (int pass = 0; pass < 2; ++pass) {
+            const double pu = dot3(perp, u) / dot3(u, u);
+            for (int i = 0; i < 3; ++i) perp[i] -= pu * u[i];
+        }
         const double l = sqrt(dot3(perp, perp));
         const double s = du >= 0.0 ? S->d[1] : -S->d[1];
         for (int i = 0; i < 3; ++i) out[i] += s * u[i];
-        if (l > 1e-13 * sqrt(dot3(dir, dir)))
+        if (l > 1e-9 * sqrt(dot3(dir, dir)))
             for (int i = 0; i < 3; ++i) out[i] += S->d[0] / l * perp[i];
     }
 }
