@@ -311,9 +311,12 @@ __device__ __forceinline__ void eval_cand(const WCtx& C, const Cand& K) {
         const GjkOut g = gjk_distance<kGjkItersDist>(K.A, K.B, best + K.m, -FLT_MAX, 2e-5f, 4e-5f);
         if (g.pruned) return;
         // overlapping cores: the signed distance continues below -(mA + mB) by the cores' penetration depth (EPA, out of line)
+        // ... and so does the contact regime: |v| below 5e-5 is grazing contact only if that part of the simplex lies on the
+        // boundary; a chord through the interior of a DEEP overlap passes that close to the origin about once in 10^4 pairs
+        // (and always in exactly symmetric poses), and core_penetration tells the two apart (depth 0 for a real graze)
         float d;
-        if (g.overlap) d = -K.m - core_penetration(K.A, K.B).depth;
-        else d = g.contact ? (-K.m - 1e-6f) : (g.d - K.m);
+        if (g.overlap || g.contact) d = -K.m - core_penetration(K.A, K.B).depth;
+        else d = g.d - K.m;
         atomicMin(&C.flag[K.fi], dist_entry(d, K.pc));
     } else {
         volatile uint8_t* f = C.gflag + K.fi;
@@ -337,7 +340,7 @@ __device__ __forceinline__ void eval_cand(const WCtx& C, const Cand& K) {
         } else if (MODE == kSplitNeg) {
             // negative threshold beyond this pair's margins: only cores that interpenetrate by more than -lim collide
             const GjkOut g = gjk_distance<kGjkIters>(K.A, K.B, 1e-6f, -1.f, 2e-5f, 1e-5f, C.gjk_iters);
-            hit = g.overlap && core_penetration(K.A, K.B).depth > -lim;
+            hit = (g.overlap || g.contact) && core_penetration(K.A, K.B).depth > -lim;
         }
         if (hit) {
             *f = (uint8_t)C.hit_value;
@@ -1339,6 +1342,15 @@ __global__ void bisect_step_kernel(double* __restrict__ lo, double* __restrict__
 // ---------------------------------------------------------------------------------------------
 int fill_scene_dev(const nbx_chain* ch, const nbx_scene* sc, const double* base_pose, SceneDev& S) {
     NBX_REQUIRE(ch != nullptr && sc != nullptr, "NULL handle");
+    {
+        // a CUDA error left behind by somebody else's unchecked call (ours are all checked) would otherwise be blamed on
+        // the next launch below: report it as what it is
+        const cudaError_t stale = cudaGetLastError();
+        if (stale != cudaSuccess) {
+            nbx_set_error("stale CUDA error found before a collision launch: %s", cudaGetErrorString(stale));
+            return NBX_ERR_CUDA;
+        }
+    }
     NBX_REQUIRE(sc->chain == ch, "scene was created for a different chain");
     NBX_REQUIRE(base_pose != nullptr, "base_pose is NULL");
     S.tree = ch->d_tree;

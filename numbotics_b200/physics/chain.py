@@ -122,6 +122,9 @@ class Chain:
         # baseInertialFramePosition = base_link._offset, :433-434): a chain created at the world
         # origin therefore reports base_link._offset.  The hot path takes it as a given 4x4.
         self._base_pose = np.array(links[0]._offset, dtype=np.float64) if base_pose is None else np.asarray(base_pose, dtype=np.float64)
+        # the chain's CURRENT joint state (reference physics/chain.py:679-685 keeps it in PyBullet): only read when this chain
+        # is a collision TARGET of another arm (reference robots/arm.py:239-241), whose scene then holds its links as posed here
+        self._configuration = np.zeros(self._dof, dtype=np.float64)
         world.register(self)
 
     def __hash__(self):
@@ -141,6 +144,18 @@ class Chain:
     @property
     def dof(self):
         return self._dof
+
+    @property
+    def configuration(self):
+        return self._configuration.copy()
+
+    @configuration.setter
+    def configuration(self, q):
+        q = np.asarray(q, dtype=np.float64).reshape(-1)
+        if q.shape[0] != self._dof:
+            raise ValueError(f"q must have {self._dof} elements")
+        self._configuration = q.copy()
+        self.world.touch()
 
     @property
     def base_pose(self):

@@ -93,6 +93,28 @@ class Proximities:
         return np.where(env, self.obstacles[np.where(env & (i >= 0), i, none_o)], self.links[np.where(~env & (i >= 0), i, none_l)])
 
 
+class LinkTarget:
+    """A link of ANOTHER chain in the world as a collision target (reference robots/arm.py:239-241): the link's own
+    collision shape, posed by that chain's current `configuration`.  Quacks like a `PhysicsObject` for the scene flattening."""
+
+    def __init__(self, link, pose):
+        self.link = link
+        self._collision_shape = link._collision_shape
+        self.pose = np.asarray(pose, dtype=np.float64)
+        self.name = link.name
+
+    def __hash__(self):
+        return hash(self.link)
+
+    def __eq__(self, other):
+        return isinstance(other, LinkTarget) and other.link is self.link
+
+
+def _public(obj):
+    """The object a caller knows: the foreign Link behind a LinkTarget, else the object itself."""
+    return obj.link if isinstance(obj, LinkTarget) else obj
+
+
 class Arm:
 
     def __init__(self, chain: GraphChain, device: int | None = None, margin_model: str = "bullet"):
@@ -198,8 +220,15 @@ class Arm:
         """Current obstacles + allowed pairs as nbx_scene_desc arrays (also used by the tests).
         `static_threshold` not None -> obstacle pairs that can never come within it are dropped."""
         self_pairs = self.self_collision_pairs()
-        env_pairs = [p for p in self.collision_pairs().difference(self_pairs)
-                     if isinstance(p[1], PhysicsObject)]
+        env_pairs = []
+        targets = {}
+        for a, b in self.collision_pairs().difference(self_pairs):
+            if isinstance(b, PhysicsObject):
+                env_pairs.append((a, b))
+            elif isinstance(b, Link) and b not in self._chain._links and b._collision_shape.shape != Shape.EMPTY:
+                if b not in targets:
+                    targets[b] = LinkTarget(b, self._foreign_link_pose(b))
+                env_pairs.append((a, targets[b]))
         prune = None if static_threshold is None else (self.base_pose, self.joint_limits, static_threshold)
         return descriptor.flatten_scene(self._arrays, self_pairs, env_pairs, self._margin_model, prune)
 
@@ -226,8 +255,20 @@ class Arm:
         return self._self_collision_pairs.union(
             self._additional_self_collision_pairs).difference(self._void_self_collision_pairs)
 
+    def _foreign_link_pose(self, link):
+        """World pose of a link of another chain at that chain's current configuration -- through that chain's own
+        batched-FK path (a lazily built `Arm` on the same device), not a CPU restatement."""
+        for obj in self._chain.world.objects():
+            if isinstance(obj, Chain) and obj is not self._chain and link in obj._links:
+                other = getattr(obj, "_nbx_arm", None)
+                if other is None:
+                    other = Arm(obj, device=self.device_index, margin_model=self._margin_model)
+                    obj._nbx_arm = other
+                return np.asarray(other.forward_kinematics(np.asarray(obj.configuration, dtype=np.float64), link._name))
+        raise ValueError(f"Object name: {link._name} must be a valid object in the world")
+
     def collision_pairs(self):
-        """reference arm.py:226-250 (other chains in the world are not supported on this path)."""
+        """reference arm.py:226-250, including the links of the OTHER chains in the world (:239-241)."""
         pairs = set()
         for link in self._chain._links:
             if link._collision_shape.shape == Shape.EMPTY:
@@ -239,6 +280,9 @@ class Arm:
                     if obj._collision_shape.shape == Shape.EMPTY:
                         continue
                     pairs.add((link, obj))
+                elif isinstance(obj, Chain):
+                    for obj_link in obj._links:
+                        pairs.add((link, obj_link))
         return pairs.union(self.self_collision_pairs()).union(
             self._additional_collision_pairs).difference(self._void_collision_pairs)
 
@@ -553,13 +597,16 @@ class Arm:
         return verdict, dist
 
     # ------------------------------------------------------------------ every allowed pair
-    def pair_distances(self, q, points: bool = False):
+    def pair_distances(self, q, points: bool = False, gradient: bool = False):
         """Batched `Arm.collisions` (reference arm.py:555-580): one proximity per allowed pair and configuration.
 
         Returns `(pairs, distance)` with `pairs` the list of `(subject, target)` objects (self pairs first) and
         `distance (..., P)`; with `points=True` a `Proximities`-like dict of arrays
-        `{distance, position_on_subject, position_on_target, normal_target_to_subject, valid}` of shape `(..., P[, 3])`.
+        `{distance, position_on_subject, position_on_target, normal_target_to_subject, valid}` of shape `(..., P[, 3])`;
+        `gradient=True` (implies the dict form) adds `gradient (..., P, dof)`: d distance / d q of every pair, i.e.
+        `jacobian_proximity` (reference arm.py:621-632) for all allowed pairs at once.
         """
+        points = points or gradient
         self._check_q(q)
         in_torch = _is_torch(q)
         q_shape = tuple(q.shape)
@@ -568,7 +615,7 @@ class Arm:
         scene = self._scene(0.0, exact_distance=True)
         arrays = self._scene_arrays
         link_of_prim = {p: l for l, p in self._arrays["prim_of_link"].items()}
-        obstacles = arrays["obstacles"]
+        obstacles = [_public(o) for o in arrays["obstacles"]]
         pairs = [(link_of_prim[int(a)], link_of_prim[int(b)]) for a, b in arrays["self_pairs"]]
         pairs += [(link_of_prim[int(a)], obstacles[int(o)]) for a, o in arrays["env_pairs"]]
         P = len(pairs)
@@ -583,10 +630,16 @@ class Arm:
             dist = f(B, P)
             ps, pt, nrm = (f(B, P, 3), f(B, P, 3), f(B, P, 3)) if points else (None, None, None)
             ok = torch.empty((B, P), dtype=torch.uint8, device=qd.device) if points else None
-            _cabi.check(lib.nbx_pair_distances_f32(
-                self._handle().ptr, scene.ptr, qd.data_ptr(), B, base_ptr, dist.data_ptr(),
-                ps.data_ptr() if points else None, pt.data_ptr() if points else None, nrm.data_ptr() if points else None,
-                ok.data_ptr() if points else None, _cuda_stream_ptr(dev_index)))
+            grad = f(B, P, self.dof) if gradient else None
+            if gradient:
+                _cabi.check(lib.nbx_pair_distances_grad_f32(
+                    self._handle().ptr, scene.ptr, qd.data_ptr(), B, base_ptr, dist.data_ptr(), ps.data_ptr(), pt.data_ptr(),
+                    nrm.data_ptr(), ok.data_ptr(), grad.data_ptr(), _cuda_stream_ptr(dev_index)))
+            else:
+                _cabi.check(lib.nbx_pair_distances_f32(
+                    self._handle().ptr, scene.ptr, qd.data_ptr(), B, base_ptr, dist.data_ptr(),
+                    ps.data_ptr() if points else None, pt.data_ptr() if points else None, nrm.data_ptr() if points else None,
+                    ok.data_ptr() if points else None, _cuda_stream_ptr(dev_index)))
         del base_keep
         if in_torch:
             conv = lambda x: x.to(q.device)
@@ -597,9 +650,12 @@ class Arm:
         dist_o = conv(dist).reshape(*shape, P)
         if not points:
             return pairs, dist_o
-        return pairs, {"distance": dist_o, "position_on_subject": conv(ps).reshape(*shape, P, 3),
-                       "position_on_target": conv(pt).reshape(*shape, P, 3),
-                       "normal_target_to_subject": conv(nrm).reshape(*shape, P, 3), "valid": conv(ok.to(torch.bool)).reshape(*shape, P)}
+        rec = {"distance": dist_o, "position_on_subject": conv(ps).reshape(*shape, P, 3),
+               "position_on_target": conv(pt).reshape(*shape, P, 3),
+               "normal_target_to_subject": conv(nrm).reshape(*shape, P, 3), "valid": conv(ok.to(torch.bool)).reshape(*shape, P)}
+        if gradient:
+            rec["gradient"] = conv(grad).reshape(*shape, P, self.dof)
+        return pairs, rec
 
     def collisions(self, q):
         """reference arm.py:555-580 for one configuration: the list of `Proximity` records of every allowed pair."""
@@ -616,9 +672,31 @@ class Arm:
         links = set(self._arrays["prim_of_link"].keys())
         return [p for p in self.collisions(q) if p.target in links]
 
+    @staticmethod
+    def _involves(subject, target, obj):
+        """`obj` as the reference's distance_to / jacobian_proximity accept it: a PhysicsObject, a Link, or a whole Chain."""
+        if isinstance(obj, Chain):
+            return target in obj._links or subject in obj._links
+        return target is obj or subject is obj
+
+    def jacobian_proximity(self, q, obj, link=None):
+        """`Arm.jacobian_proximity(q, obj, link)` (reference arm.py:621-632), batched: for every allowed pair between the arm
+        (or its one `link`) and `obj` the row `n . J_v(subject, p_subject) - n . J_v(target, p_target)` = d distance / d q.
+
+        `q (dof,)` -> `(n_pairs, dof)`, or `(dof,)` when there is exactly one pair (reference :630-632); `q (..., dof)` ->
+        `(..., n_pairs, dof)` / `(..., dof)`.  Pairs come in the order of `pair_distances`."""
+        pairs, rec = self.pair_distances(q, gradient=True)
+        cols = [i for i, (s_, t_) in enumerate(pairs) if self._involves(s_, t_, obj)]
+        if link is not None:
+            cols = [i for i in cols if pairs[i][0] is link or pairs[i][1] is link]
+            if not cols:
+                raise ValueError(f"Collision pair ({link.name}, {obj.name}) not valid")
+        J = rec["gradient"][..., cols, :]
+        return J[..., 0, :] if len(cols) == 1 else J
+
     def distance_to(self, q, obj, link=None):
         """reference arm.py:607-618: the proximities between the arm (or one `link`) and `obj`, one configuration."""
-        prox = [p for p in self.collisions(q) if p.target is obj or p.subject is obj]
+        prox = [p for p in self.collisions(q) if self._involves(p.subject, p.target, obj)]
         if link is None:
             return prox
         out = [p for p in prox if p.subject is link or p.target is link]
@@ -664,7 +742,7 @@ class Arm:
         # subject / target as indices (kept on the device for CUDA inputs) + lookup tables; object arrays on demand
         prim_of_link = self._arrays["prim_of_link"]
         n_prims = max(prim_of_link.values()) + 1 if prim_of_link else 0
-        obstacles = arrays["obstacles"]
+        obstacles = [_public(o) for o in arrays["obstacles"]]
         link_tab = np.empty(n_prims + 1, dtype=object)            # last entry: None (no pair)
         for l, p in prim_of_link.items():
             link_tab[p] = l

@@ -173,12 +173,16 @@ class SceneOracle:
     """Built from an Arm-like object exposing `_link_joint_sequence`, `_links_from_nodes`, `dof`, `base_pose`,
     `self_collision_pairs()`, `collision_pairs()` -- only the Python-level model, no device descriptors."""
 
-    def __init__(self, arm, margin_model="bullet"):
+    def __init__(self, arm, margin_model="bullet", foreign_link_poses=None):
+        """`foreign_link_poses`: {Link of ANOTHER chain: 4x4 world pose} -- such links are static targets (reference
+        arm.py:239-241); the caller computes their poses independently (e.g. with an ArmOracle of that chain)."""
         self.fk = fkjac.ArmOracle(arm._link_joint_sequence, arm.dof, arm.base_pose)
         self.dof = arm.dof
+        foreign = foreign_link_poses or {}
         node_of_link = {link: node for node, link in arm._links_from_nodes.items()}
         self_pairs = arm.self_collision_pairs()
-        env_pairs = [p for p in arm.collision_pairs().difference(self_pairs) if not hasattr(p[1], "_index")]
+        env_pairs = [p for p in arm.collision_pairs().difference(self_pairs)
+                     if (not hasattr(p[1], "_index") or p[1] in foreign) and p[1]._collision_shape.shape.name != "EMPTY"]
         links = []
         for a, b in self_pairs:
             for l in (a, b):
@@ -201,7 +205,8 @@ class SceneOracle:
         self.types = np.asarray(types, np.int32)
         self.dims = np.asarray(dims, np.float64).reshape(-1, 3)
         self.margins = np.asarray(margins, np.float64)
-        self.static_poses = np.asarray([(o.pose @ o._collision_shape.offset)[:3, :4].reshape(12) for o in objs], np.float64).reshape(-1, 12)
+        self.static_poses = np.asarray([((foreign[o] if o in foreign else o.pose) @ o._collision_shape.offset)[:3, :4].reshape(12)
+                                        for o in objs], np.float64).reshape(-1, 12)
         li = {l: i for i, l in enumerate(links)}
         oi = {o: len(links) + i for i, o in enumerate(objs)}
         pairs = [(li[a], li[b]) for a, b in self_pairs if a in li and b in li]

@@ -77,7 +77,9 @@ def test_pair_distance_and_verdict(cuda, link_kind, obs_kind, margin_model):
     err = np.abs(dist[d > 0] - d[d > 0])
     assert err.max() < 1e-4, (err.max(), d[d > 0][np.argmax(err)], dist[d > 0][np.argmax(err)])   # = the stated band
     neg = d < -2e-4
-    assert np.all(dist[neg] < 0), (d[neg][dist[neg] >= 0][:5], dist[neg][dist[neg] >= 0][:5], q[neg][dist[neg] >= 0][:3])
+    assert np.all(dist[neg] <= 0), (d[neg][dist[neg] > 0][:5], dist[neg][dist[neg] > 0][:5], q[neg][dist[neg] > 0][:3])
+    errn = np.abs(dist[d < 0] - d[d < 0])                      # signed: penetration depth from the EPA on both sides
+    assert errn.max() < 2e-4, (errn.max(), d[d < 0][np.argmax(errn)], dist[d < 0][np.argmax(errn)])
 
 
 def test_known_answers_on_device(cuda):
