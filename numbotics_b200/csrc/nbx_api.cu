@@ -315,6 +315,7 @@ int nbx_scene_create(const nbx_chain* ch, const nbx_scene_desc* d, nbx_scene** o
     if (!sc) { nbx_set_error("out of host memory"); return NBX_ERR_NOMEM; }
     struct Guard { nbx_scene* s; ~Guard() { if (s) nbx_scene_destroy(s); } } guard{sc};
     sc->chain = ch;
+    sc->device = ch->device;
     sc->n_obs = d->n_obs; sc->n_self = d->n_self_pairs; sc->n_env = d->n_env_pairs;
     sc->d_prims = nullptr; sc->d_obs = nullptr; sc->d_self = nullptr; sc->d_env = nullptr;
     sc->d_pair_desc = nullptr; sc->d_env_begin = nullptr;
@@ -405,7 +406,9 @@ int nbx_scene_create(const nbx_chain* ch, const nbx_scene_desc* d, nbx_scene** o
 
 void nbx_scene_destroy(nbx_scene* sc) {
     if (!sc) return;
-    if (sc->chain) cudaSetDevice(sc->chain->device);
+    // the scene's OWN copy of the device index: Python may finalise the chain handle first, and reading sc->chain->device
+    // from a freed chain handed cudaSetDevice a garbage ordinal ("invalid device ordinal" surfacing at the next launch)
+    cudaSetDevice(sc->device);
     if (sc->d_prims) cudaFree(sc->d_prims);
     if (sc->d_obs) cudaFree(sc->d_obs);
     if (sc->d_self) cudaFree(sc->d_self);

@@ -167,7 +167,8 @@ struct nbx_chain {
 };
 
 struct nbx_scene {
-    const nbx_chain* chain;
+    const nbx_chain* chain;          // identity check only (the chain may be destroyed before the scene: never dereferenced)
+    int device;
     int n_obs, n_self, n_env;
     int scratch_floats;              // per-thread scratch for stored primitive poses
     std::vector<PrimK> h_prims;      // chain prims with `slot` resolved for this pair set
