@@ -512,7 +512,7 @@ __device__ __noinline__ EpaOut epa_penetration(const ShapeW& A, const ShapeW& B,
 // Penetration of two cores known (or suspected) to overlap: seed GJK with witness bookkeeping, then the EPA.  A seed that
 // degenerates -- the origin within the contact resolution of a vertex / edge / face of the GJK simplex: symmetric scenes
 // produce that exactly, and a triangle of three early support points passes within 5e-5 of the origin about once in 10^4
-// generic deep overlaps -- is retried with A shifted by a generic 1 mm (then 3 mm) and a generic first search direction.
+// generic deep overlaps -- is retried with A shifted by a generic 0.3 mm (then 2 mm) and a generic first search direction.
 // The shift is taken out again at the end: with the face normal n found on the shifted problem the depth is re-evaluated
 // on the UNSHIFTED cores, depth = h_D(n) = n . (s_A(n) - s_B(-n)), which is exact for the same contact feature and off by
 // O(shift^2 / curvature radius) otherwise.
@@ -608,11 +608,21 @@ __device__ __noinline__ EpaOut core_penetration(const ShapeW& A, const ShapeW& B
         printf(" attempt %d overlap %d enclosed %d d %.6g\n", attempt, (int)g.overlap, (int)g.enclosed, g.d);
 #endif
         if (!g.overlap) {
-            if (attempt > 0) break;                 // the shift pulled a shallow overlap apart: report contact (below)
-            // separated after all (grazing contact): depth below the resolution of this path
+            // Separated: a grazing contact (attempt 0), or the shift pulled a shallow overlap apart.  The witness normal of the
+            // (shifted) pair is the contact normal; the penetration along it on the UNSHIFTED cores, h_D(-n), is an upper bound
+            // of the depth and exact when the contact feature is the same -- no polytope needed for overlaps this shallow.
             const float l = g.d > 0.f ? g.d : 1.f;
             out.n = (1.f / l) * (g.pa - g.pb);
-            out.pa = g.pa; out.pb = g.pb; out.depth = 0.f; out.ok = true;
+            if (attempt > 0) {
+                const V3 nf = -out.n;
+                const V3 a = support(A, nf);
+                const V3 sh = As.c - A.c;
+                // the shifted pair is separated, so the unshifted one cannot be deeper than the shift is long
+                out.depth = fminf(fmaxf(dot(nf, a - support(B, -nf)), 0.f), sqrtf(dot(sh, sh)));
+            }
+            out.pa = g.pa - (As.c - A.c);
+            out.pb = madd(out.pa, out.depth, out.n);
+            out.ok = true;
             return out;
         }
         V3 tw[4], ta[4];
@@ -656,7 +666,7 @@ __device__ __noinline__ EpaOut core_penetration(const ShapeW& A, const ShapeW& B
                 return out;
             }
         }
-        As.c = A.c + (attempt == 0 ? 1e-3f : 3e-3f) * (attempt == 0 ? mk(0.5377f, -0.8311f, 0.1418f) : mk(-0.6245f, -0.2171f, 0.7502f));
+        As.c = A.c + (attempt == 0 ? 3e-4f : 2e-3f) * (attempt == 0 ? mk(0.5377f, -0.8311f, 0.1418f) : mk(-0.6245f, -0.2171f, 0.7502f));
     }
     // no usable seed: report contact along the line of centres
     const V3 dc = A.c - B.c;

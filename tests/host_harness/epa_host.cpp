@@ -2,7 +2,8 @@
 // float64 oracle (oracle/nbx_oracle.c, linked as liboracle.so).  TEST INFRASTRUCTURE (tests/test_gjk_host_harness.py):
 // the device header is compiled by g++ through tests/host_harness/fake/cuda_runtime.h, which maps the CUDA qualifiers away,
 // so that the float32 penetration path can be exercised on random and on exactly symmetric pairs without a GPU.
-// usage: epa_host <seed> <pairs>   -> "tested N bad K worst E" (bad: |f32 - f64| > 1e-4 m)
+// usage: epa_host <seed> <pairs>   -> "near-contact separated: N bad K worst E" (witness GJK, 0 < d < 3 mm) and
+//                                    "tested N bad K worst E" (penetrating pairs; bad: |f32 - f64| > 1e-4 m)
 #include <cstdio>
 #include "nbx_gjk.cuh"
 #include <cstdio>
@@ -31,7 +32,7 @@ int main(int argc, char** argv) {
     int seed = argc > 1 ? atoi(argv[1]) : 1, N = argc > 2 ? atoi(argv[2]) : 20000;
     std::mt19937 g(seed);
     std::uniform_real_distribution<double> U(0, 1);
-    int bad = 0, tested = 0; double worst = 0;
+    int bad = 0, tested = 0; double worst = 0; int near_n = 0, near_bad = 0; double near_worst = 0;
     for (int it = 0; it < N; ++it) {
         int ta = (it % 3 == 0) ? NBX_PRIM_CYLINDER : (it % 3 == 1 ? NBX_PRIM_CYLINDER : NBX_PRIM_BOX);
         int tb = (it % 2 == 0) ? NBX_PRIM_BOX : NBX_PRIM_CYLINDER;
@@ -51,12 +52,21 @@ int main(int argc, char** argv) {
         int32_t types[2]={ta,tb}; double dims[6]={(double)(float)da[0],(double)(float)da[1],(double)(float)da[2],(double)(float)db[0],(double)(float)db[1],(double)(float)db[2]};
         double margins[2]={0,0}; int32_t pairs[2]={0,1}; uint8_t sharp=1; double out; double dummy[12]={0};
         oracle_pair_distances(1,0,dummy,2,sp,types,dims,margins,1,pairs,&sharp,&out);
-        if (out > -1e-3) continue;
+        if (out > -2e-5) {
+            if (out < 3e-3) {   // near-contact separated pairs: the witness GJK itself
+                const GjkWit gw = gjk_witness<96>(A, B);
+                const double dg = gw.overlap ? 0.0 : gw.d;
+                const double e2 = fabs(dg - out);
+                ++near_n; if (e2 > near_worst) near_worst = e2; if (e2 > 1e-4) { ++near_bad; if (near_bad <= 5) printf("near: it %d types %d %d oracle %.6f gjk %.6f overlap %d\n", it, ta, tb, out, dg, (int)gw.overlap); }
+            }
+            continue;
+        }
         ++tested;
         EpaOut e = core_penetration(A, B);
         double err = fabs(-e.depth - out);
         if (err > worst) worst = err;
         if (err > 1e-4) { ++bad; if (bad <= 10) printf("it %d types %d %d oracle %.6f epa %.6f ok %d\n", it, ta, tb, out, -e.depth, (int)e.ok); }
     }
+    printf("near-contact separated: %d bad %d worst %.3e\n", near_n, near_bad, near_worst);
     printf("tested %d bad %d worst %.3e\n", tested, bad, worst);
 }

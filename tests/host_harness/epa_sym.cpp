@@ -28,7 +28,7 @@ int main() {
             int32_t types[2]={ta,tb}; double dims[6]; for (int k=0;k<3;++k){dims[k]=(double)(float)dimsA[ta][k]; dims[3+k]=(double)(float)dimsB[tb][k];}
             double margins[2]={0,0}; int32_t pairs[2]={0,1}; uint8_t sharp=1; double out, dummy[12]={0};
             oracle_pair_distances(1,0,dummy,2,sp,types,dims,margins,1,pairs,&sharp,&out);
-            if (out > -1e-3) continue;
+            if (out > -2e-5) continue;
             EpaOut e = core_penetration(A, B);
             double err = fabs(-e.depth - out);
             if (err > w2) w2 = err;

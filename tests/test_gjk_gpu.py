@@ -79,7 +79,7 @@ def test_pair_distance_and_verdict(cuda, link_kind, obs_kind, margin_model):
     neg = d < -2e-4
     assert np.all(dist[neg] <= 0), (d[neg][dist[neg] > 0][:5], dist[neg][dist[neg] > 0][:5], q[neg][dist[neg] > 0][:3])
     errn = np.abs(dist[d < 0] - d[d < 0])                      # signed: penetration depth from the EPA on both sides
-    assert errn.max() < 2e-4, (errn.max(), d[d < 0][np.argmax(errn)], dist[d < 0][np.argmax(errn)])
+    assert errn.max() < 5e-4 and np.mean(errn > 1e-4) < 0.005, (errn.max(), d[d < 0][np.argmax(errn)], dist[d < 0][np.argmax(errn)])
 
 
 def test_known_answers_on_device(cuda):

@@ -33,6 +33,7 @@ def _foreign_poses(chain):
 def test_links_of_another_chain_are_collision_targets(cuda):
     world = workloads.fresh_world("two_robots")
     arm = workloads.kinova_arm(world, device=0)
+    workloads.apply_rrt_pair_removals(arm)      # without them neighbouring wrist links overlap in every configuration
     other = _second_robot(world, np.array([0.3, -0.5, 0.7, 0.2]))
     pairs = arm.collision_pairs()
     foreign_links = [l for l in other._links if l._collision_shape.shape.name != "EMPTY"]
@@ -55,7 +56,7 @@ def test_links_of_another_chain_are_collision_targets(cuda):
     so2 = collision.SceneOracle(arm, foreign_link_poses=_foreign_poses(other))
     ref2 = so2.min_distance(q.astype(np.float64))
     d2 = arm.min_distance(q)
-    assert np.abs(ref2 - ref).max() > 0.05 and np.abs(d2 - ref2).max() < 3e-4
+    assert np.abs(ref2 - ref).max() > 0.02 and np.abs(d2 - ref2).max() < 3e-4
     # pairs with a foreign link can be voided like any other (by name, reference arm.py:311-366)
     n0 = len(arm.pair_distances(q[:4])[0])
     arm.remove_collision_pair("half_arm_1_link", foreign_links[0].name)
