@@ -798,8 +798,9 @@ in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict_
 // shorter than float32 eps) and per-block sums;  (2) + (3) a two-level exclusive scan turns the counts into int64 offsets
 // of ONE flat sample space;  (4) edges_flat_kernel -- a persistent grid whose warps draw chunks of consecutive 32-sample
 // tiles from an atomic counter (dynamic: edge lengths vary and a static split leaves a ragged last wave).  A lane finds
-// its (edge, sample) through a 34-entry window of the offset array that the warp stages in shared memory, interpolates its
-// own configuration into the warp's q tile, and the tile goes through phase 1 like a tile of in_collision.  The narrow
+// its (edge, sample) in the 32 edges the warp keeps staged in shared memory (offsets, {step, T_f}, start and goal rows:
+// restaged, coalesced, once per ~13 tiles -- no dependent global load per tile), interpolates its own configuration into
+// the warp's q tile, and the tile goes through phase 1 like a tile of in_collision.  The narrow
 // kernel clears valid[e] when a candidate of the edge collides (and keeps the smallest colliding sample index when the
 // caller asks for it: that is how "useful" samples -- the ones the sequential reference evaluates -- are counted).
 // ---------------------------------------------------------------------------------------------
@@ -894,7 +895,12 @@ edge_offsets_kernel(long long* __restrict__ offs, int64_t E, const long long* __
     if (e < E) offs[e + 1] = base + x;
 }
 
-constexpr int kEdgeWin = 34;           // offsets of the tile's first edge .. +33 (>= 1 sample per live edge: a tile spans <= 32 live edges)
+constexpr int kEdgeStage = 32;         // edges a warp keeps staged in shared memory (offsets, {step, T_f}, start and goal rows)
+
+__host__ __device__ inline int edge_extra_floats(int dof) {
+    // [32][dof] configurations of the tile + start / goal rows of the staged edges + {step, T_f} + relative offsets
+    return kWT * dof + 2 * kEdgeStage * dof + 4 * kEdgeStage + (kEdgeStage + 4);
+}
 
 template <bool FAST, int MODE>
 __global__ void __launch_bounds__(kWarps * 32, 4)
@@ -905,12 +911,14 @@ edges_flat_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ 
     WCtx C;
     unsigned char* p = stage_scene(S, smem_raw, C.V);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int extra = kWT * dof + 2 * (kEdgeWin + 2);      // the tile's configurations [32][dof], the offset window (int)
-    const size_t wbytes = warp_smem_bytes(kSplit, S.scratch_floats, extra);
+    const size_t wbytes = warp_smem_bytes(kSplit, S.scratch_floats, edge_extra_floats(dof));
     p = carve_warp<MODE>(C, p + (size_t)wid * wbytes, S.scratch_floats);
     C.item_aux = C.item_fi + kWT;                           // carve_warp reserves 2 x kWT ints
-    float* sq = reinterpret_cast<float*>(p);               // [32][dof]
-    int* s_win = reinterpret_cast<int*>(sq + (size_t)kWT * dof);   // [kEdgeWin] offsets relative to the tile's first sample
+    double* s_meta = reinterpret_cast<double*>(p);         // [32] {step, T_f}   (16-byte aligned: first in the extra area)
+    float* sq = reinterpret_cast<float*>(s_meta + 2 * kEdgeStage);   // [32][dof] configurations of the tile
+    float* s_start = sq + (size_t)kWT * dof;               // [32][dof] start rows of the staged edges
+    float* s_goal = s_start + (size_t)kEdgeStage * dof;    // [32][dof]
+    int* s_rel = reinterpret_cast<int*>(s_goal + (size_t)kEdgeStage * dof);   // [33] sample offsets relative to the first staged edge
     C.base = S.base;
     C.n_mov = S.n_mov; C.n_prims = S.n_prims; C.n_base_prims = S.n_base_prims;
     C.thr = thr;
@@ -920,11 +928,14 @@ edges_flat_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ 
     stage_wait();
     __syncthreads();
 
-    const long long total = offs[E];
+    const long long total = __ldg(offs + E);
     const long long n_tiles = (total + kWT - 1) / kWT;
-    // tiles per draw: enough draws per warp to even out the tail, few enough that the binary search per draw stays small
+    // tiles per draw: >= 24 draws per warp so that the last draw (the tail) is a few per cent of a warp's work, <= 8 tiles
+    // so that the one binary search per draw stays small next to them
     const long long warps = (long long)gridDim.x * kWarps;
-    const int tpc = (int)max(1LL, min(8LL, n_tiles / (warps * 8)));
+    const int tpc = (int)max(1LL, min(8LL, n_tiles / (warps * 24)));
+    // staged edges: [st_e, st_e + 32), their first flat sample st_s; samples st_s + s_rel[i] start edge st_e + i
+    long long st_e = -1, st_s = 0;
     int npend = 0, qn = 0;
 #pragma unroll 1
     for (;;) {
@@ -941,7 +952,7 @@ edges_flat_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ 
             long long lo = 0, hi = E - 1;
             while (lo < hi) {
                 const long long mid = (lo + hi + 1) >> 1;
-                if (offs[mid] <= s_first) lo = mid; else hi = mid - 1;
+                if (__ldg(offs + mid) <= s_first) lo = mid; else hi = mid - 1;
             }
             e_cur = lo;
         }
@@ -950,46 +961,63 @@ edges_flat_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ 
             const long long s0 = tile * kWT;
             const long long s = s0 + lane;
             const bool have = s < total;
+            const long long s_last = min(s0 + kWT - 1, total - 1);
             __syncwarp();                                   // the previous tile's materialise has read item_fi / item_aux
-            // stage the window: offsets of edges e_cur .. e_cur + 33 relative to s0, clamped into int range
-            for (int i = lane; i < kEdgeWin; i += 32) {
-                const long long ei = min(e_cur + i, (long long)E);
-                s_win[i] = (int)max(-0x40000000LL, min(0x40000000LL, offs[ei] - s0));
+            // (re)stage when the tile is not inside the staged edges: offsets, {step, T_f}, start / goal rows of 32 edges from
+            // e_cur on, coalesced -- once per ~32 edges (~13 tiles at 13 samples per edge); everything a tile needs then comes
+            // from shared memory, no dependent global loads per tile
+            const bool covered = st_e >= 0 && e_cur >= st_e && s0 >= st_s && (s_last - st_s) < (long long)s_rel[kEdgeStage];
+            if (!covered) {
+                st_e = e_cur;
+                st_s = __ldg(offs + st_e);
+                const int nE = (int)min((long long)kEdgeStage, E - st_e);
+                for (int i = lane; i <= kEdgeStage; i += 32)
+                    s_rel[i] = (int)min(0x3fffffffLL, __ldg(offs + min(st_e + i, (long long)E)) - st_s);
+                if (lane < nE) {
+                    const EdgeMeta m = meta[st_e + lane];
+                    s_meta[2 * lane] = m.step; s_meta[2 * lane + 1] = m.tf;
+                }
+                const float* gs = starts + st_e * dof;
+                const float* gg = goals + st_e * dof;
+                for (int i = lane; i < nE * dof; i += 32) { s_start[i] = __ldg(gs + i); s_goal[i] = __ldg(gg + i); }
+                __syncwarp();
             }
-            __syncwarp();
             long long e = e_cur;
-            int k = 0, last = 0;
+            int k = 0;
             if (have) {
-                int j;
-                if (lane >= s_win[kEdgeWin - 2] && e_cur + kEdgeWin - 2 < E) {
-                    // more than 32 edges inside one tile: only possible with edges that have no samples at all
-                    long long lo = e_cur, hi = E - 1;
+                const int r = (int)min(0x3fffffffLL, s - st_s);
+                float t;
+                const float *a, *g;
+                if (r >= s_rel[kEdgeStage] && st_e + kEdgeStage < E) {
+                    // beyond the staged edges although they start at the tile's first edge: more than 32 edges inside one tile,
+                    // only possible with edges that have no samples at all -- look the edge up the long way
+                    long long lo = st_e, hi = E - 1;
                     while (lo < hi) {
                         const long long mid = (lo + hi + 1) >> 1;
-                        if (offs[mid] <= s) lo = mid; else hi = mid - 1;
+                        if (__ldg(offs + mid) <= s) lo = mid; else hi = mid - 1;
                     }
                     e = lo;
-                    k = (int)(s - offs[e]);
-                    last = (int)(offs[e + 1] - offs[e]) - 1;
+                    k = (int)(s - __ldg(offs + e));
+                    const int last = (int)(__ldg(offs + e + 1) - __ldg(offs + e)) - 1;
+                    const EdgeMeta m = meta[e];
+                    t = (float)((k == last) ? m.tf : (double)k * m.step);
+                    a = starts + e * dof; g = goals + e * dof;
                 } else {
-                    int lo = 0, hi = kEdgeWin - 2;          // last j with s_win[j] <= lane
+                    int lo = 0, hi = kEdgeStage - 1;          // last j with s_rel[j] <= r
                     while (lo < hi) {
                         const int mid = (lo + hi + 1) >> 1;
-                        if (s_win[mid] <= lane) lo = mid; else hi = mid - 1;
+                        if (s_rel[mid] <= r) lo = mid; else hi = mid - 1;
                     }
-                    j = lo;
-                    e = e_cur + j;
-                    k = lane - s_win[j];
-                    last = s_win[j + 1] - s_win[j] - 1;
+                    e = st_e + lo;
+                    k = r - s_rel[lo];
+                    const int last = s_rel[lo + 1] - s_rel[lo] - 1;
+                    t = (float)((k == last) ? s_meta[2 * lo + 1] : (double)k * s_meta[2 * lo]);
+                    a = s_start + lo * dof; g = s_goal + lo * dof;
                 }
-                const EdgeMeta m = meta[e];
-                const float t = (float)((k == last) ? m.tf : (double)k * m.step);
-                const float* a = starts + e * dof;
-                const float* g = goals + e * dof;
                 float* mq = sq + lane * dof;
                 for (int col = 0; col < dof; ++col) {
-                    const float av = __ldg(a + col);
-                    mq[col] = fmaf(t, __ldg(g + col), fmaf(-t, av, av));
+                    const float av = a[col];
+                    mq[col] = fmaf(t, g[col], fmaf(-t, av, av));
                 }
             }
             C.item_fi[lane] = (int)e;
@@ -1469,7 +1497,7 @@ int launch_edges(const nbx_chain* ch, const nbx_scene* sc, const float* starts, 
     NBX_CUDA_OK(cudaSetDevice(ch->device));
     const int dof = ch->dof;
     const size_t smem = scene_smem_bytes(S.n_mov, S.n_prims, S.n_obs, S.n_self, S.n_env) +
-                        kWarps * warp_smem_bytes(kSplit, S.scratch_floats, kWT * dof + 2 * (kEdgeWin + 2));
+                        kWarps * warp_smem_bytes(kSplit, S.scratch_floats, edge_extra_floats(dof));
     NBX_REQUIRE(smem <= 220 * 1024, "scene too large for shared memory (%zu bytes)", smem);
     SplitWs ws;
     if ((rc = ws.alloc(ch->device, E * 8, stream)) != NBX_OK) return rc;
