@@ -902,11 +902,39 @@ __host__ __device__ inline int edge_extra_floats(int dof) {
     return kWT * dof + 2 * kEdgeStage * dof + 4 * kEdgeStage + (kEdgeStage + 4);
 }
 
+// tiles per draw: >= 24 draws per warp so that the last draw (the tail) is a few per cent of a warp's work, <= 8 tiles so
+// that a draw's fixed cost stays small next to them -- and never more than kMaxDraws draws, the size of the draw table
+constexpr int kMaxDraws = 1 << 16;
+__device__ __forceinline__ long long edge_tiles_per_draw(long long n_tiles, long long warps) {
+    long long tpc = max(1LL, min(8LL, n_tiles / (warps * 24)));
+    return max(tpc, (n_tiles + kMaxDraws - 1) / kMaxDraws);
+}
+
+// first edge of every draw: the LAST e with offs[e] <= the draw's first sample (edges without samples share their successor's
+// offset).  One binary search per draw, all in parallel, instead of ~20 dependent L2 loads in front of every draw of the
+// persistent kernel (where they cost ~5 % at 10^6 edges).
+__global__ void __launch_bounds__(256)
+edge_draws_kernel(const long long* __restrict__ offs, int64_t E, long long warps, int* __restrict__ draw_edge) {
+    const long long total = __ldg(offs + E);
+    const long long n_tiles = (total + kWT - 1) / kWT;
+    const long long tpc = edge_tiles_per_draw(n_tiles, warps);
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c * tpc >= n_tiles) return;
+    const long long s_first = c * tpc * kWT;
+    long long lo = 0, hi = E - 1;
+    while (lo < hi) {
+        const long long mid = (lo + hi + 1) >> 1;
+        if (__ldg(offs + mid) <= s_first) lo = mid; else hi = mid - 1;
+    }
+    draw_edge[c] = (int)lo;
+}
+
 template <bool FAST, int MODE>
 __global__ void __launch_bounds__(kWarps * 32, 4)
 edges_flat_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ starts, const float* __restrict__ goals,
                   int64_t E, int dof, float thr, uint8_t* __restrict__ valid, const EdgeMeta* __restrict__ meta,
-                  const long long* __restrict__ offs, int* __restrict__ tile_counter, const SplitArgs G) {
+                  const long long* __restrict__ offs, int* __restrict__ tile_counter, const int* __restrict__ draw_edge,
+                  const SplitArgs G) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WCtx C;
     unsigned char* p = stage_scene(S, smem_raw, C.V);
@@ -930,10 +958,8 @@ edges_flat_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ 
 
     const long long total = __ldg(offs + E);
     const long long n_tiles = (total + kWT - 1) / kWT;
-    // tiles per draw: >= 24 draws per warp so that the last draw (the tail) is a few per cent of a warp's work, <= 8 tiles
-    // so that the one binary search per draw stays small next to them
     const long long warps = (long long)gridDim.x * kWarps;
-    const int tpc = (int)max(1LL, min(8LL, n_tiles / (warps * 24)));
+    const long long tpc = edge_tiles_per_draw(n_tiles, warps);
     // staged edges: [st_e, st_e + 32), their first flat sample st_s; samples st_s + s_rel[i] start edge st_e + i
     long long st_e = -1, st_s = 0;
     int npend = 0, qn = 0;
@@ -945,17 +971,7 @@ edges_flat_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ 
         const long long t_begin = (long long)c * tpc;
         if (t_begin >= n_tiles) break;
         const long long t_end = min(n_tiles, t_begin + tpc);
-        // first edge of the draw: the LAST e with offs[e] <= first sample (edges without samples share their successor's offset)
-        long long e_cur;
-        {
-            const long long s_first = t_begin * kWT;
-            long long lo = 0, hi = E - 1;
-            while (lo < hi) {
-                const long long mid = (lo + hi + 1) >> 1;
-                if (__ldg(offs + mid) <= s_first) lo = mid; else hi = mid - 1;
-            }
-            e_cur = lo;
-        }
+        long long e_cur = __ldg(draw_edge + c);             // first edge of the draw (edge_draws_kernel)
 #pragma unroll 1
         for (long long tile = t_begin; tile < t_end; ++tile) {
             const long long s0 = tile * kWT;
@@ -1506,27 +1522,30 @@ int launch_edges(const nbx_chain* ch, const nbx_scene* sc, const float* starts, 
     const int n_blocks = (int)((E + kPrepBlock - 1) / kPrepBlock);
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t b_offs = up(sizeof(long long) * (size_t)(E + 1)), b_meta = up(sizeof(EdgeMeta) * (size_t)E),
-                 b_sums = up(sizeof(long long) * (size_t)n_blocks);
+                 b_sums = up(sizeof(long long) * (size_t)n_blocks), b_draws = up(sizeof(int) * (size_t)kMaxDraws);
     cudaMemPool_t pool = nullptr;
     if ((rc = nbx_workspace_pool(ch->device, &pool)) != NBX_OK) return rc;
     struct Tmp { void* p = nullptr; cudaStream_t st = nullptr; ~Tmp() { if (p) cudaFreeAsync(p, st); } } tmp;
     tmp.st = stream;
-    NBX_CUDA_OK(cudaMallocFromPoolAsync(&tmp.p, b_offs + b_meta + b_sums + 256, pool, stream));
+    NBX_CUDA_OK(cudaMallocFromPoolAsync(&tmp.p, b_offs + b_meta + b_sums + b_draws + 256, pool, stream));
     unsigned char* w = static_cast<unsigned char*>(tmp.p);
     long long* offs = reinterpret_cast<long long*>(w);
     EdgeMeta* meta = reinterpret_cast<EdgeMeta*>(w + b_offs);
     long long* sums = reinterpret_cast<long long*>(w + b_offs + b_meta);
-    int* counter = reinterpret_cast<int*>(w + b_offs + b_meta + b_sums);
+    int* draws = reinterpret_cast<int*>(w + b_offs + b_meta + b_sums);
+    int* counter = reinterpret_cast<int*>(w + b_offs + b_meta + b_sums + b_draws);
+    const int grid_main = edges_grid(ch);
     edge_prepare_kernel<<<(unsigned)n_blocks, kPrepBlock, 0, stream>>>(starts, goals, E, dof, resolution, max_distance, valid, n_samples,
                                                                         first_invalid, meta, offs, sums);
     edge_scan_blocks_kernel<<<1, 1024, 0, stream>>>(sums, n_blocks, counter);
     edge_offsets_kernel<<<(unsigned)n_blocks, kPrepBlock, 0, stream>>>(offs, E, sums);
-    nbx_count_launch(3);
+    edge_draws_kernel<<<kMaxDraws / 256, 256, 0, stream>>>(offs, E, (long long)grid_main * kWarps, draws);
+    nbx_count_launch(4);
     NBX_CUDA_OK(cudaGetLastError());
     auto kern = thr < 0.f ? (ch->fast_walk ? edges_flat_kernel<true, kSplitNeg> : edges_flat_kernel<false, kSplitNeg>)
                           : (ch->fast_walk ? edges_flat_kernel<true, kSplit> : edges_flat_kernel<false, kSplit>);
     NBX_SMEM_LIMIT(kern, smem);
-    kern<<<(unsigned)edges_grid(ch), kWarps * 32, smem, stream>>>(S, starts, goals, E, dof, thr, valid, meta, offs, counter, ws.args);
+    kern<<<(unsigned)grid_main, kWarps * 32, smem, stream>>>(S, starts, goals, E, dof, thr, valid, meta, offs, counter, draws, ws.args);
     nbx_count_launch();
     NBX_CUDA_OK(cudaGetLastError());
     return launch_narrow(ch, ws.args, thr, valid, 0, stream);
