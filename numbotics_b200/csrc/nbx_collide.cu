@@ -796,8 +796,8 @@ in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict_
 // Round 1 gave every warp 32 edges; at 125 k edges per GPU that was 1.65 waves of ragged CTAs (strong scaling 0.56 on 8
 // GPUs).  Now:  (1) edge_prepare_kernel  -- one thread per edge: sample count, {step, T_f}, valid[e] = 1 (0 for an edge
 // shorter than float32 eps) and per-block sums;  (2) + (3) a two-level exclusive scan turns the counts into int64 offsets
-// of ONE flat sample space;  (4) edges_flat_kernel -- a persistent grid whose warps draw chunks of consecutive 32-sample
-// tiles from an atomic counter (dynamic: edge lengths vary and a static split leaves a ragged last wave).  A lane finds
+// of ONE flat sample space;  (4) edges_flat_kernel -- a persistent grid whose warps each own one contiguous, equally long
+// range of 32-sample tiles of that space (equal SAMPLE counts, not edge counts: edge lengths vary).  A lane finds
 // its (edge, sample) in the 32 edges the warp keeps staged in shared memory (offsets, {step, T_f}, start and goal rows:
 // restaged, coalesced, once per ~13 tiles -- no dependent global load per tile), interpolates its own configuration into
 // the warp's q tile, and the tile goes through phase 1 like a tile of in_collision.  The narrow
@@ -898,43 +898,24 @@ edge_offsets_kernel(long long* __restrict__ offs, int64_t E, const long long* __
 constexpr int kEdgeStage = 32;         // edges a warp keeps staged in shared memory (offsets, {step, T_f}, start and goal rows)
 
 __host__ __device__ inline int edge_extra_floats(int dof) {
-    // [32][dof] configurations of the tile + start / goal rows of the staged edges + {step, T_f} + relative offsets
-    return kWT * dof + 2 * kEdgeStage * dof + 4 * kEdgeStage + (kEdgeStage + 4);
+    // [32][dof] configurations of the tile + start / goal rows of the staged edges + {step, T_f} (double) + offsets (int64)
+    return kWT * dof + 2 * kEdgeStage * dof + 4 * kEdgeStage + 2 * (kEdgeStage + 2);
 }
 
-// tiles per draw: >= 24 draws per warp so that the last draw (the tail) is a few per cent of a warp's work, <= 8 tiles so
-// that a draw's fixed cost stays small next to them -- and never more than kMaxDraws draws, the size of the draw table
-constexpr int kMaxDraws = 1 << 16;
-__device__ __forceinline__ long long edge_tiles_per_draw(long long n_tiles, long long warps) {
-    long long tpc = max(1LL, min(8LL, n_tiles / (warps * 24)));
-    return max(tpc, (n_tiles + kMaxDraws - 1) / kMaxDraws);
+__device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
 }
 
-// first edge of every draw: the LAST e with offs[e] <= the draw's first sample (edges without samples share their successor's
-// offset).  One binary search per draw, all in parallel, instead of ~20 dependent L2 loads in front of every draw of the
-// persistent kernel (where they cost ~5 % at 10^6 edges).
-__global__ void __launch_bounds__(256)
-edge_draws_kernel(const long long* __restrict__ offs, int64_t E, long long warps, int* __restrict__ draw_edge) {
-    const long long total = __ldg(offs + E);
-    const long long n_tiles = (total + kWT - 1) / kWT;
-    const long long tpc = edge_tiles_per_draw(n_tiles, warps);
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c * tpc >= n_tiles) return;
-    const long long s_first = c * tpc * kWT;
-    long long lo = 0, hi = E - 1;
-    while (lo < hi) {
-        const long long mid = (lo + hi + 1) >> 1;
-        if (__ldg(offs + mid) <= s_first) lo = mid; else hi = mid - 1;
-    }
-    draw_edge[c] = (int)lo;
-}
-
+// Every warp of the (resident, persistent) grid owns ONE contiguous range of 32-sample tiles of the flat sample space, all
+// ranges the same length +-1 (tiles cost the same to first order: 32 tree walks and culls each).  The 32 edges a tile's
+// samples can belong to are staged in shared memory -- their offsets, {step, T_f}, start and goal rows -- and the NEXT
+// window is requested with cp.async right after the tile's configurations have been interpolated, so it lands during that
+// tile's walk and culls (the in_collision kernel's q-tile trick): no dependent global load in front of any tile but the first.
 template <bool FAST, int MODE>
 __global__ void __launch_bounds__(kWarps * 32, 4)
 edges_flat_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ starts, const float* __restrict__ goals,
                   int64_t E, int dof, float thr, uint8_t* __restrict__ valid, const EdgeMeta* __restrict__ meta,
-                  const long long* __restrict__ offs, int* __restrict__ tile_counter, const int* __restrict__ draw_edge,
-                  const SplitArgs G) {
+                  const long long* __restrict__ offs, const SplitArgs G) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WCtx C;
     unsigned char* p = stage_scene(S, smem_raw, C.V);
@@ -943,10 +924,10 @@ edges_flat_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ 
     p = carve_warp<MODE>(C, p + (size_t)wid * wbytes, S.scratch_floats);
     C.item_aux = C.item_fi + kWT;                           // carve_warp reserves 2 x kWT ints
     double* s_meta = reinterpret_cast<double*>(p);         // [32] {step, T_f}   (16-byte aligned: first in the extra area)
-    float* sq = reinterpret_cast<float*>(s_meta + 2 * kEdgeStage);   // [32][dof] configurations of the tile
+    long long* s_off = reinterpret_cast<long long*>(s_meta + 2 * kEdgeStage);   // [33] first flat sample of the staged edges
+    float* sq = reinterpret_cast<float*>(s_off + kEdgeStage + 2);    // [32][dof] configurations of the tile
     float* s_start = sq + (size_t)kWT * dof;               // [32][dof] start rows of the staged edges
     float* s_goal = s_start + (size_t)kEdgeStage * dof;    // [32][dof]
-    int* s_rel = reinterpret_cast<int*>(s_goal + (size_t)kEdgeStage * dof);   // [33] sample offsets relative to the first staged edge
     C.base = S.base;
     C.n_mov = S.n_mov; C.n_prims = S.n_prims; C.n_base_prims = S.n_base_prims;
     C.thr = thr;
@@ -958,94 +939,91 @@ edges_flat_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ 
 
     const long long total = __ldg(offs + E);
     const long long n_tiles = (total + kWT - 1) / kWT;
-    const long long warps = (long long)gridDim.x * kWarps;
-    const long long tpc = edge_tiles_per_draw(n_tiles, warps);
-    // staged edges: [st_e, st_e + 32), their first flat sample st_s; samples st_s + s_rel[i] start edge st_e + i
-    long long st_e = -1, st_s = 0;
+    const long long warps = (long long)gridDim.x * kWarps, w = (long long)blockIdx.x * kWarps + wid;
+    const long long t_begin = n_tiles * w / warps, t_end = n_tiles * (w + 1) / warps;
+    if (t_begin >= t_end) return;
+    // request the window of 32 edges that starts at edge e0 into the staging buffers (asynchronous)
+    auto request_window = [&](long long e0) {
+        const int nE = (int)min((long long)kEdgeStage, E - e0);
+        for (int i = lane; i <= kEdgeStage; i += 32) cp_async8(s_off + i, offs + min(e0 + i, (long long)E));
+        if (lane < nE) cp_async16(s_meta + 2 * lane, meta + e0 + lane);
+        const float* gs = starts + e0 * dof;
+        const float* gg = goals + e0 * dof;
+        for (int i = lane; i < nE * dof; i += 32) { cp_async4(s_start + i, gs + i); cp_async4(s_goal + i, gg + i); }
+    };
+    // first edge of the range: the LAST e with offs[e] <= first sample (edges without samples share their successor's offset)
+    long long st_e;
+    {
+        const long long s_first = t_begin * kWT;
+        long long lo = 0, hi = E - 1;
+        while (lo < hi) {
+            const long long mid = (lo + hi + 1) >> 1;
+            if (__ldg(offs + mid) <= s_first) lo = mid; else hi = mid - 1;
+        }
+        st_e = lo;
+    }
+    request_window(st_e);
+    cp_async_commit();
     int npend = 0, qn = 0;
 #pragma unroll 1
-    for (;;) {
-        int c = 0;
-        if (lane == 0) c = atomicAdd(tile_counter, 1);
-        c = __shfl_sync(0xffffffffu, c, 0);
-        const long long t_begin = (long long)c * tpc;
-        if (t_begin >= n_tiles) break;
-        const long long t_end = min(n_tiles, t_begin + tpc);
-        long long e_cur = __ldg(draw_edge + c);             // first edge of the draw (edge_draws_kernel)
-#pragma unroll 1
-        for (long long tile = t_begin; tile < t_end; ++tile) {
-            const long long s0 = tile * kWT;
-            const long long s = s0 + lane;
-            const bool have = s < total;
-            const long long s_last = min(s0 + kWT - 1, total - 1);
-            __syncwarp();                                   // the previous tile's materialise has read item_fi / item_aux
-            // (re)stage when the tile is not inside the staged edges: offsets, {step, T_f}, start / goal rows of 32 edges from
-            // e_cur on, coalesced -- once per ~32 edges (~13 tiles at 13 samples per edge); everything a tile needs then comes
-            // from shared memory, no dependent global loads per tile
-            const bool covered = st_e >= 0 && e_cur >= st_e && s0 >= st_s && (s_last - st_s) < (long long)s_rel[kEdgeStage];
-            if (!covered) {
-                st_e = e_cur;
-                st_s = __ldg(offs + st_e);
-                const int nE = (int)min((long long)kEdgeStage, E - st_e);
-                for (int i = lane; i <= kEdgeStage; i += 32)
-                    s_rel[i] = (int)min(0x3fffffffLL, __ldg(offs + min(st_e + i, (long long)E)) - st_s);
-                if (lane < nE) {
-                    const EdgeMeta m = meta[st_e + lane];
-                    s_meta[2 * lane] = m.step; s_meta[2 * lane + 1] = m.tf;
+    for (long long tile = t_begin; tile < t_end; ++tile) {
+        const long long s0 = tile * kWT;
+        const long long s = s0 + lane;
+        const bool have = s < total;
+        cp_async_wait_all();                                // the window of this tile (requested during the previous one)
+        __syncwarp();                                       // ... visible to all lanes; previous materialise has read item_fi / item_aux
+        long long e = st_e;
+        int k = 0;
+        if (have) {
+            float t;
+            const float *a, *g;
+            if (s >= s_off[kEdgeStage] && st_e + kEdgeStage < E) {
+                // beyond the staged edges although they start at the tile's first edge: more than 32 edges inside one tile,
+                // only possible with edges that have no samples at all -- look the edge up the long way
+                long long lo = st_e, hi = E - 1;
+                while (lo < hi) {
+                    const long long mid = (lo + hi + 1) >> 1;
+                    if (__ldg(offs + mid) <= s) lo = mid; else hi = mid - 1;
                 }
-                const float* gs = starts + st_e * dof;
-                const float* gg = goals + st_e * dof;
-                for (int i = lane; i < nE * dof; i += 32) { s_start[i] = __ldg(gs + i); s_goal[i] = __ldg(gg + i); }
-                __syncwarp();
+                e = lo;
+                k = (int)(s - __ldg(offs + e));
+                const int last = (int)(__ldg(offs + e + 1) - __ldg(offs + e)) - 1;
+                const EdgeMeta m = meta[e];
+                t = (float)((k == last) ? m.tf : (double)k * m.step);
+                a = starts + e * dof; g = goals + e * dof;
+            } else {
+                int lo = 0, hi = kEdgeStage - 1;            // last j with s_off[j] <= s
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (s_off[mid] <= s) lo = mid; else hi = mid - 1;
+                }
+                e = st_e + lo;
+                k = (int)(s - s_off[lo]);
+                const int last = (int)(s_off[lo + 1] - s_off[lo]) - 1;
+                t = (float)((k == last) ? s_meta[2 * lo + 1] : (double)k * s_meta[2 * lo]);
+                a = s_start + lo * dof; g = s_goal + lo * dof;
             }
-            long long e = e_cur;
-            int k = 0;
-            if (have) {
-                const int r = (int)min(0x3fffffffLL, s - st_s);
-                float t;
-                const float *a, *g;
-                if (r >= s_rel[kEdgeStage] && st_e + kEdgeStage < E) {
-                    // beyond the staged edges although they start at the tile's first edge: more than 32 edges inside one tile,
-                    // only possible with edges that have no samples at all -- look the edge up the long way
-                    long long lo = st_e, hi = E - 1;
-                    while (lo < hi) {
-                        const long long mid = (lo + hi + 1) >> 1;
-                        if (__ldg(offs + mid) <= s) lo = mid; else hi = mid - 1;
-                    }
-                    e = lo;
-                    k = (int)(s - __ldg(offs + e));
-                    const int last = (int)(__ldg(offs + e + 1) - __ldg(offs + e)) - 1;
-                    const EdgeMeta m = meta[e];
-                    t = (float)((k == last) ? m.tf : (double)k * m.step);
-                    a = starts + e * dof; g = goals + e * dof;
-                } else {
-                    int lo = 0, hi = kEdgeStage - 1;          // last j with s_rel[j] <= r
-                    while (lo < hi) {
-                        const int mid = (lo + hi + 1) >> 1;
-                        if (s_rel[mid] <= r) lo = mid; else hi = mid - 1;
-                    }
-                    e = st_e + lo;
-                    k = r - s_rel[lo];
-                    const int last = s_rel[lo + 1] - s_rel[lo] - 1;
-                    t = (float)((k == last) ? s_meta[2 * lo + 1] : (double)k * s_meta[2 * lo]);
-                    a = s_start + lo * dof; g = s_goal + lo * dof;
-                }
-                float* mq = sq + lane * dof;
-                for (int col = 0; col < dof; ++col) {
-                    const float av = a[col];
-                    mq[col] = fmaf(t, g[col], fmaf(-t, av, av));
-                }
+            float* mq = sq + lane * dof;
+            for (int col = 0; col < dof; ++col) {
+                const float av = a[col];
+                mq[col] = fmaf(t, g[col], fmaf(-t, av, av));
             }
-            C.item_fi[lane] = (int)e;
-            C.item_aux[lane] = k;
-            __syncwarp();
-            const float* myq = sq + lane * dof;
-            phase1<MODE, FAST>(C, have, [myq](int col) { return myq[col]; }, S.n_obs, S.n_self, npend, qn);
-            materialise<MODE>(C, npend, qn);
-            // the next tile starts at, or after, the edge of this tile's last sample
-            e_cur = __shfl_sync(0xffffffffu, e, 31);
-            if (!__shfl_sync(0xffffffffu, (int)have, 31)) break;      // ragged last tile of the whole sample space
         }
+        C.item_fi[lane] = (int)e;
+        C.item_aux[lane] = k;
+        // the next tile starts at, or after, the edge of this tile's last sample; is it still inside the staged edges?
+        const long long e_next = __shfl_sync(0xffffffffu, e, 31);
+        const long long s_last_next = min(s0 + 2 * kWT - 1, total - 1);
+        const bool next_covered = e_next >= st_e && e_next < st_e + kEdgeStage && s_last_next < s_off[kEdgeStage];
+        __syncwarp();                                       // every lane is done with the staged edges (and s_off above)
+        if (tile + 1 < t_end && !next_covered) {
+            st_e = e_next;
+            request_window(st_e);                           // lands while this tile is walked and culled
+        }
+        cp_async_commit();
+        const float* myq = sq + lane * dof;
+        phase1<MODE, FAST>(C, have, [myq](int col) { return myq[col]; }, S.n_obs, S.n_self, npend, qn);
+        materialise<MODE>(C, npend, qn);
     }
 }
 
@@ -1522,30 +1500,28 @@ int launch_edges(const nbx_chain* ch, const nbx_scene* sc, const float* starts, 
     const int n_blocks = (int)((E + kPrepBlock - 1) / kPrepBlock);
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t b_offs = up(sizeof(long long) * (size_t)(E + 1)), b_meta = up(sizeof(EdgeMeta) * (size_t)E),
-                 b_sums = up(sizeof(long long) * (size_t)n_blocks), b_draws = up(sizeof(int) * (size_t)kMaxDraws);
+                 b_sums = up(sizeof(long long) * (size_t)n_blocks);
     cudaMemPool_t pool = nullptr;
     if ((rc = nbx_workspace_pool(ch->device, &pool)) != NBX_OK) return rc;
     struct Tmp { void* p = nullptr; cudaStream_t st = nullptr; ~Tmp() { if (p) cudaFreeAsync(p, st); } } tmp;
     tmp.st = stream;
-    NBX_CUDA_OK(cudaMallocFromPoolAsync(&tmp.p, b_offs + b_meta + b_sums + b_draws + 256, pool, stream));
+    NBX_CUDA_OK(cudaMallocFromPoolAsync(&tmp.p, b_offs + b_meta + b_sums + 256, pool, stream));
     unsigned char* w = static_cast<unsigned char*>(tmp.p);
     long long* offs = reinterpret_cast<long long*>(w);
     EdgeMeta* meta = reinterpret_cast<EdgeMeta*>(w + b_offs);
     long long* sums = reinterpret_cast<long long*>(w + b_offs + b_meta);
-    int* draws = reinterpret_cast<int*>(w + b_offs + b_meta + b_sums);
-    int* counter = reinterpret_cast<int*>(w + b_offs + b_meta + b_sums + b_draws);
+    int* counter = reinterpret_cast<int*>(w + b_offs + b_meta + b_sums);      // scratch word of the scan kernel
     const int grid_main = edges_grid(ch);
     edge_prepare_kernel<<<(unsigned)n_blocks, kPrepBlock, 0, stream>>>(starts, goals, E, dof, resolution, max_distance, valid, n_samples,
                                                                         first_invalid, meta, offs, sums);
     edge_scan_blocks_kernel<<<1, 1024, 0, stream>>>(sums, n_blocks, counter);
     edge_offsets_kernel<<<(unsigned)n_blocks, kPrepBlock, 0, stream>>>(offs, E, sums);
-    edge_draws_kernel<<<kMaxDraws / 256, 256, 0, stream>>>(offs, E, (long long)grid_main * kWarps, draws);
-    nbx_count_launch(4);
+    nbx_count_launch(3);
     NBX_CUDA_OK(cudaGetLastError());
     auto kern = thr < 0.f ? (ch->fast_walk ? edges_flat_kernel<true, kSplitNeg> : edges_flat_kernel<false, kSplitNeg>)
                           : (ch->fast_walk ? edges_flat_kernel<true, kSplit> : edges_flat_kernel<false, kSplit>);
     NBX_SMEM_LIMIT(kern, smem);
-    kern<<<(unsigned)grid_main, kWarps * 32, smem, stream>>>(S, starts, goals, E, dof, thr, valid, meta, offs, counter, draws, ws.args);
+    kern<<<(unsigned)grid_main, kWarps * 32, smem, stream>>>(S, starts, goals, E, dof, thr, valid, meta, offs, ws.args);
     nbx_count_launch();
     NBX_CUDA_OK(cudaGetLastError());
     return launch_narrow(ch, ws.args, thr, valid, 0, stream);
