@@ -796,8 +796,8 @@ in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict_
 // Round 1 gave every warp 32 edges; at 125 k edges per GPU that was 1.65 waves of ragged CTAs (strong scaling 0.56 on 8
 // GPUs).  Now:  (1) edge_prepare_kernel  -- one thread per edge: sample count, {step, T_f}, valid[e] = 1 (0 for an edge
 // shorter than float32 eps) and per-block sums;  (2) + (3) a two-level exclusive scan turns the counts into int64 offsets
-// of ONE flat sample space;  (4) edges_flat_kernel -- a persistent grid whose warps each own one contiguous, equally long
-// range of 32-sample tiles of that space (equal SAMPLE counts, not edge counts: edge lengths vary).  A lane finds
+// of ONE flat sample space and a fourth writes the first edge of every draw;  (4) edges_flat_kernel -- a persistent grid whose
+// warps draw runs of consecutive 32-sample tiles of that space from an atomic counter.  A lane finds
 // its (edge, sample) in the 32 edges the warp keeps staged in shared memory (offsets, {step, T_f}, start and goal rows:
 // restaged, coalesced, once per ~13 tiles -- no dependent global load per tile), interpolates its own configuration into
 // the warp's q tile, and the tile goes through phase 1 like a tile of in_collision.  The narrow
@@ -906,16 +906,46 @@ __device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
 }
 
-// Every warp of the (resident, persistent) grid owns ONE contiguous range of 32-sample tiles of the flat sample space, all
-// ranges the same length +-1 (tiles cost the same to first order: 32 tree walks and culls each).  The 32 edges a tile's
-// samples can belong to are staged in shared memory -- their offsets, {step, T_f}, start and goal rows -- and the NEXT
-// window is requested with cp.async right after the tile's configurations have been interpolated, so it lands during that
-// tile's walk and culls (the in_collision kernel's q-tile trick): no dependent global load in front of any tile but the first.
+// tiles per draw: >= 24 draws per warp so that the last draw (the tail) is a few per cent of a warp's work, <= 8 tiles so
+// that a draw's fixed cost stays small next to them -- and never more than kMaxDraws draws, the size of the draw table
+constexpr int kMaxDraws = 1 << 16;
+__device__ __forceinline__ long long edge_tiles_per_draw(long long n_tiles, long long warps) {
+    long long tpc = max(1LL, min(8LL, n_tiles / (warps * 24)));
+    return max(tpc, (n_tiles + kMaxDraws - 1) / kMaxDraws);
+}
+
+// first edge of every draw: the LAST e with offs[e] <= the draw's first sample (edges without samples share their successor's
+// offset).  One binary search per draw, all in parallel, instead of ~20 dependent L2 loads in front of every draw.
+__global__ void __launch_bounds__(256)
+edge_draws_kernel(const long long* __restrict__ offs, int64_t E, long long warps, int* __restrict__ draw_edge) {
+    const long long total = __ldg(offs + E);
+    const long long n_tiles = (total + kWT - 1) / kWT;
+    const long long tpc = edge_tiles_per_draw(n_tiles, warps);
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c * tpc >= n_tiles) return;
+    const long long s_first = c * tpc * kWT;
+    long long lo = 0, hi = E - 1;
+    while (lo < hi) {
+        const long long mid = (lo + hi + 1) >> 1;
+        if (__ldg(offs + mid) <= s_first) lo = mid; else hi = mid - 1;
+    }
+    draw_edge[c] = (int)lo;
+}
+
+// The warps of the (resident, persistent) grid DRAW runs of consecutive 32-sample tiles of the flat sample space from an
+// atomic counter: tiles cost the same only to first order (a tile with survivors also builds their queue entries), and with
+// ~20 tiles per warp on an eighth of the edges a static split ends when the unluckiest of 2 368 warps does (measured:
+// 0.38 ms against 0.34 ms for 125 k edges).  Nothing a tile needs is loaded when it starts: the 32 edges its samples can
+// belong to -- offsets, {step, T_f}, start and goal rows -- are staged in shared memory by cp.async issued right after the
+// PREVIOUS tile's configurations were interpolated (they land during that tile's walk and culls, the in_collision kernel's
+// q-tile trick); the draw after next is taken from the counter, and the next draw's first edge read from the draw table, one
+// tile ahead of their use.
 template <bool FAST, int MODE>
 __global__ void __launch_bounds__(kWarps * 32, 4)
 edges_flat_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ starts, const float* __restrict__ goals,
                   int64_t E, int dof, float thr, uint8_t* __restrict__ valid, const EdgeMeta* __restrict__ meta,
-                  const long long* __restrict__ offs, const SplitArgs G) {
+                  const long long* __restrict__ offs, int* __restrict__ tile_counter, const int* __restrict__ draw_edge,
+                  const SplitArgs G) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WCtx C;
     unsigned char* p = stage_scene(S, smem_raw, C.V);
@@ -939,9 +969,9 @@ edges_flat_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ 
 
     const long long total = __ldg(offs + E);
     const long long n_tiles = (total + kWT - 1) / kWT;
-    const long long warps = (long long)gridDim.x * kWarps, w = (long long)blockIdx.x * kWarps + wid;
-    const long long t_begin = n_tiles * w / warps, t_end = n_tiles * (w + 1) / warps;
-    if (t_begin >= t_end) return;
+    const long long warps = (long long)gridDim.x * kWarps;
+    const long long tpc = edge_tiles_per_draw(n_tiles, warps);
+    const long long n_draws = (n_tiles + tpc - 1) / tpc;
     // request the window of 32 edges that starts at edge e0 into the staging buffers (asynchronous)
     auto request_window = [&](long long e0) {
         const int nE = (int)min((long long)kEdgeStage, E - e0);
@@ -951,22 +981,22 @@ edges_flat_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ 
         const float* gg = goals + e0 * dof;
         for (int i = lane; i < nE * dof; i += 32) { cp_async4(s_start + i, gs + i); cp_async4(s_goal + i, gg + i); }
     };
-    // first edge of the range: the LAST e with offs[e] <= first sample (edges without samples share their successor's offset)
-    long long st_e;
-    {
-        const long long s_first = t_begin * kWT;
-        long long lo = 0, hi = E - 1;
-        while (lo < hi) {
-            const long long mid = (lo + hi + 1) >> 1;
-            if (__ldg(offs + mid) <= s_first) lo = mid; else hi = mid - 1;
-        }
-        st_e = lo;
-    }
+    auto draw = [&]() { int c = 0; if (lane == 0) c = atomicAdd(tile_counter, 1); return c; };      // lane 0 holds the result
+    auto first_edge = [&](long long c) { return c < n_draws ? (long long)__ldg(draw_edge + c) : 0LL; };
+    // pipeline: cA = the draw being worked on (its window requested), cB = the next one (eB = its first edge), cC = the one after
+    long long cA = __shfl_sync(0xffffffffu, draw(), 0);
+    if (cA >= n_draws) return;
+    long long cB = __shfl_sync(0xffffffffu, draw(), 0);
+    int cC_raw = draw();
+    long long st_e = first_edge(cA), eB = first_edge(cB);
     request_window(st_e);
     cp_async_commit();
     int npend = 0, qn = 0;
 #pragma unroll 1
-    for (long long tile = t_begin; tile < t_end; ++tile) {
+    for (;;) {
+        const long long t_begin = cA * tpc, t_end = min(n_tiles, t_begin + tpc);
+#pragma unroll 1
+        for (long long tile = t_begin; tile < t_end; ++tile) {
         const long long s0 = tile * kWT;
         const long long s = s0 + lane;
         const bool have = s < total;
@@ -1016,14 +1046,24 @@ edges_flat_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ 
         const long long s_last_next = min(s0 + 2 * kWT - 1, total - 1);
         const bool next_covered = e_next >= st_e && e_next < st_e + kEdgeStage && s_last_next < s_off[kEdgeStage];
         __syncwarp();                                       // every lane is done with the staged edges (and s_off above)
-        if (tile + 1 < t_end && !next_covered) {
-            st_e = e_next;
-            request_window(st_e);                           // lands while this tile is walked and culled
+        if (tile + 1 < t_end) {
+            if (!next_covered) { st_e = e_next; request_window(st_e); }      // lands while this tile is walked and culled
+        } else if (cB < n_draws) {
+            st_e = eB;                                      // last tile of the draw: the next draw's window
+            request_window(st_e);
         }
         cp_async_commit();
         const float* myq = sq + lane * dof;
         phase1<MODE, FAST>(C, have, [myq](int col) { return myq[col]; }, S.n_obs, S.n_self, npend, qn);
         materialise<MODE>(C, npend, qn);
+        }
+        // rotate the pipeline: the atomic of the draw after next was issued a whole draw ago, its table entry is read now and
+        // used one draw from now
+        if (cB >= n_draws) break;
+        cA = cB;
+        cB = __shfl_sync(0xffffffffu, cC_raw, 0);
+        eB = first_edge(cB);
+        cC_raw = draw();
     }
 }
 
@@ -1500,28 +1540,30 @@ int launch_edges(const nbx_chain* ch, const nbx_scene* sc, const float* starts, 
     const int n_blocks = (int)((E + kPrepBlock - 1) / kPrepBlock);
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t b_offs = up(sizeof(long long) * (size_t)(E + 1)), b_meta = up(sizeof(EdgeMeta) * (size_t)E),
-                 b_sums = up(sizeof(long long) * (size_t)n_blocks);
+                 b_sums = up(sizeof(long long) * (size_t)n_blocks), b_draws = up(sizeof(int) * (size_t)kMaxDraws);
     cudaMemPool_t pool = nullptr;
     if ((rc = nbx_workspace_pool(ch->device, &pool)) != NBX_OK) return rc;
     struct Tmp { void* p = nullptr; cudaStream_t st = nullptr; ~Tmp() { if (p) cudaFreeAsync(p, st); } } tmp;
     tmp.st = stream;
-    NBX_CUDA_OK(cudaMallocFromPoolAsync(&tmp.p, b_offs + b_meta + b_sums + 256, pool, stream));
+    NBX_CUDA_OK(cudaMallocFromPoolAsync(&tmp.p, b_offs + b_meta + b_sums + b_draws + 256, pool, stream));
     unsigned char* w = static_cast<unsigned char*>(tmp.p);
     long long* offs = reinterpret_cast<long long*>(w);
     EdgeMeta* meta = reinterpret_cast<EdgeMeta*>(w + b_offs);
     long long* sums = reinterpret_cast<long long*>(w + b_offs + b_meta);
-    int* counter = reinterpret_cast<int*>(w + b_offs + b_meta + b_sums);      // scratch word of the scan kernel
+    int* draws = reinterpret_cast<int*>(w + b_offs + b_meta + b_sums);
+    int* counter = reinterpret_cast<int*>(w + b_offs + b_meta + b_sums + b_draws);
     const int grid_main = edges_grid(ch);
     edge_prepare_kernel<<<(unsigned)n_blocks, kPrepBlock, 0, stream>>>(starts, goals, E, dof, resolution, max_distance, valid, n_samples,
                                                                         first_invalid, meta, offs, sums);
     edge_scan_blocks_kernel<<<1, 1024, 0, stream>>>(sums, n_blocks, counter);
     edge_offsets_kernel<<<(unsigned)n_blocks, kPrepBlock, 0, stream>>>(offs, E, sums);
-    nbx_count_launch(3);
+    edge_draws_kernel<<<kMaxDraws / 256, 256, 0, stream>>>(offs, E, (long long)grid_main * kWarps, draws);
+    nbx_count_launch(4);
     NBX_CUDA_OK(cudaGetLastError());
     auto kern = thr < 0.f ? (ch->fast_walk ? edges_flat_kernel<true, kSplitNeg> : edges_flat_kernel<false, kSplitNeg>)
                           : (ch->fast_walk ? edges_flat_kernel<true, kSplit> : edges_flat_kernel<false, kSplit>);
     NBX_SMEM_LIMIT(kern, smem);
-    kern<<<(unsigned)grid_main, kWarps * 32, smem, stream>>>(S, starts, goals, E, dof, thr, valid, meta, offs, ws.args);
+    kern<<<(unsigned)grid_main, kWarps * 32, smem, stream>>>(S, starts, goals, E, dof, thr, valid, meta, offs, counter, draws, ws.args);
     nbx_count_launch();
     NBX_CUDA_OK(cudaGetLastError());
     return launch_narrow(ch, ws.args, thr, valid, 0, stream);
