@@ -795,9 +795,9 @@ in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict_
 //
 // Round 1 gave every warp 32 edges; at 125 k edges per GPU that was 1.65 waves of ragged CTAs (strong scaling 0.56 on 8
 // GPUs).  Now:  (1) edge_prepare_kernel  -- one thread per edge: sample count, {step, T_f}, valid[e] = 1 (0 for an edge
-// shorter than float32 eps) and per-block sums;  (2) + (3) a two-level exclusive scan turns the counts into int64 offsets
-// of ONE flat sample space and a fourth writes the first edge of every draw;  (4) edges_flat_kernel -- a persistent grid whose
-// warps draw runs of consecutive 32-sample tiles of that space from an atomic counter.  A lane finds
+// shorter than float32 eps) and per-block sums;  (2) edge_offsets_kernel turns the counts into int64 offsets of ONE flat
+// sample space and writes the first edge of every draw;  (3) edges_flat_kernel -- a persistent grid whose warps draw runs
+// of consecutive 32-sample tiles of that space from an atomic counter.  A lane finds
 // its (edge, sample) in the 32 edges the warp keeps staged in shared memory (offsets, {step, T_f}, start and goal rows:
 // restaged, coalesced, once per ~13 tiles -- no dependent global load per tile), interpolates its own configuration into
 // the warp's q tile, and the tile goes through phase 1 like a tile of in_collision.  The narrow
@@ -811,8 +811,9 @@ __global__ void __launch_bounds__(kPrepBlock)
 edge_prepare_kernel(const float* __restrict__ starts, const float* __restrict__ goals, int64_t E, int dof, double resolution,
                     double max_distance, uint8_t* __restrict__ valid, int32_t* __restrict__ n_samples, int* __restrict__ first_bad,
                     EdgeMeta* __restrict__ meta, long long* __restrict__ offs /* [E + 1]: offs[e + 1] = count */,
-                    long long* __restrict__ block_sums) {
+                    long long* __restrict__ block_sums, int* __restrict__ gq_count, int* __restrict__ tile_counter) {
     const int64_t e = (int64_t)blockIdx.x * kPrepBlock + threadIdx.x;
+    if (e == 0) { gq_count[0] = 0; gq_count[1] = 0; *tile_counter = 0; }     // no memset node in front of the query
     int cnt = 0;
     if (e < E) {
         int dead = 1;            // edges shorter than float32 eps have no samples and are invalid
@@ -854,45 +855,59 @@ edge_prepare_kernel(const float* __restrict__ starts, const float* __restrict__ 
     }
 }
 
-// exclusive scan of the block sums by ONE block (n_blocks = E / 256: 3907 for 10^6 edges); also resets the tile counter
-__global__ void __launch_bounds__(1024)
-edge_scan_blocks_kernel(long long* __restrict__ block_sums, int n_blocks, int* __restrict__ tile_counter) {
-    __shared__ long long part[1024];
-    const int per = (n_blocks + 1023) / 1024;
-    const int b0 = threadIdx.x * per, b1 = min(n_blocks, b0 + per);
-    long long t = 0;
-    for (int i = b0; i < b1; ++i) t += block_sums[i];
-    part[threadIdx.x] = t;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {          // Hillis-Steele inclusive scan of the 1024 partial sums
-        const long long y = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
-        __syncthreads();
-        part[threadIdx.x] += y;
-        __syncthreads();
-    }
-    long long run = part[threadIdx.x] - t;        // exclusive
-    for (int i = b0; i < b1; ++i) { const long long c = block_sums[i]; block_sums[i] = run; run += c; }
-    if (threadIdx.x == 0) *tile_counter = 0;
+// tiles per draw: >= 24 draws per warp so that the last draw (the tail) is a few per cent of a warp's work, <= 8 tiles so
+// that a draw's fixed cost stays small next to them -- and never more than kMaxDraws draws, the size of the draw table
+constexpr int kMaxDraws = 1 << 16;
+__device__ __forceinline__ long long edge_tiles_per_draw(long long n_tiles, long long warps) {
+    long long tpc = max(1LL, min(8LL, n_tiles / (warps * 24)));
+    return max(tpc, (n_tiles + kMaxDraws - 1) / kMaxDraws);
 }
 
-// offs[e + 1] (count) -> inclusive prefix, i.e. offs[e] = first flat sample of edge e and offs[E] = total
+// offs[e + 1] (count) -> inclusive prefix, i.e. offs[e] = first flat sample of edge e and offs[E] = total; and the DRAW
+// TABLE: draw c of the persistent kernel starts at flat sample c * tpc * 32, draw_edge[c] = the edge that sample belongs to.
+// Every block adds up the sums of ALL blocks itself (a few thousand numbers from L2) instead of waiting for a scan kernel:
+// that gives it its own base and the grand total -- hence tiles-per-draw -- in one launch (round 2 started with four
+// preparation launches in front of the edge kernel; at 125 k edges per GPU they were 10 % of the call).
 __global__ void __launch_bounds__(kPrepBlock)
-edge_offsets_kernel(long long* __restrict__ offs, int64_t E, const long long* __restrict__ block_sums) {
-    const int64_t e = (int64_t)blockIdx.x * kPrepBlock + threadIdx.x;
-    long long c = e < E ? offs[e + 1] : 0;
-    long long x = c;
+edge_offsets_kernel(long long* __restrict__ offs, int64_t E, const long long* __restrict__ block_sums, int n_blocks,
+                    long long warps, int* __restrict__ draw_edge) {
+    __shared__ long long red[2][kPrepBlock / 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    long long below = 0, all = 0;
+    for (int i = threadIdx.x; i < n_blocks; i += kPrepBlock) {
+        const long long v = __ldg(block_sums + i);
+        all += v;
+        if (i < (int)blockIdx.x) below += v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        below += __shfl_down_sync(0xffffffffu, below, o);
+        all += __shfl_down_sync(0xffffffffu, all, o);
+    }
+    if (lane == 0) { red[0][wid] = below; red[1][wid] = all; }
+    __syncthreads();
+    long long base = 0, total = 0;
+    for (int i = 0; i < kPrepBlock / 32; ++i) { base += red[0][i]; total += red[1][i]; }
+    __syncthreads();
+
+    const int64_t e = (int64_t)blockIdx.x * kPrepBlock + threadIdx.x;
+    const long long c = e < E ? offs[e + 1] : 0;
+    long long x = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const long long y = __shfl_up_sync(0xffffffffu, x, o);
         if (lane >= o) x += y;
     }
-    __shared__ long long wsum[kPrepBlock / 32];
-    if (lane == 31) wsum[wid] = x;
+    if (lane == 31) red[0][wid] = x;
     __syncthreads();
-    long long base = block_sums[blockIdx.x];
-    for (int i = 0; i < wid; ++i) base += wsum[i];
-    if (e < E) offs[e + 1] = base + x;
+    for (int i = 0; i < wid; ++i) base += red[0][i];
+    if (e >= E) return;
+    const long long hi = base + x, lo = hi - c;              // edge e owns the flat samples [lo, hi)
+    offs[e + 1] = hi;
+    // draws that start inside this edge
+    const long long n_tiles = (total + kWT - 1) / kWT;
+    const long long span = edge_tiles_per_draw(n_tiles, warps) * kWT;
+    for (long long d = (lo + span - 1) / span; d * span < hi; ++d) draw_edge[d] = (int)e;
 }
 
 constexpr int kEdgeStage = 32;         // edges a warp keeps staged in shared memory (offsets, {step, T_f}, start and goal rows)
@@ -904,32 +919,6 @@ __host__ __device__ inline int edge_extra_floats(int dof) {
 
 __device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
-}
-
-// tiles per draw: >= 24 draws per warp so that the last draw (the tail) is a few per cent of a warp's work, <= 8 tiles so
-// that a draw's fixed cost stays small next to them -- and never more than kMaxDraws draws, the size of the draw table
-constexpr int kMaxDraws = 1 << 16;
-__device__ __forceinline__ long long edge_tiles_per_draw(long long n_tiles, long long warps) {
-    long long tpc = max(1LL, min(8LL, n_tiles / (warps * 24)));
-    return max(tpc, (n_tiles + kMaxDraws - 1) / kMaxDraws);
-}
-
-// first edge of every draw: the LAST e with offs[e] <= the draw's first sample (edges without samples share their successor's
-// offset).  One binary search per draw, all in parallel, instead of ~20 dependent L2 loads in front of every draw.
-__global__ void __launch_bounds__(256)
-edge_draws_kernel(const long long* __restrict__ offs, int64_t E, long long warps, int* __restrict__ draw_edge) {
-    const long long total = __ldg(offs + E);
-    const long long n_tiles = (total + kWT - 1) / kWT;
-    const long long tpc = edge_tiles_per_draw(n_tiles, warps);
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c * tpc >= n_tiles) return;
-    const long long s_first = c * tpc * kWT;
-    long long lo = 0, hi = E - 1;
-    while (lo < hi) {
-        const long long mid = (lo + hi + 1) >> 1;
-        if (__ldg(offs + mid) <= s_first) lo = mid; else hi = mid - 1;
-    }
-    draw_edge[c] = (int)lo;
 }
 
 // The warps of the (resident, persistent) grid DRAW runs of consecutive 32-sample tiles of the flat sample space from an
@@ -1442,7 +1431,7 @@ struct SplitWs {
     void* p = nullptr;
     cudaStream_t st = nullptr;
     SplitArgs args{nullptr, nullptr, 0, kGjkIters, nullptr};
-    int alloc(int device, int64_t n_items, cudaStream_t stream) {
+    int alloc(int device, int64_t n_items, cudaStream_t stream, bool zero_counters = true) {
         st = stream;
         cudaMemPool_t pool = nullptr;
         int rc = nbx_workspace_pool(device, &pool);
@@ -1453,7 +1442,7 @@ struct SplitWs {
         half = (half + 31) & ~(int64_t)31;
         const size_t bytes = 256 + sizeof(float) * (size_t)kEW * 2 * (size_t)half;
         NBX_CUDA_OK(cudaMallocFromPoolAsync(&p, bytes, pool, stream));
-        NBX_CUDA_OK(cudaMemsetAsync(p, 0, 256, stream));
+        if (zero_counters) NBX_CUDA_OK(cudaMemsetAsync(p, 0, 256, stream));
         args.gq_count = static_cast<int*>(p);
         args.gq = reinterpret_cast<float*>(static_cast<unsigned char*>(p) + 256);
         args.gq_half = (int)half;
@@ -1534,7 +1523,7 @@ int launch_edges(const nbx_chain* ch, const nbx_scene* sc, const float* starts, 
                         kWarps * warp_smem_bytes(kSplit, S.scratch_floats, edge_extra_floats(dof));
     NBX_REQUIRE(smem <= 220 * 1024, "scene too large for shared memory (%zu bytes)", smem);
     SplitWs ws;
-    if ((rc = ws.alloc(ch->device, E * 8, stream)) != NBX_OK) return rc;
+    if ((rc = ws.alloc(ch->device, E * 8, stream, /*zero_counters=*/false)) != NBX_OK) return rc;      // edge_prepare_kernel zeroes them
     ws.args.first_bad = first_invalid;
     // per-call workspace: offsets (int64 [E + 1]), {step, T_f} per edge, block sums, the tile counter
     const int n_blocks = (int)((E + kPrepBlock - 1) / kPrepBlock);
@@ -1554,11 +1543,9 @@ int launch_edges(const nbx_chain* ch, const nbx_scene* sc, const float* starts, 
     int* counter = reinterpret_cast<int*>(w + b_offs + b_meta + b_sums + b_draws);
     const int grid_main = edges_grid(ch);
     edge_prepare_kernel<<<(unsigned)n_blocks, kPrepBlock, 0, stream>>>(starts, goals, E, dof, resolution, max_distance, valid, n_samples,
-                                                                        first_invalid, meta, offs, sums);
-    edge_scan_blocks_kernel<<<1, 1024, 0, stream>>>(sums, n_blocks, counter);
-    edge_offsets_kernel<<<(unsigned)n_blocks, kPrepBlock, 0, stream>>>(offs, E, sums);
-    edge_draws_kernel<<<kMaxDraws / 256, 256, 0, stream>>>(offs, E, (long long)grid_main * kWarps, draws);
-    nbx_count_launch(4);
+                                                                        first_invalid, meta, offs, sums, ws.args.gq_count, counter);
+    edge_offsets_kernel<<<(unsigned)n_blocks, kPrepBlock, 0, stream>>>(offs, E, sums, n_blocks, (long long)grid_main * kWarps, draws);
+    nbx_count_launch(2);
     NBX_CUDA_OK(cudaGetLastError());
     auto kern = thr < 0.f ? (ch->fast_walk ? edges_flat_kernel<true, kSplitNeg> : edges_flat_kernel<false, kSplitNeg>)
                           : (ch->fast_walk ? edges_flat_kernel<true, kSplit> : edges_flat_kernel<false, kSplit>);
