@@ -1057,69 +1057,29 @@ edges_flat_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Narrow kernel of the verdict queries: the GJK over the candidate queue, PERSISTENT LANES.  Most candidates are decided by
-// the first separating plane (one support evaluation), those close to the threshold iterate up to 48 times; with one thread
-// per entry a warp ran as long as its slowest lane and 8 of 32 lanes were active on average (round-1 ncu).  Here every lane
-// carries its own pair AND its own iteration state (gjk_step): each trip of the loop is one GJK iteration for all lanes that
-// have a pair, and a lane whose pair is decided takes the next entry of the warp's range in the same trip (ballot + prefix
-// count, no atomics: the range is the warp's alone).  Environment pairs first, then self pairs: a warp's contiguous range
-// lies in one kind except at the seam.  The entry count lives on the device: no host round trip.
+// Narrow kernel of the verdict queries: one thread per queue entry, grid-stride, first the environment pairs, then
+// the self pairs (a warp works on one kind of pair).  The entry count lives on the device: no host round trip.
 template <int MODE>
 __global__ void __launch_bounds__(128)
 narrow_kernel(const float* __restrict__ gq, const int* __restrict__ gq_count, int gq_half, float thr,
               uint8_t* __restrict__ gflag, int hit_value, int gjk_iters, int* __restrict__ first_bad) {
-    const int lane = threadIdx.x & 31;
+    WCtx C;
+    C.first_bad = first_bad;
+    C.item_aux = nullptr;
+    C.thr = thr;
+    C.gflag = gflag;
+    C.hit_value = hit_value;
+    C.gjk_iters = gjk_iters;
     const int n_env = min(gq_count[0], gq_half), n_self = min(gq_count[1], gq_half);
-    const long long total = (long long)n_env + n_self;
-    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5, w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    long long cursor = total * w / warps;
-    const long long w_end = total * (w + 1) / warps;
-    Cand K;
-    GjkState st;
-    GjkOut g;
-    float lim = 0.f;
-    bool active = false;
-#pragma unroll 1
-    for (;;) {
-        // lanes without a pair take the next entries of the warp's range
-        const unsigned need = __ballot_sync(0xffffffffu, !active);
-        if (need != 0u && cursor < w_end) {
-            const long long mine = cursor + __popc(need & ((1u << lane) - 1u));
-            if (!active && mine < w_end) {
-                const int slot = mine < n_env ? (int)mine : gq_half + (int)(mine - n_env);
-                load_cand(gq, slot, K, 2 * gq_half);
-                bool skip;
-                if (first_bad == nullptr) skip = ((volatile uint8_t*)gflag)[K.fi] == (uint8_t)hit_value;   // unit already decided
-                else skip = ((volatile int*)first_bad)[K.fi] <= (int)K.pc;        // an earlier sample of this edge already collides
-                if (!skip) {
-                    lim = thr + K.m;                       // the pair collides iff  core distance < lim
-                    gjk_begin(st, K.A, K.B, g);
-                    active = true;
-                }
-            }
-            cursor += __popc(need);
-        }
-        if (__ballot_sync(0xffffffffu, active) == 0u) {
-            if (cursor >= w_end) break;
-            continue;                                       // everything fetched in this trip was already decided
-        }
-        if (active) {
-            bool done, hit = false;
-            if (MODE != kSplitNeg || lim > 0.f) {
-                // (tolerances and the "free only on proof" rule: see eval_cand)
-                done = gjk_step(st, K.A, K.B, lim, lim, 2e-5f, 1e-5f, gjk_iters, g);
-                hit = !g.pruned;
-            } else {
-                done = gjk_step(st, K.A, K.B, 1e-6f, -1.f, 2e-5f, 1e-5f, gjk_iters, g);
-                if (done) hit = (g.overlap || g.contact) && core_penetration(K.A, K.B).depth > -lim;
-            }
-            if (done) {
-                if (hit) {
-                    gflag[K.fi] = (uint8_t)hit_value;
-                    if (first_bad != nullptr) atomicMin(&first_bad[K.fi], (int)K.pc);
-                }
-                active = false;
-            }
+    const int stride = gridDim.x * blockDim.x;
+    const int first = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int half = 0; half < 2; ++half) {
+        const int n = half == 0 ? n_env : n_self;
+        const int off = half == 0 ? 0 : gq_half;
+        for (int i = first; i < n; i += stride) {
+            Cand K;
+            load_cand(gq, off + i, K, 2 * gq_half);
+            eval_cand<MODE>(C, K);
         }
     }
 }

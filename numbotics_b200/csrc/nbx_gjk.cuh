@@ -110,153 +110,120 @@ struct GjkOut {
     bool pruned;
 };
 
-// The iteration is written as a resumable step so that the narrow kernel can keep every lane of a warp on ITS OWN pair and
-// iteration (persistent lanes: a lane whose pair is decided fetches the next one while its neighbours keep iterating);
-// gjk_distance below is the plain loop over the same step.
-struct GjkState {
-    V3 v, s0, s1, s2;
-    float vv, ub;
-    int n, it;
-    bool have_ub;   // v is a point of the difference only after the first support call
-};
-
-__device__ __forceinline__ void gjk_begin(GjkState& st, const ShapeW& A, const ShapeW& B, GjkOut& out) {
+template <int MAX_ITER>
+__device__ GjkOut gjk_distance(const ShapeW& A, const ShapeW& B, float stop_above, float stop_below,
+                                float conv_abs = 1e-6f, float conv_rel = 1e-5f, int max_iter = MAX_ITER) {
+    GjkOut out;
     out.lb = 0.f;
     out.overlap = false;
     out.contact = false;
     out.pruned = false;
-    st.v = A.c - B.c;
-    st.vv = dot(st.v, st.v);
-    if (st.vv < 1e-20f) { st.v = mk(1.f, 0.f, 0.f); st.vv = 1.f; }
-    st.s0 = mk(0, 0, 0); st.s1 = st.s0; st.s2 = st.s0;
-    st.n = 0; st.it = 0;
-    st.have_ub = false;
-    st.ub = FLT_MAX;
-}
-
-// one iteration; true = finished (`out` is final)
-__device__ __forceinline__ bool gjk_step(GjkState& st, const ShapeW& A, const ShapeW& B, float stop_above, float stop_below,
-                                         float conv_abs, float conv_rel, int max_iter, GjkOut& out) {
-    V3& v = st.v; V3& s0 = st.s0; V3& s1 = st.s1; V3& s2 = st.s2;
-    float& vv = st.vv; float& ub = st.ub; int& n = st.n; bool& have_ub = st.have_ub;
-    bool stop = st.it >= max_iter;            // out of iterations: the bracket stays open
-    if (!stop) {
-        ++st.it;
+    V3 v = A.c - B.c;
+    float vv = dot(v, v);
+    if (vv < 1e-20f) { v = mk(1.f, 0.f, 0.f); vv = 1.f; }
+    V3 s0 = mk(0, 0, 0), s1 = s0, s2 = s0;
+    int n = 0;
+    bool have_ub = false;   // v is a point of the difference only after the first support call
+    float ub = FLT_MAX;
+#pragma unroll 1
+    for (int it = 0; it < max_iter; ++it) {
         const V3 w = support(A, -v) - support(B, v);
         const float vw = dot(v, w);
         // separating-plane lower bound: the difference lies in the half space {x : x.v >= v.w}
         if (vw > 0.f) {
             const float lb = vw * rsqrtf(vv);
             out.lb = fmaxf(out.lb, lb);
-            if (lb > stop_above) { out.d = lb; out.pruned = true; return true; }
-            if (have_ub && ub - lb <= conv_abs + conv_rel * ub) stop = true;   // converged: the distance lies in [lb, ub]
+            if (lb > stop_above) { out.d = lb; out.pruned = true; return out; }
+            if (have_ub && ub - lb <= conv_abs + conv_rel * ub) break;   // converged: the distance lies in [lb, ub]
         }
-        if (!stop && have_ub && vv - vw <= 1e-7f * vv) stop = true;            // no progress possible
-        if (!stop) {
-            // closest point of conv(simplex + w) to the origin
-            V3 nv;
-            if (n == 0) {
-                s0 = w; n = 1; nv = w;
-            } else if (n == 1) {
-                const V3 ab = s0 - w;              // a = w (newest), b = s0
-                const float t = -dot(w, ab);
-                const float den = dot(ab, ab);
-                if (t <= 0.f || den <= 0.f) { s0 = w; n = 1; nv = w; }
-                else if (t >= den) { nv = s0; }
-                else { nv = madd(w, t / den, ab); s1 = w; n = 2; }
-            } else if (n == 2) {
-                int m;
-                nv = closest_tri(w, s0, s1, &m);
-                // compact: bit0 = w, bit1 = s0, bit2 = s1
-                V3 q0 = s0, q1 = s1;
-                int k = 0;
-                if (m & 2) { q0 = s0; k = 1; }
-                if (m & 4) { if (k == 0) q0 = s1; else q1 = s1; ++k; }
-                if (m & 1) { if (k == 0) q0 = w; else if (k == 1) q1 = w; else s2 = w; ++k; }
-                s0 = q0; s1 = q1; n = k;
-            } else {
-                // tetrahedron (w, s0, s1, s2): test the three faces that contain the new vertex and the old face
-                const V3 a = w, b = s0, c = s1, d = s2;
-                float best = FLT_MAX;
-                int bm = 0;
-                V3 bp = mk(0, 0, 0);
-                bool outside_any = false;
+        if (have_ub && vv - vw <= 1e-7f * vv) break;               // no progress possible
+        // closest point of conv(simplex + w) to the origin
+        V3 nv;
+        if (n == 0) {
+            s0 = w; n = 1; nv = w;
+        } else if (n == 1) {
+            const V3 ab = s0 - w;              // a = w (newest), b = s0
+            const float t = -dot(w, ab);
+            const float den = dot(ab, ab);
+            if (t <= 0.f || den <= 0.f) { s0 = w; n = 1; nv = w; }
+            else if (t >= den) { nv = s0; }
+            else { nv = madd(w, t / den, ab); s1 = w; n = 2; }
+        } else if (n == 2) {
+            int m;
+            nv = closest_tri(w, s0, s1, &m);
+            // compact: bit0 = w, bit1 = s0, bit2 = s1
+            V3 q0 = s0, q1 = s1;
+            int k = 0;
+            if (m & 2) { q0 = s0; k = 1; }
+            if (m & 4) { if (k == 0) q0 = s1; else q1 = s1; ++k; }
+            if (m & 1) { if (k == 0) q0 = w; else if (k == 1) q1 = w; else s2 = w; ++k; }
+            s0 = q0; s1 = q1; n = k;
+        } else {
+            // tetrahedron (w, s0, s1, s2): test the three faces that contain the new vertex and the old face
+            const V3 a = w, b = s0, c = s1, d = s2;
+            float best = FLT_MAX;
+            int bm = 0;
+            V3 bp = mk(0, 0, 0);
+            bool outside_any = false;
 #define NBX_FACE(P0, P1, P2, OPP, B0, B1, B2)                                         \
-                {                                                                      \
-                    const V3 nrm = cross(P1 - P0, P2 - P0);                            \
-                    const float sp = -dot(P0, nrm);                                    \
-                    const float sd = dot(OPP - P0, nrm);                               \
-                    /* height of OPP over the face below fp32 resolution of the coordinates: the   */ \
-                    /* tetrahedron is flat (coplanar support points) and its 'inside' test is noise */ \
-                    const float flat = 4e-6f * (fabsf(P0.x) + fabsf(P0.y) + fabsf(P0.z) + 1e-3f);  \
-                    const bool degenerate = sd * sd <= flat * flat * dot(nrm, nrm);    \
-                    if (degenerate || sp * sd < 0.f) {                                 \
-                        outside_any = true;                                            \
-                        int m3;                                                        \
-                        const V3 cp = closest_tri(P0, P1, P2, &m3);                    \
-                        const float dd = dot(cp, cp);                                  \
-                        if (dd < best) {                                               \
-                            best = dd; bp = cp;                                        \
-                            bm = ((m3 & 1) ? B0 : 0) | ((m3 & 2) ? B1 : 0) | ((m3 & 4) ? B2 : 0); \
-                        }                                                              \
+            {                                                                          \
+                const V3 nrm = cross(P1 - P0, P2 - P0);                                \
+                const float sp = -dot(P0, nrm);                                        \
+                const float sd = dot(OPP - P0, nrm);                                   \
+                /* height of OPP over the face below fp32 resolution of the coordinates: the   */ \
+                /* tetrahedron is flat (coplanar support points) and its 'inside' test is noise */ \
+                const float flat = 4e-6f * (fabsf(P0.x) + fabsf(P0.y) + fabsf(P0.z) + 1e-3f);  \
+                const bool degenerate = sd * sd <= flat * flat * dot(nrm, nrm);        \
+                if (degenerate || sp * sd < 0.f) {                                     \
+                    outside_any = true;                                                \
+                    int m3;                                                            \
+                    const V3 cp = closest_tri(P0, P1, P2, &m3);                        \
+                    const float dd = dot(cp, cp);                                      \
+                    if (dd < best) {                                                   \
+                        best = dd; bp = cp;                                            \
+                        bm = ((m3 & 1) ? B0 : 0) | ((m3 & 2) ? B1 : 0) | ((m3 & 4) ? B2 : 0); \
                     }                                                                  \
-                }
-                NBX_FACE(a, b, c, d, 1, 2, 4)
-                NBX_FACE(a, c, d, b, 1, 4, 8)
-                NBX_FACE(a, d, b, c, 1, 8, 2)
-                NBX_FACE(b, d, c, a, 2, 8, 4)
+                }                                                                      \
+            }
+            NBX_FACE(a, b, c, d, 1, 2, 4)
+            NBX_FACE(a, c, d, b, 1, 4, 8)
+            NBX_FACE(a, d, b, c, 1, 8, 2)
+            NBX_FACE(b, d, c, a, 2, 8, 4)
 #undef NBX_FACE
-                if (!outside_any) { out.d = 0.f; out.overlap = true; return true; }
-                nv = bp;
-                V3 q0 = s0, q1 = s1, q2 = s2;
-                int k = 0;
-                if (bm & 2) { q0 = b; k = 1; }
-                if (bm & 4) { if (k == 0) q0 = c; else q1 = c; ++k; }
-                if (bm & 8) { if (k == 0) q0 = d; else if (k == 1) q1 = d; else q2 = d; ++k; }
-                if (bm & 1) { if (k == 0) q0 = a; else if (k == 1) q1 = a; else q2 = a; ++k; }
-                s0 = q0; s1 = q1; s2 = q2; n = k;
-                if (n == 4) { out.d = 0.f; out.overlap = true; return true; }
-            }
-            float nvv = dot(nv, nv);
-            if (have_ub && nvv >= vv) {
-                // The sub-simplex classification lost to rounding (flat / collinear simplices).  Fall back to
-                // one Frank-Wolfe step: the old closest point v is itself a point of the difference, so
-                // [v, w] is a valid simplex and its closest point is strictly closer whenever v.w < v.v.
-                const V3 e = v - w;
-                const float den = dot(e, e);
-                const float t = -dot(w, e);
-                if (!(den > 0.f) || t <= 0.f || t >= den) stop = true;
-                else {
-                    nv = madd(w, t / den, e);
-                    nvv = dot(nv, nv);
-                    if (nvv >= vv) stop = true;
-                    else { s0 = v; s1 = w; n = 2; }
-                }
-            }
-            if (!stop) {
-                v = nv; vv = nvv; have_ub = true;
-                ub = sqrtf(vv);
-                // Contact regime: below 50 um the fp32 simplex arithmetic cannot tell grazing separation from shallow
-                // penetration (the iteration stalls at |v| ~ 1e-5 instead of enclosing the origin), so it is reported
-                // as contact.  Half of the stated 1e-4 m band.
-                if (vv <= 2.5e-9f) { out.d = 0.f; out.contact = true; return true; }
-                if (ub < stop_below) { out.d = ub; return true; }
-                return false;
-            }
+            if (!outside_any) { out.d = 0.f; out.overlap = true; return out; }
+            nv = bp;
+            V3 q0 = s0, q1 = s1, q2 = s2;
+            int k = 0;
+            if (bm & 2) { q0 = b; k = 1; }
+            if (bm & 4) { if (k == 0) q0 = c; else q1 = c; ++k; }
+            if (bm & 8) { if (k == 0) q0 = d; else if (k == 1) q1 = d; else q2 = d; ++k; }
+            if (bm & 1) { if (k == 0) q0 = a; else if (k == 1) q1 = a; else q2 = a; ++k; }
+            s0 = q0; s1 = q1; s2 = q2; n = k;
+            if (n == 4) { out.d = 0.f; out.overlap = true; return out; }
         }
+        float nvv = dot(nv, nv);
+        if (have_ub && nvv >= vv) {
+            // The sub-simplex classification lost to rounding (flat / collinear simplices).  Fall back to
+            // one Frank-Wolfe step: the old closest point v is itself a point of the difference, so
+            // [v, w] is a valid simplex and its closest point is strictly closer whenever v.w < v.v.
+            const V3 e = v - w;
+            const float den = dot(e, e);
+            const float t = -dot(w, e);
+            if (!(den > 0.f) || t <= 0.f || t >= den) break;
+            nv = madd(w, t / den, e);
+            nvv = dot(nv, nv);
+            if (nvv >= vv) break;
+            s0 = v; s1 = w; n = 2;
+        }
+        v = nv; vv = nvv; have_ub = true;
+        ub = sqrtf(vv);
+        // Contact regime: below 50 um the fp32 simplex arithmetic cannot tell grazing separation from shallow
+        // penetration (the iteration stalls at |v| ~ 1e-5 instead of enclosing the origin), so it is reported
+        // as contact.  Half of the stated 1e-4 m band.
+        if (vv <= 2.5e-9f) { out.d = 0.f; out.contact = true; return out; }
+        if (ub < stop_below) { out.d = ub; return out; }
     }
     out.d = have_ub ? ub : sqrtf(vv);
-    return true;
-}
-
-template <int MAX_ITER>
-__device__ GjkOut gjk_distance(const ShapeW& A, const ShapeW& B, float stop_above, float stop_below,
-                                float conv_abs = 1e-6f, float conv_rel = 1e-5f, int max_iter = MAX_ITER) {
-    GjkOut out;
-    GjkState st;
-    gjk_begin(st, A, B, out);
-#pragma unroll 1
-    while (!gjk_step(st, A, B, stop_above, stop_below, conv_abs, conv_rel, max_iter, out)) {}
     return out;
 }
 
