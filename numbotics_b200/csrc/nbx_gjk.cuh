@@ -443,8 +443,11 @@ __device__ __noinline__ EpaOut epa_penetration(const ShapeW& A, const ShapeW& B,
         lower = fd;
         if (h < best_h) { best_h = h; bf = F[f]; }
         // the bracket [closest face, smallest h] is closed to a fraction of the stated 1e-4 m band: stop BEFORE the new vertex
-        // lands in the plane of its face (the slivers that come out of such an expansion have garbage normals)
-        if (h - fd <= 1e-5f + 5e-5f * fabsf(h) || nv >= kEpaV) break;
+        // lands in the plane of its face (the slivers that come out of such an expansion have garbage normals).  Converged: the
+        // CLOSEST face carries the normal and the witness points (an earlier face can own the smallest h by a hair while its
+        // own plane is millimetres closer to the origin -- witnesses taken from it would not be points of the shapes)
+        if (h - fd <= 1e-5f + 5e-5f * fabsf(h)) { bf = F[f]; break; }
+        if (nv >= kEpaV) break;
         W[nv] = w; PA[nv] = a;
         int ne = 0, nvis = 0;
         const float eps = 1e-6f * (1.f + fabsf(h));

@@ -111,8 +111,8 @@ def test_every_frame_against_oracle(kinova):
 def test_serial30_golden(cuda, golden_serial30):
     g = golden_serial30
     arm = workloads.serial_arm(30, device=0)
-    for dtype, tol in ((np.float64, RTOL64), (np.float32, 3e-5)):
-        # 30 chained fp32 rotations: the stated tolerance for the deep chain is 3e-5
+    for dtype, tol in ((np.float64, RTOL64), (np.float32, 1e-5)):
+        # 30 chained fp32 rotations stay inside north_star's 1e-5 (measured 5.5e-7, profiles/r02_fp32_error_vs_depth.txt)
         T, J = arm.fk_jacobian(g["q"].astype(dtype), "tool")
         assert rel_err(T, g["tool/T"]) <= tol
         assert rel_err(J, g["tool/J"]) <= tol

@@ -98,5 +98,5 @@ def test_serial30_4M_configs(cuda):
     ora = fkjac.ArmOracle(arm._link_joint_sequence, 30, arm.base_pose)
     qs = q[idx].double().cpu().numpy()
     rel = lambda a, b: float(np.abs(a - b).max())
-    assert rel(T[idx].cpu().numpy(), ora.forward_kinematics(qs, "tool")) < 3e-5
-    assert rel(J[idx].cpu().numpy(), ora.jacobian(qs, "tool")) < 3e-5
+    assert rel(T[idx].cpu().numpy(), ora.forward_kinematics(qs, "tool")) < 1e-5
+    assert rel(J[idx].cpu().numpy(), ora.jacobian(qs, "tool")) < 1e-5
