@@ -621,8 +621,9 @@ def secondary_measurements(arm, q, dev, rank, world, clocks_mhz):
                                     "note": "useful = samples up to and including the first invalid one of each edge (what the sequential reference "
                                             "evaluates, connectors.py:71-73; the roofline numerator of SURVEY 8d), from nbx_edges_valid_detail_f32's "
                                             "first_invalid output; issued = every sample of every edge (what the kernel evaluates)"},
-                                "kernels": "edge_prepare + 2-level scan + edges_flat_kernel (persistent grid, dynamic 32-sample tiles over the flat "
+                                "kernels": "edge_prepare + edge_offsets + edges_flat_kernel (persistent grid, dynamic 32-sample tiles over the flat "
                                            "(edge, sample) space) + narrow_kernel",
+                                "roofline": {"bound": "issue (fp32 pipe)", "ncu": recorded_traffic("edges_flat_ncu")},
                                 "workload": "BASELINE configs[3]: 100k nodes x 10-NN = 1M edges, resolution 0.1, contiguous E/G slices"}
     En = int(hi - lo)
     sh, gh = torch.empty((En, DOF), dtype=torch.float32).pin_memory(), torch.empty((En, DOF), dtype=torch.float32).pin_memory()
