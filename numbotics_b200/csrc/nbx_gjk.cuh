@@ -405,7 +405,13 @@ __device__ __forceinline__ bool epa_make_face(EpaFace& f, const V3* W, int i0, i
     f.v0 = (unsigned char)i0; f.v1 = (unsigned char)i1; f.v2 = (unsigned char)i2;
     if (dot(n, W[i0] - inside) < 0.f) { f.v1 = (unsigned char)i2; f.v2 = (unsigned char)i1; n = -n; }
     f.nx = n.x; f.ny = n.y; f.nz = n.z;
-    f.d = dot(n, W[i0]);
+    // distance from the origin to the TRIANGLE, not to its plane: the two agree on a convex polytope (the origin projects
+    // into its closest face), but in float32 a sliver whose plane passes near the origin while the triangle itself lies far
+    // away would otherwise be taken for the closest face -- and witnesses read off it are not points of the shapes
+    float l0, l1, l2f;
+    closest_tri_bary(W[f.v0], W[f.v1], W[f.v2], &l0, &l1, &l2f);
+    const V3 cp = madd(madd(l0 * W[f.v0], l1, W[f.v1]), l2f, W[f.v2]);
+    f.d = fmaxf(sqrtf(dot(cp, cp)), dot(n, W[i0]));
     f.alive = 1;
     return true;
 }
@@ -499,11 +505,7 @@ __device__ __noinline__ EpaOut epa_penetration(const ShapeW& A, const ShapeW& B,
     (void)lower;
     const float d = fmaxf(best_h, 0.f);
     float l0, l1, l2;
-    {
-        // barycentric coordinates of the projection of the origin on the best face (in the face's own frame: shift by -proj)
-        const V3 proj = bf.d * n;
-        closest_tri_bary(W[bf.v0] - proj, W[bf.v1] - proj, W[bf.v2] - proj, &l0, &l1, &l2);
-    }
+    closest_tri_bary(W[bf.v0], W[bf.v1], W[bf.v2], &l0, &l1, &l2);       // the point of the best face closest to the origin
     out.pa = madd(madd(l0 * PA[bf.v0], l1, PA[bf.v1]), l2, PA[bf.v2]);
     out.n = -n;
     out.pb = madd(out.pa, -d, n);

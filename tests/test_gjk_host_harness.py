@@ -47,3 +47,63 @@ def test_f32_penetration_depth_on_symmetric_poses(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     worst = float(re.search(r"^worst ([0-9.e+-]+)", r.stdout, re.M).group(1))
     assert worst < 1e-4, r.stdout[-3000:]
+
+
+def test_f32_penetration_witnesses_are_points_of_the_shapes(tmp_path):
+    """Penetrating pairs of the PRM scene (contact-rich configurations, poses from the float64 FK oracle): the host-compiled
+    float32 witness GJK / EPA against the oracle pair by pair -- signed distance, and the two witness points moved onto the
+    rounded surfaces must be points of their own shapes (oracle point-to-shape distance <= 3e-4 outside, sagitta inside)."""
+    import ctypes as C
+    import numpy as np
+    from numbotics_b200 import workloads
+    from oracle import collision
+    lib_path = str(tmp_path / "libgjkhost.so")
+    cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=fast", "-shared", "-fPIC", "-I", os.path.join(H, "fake"),
+           "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "numbotics_b200", "csrc"),
+           os.path.join(H, "gjk_host_lib.cpp"), "-o", lib_path]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lib = C.CDLL(lib_path)
+    arm, cubes = workloads.prm_scene(device=0)          # model only: no device call is made
+    so = collision.SceneOracle(arm)
+    rng = np.random.default_rng(31)
+    n = 1200
+    sgn = lambda k: rng.choice([-1.0, 1.0], k)
+    q = rng.normal(scale=0.5, size=(n, 7))
+    q[:, 1] = rng.uniform(1.2, 2.41, n) * sgn(n)
+    q[:, 3] = rng.uniform(2.2, 2.66, n) * sgn(n)
+    q[:, 5] = rng.uniform(1.5, 2.23, n) * sgn(n)
+    q = q.astype(np.float32).astype(np.float64)
+    pd = so.pair_distances(q)
+    poses = so.link_poses(q)
+    dp = C.POINTER(C.c_double)
+
+    def core(k, m):
+        t, d = so.types[k], so.dims[k].copy()
+        if t == collision.PRIM_BOX:
+            d = d - m
+        elif t == collision.PRIM_CYL:
+            d[0] -= m; d[1] -= m
+        else:
+            d[:] = 0
+        return np.ascontiguousarray(d)
+
+    bi, pi = np.where(pd < -1e-3)
+    assert len(bi) > 1000
+    err, off = [], []
+    for i, c in zip(bi, pi):
+        a, b = so.pairs[c]
+        pa = np.ascontiguousarray(poses[i, a])
+        pb = np.ascontiguousarray(poses[i, b] if b < so.n_link else so.static_poses[b - so.n_link])
+        ma, mb = so.margins[a], so.margins[b]
+        out = np.zeros(10)
+        lib.host_core_signed_distance(int(so.types[a]), pa.ctypes.data_as(dp), core(a, ma).ctypes.data_as(dp), int(so.types[b]),
+                                      pb.ctypes.data_as(dp), core(b, mb).ctypes.data_as(dp), out.ctypes.data_as(dp))
+        nrm, A, B = out[1:4], out[4:7], out[7:10]
+        err.append(abs(out[0] - ma - mb - pd[i, c]))
+        ps, pt = A - ma * nrm, B + mb * nrm
+        off.append(max(so.point_to_shape(a, pa[None], ps[None])[0], so.point_to_shape(b, pb[None], pt[None])[0]))
+        assert abs(np.linalg.norm(nrm) - 1) < 1e-4 and np.abs((A - B) - out[0] * nrm).max() < 1e-4
+    err, off = np.asarray(err), np.asarray(off)
+    assert err.max() < 2e-4, err.max()
+    assert off.max() < 3e-4, (off.max(), np.argmax(off))
