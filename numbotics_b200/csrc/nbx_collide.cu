@@ -595,8 +595,11 @@ __device__ __forceinline__ void phase1(const WCtx& C, bool valid, QF qf, int n_o
             const float reach = rec.w + cut0;
             surv = valid && cd2 <= reach * reach;
         }
-        if (surv && (__float_as_uint(rec.x) >> 24)) {
-            // thin links: capsule bound  d(cyl, cyl) >= d(axis segment, axis segment) - rA - rB
+        if (WANT_DIST && surv && (__float_as_uint(rec.x) >> 24)) {
+            // thin links: capsule bound  d(cyl, cyl) >= d(axis segment, axis segment) - rA - rB.  Distance queries refine here
+            // (the cut is the item's own upper bound); verdict queries refine in materialise, lane = survivor: here the
+            // refinement ran behind a divergent branch with 1-2 lanes active for ~12 of the 28 pairs of a tile (ncu: a fifth of
+            // the issue slots of the broad kernel)
             const PairK pr = C.V.self_pairs[e];
             const PrimK& ka = C.V.prims[pr.a];
             const PrimK& kb = C.V.prims[pr.b];
@@ -630,6 +633,25 @@ __device__ __forceinline__ void drain(const WCtx& C, int& qn, bool all) {
     }
 }
 
+// Verdict queries: the capsule bound of a bounding-sphere survivor (self pair of two cylinders),
+//   d(cyl, cyl) >= d(axis segment, axis segment) - rA - rB,
+// evaluated by the lane that holds the survivor, from the tile's pose scratch.  false = the pair cannot be within the threshold.
+__device__ __forceinline__ bool capsule_keep(const WCtx& C, uint32_t code) {
+    const int item = (int)(code & 0xffu);
+    const PairK pr = C.V.self_pairs[code >> 8];
+    if (!pr.both_cyl) return true;
+    const PrimK& ka = C.V.prims[pr.a];
+    const PrimK& kb = C.V.prims[pr.b];
+    const float* pa = reinterpret_cast<const float*>(reinterpret_cast<const char*>(C.poses + item) + pr.off_a);
+    const float* pb = reinterpret_cast<const float*>(reinterpret_cast<const char*>(C.poses + item) + pr.off_b);
+    constexpr int NT = kWT;
+    const V3 ca = mk(pa[0], pa[NT], pa[2 * NT]), ua = mk(pa[3 * NT], pa[4 * NT], pa[5 * NT]);
+    const V3 cb = mk(pb[0], pb[NT], pb[2 * NT]), ub = mk(pb[3 * NT], pb[4 * NT], pb[5 * NT]);
+    const float d = seg_seg_distance(ca, ua, ka.dims[1] + ka.margin, cb, ub, kb.dims[1] + kb.margin) -
+                    (ka.dims[0] + ka.margin) - (kb.dims[0] + kb.margin);
+    return d <= C.thr + 1e-6f;
+}
+
 // pending survivors of the tile just walked -> self-contained queue entries (the scratch is overwritten by the next
 // tile).  kDist: the warp's shared-memory queue, drained as soon as it holds 32 entries.  kSplit: the global queue;
 // one atomic per (tile, pair kind) reserves the slots.
@@ -652,9 +674,10 @@ __device__ __forceinline__ void materialise(const WCtx& C, int& npend, int& qn) 
             drain(C, qn, false);
         } else {
             const int chunk = min(32, npend - done);
-            const bool have = lane < chunk;
+            bool have = lane < chunk;
             const uint32_t code = have ? C.pend[done + lane] : 0u;
             const bool env = have && (code & kEnvFlag) != 0;
+            if (have && !env) have = capsule_keep(C, code);      // self pairs of two cylinders: the capsule bound, lane = survivor
             const bool slf = have && !env;
             const unsigned menv = __ballot_sync(0xffffffffu, env), mslf = __ballot_sync(0xffffffffu, slf);
             int benv = 0, bslf = 0;
@@ -765,10 +788,13 @@ in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict_
         const int nv = min(kWT, rangeN - t0);
         cp_async_wait_all();                             // this tile's q (requested during the previous tile's broad phase)
         __syncwarp();                                    // the previous tile's materialise has read item_fi
-        C.item_fi[lane] = (MODE == kDist) ? t0 + lane : (int)(range0 + t0 + lane);
+        // lanes beyond a ragged last tile repeat its first item (the same candidates twice: harmless for a verdict flag and
+        // for the running minimum) -- so phase 1 carries no per-lane `valid` predicate through its joint and pair loops
+        const int src = lane < nv ? lane : 0;
+        C.item_fi[lane] = (MODE == kDist) ? t0 + src : (int)(range0 + t0 + src);
         __syncwarp();
-        const float* myq = sq + lane * dof;
-        phase1<MODE, FAST>(C, lane < nv, [myq](int col) { return myq[col]; }, S.n_obs, S.n_self, npend, qn,
+        const float* myq = sq + src * dof;
+        phase1<MODE, FAST>(C, true, [myq](int col) { return myq[col]; }, S.n_obs, S.n_self, npend, qn,
                            [&]() { if (t0 + kWT < rangeN) request_q(t0 + kWT); });
         materialise<MODE>(C, npend, qn);
     }
@@ -987,8 +1013,8 @@ edges_flat_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ 
 #pragma unroll 1
         for (long long tile = t_begin; tile < t_end; ++tile) {
         const long long s0 = tile * kWT;
-        const long long s = s0 + lane;
-        const bool have = s < total;
+        const long long s = min(s0 + lane, total - 1);      // lanes beyond the very last sample repeat it (harmless duplicates),
+        constexpr bool have = true;                         // so phase 1 carries no per-lane predicate through its loops
         cp_async_wait_all();                                // the window of this tile (requested during the previous one)
         __syncwarp();                                       // ... visible to all lanes; previous materialise has read item_fi / item_aux
         long long e = st_e;

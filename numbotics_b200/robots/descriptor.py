@@ -140,20 +140,31 @@ def flatten_chain(chain, margin_model: str = "bullet") -> dict:
     }
 
 
-def primitive_reach(chain_arrays: dict, joint_limits) -> np.ndarray:
+def primitive_reach(chain_arrays: dict, joint_limits, from_first_joint: bool = False):
     """Upper bound, per link primitive, on the distance of ANY of its points from the base-frame origin,
     over every configuration: sum of the translation norms along the path (rotations preserve norms;
     anything behind a prismatic joint is unbounded) + the primitive's own offset + its bounding radius.
     `joint_limits` is accepted for signature stability and not used: verdicts must not depend on limits that
-    q is never checked against."""
+    q is never checked against.
+
+    `from_first_joint=True` returns `(reach, root)` instead: the same bound measured from the origin of the
+    primitive's FIRST movable joint (`root[p]`, -1 = the primitive hangs off the base) -- that origin is
+    `base_pose . t_root`, the same point for every configuration, so the first link offset does not count
+    towards the reach (for a Kinova on a pedestal that is 0.16 m of a 1.3 m bound)."""
     A = chain_arrays
     n_mov = len(A["mov_type"])
     off = np.asarray(A["mov_offset"]).reshape(n_mov, 12)
-    axis = np.asarray(A["mov_axis"]).reshape(n_mov, 3)
     reach_j = np.zeros(n_mov)
+    root_j = np.zeros(n_mov, dtype=np.int64)
     for j in range(n_mov):
         par = int(A["mov_parent"][j])
-        r = (reach_j[par] if par >= 0 else 0.0) + np.linalg.norm(off[j, [3, 7, 11]])
+        if from_first_joint:
+            root_j[j] = j if par < 0 else root_j[par]
+            r = 0.0 if par < 0 else reach_j[par] + np.linalg.norm(off[j, [3, 7, 11]])
+            if par >= 0 and not np.isfinite(reach_j[par]):
+                r = np.inf
+        else:
+            r = (reach_j[par] if par >= 0 else 0.0) + np.linalg.norm(off[j, [3, 7, 11]])
         if int(A["mov_type"][j]) == _cabi.NBX_JOINT_PRISMATIC:
             # q is never clamped to the joint limits (the reference does not clamp either), so a slider's travel is
             # unbounded as far as pruning is concerned: nothing downstream of a prismatic joint is ever pruned
@@ -169,6 +180,10 @@ def primitive_reach(chain_arrays: dict, joint_limits) -> np.ndarray:
         t = int(A["prim_type"][p])
         brad = dims[p, 0] if t == _cabi.NBX_PRIM_SPHERE else (np.linalg.norm(dims[p]) if t == _cabi.NBX_PRIM_BOX else np.hypot(dims[p, 0], dims[p, 1]))
         out[p] = (reach_j[j] if j >= 0 else 0.0) + np.linalg.norm(tail[f, [3, 7, 11]]) + np.linalg.norm(poff[p, [3, 7, 11]]) + brad
+    if from_first_joint:
+        root = np.array([root_j[int(A["frame_mov"][int(A["prim_frame"][p])])] if int(A["frame_mov"][int(A["prim_frame"][p])]) >= 0 else -1
+                         for p in range(len(out))], dtype=np.int64)
+        return out, root
     return out
 
 
@@ -207,13 +222,31 @@ def flatten_scene(chain_arrays: dict, self_pairs, env_pairs, margin_model: str =
     n_before = len(env_pairs)
     if prune is not None:
         base_pose, joint_limits, thr = prune
-        reach = primitive_reach(chain_arrays, np.asarray(joint_limits, dtype=np.float64).reshape(-1, 2))
+        limits = np.asarray(joint_limits, dtype=np.float64).reshape(-1, 2)
+        base = np.asarray(base_pose, dtype=np.float64)
+        reach = primitive_reach(chain_arrays, limits)
+        # the same bound from the (fixed) origin of the primitive's first movable joint: tighter by the first link offset
+        reach1, root1 = primitive_reach(chain_arrays, limits, from_first_joint=True)
+        n_mov = len(chain_arrays["mov_type"])
+        off = np.asarray(chain_arrays["mov_offset"]).reshape(n_mov, 12)
+        origin_of = {}
         gaps = {}
         kept = []
         for link, obj in env_pairs:
-            if obj not in gaps:
-                gaps[obj] = obstacle_gap_from(np.asarray(base_pose, dtype=np.float64), obj)
-            if gaps[obj] - reach[prim_of_link[link]] <= thr + 1e-9:
+            p = prim_of_link[link]
+            if (obj, -1) not in gaps:
+                gaps[(obj, -1)] = obstacle_gap_from(base, obj)
+            far = gaps[(obj, -1)] - reach[p] > thr + 1e-9
+            r = int(root1[p])
+            if not far and r >= 0 and np.isfinite(reach1[p]):
+                if (obj, r) not in gaps:
+                    if r not in origin_of:
+                        X = np.eye(4)
+                        X[:3, 3] = off[r, [3, 7, 11]]
+                        origin_of[r] = base @ X
+                    gaps[(obj, r)] = obstacle_gap_from(origin_of[r], obj)
+                far = gaps[(obj, r)] - reach1[p] > thr + 1e-9
+            if not far:
                 kept.append((link, obj))
         env_pairs = kept
     obstacles = sorted({obj for _, obj in env_pairs}, key=lambda o: o.name)   # independent of set order

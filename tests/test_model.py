@@ -208,3 +208,43 @@ def test_spherical_joints_rejected():
     G.add_edge("a", "b", joint=Joint(np.eye(4), np.array([0, 0, 1.0]), Constraint.SPHERICAL))
     with pytest.raises(NotImplementedError, match="SPHERICAL"):
         Arm(GraphChain(G, world_name=w.name))
+
+
+def test_static_pruning_bounds_hold_on_sampled_kinematics():
+    """The two reach bounds behind the static pruning of obstacle pairs (descriptor.flatten_scene): every point of a link
+    primitive stays within `reach` of the base origin and within `reach1` of the FIXED origin of its first movable joint;
+    every obstacle pair the PRM scene drops at 0.05 m really stays farther than that from its obstacle (float64 oracle)."""
+    from oracle import collision
+    arm, cubes = workloads.prm_scene(device=None)
+    so = collision.SceneOracle(arm)
+    q = workloads.random_configs_np(arm, 4000, seed=5)
+    A = arm._arrays
+    reach = descriptor.primitive_reach(A, arm.joint_limits)
+    reach1, root1 = descriptor.primitive_reach(A, arm.joint_limits, from_first_joint=True)
+    assert np.all(reach1 <= reach + 1e-12) and set(root1.tolist()) == {-1, 0}      # -1: the base link's own primitive
+    off = np.asarray(A["mov_offset"]).reshape(-1, 12)
+    X = np.eye(4)
+    X[:3, 3] = off[0, [3, 7, 11]]
+    origin1 = (arm.base_pose @ X)[:3, 3]
+    for node, o in zip(so.link_nodes, so.link_offsets):
+        p = A["prim_of_link"][arm._links_from_nodes[node]]
+        centers = (so.fk.forward_kinematics(q, node) @ o)[:, :3, 3]
+        t = int(A["prim_type"][p])
+        d = np.asarray(A["prim_dims"]).reshape(-1, 3)[p]
+        brad = d[0] if t == 0 else (np.linalg.norm(d) if t == 1 else np.hypot(d[0], d[1]))
+        assert np.linalg.norm(centers - arm.base_pose[:3, 3], axis=1).max() + brad <= reach[p] + 1e-9
+        if root1[p] == 0:
+            assert np.linalg.norm(centers - origin1, axis=1).max() + brad <= reach1[p] + 1e-9
+    pruned = arm.scene_arrays(0.05)
+    kept = {(int(a), pruned["obstacles"][int(o)].name) for a, o in pruned["env_pairs"]}
+    assert len(kept) == 5 and pruned["n_env_pairs_before_pruning"] == 30
+    D = so.pair_distances(q)
+    n_dropped = 0
+    for k, (a, b) in enumerate(so.pairs):
+        if b < so.n_link:
+            continue
+        key = (A["prim_of_link"][so.links[a]], so.objs[b - so.n_link].name)
+        if key not in kept:
+            n_dropped += 1
+            assert D[:, k].min() > 0.05
+    assert n_dropped == 25
