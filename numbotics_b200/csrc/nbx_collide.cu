@@ -150,7 +150,9 @@ __device__ __forceinline__ void unround(ShapeW& S, float margin) {
 //   * verdict queries (in_collision, edge validation) are SPLIT over two kernels: the broad kernel appends its
 //     entries to a global queue (env pairs in the first half, self pairs in the second, so that GJK warps see one
 //     kind of pair) and a second, small kernel runs the GJK over the queue at full lane utilisation.  The broad
-//     kernel then carries no GJK state: <= 96 registers and ~9 KB of shared memory per warp, 20 warps per SM.
+//     kernel then carries no GJK state: ~9 KB of shared memory per warp, 128 registers, 16 warps per SM (at 96 registers /
+//     20 warps per SM the outer-loop state of a tile lived in local memory and a fifth of the warp samples waited on its
+//     reloads: ncu long_scoreboard 1.57 per issue; 2^22 configurations 0.60 -> 0.56 ms with the spills gone).
 //   * distance queries (min_distance) stay FUSED: the warp keeps a shared-memory queue and drains it itself whenever
 //     32 entries have accumulated, because the running minimum of a configuration prunes its later candidates.
 // The block-cooperative predecessor (phase 2 right after each tile's phase 1, between two __syncthreads) spent 26 % of
@@ -740,7 +742,7 @@ struct SplitArgs {
 // in_collision.  MODE kSplit: broad kernel of the verdict query (verdict[b] = 0 here, the narrow kernel raises it);
 // MODE kDist: fused distance query (min_dist[b] and the verdict at the end of the warp's range).
 template <int MODE, bool FAST>
-__global__ void __launch_bounds__(kWarps * 32, MODE == kSplit ? 5 : (MODE == kSplitNeg ? 4 : 1))
+__global__ void __launch_bounds__(kWarps * 32, MODE == kDist ? 1 : 4)
 in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ q, int64_t B, int dof, float thr,
                     uint8_t* __restrict__ verdict, float* __restrict__ min_dist, uint32_t* __restrict__ pair_code, int upw,
                     const SplitArgs G) {
@@ -1446,7 +1448,13 @@ int fill_scene_dev(const nbx_chain* ch, const nbx_scene* sc, const double* base_
 // every SM busy for several waves
 int units_per_warp(int64_t n_units, int sm_count, int warps_per_sm, int waves = 6) {
     static const int env = std::getenv("NBX_COLLIDE_UPW") ? std::atoi(std::getenv("NBX_COLLIDE_UPW")) : 0;   // tuning only
-    int64_t u = n_units / ((int64_t)sm_count * warps_per_sm * waves * kWT);
+    const int64_t tiles = (n_units + kWT - 1) / kWT, resident = (int64_t)sm_count * warps_per_sm;
+    int64_t u;
+    if (tiles <= resident * (kMaxRange / kWT))
+        u = (tiles + resident - 1) / resident;            // small batch (a bisection round, a planner's query): ONE wave, every
+                                                          // warp resident from the start instead of a ragged second wave
+    else
+        u = n_units / (resident * waves * kWT);
     u = std::max<int64_t>(1, std::min<int64_t>(u, kMaxRange / kWT));
     if (env > 0) u = std::min(env, kMaxRange / kWT);
     return (int)u * kWT;
@@ -1505,7 +1513,7 @@ int launch_in_collision(const nbx_chain* ch, const nbx_scene* sc, const float* q
     const int mode = min_dist != nullptr ? kDist : kSplit;
     const size_t smem = scene_smem_bytes(S.n_mov, S.n_prims, S.n_obs, S.n_self, S.n_env) + kWarps * warp_smem_bytes(mode, S.scratch_floats, kWT * ch->dof);
     NBX_REQUIRE(smem <= 220 * 1024, "scene too large for shared memory (%zu bytes)", smem);
-    const int upw = units_per_warp(B, ch->sm_count, mode == kDist ? 12 : 20);
+    const int upw = units_per_warp(B, ch->sm_count, mode == kDist ? 12 : 16);
     const int64_t grid = (B + (int64_t)kWarps * upw - 1) / ((int64_t)kWarps * upw);
     if (mode == kDist) {
         NBX_SMEM_LIMIT((in_collision_kernel<kDist, false>), smem);

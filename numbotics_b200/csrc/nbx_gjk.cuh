@@ -110,6 +110,11 @@ struct GjkOut {
     bool pruned;
 };
 
+// host builds of this header (tests/host_harness, scripts/) may define NBX_GJK_COUNT_ITER(it) to record iteration counts
+#ifndef NBX_GJK_COUNT_ITER
+#define NBX_GJK_COUNT_ITER(it)
+#endif
+
 template <int MAX_ITER>
 __device__ GjkOut gjk_distance(const ShapeW& A, const ShapeW& B, float stop_above, float stop_below,
                                 float conv_abs = 1e-6f, float conv_rel = 1e-5f, int max_iter = MAX_ITER) {
@@ -127,6 +132,7 @@ __device__ GjkOut gjk_distance(const ShapeW& A, const ShapeW& B, float stop_abov
     float ub = FLT_MAX;
 #pragma unroll 1
     for (int it = 0; it < max_iter; ++it) {
+        NBX_GJK_COUNT_ITER(it)
         const V3 w = support(A, -v) - support(B, v);
         const float vw = dot(v, w);
         // separating-plane lower bound: the difference lies in the half space {x : x.v >= v.w}
