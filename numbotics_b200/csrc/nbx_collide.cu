@@ -1488,10 +1488,12 @@ struct SplitWs {
 };
 
 int launch_narrow(const nbx_chain* ch, const SplitArgs& G, float thr, uint8_t* gflag, int hit_value, cudaStream_t stream) {
+    static const int per_sm_env = std::getenv("NBX_NARROW_CTAS_PER_SM") ? std::atoi(std::getenv("NBX_NARROW_CTAS_PER_SM")) : 0;   // tuning only
+    const unsigned grid = (unsigned)(ch->sm_count * (per_sm_env > 0 ? per_sm_env : 10));      // 5 CTAs of 89 registers are resident per SM: two even waves
     if (thr < 0.f)
-        narrow_kernel<kSplitNeg><<<(unsigned)(ch->sm_count * 8), 128, 0, stream>>>(G.gq, G.gq_count, G.gq_half, thr, gflag, hit_value, G.gjk_iters, G.first_bad);
+        narrow_kernel<kSplitNeg><<<grid, 128, 0, stream>>>(G.gq, G.gq_count, G.gq_half, thr, gflag, hit_value, G.gjk_iters, G.first_bad);
     else
-        narrow_kernel<kSplit><<<(unsigned)(ch->sm_count * 8), 128, 0, stream>>>(G.gq, G.gq_count, G.gq_half, thr, gflag, hit_value, G.gjk_iters, G.first_bad);
+        narrow_kernel<kSplit><<<grid, 128, 0, stream>>>(G.gq, G.gq_count, G.gq_half, thr, gflag, hit_value, G.gjk_iters, G.first_bad);
     nbx_count_launch();
     NBX_CUDA_OK(cudaGetLastError());
     return NBX_OK;
