@@ -337,9 +337,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: numbotics_b200 has no CPU path")
     lib = _cabi.load()
     if world > 1:
-        # rank 0 prints exactly one line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) out of it
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # rank 0 prints exactly one line on stdout: NCCL writes its debug output -- at the VERSION and WARN levels that is the
+        # "NCCL version ..." banner -- to stdout unless told otherwise; whatever level the box asks for goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         init_from_env("nccl")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
