@@ -172,6 +172,18 @@ def reference_numba_available() -> bool:
         return False
 
 
+_STDOUT_FD = None
+
+
+def emit_line(line: dict) -> None:
+    """The one JSON line, to the real stdout (main() points descriptor 1 at stderr while the run lasts)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _STDOUT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_STDOUT_FD, data)
+
+
 def run_reference(args, rank):
     """`--impl reference`: the reference's CPU implementation of the path on the host cores (rank 0 only)."""
     if rank != 0:
@@ -240,7 +252,7 @@ def run_reference(args, rank):
         "gpu_launches": 0,
     }
     line.update(line_extra)
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 def cpu_baseline_block(arm, dev):
@@ -322,6 +334,13 @@ def main():
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its "NCCL version ..." banner to
+    # stdout at NCCL_DEBUG=VERSION / WARN, whatever NCCL_DEBUG_FILE says): file descriptor 1 is pointed at stderr for the
+    # whole run and the line goes to the saved descriptor at the end.
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
@@ -337,9 +356,6 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: numbotics_b200 has no CPU path")
     lib = _cabi.load()
     if world > 1:
-        # rank 0 prints exactly one line on stdout: NCCL writes its debug output -- at the VERSION and WARN levels that is the
-        # "NCCL version ..." banner -- to stdout unless told otherwise; whatever level the box asks for goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         init_from_env("nccl")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -494,7 +510,7 @@ def main():
         "parity": parity,
         "extras": extras,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
