@@ -12,6 +12,11 @@
 #ifndef NBX_DENSE_MINB
 #define NBX_DENSE_MINB 5   // float kernels: <= 96 registers, 5 CTAs of 128 threads per SM
 #endif
+#ifndef NBX_DENSE_MINB_F64
+#define NBX_DENSE_MINB_F64 3   // double kernels: <= 168 registers, 3 CTAs per SM (what 74 KB of shared memory per CTA allows at 7 joints).
+                               // Unbounded they took 188 registers = 2 CTAs = 8 warps per SM: ncu issue 0.31, FP64 pipe 27 %, DRAM 63 % --
+                               // latency-bound, not FP64-bound; 2^24 x 7-DoF 1.68 -> 1.37 ms (0.79 -> 0.97 of the measured HBM copy rate)
+#endif
 
 namespace nbxd {
 using namespace nbxj;
@@ -99,7 +104,7 @@ __device__ __forceinline__ void load_q_tile(T* sq, const T* __restrict__ q, int6
 // still draining through the TMA engine.
 // =============================================================================================
 template <typename T, int NJ, int TILE, int ALLZ, int KT, int CAP>
-__global__ void __launch_bounds__(TILE, (sizeof(T) == 4 && TILE == 128) ? NBX_DENSE_MINB : 1)   // float: <= 96 registers, 5 CTAs per SM
+__global__ void __launch_bounds__(TILE, (sizeof(T) == 4 && TILE == 128) ? NBX_DENSE_MINB : ((sizeof(T) == 8 && TILE == 128) ? NBX_DENSE_MINB_F64 : 1))   // float: <= 96 registers, 5 CTAs per SM
 fkjac_dense_kernel(const __grid_constant__ PathK<T, CAP> P, const T* __restrict__ q, int64_t B,
                    const T* __restrict__ lp, int64_t lps, const T* __restrict__ gp, int64_t gps,
                    T* __restrict__ T_out, T* __restrict__ J_out, int vec_ok, int64_t ntiles) {
