@@ -122,7 +122,11 @@ __device__ __forceinline__ void chol_solve6(T* L, const T* b, T* x) {
 // iteration for all lanes whatever their iteration number.  A freshly loaded problem spends its first trip as a degenerate
 // iteration with x = 0: walk B then leaves q untouched and returns FK(q0), the error the reference computes before its
 // loop -- so loading costs no divergent code beyond the copies themselves.  Results do not depend on the schedule.
-template <typename T>
+// STORE: walk A parks the Jacobian columns in shared memory ([joint][row][thread]) and walk B reads them back instead of
+// walking the OLD configuration a second time (a third of an iteration's instructions, and an iteration is a dependent chain:
+// batches of a few 10^5 problems are bound by the latency of the problems that run to max_iter, float and double alike).
+// Chains whose columns do not fit (6 n values per thread) recompute them.
+template <typename T, bool STORE>
 __global__ void __launch_bounds__(kIkTile)
 ik_dls_kernel(const __grid_constant__ PathK<T, NBX_MAX_PATH> P, const __grid_constant__ IkParams<T> K,
               const T* __restrict__ target, int64_t target_stride, const T* __restrict__ q0, int64_t B,
@@ -132,6 +136,7 @@ ik_dls_kernel(const __grid_constant__ PathK<T, NBX_MAX_PATH> P, const __grid_con
     const int dof = P.dof, n = P.n;
     const int lane = threadIdx.x & 31;
     T* myq = reinterpret_cast<T*>(smem_raw) + (size_t)threadIdx.x * dof;     // this lane's configuration
+    T* mycol = reinterpret_cast<T*>(smem_raw) + (size_t)kIkTile * dof + threadIdx.x;   // STORE: [joint][row][thread]
     auto reset = [&](Pose<T>& X) {
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -205,6 +210,10 @@ ik_dls_kernel(const __grid_constant__ PathK<T, NBX_MAX_PATH> P, const __grid_con
             joint_step<T, JointK<T>>(X, P.j[i], myq[P.j[i].qidx]);
             T col[6];
             joint_column<T>(X, P.j[i], pe, col);
+            if (STORE) {
+#pragma unroll
+                for (int r = 0; r < 6; ++r) mycol[(size_t)(i * 6 + r) * kIkTile] = col[r];
+            }
 #pragma unroll
             for (int r = 0; r < 6; ++r)
 #pragma unroll
@@ -224,9 +233,14 @@ ik_dls_kernel(const __grid_constant__ PathK<T, NBX_MAX_PATH> P, const __grid_con
         for (int i = 0; i < n; ++i) {
             const int col_q = P.j[i].qidx;
             const T qi = myq[col_q];
-            joint_step<T, JointK<T>>(X, P.j[i], qi);
             T col[6];
-            joint_column<T>(X, P.j[i], pe, col);
+            if (STORE) {
+#pragma unroll
+                for (int r = 0; r < 6; ++r) col[r] = mycol[(size_t)(i * 6 + r) * kIkTile];
+            } else {
+                joint_step<T, JointK<T>>(X, P.j[i], qi);
+                joint_column<T>(X, P.j[i], pe, col);
+            }
             T dq = T(0);
 #pragma unroll
             for (int k = 0; k < 6; ++k) dq = fma_t<T>(col[k], x[k], dq);
@@ -286,9 +300,12 @@ int launch_ik(const nbx_chain* ch, int frame, const T* target, int64_t target_st
     for (int i = 0; i < NBX_MAX_PATH; ++i) { K.lower[i] = (T)0; K.upper[i] = (T)0; }
     if (use_limits)
         for (int i = 0; i < P.n; ++i) { K.lower[i] = (T)lower[ch->mov_qidx[path[i]]]; K.upper[i] = (T)upper[ch->mov_qidx[path[i]]]; }
-    const size_t smem = sizeof(T) * (size_t)kIkTile * std::max(ch->dof, 1);
+    const size_t smem_q = sizeof(T) * (size_t)kIkTile * std::max(ch->dof, 1);
+    const size_t smem_cols = sizeof(T) * (size_t)kIkTile * 6 * std::max(P.n, 1);
+    const bool store = smem_cols <= 24 * 1024;          // 7-DoF: 10.5 KB (float) / 21 KB (double) per CTA of 64 threads
+    const size_t smem = smem_q + (store ? smem_cols : 0);
     NBX_REQUIRE(smem <= 200 * 1024, "dof %d too large for the IK kernel", ch->dof);
-    auto kern = ik_dls_kernel<T>;
+    auto kern = store ? ik_dls_kernel<T, true> : ik_dls_kernel<T, false>;
     NBX_SMEM_LIMIT(kern, smem);
     // persistent lanes: enough CTAs to fill the machine a few times over, never more than the problems need
     static const int cps_env = std::getenv("NBX_IK_CTAS_PER_SM") ? std::atoi(std::getenv("NBX_IK_CTAS_PER_SM")) : 0;   // tuning only
