@@ -163,6 +163,7 @@ constexpr int kWarps = 4;            // autonomous warps per CTA (they only shar
 constexpr int kWT = NBX_WARP_TILE;   // items per tile
 constexpr int kQCap = 48;            // materialised candidates per warp
 constexpr int kPendCap = 256;        // survivors of one tile awaiting materialisation
+constexpr int kEpaCap = 40;          // kDist: overlapping candidates awaiting the EPA (run as soon as more than 8 wait: <= 8 + 32)
 constexpr int kEW = 34;              // words per queue entry
 constexpr int kMaxRange = 256;       // units a warp owns (flags kept in shared memory until the range is done)
 constexpr uint32_t kEnvFlag = 0x80000000u;
@@ -179,6 +180,8 @@ struct WCtx {
     const float* base;        // 12 floats (kernel parameter)
     float* poses;             // [pose_floats][32]
     float* queue;             // kDist: [kEW][kQCap] in shared memory, word-major so that lanes = entries is conflict free
+    float* epa_q;             // kDist: [kEW][kEpaCap] candidates whose cores overlap, awaiting the EPA
+    int* nepa;                // kDist: how many (warp-uniform, in shared memory)
     uint32_t* pend;           // [kPendCap] survivor codes: env flag | pair << 8 | item lane
     unsigned long long* flag; // kDist: [kMaxRange] running minimum: (ordered key of the distance) << 32 | pair code
     int* item_fi;             // [32] item lane -> flag index (kDist: within the warp's range; kSplit: global unit index)
@@ -620,17 +623,55 @@ __device__ __forceinline__ void phase1(const WCtx& C, bool valid, QF qf, int n_o
     }
 }
 
-// kDist: GJK on the 32 newest queue entries (all lanes busy), or on what is left at the end of the range
+// kDist: the EPA on the overlapping candidates that have been set aside, lane = candidate.  Run inline behind the GJK of a
+// drain pass it had 1.2 of 32 lanes active (3 % of random configurations collide) and was two thirds of the distance
+// kernel's time (ncu, profiles/r02_min_distance_*): an EPA is ~30 k instructions, a GJK a few hundred.
+__device__ __noinline__ void run_epa(const WCtx& C) {
+    const int lane = threadIdx.x & 31;
+    int n = *C.nepa;
+    __syncwarp();
+    while (n > 0) {
+        const int take = min(n, 32);
+        if (lane < take) {
+            Cand K;
+            load_cand(C.epa_q, n - take + lane, K, kEpaCap);
+            const float d = -K.m - core_penetration(K.A, K.B).depth;
+            atomicMin(&C.flag[K.fi], dist_entry(d, K.pc));
+        }
+        n -= take;
+    }
+    __syncwarp();
+    if (lane == 0) *C.nepa = 0;
+    __syncwarp();
+}
+
+// kDist: GJK on the 32 newest queue entries (all lanes busy), or on what is left at the end of the range.  Candidates
+// whose cores overlap (or sit in the contact regime) are set aside for run_epa.
 __device__ __forceinline__ void drain(const WCtx& C, int& qn, bool all) {
     const int lane = threadIdx.x & 31;
     while (qn >= 32 || (all && qn > 0)) {
         const int take = min(qn, 32);
+        bool need_epa = false;
+        Cand K;
         if (lane < take) {
-            Cand K;
             load_cand(C.queue, qn - take + lane, K, kQCap);
-            eval_cand<kDist>(C, K);
+            const float best = entry_dist(((volatile unsigned long long*)C.flag)[K.fi]);
+            const GjkOut g = gjk_distance<kGjkItersDist>(K.A, K.B, best + K.m, -FLT_MAX, 2e-5f, 4e-5f);     // as eval_cand<kDist>
+            if (!g.pruned) {
+                need_epa = g.overlap || g.contact;
+                if (!need_epa) atomicMin(&C.flag[K.fi], dist_entry(g.d - K.m, K.pc));
+            }
         }
         qn -= take;
+        const unsigned m = __ballot_sync(0xffffffffu, need_epa);
+        if (m != 0) {
+            const int base = *C.nepa;
+            if (need_epa) store_cand(C.epa_q, base + __popc(m & ((1u << lane) - 1u)), K, kEpaCap);
+            __syncwarp();
+            if (lane == 0) *C.nepa = base + __popc(m);
+            __syncwarp();
+            if (base + __popc(m) > kEpaCap - 32) run_epa(C);
+        }
         __syncwarp();
     }
 }
@@ -709,7 +750,8 @@ __device__ __forceinline__ void materialise(const WCtx& C, int& npend, int& qn) 
 // per-warp work area: pose scratch, queue, pending list, flags, item -> flag map, + `extra_floats` for the caller
 __host__ __device__ inline size_t warp_smem_bytes(int mode, int pose_floats, int extra_floats) {
     return align16(sizeof(float) * (size_t)kWT * (pose_floats > 0 ? pose_floats : 1)) +
-           (mode == kDist ? align16(sizeof(float) * (size_t)kEW * kQCap) + align16(sizeof(unsigned long long) * kMaxRange) : 0) +
+           (mode == kDist ? align16(sizeof(float) * (size_t)kEW * kQCap) + align16(sizeof(unsigned long long) * kMaxRange) +
+                                align16(sizeof(float) * (size_t)kEW * kEpaCap) + 16 : 0) +
            align16(sizeof(uint32_t) * kPendCap) + 2 * align16(sizeof(int) * kWT) + align16(sizeof(float) * (size_t)extra_floats);
 }
 
@@ -718,9 +760,13 @@ __device__ __forceinline__ unsigned char* carve_warp(WCtx& C, unsigned char* p, 
     C.poses = reinterpret_cast<float*>(p);      p += align16(sizeof(float) * (size_t)kWT * max(pose_floats, 1));
     C.queue = nullptr;
     C.flag = nullptr;
+    C.epa_q = nullptr;
+    C.nepa = nullptr;
     if (MODE == kDist) {
         C.queue = reinterpret_cast<float*>(p);  p += align16(sizeof(float) * (size_t)kEW * kQCap);
         C.flag = reinterpret_cast<unsigned long long*>(p);   p += align16(sizeof(unsigned long long) * kMaxRange);
+        C.epa_q = reinterpret_cast<float*>(p);  p += align16(sizeof(float) * (size_t)kEW * kEpaCap);
+        C.nepa = reinterpret_cast<int*>(p);     p += 16;
     }
     C.pend = reinterpret_cast<uint32_t*>(p);    p += align16(sizeof(uint32_t) * kPendCap);
     C.item_fi = reinterpret_cast<int*>(p);      p += align16(sizeof(int) * kWT);
@@ -784,6 +830,10 @@ in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict_
         if (MODE == kDist) C.flag[i] = dist_entry(FLT_MAX, 0xffffffffu);
         else verdict[range0 + i] = 0;
     }
+    if (MODE == kDist) {
+        if (lane == 0) *C.nepa = 0;
+        __syncwarp();
+    }
     int npend = 0, qn = 0;
 #pragma unroll 1
     for (int t0 = 0; t0 < rangeN; t0 += kWT) {
@@ -802,6 +852,7 @@ in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict_
     }
     if (MODE == kDist) {
         drain(C, qn, true);
+        run_epa(C);
         __syncwarp();
         for (int i = lane; i < rangeN; i += 32) {
             const unsigned long long e = C.flag[i];
