@@ -399,8 +399,9 @@ struct EpaOut {
 };
 
 struct EpaFace {
-    unsigned char v0, v1, v2, alive;
+    unsigned char v0, v1, v2, pad;
     float nx, ny, nz, d;
+    float pd;       // plane offset n . W[v0]: the visibility test of an expansion needs no vertex gather
 };
 
 __device__ __forceinline__ bool epa_make_face(EpaFace& f, const V3* W, int i0, int i1, int i2, V3 inside) {
@@ -417,8 +418,9 @@ __device__ __forceinline__ bool epa_make_face(EpaFace& f, const V3* W, int i0, i
     float l0, l1, l2f;
     closest_tri_bary(W[f.v0], W[f.v1], W[f.v2], &l0, &l1, &l2f);
     const V3 cp = madd(madd(l0 * W[f.v0], l1, W[f.v1]), l2f, W[f.v2]);
-    f.d = fmaxf(sqrtf(dot(cp, cp)), dot(n, W[i0]));
-    f.alive = 1;
+    f.pd = dot(n, W[i0]);
+    f.d = fmaxf(sqrtf(dot(cp, cp)), f.pd);
+    f.pad = 0;
     return true;
 }
 
@@ -449,7 +451,7 @@ __device__ __noinline__ EpaOut epa_penetration(const ShapeW& A, const ShapeW& B,
         int f = -1;
         float fd = FLT_MAX;
         for (int i = 0; i < nf; ++i)
-            if (F[i].alive && F[i].d < fd) { fd = F[i].d; f = i; }
+            if (F[i].d < fd) { fd = F[i].d; f = i; }
         if (f < 0) break;
         const V3 n = mk(F[f].nx, F[f].ny, F[f].nz);
         const V3 a = support(A, n);
@@ -466,17 +468,23 @@ __device__ __noinline__ EpaOut epa_penetration(const ShapeW& A, const ShapeW& B,
         W[nv] = w; PA[nv] = a;
         int ne = 0, nvis = 0;
         const float eps = 1e-6f * (1.f + fabsf(h));
-        for (int i = 0; i < nf; ++i) {
-            if (!F[i].alive) continue;
-            if (dot(mk(F[i].nx, F[i].ny, F[i].nz), w - W[F[i].v0]) > eps) {
+        // faces that see the new vertex leave the list at once (the last face takes their slot): F[0 .. nf) is always exactly
+        // the current polytope, <= 2 nv - 4 faces, and both scans of an expansion are as short as they can be
+        for (int i = 0; i < nf;) {
+            if (dot(mk(F[i].nx, F[i].ny, F[i].nz), w) - F[i].pd > eps) {
                 if (ne + 3 > 3 * 24) { ne = -1; break; }       // absurdly large visible region: stop with the bracket found so far
-                F[i].alive = 0; ++nvis;
-                E0[ne] = F[i].v0; E1[ne] = F[i].v1; ++ne;
-                E0[ne] = F[i].v1; E1[ne] = F[i].v2; ++ne;
-                E0[ne] = F[i].v2; E1[ne] = F[i].v0; ++ne;
-                adj[F[i].v0] |= 1ull << F[i].v1;
-                adj[F[i].v1] |= 1ull << F[i].v2;
-                adj[F[i].v2] |= 1ull << F[i].v0;
+                ++nvis;
+                const int a0 = F[i].v0, a1 = F[i].v1, a2 = F[i].v2;
+                E0[ne] = (unsigned char)a0; E1[ne] = (unsigned char)a1; ++ne;
+                E0[ne] = (unsigned char)a1; E1[ne] = (unsigned char)a2; ++ne;
+                E0[ne] = (unsigned char)a2; E1[ne] = (unsigned char)a0; ++ne;
+                adj[a0] |= 1ull << a1;
+                adj[a1] |= 1ull << a2;
+                adj[a2] |= 1ull << a0;
+                --nf;
+                if (i != nf) F[i] = F[nf];
+            } else {
+                ++i;
             }
         }
 #ifdef EPA_TRACE
@@ -492,13 +500,7 @@ __device__ __noinline__ EpaOut epa_penetration(const ShapeW& A, const ShapeW& B,
             if (i < 64) interior |= (unsigned long long)twin << i; else interior_hi |= (unsigned long long)twin << (i - 64);
         }
         for (int i = 0; i < ne; ++i) adj[E0[i]] = 0ull;
-        if (nf + ne > kEpaF) {                     // out of slots: squeeze the dead faces out (alive <= 2 nv - 4)
-            int k = 0;
-            for (int i = 0; i < nf; ++i)
-                if (F[i].alive) { if (k != i) F[k] = F[i]; ++k; }
-            nf = k;
-            if (nf + ne > kEpaF) break;
-        }
+        if (nf + ne > kEpaF) break;                // cannot happen for a closed polytope (2 nv - 4 faces); a guard, not a path
         int added = 0;
         bool garbage = false;
         for (int i = 0; i < ne; ++i) {
