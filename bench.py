@@ -777,6 +777,117 @@ def secondary_measurements(arm, q, dev, rank, world, clocks_mhz):
             "rows": n30, "max_rel_err_T": eT, "max_rel_err_J": eJ, "tolerance": 1e-5,
             "definition": "max over rows of max|gpu - oracle| / max(max|oracle|, 1) per matrix (SURVEY 8d), fp32 kernel vs float64 oracle on the same fp32 q"}
     del q30
+
+    # ---- the callers SURVEY 8(f) ranks next: batched IK, IRIS bisection, signed minimum distance, roadmap build -----------
+    # (one GPU: these are per-call latencies of planner-sized batches, each gated against its float64 restatement)
+    if world == 1:
+        from oracle import collision as _oc, fkjac as _of, ik as _oik, iris as _oiris
+        nx = {}
+        # f.1 inverse kinematics (reference arm.py:464-552): 2^18 problems, targets = FK of random configurations
+        Bik = 1 << 18
+        qt = workloads.random_configs_cuda(arm, Bik, seed=3)
+        pose = arm.forward_kinematics(qt, "tool_frame")
+        q0 = qt + 0.3 * torch.randn(qt.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+        ok_ik, _, it_ik = arm.inverse_kinematics(pose, q0, "tool_frame", return_iters=True)
+        ms = best_ms(lambda: arm.inverse_kinematics(pose, q0, "tool_frame"), n=3, warm=1)
+        com = {n: l._offset for n, l in arm._links_from_nodes.items()}
+        ora = _of.ArmOracle(arm._link_joint_sequence, DOF, arm.base_pose, com)
+        n_ik = 128
+        q_true = workloads.random_configs_np(arm, n_ik, seed=1) * 0.6
+        pose_o = ora.forward_kinematics(q_true, "tool_frame")
+        q0_o = q_true + np.random.default_rng(0).normal(scale=0.25, size=q_true.shape)
+        okg, qg, itg = arm.inverse_kinematics(pose_o, q0_o, "tool_frame", return_iters=True)
+        oko, qo, ito = _oik.inverse_kinematics(ora, arm.joint_limits, pose_o, q0_o, "tool_frame")
+        ik_ok = bool(np.array_equal(okg, oko) and np.array_equal(itg, ito) and np.abs(qg - qo).max() < 1e-7)
+        ok_all &= ik_ok
+        nx["ik_problems_per_sec"] = {
+            "value": Bik / ms * 1e3, "best_ms": ms, "problems": Bik, "dtype": "f32", "converged_fraction": float(ok_ik.float().mean()),
+            "mean_iterations": float(it_ik.float().mean()), "api": "Arm.inverse_kinematics -> nbx_ik_dls_f32 (reference arm.py:464-552)",
+            "parity": {"rows": n_ik, "dtype": "f64", "same_convergence_flags": bool(np.array_equal(okg, oko)),
+                       "same_iteration_counts": bool(np.array_equal(itg, ito)), "max_abs_dq": float(np.abs(qg - qo).max()),
+                       "tolerance": 1e-7, "ok": ik_ok, "against": "oracle/ik.py (float64 restatement of the reference loop, iteration for iteration)"}}
+        del qt, pose, q0
+        # f.3 IRIS bisection (reference safe_sets.py:124-134): 1.2e5 colliding samples x 15 rounds towards q = 0
+        nq = 1 << 22
+        hit = arm.in_collision(q[:nq], 1e-6)
+        S = q[:nq][hit][:120000].contiguous()
+        centre = torch.zeros(DOF, device=dev)
+        ms = best_ms(lambda: arm.bisect_to_collision(centre, S, 15, 1e-6), n=3, warm=1)
+        so = _oc.SceneOracle(arm)
+        n_b = 256
+        S_o = S[:n_b].double().cpu().numpy()
+        ref, t_lo, t_hi, borderline = _oiris.bisect(so, np.zeros(DOF), S_o, 15, 1e-6, band=1e-4)
+        got = arm.bisect_to_collision(np.zeros(DOF), S_o, 15, 1e-6)
+        clear = ~borderline
+        bis_bad = int(np.sum(clear & (np.abs(got - ref).max(axis=1) > 0)))
+        seg = S_o
+        ax = np.abs(seg).argmax(axis=1)
+        t = got[np.arange(n_b), ax] / seg[np.arange(n_b), ax]
+        bis_out = int(np.sum((t <= t_lo - 1e-9) | (t > t_hi + 1e-9)))
+        # 15 rounds end inside the contact band for every sample; the bit-for-bit comparison has its teeth after 6 rounds
+        ref6, _, _, border6 = _oiris.bisect(so, np.zeros(DOF), S_o, 6, 1e-6, band=1e-4)
+        got6 = arm.bisect_to_collision(np.zeros(DOF), S_o, 6, 1e-6)
+        bis_bad6 = int(np.sum(~border6 & (np.abs(got6 - ref6).max(axis=1) > 0)))
+        ok_all &= bis_bad == 0 and bis_out == 0 and bis_bad6 == 0
+        nx["iris_bisection_samples_per_sec"] = {
+            "value": S.shape[0] / ms * 1e3, "best_ms": ms, "samples": int(S.shape[0]), "rounds": 15,
+            "midpoint_checks_per_sec": S.shape[0] * 15 / ms * 1e3, "api": "Arm.bisect_to_collision -> nbx_bisect_f32 (reference safe_sets.py:124-134)",
+            "parity": {"rows": n_b, "dtype": "f64", "band_m": 1e-4, "clear_of_band_fraction": float(clear.mean()),
+                       "bitwise_mismatches_clear_of_band": bis_bad, "far_ends_outside_the_oracle_interval": bis_out,
+                       "after_6_rounds": {"clear_of_band_fraction": float((~border6).mean()), "bitwise_mismatches_clear_of_band": bis_bad6},
+                       "against": "oracle/iris.py (float64 restatement; rows whose every tested midpoint is outside the contact band must "
+                                  "match bit for bit, the others must end inside the oracle's interval at its first in-band round)"}}
+        # f.4 signed minimum distance over all allowed pairs (reference arm.py:599-604: closest_to / in_collision's distance)
+        Bd = 1 << 20
+        ms = best_ms(lambda: arm.min_distance(q[:Bd]), n=3, warm=1)
+        n_d = 1 << 15
+        dg = arm.min_distance(q[:n_d]).cpu().numpy().astype(np.float64)
+        do = so.min_distance(q[:n_d].double().cpu().numpy())
+        err = np.abs(dg - do)
+        sep, pen, near = do > 1e-3, do < -1e-3, np.abs(do) <= 1e-3
+        mx = lambda m: float(err[m].max()) if m.any() else 0.0
+        # the bounds tests/test_signed_distance_gpu.py holds the kernels to
+        md_ok = bool(np.all(err[sep] <= 1e-4 + 3e-4 * do[sep]) and mx(pen) <= 2e-4 and mx(near) <= 5e-4)
+        ok_all &= md_ok
+        nx["min_distance_configs_per_sec"] = {
+            "value": Bd / ms * 1e3, "best_ms": ms, "configs": Bd, "api": "Arm.min_distance -> nbx_min_distance_f32 (signed: EPA for overlapping cores)",
+            "parity": {"rows": n_d, "penetrating_rows": int(pen.sum()), "near_contact_rows": int(near.sum()),
+                       "max_abs_err_separated_m": mx(sep), "max_abs_err_penetrating_m": mx(pen), "max_abs_err_near_contact_m": mx(near),
+                       "tolerance_m": "separated (d > 1 mm): 1e-4 + 3e-4 d; penetrating (d < -1 mm): 2e-4; |d| <= 1 mm: 5e-4", "ok": md_ok,
+                       "against": "oracle/collision.py SceneOracle.min_distance (float64 GJK / EPA), parity UNPINNED against Bullet"}}
+        # f.2 PRM roadmap: sample, node validity, k nearest EARLIER vertices, 10^6 edge validations, edge list
+        from numbotics_b200.planning.sampling_based import ConnectorParams, DiscreteConnector, ArmValidityChecker
+        from numbotics_b200.planning.sampling_based.roadmap import BatchedPRM, knn_earlier
+        conn = DiscreteConnector(ConnectorParams(resolution=0.1, max_distance=np.pi, validity_checker=ArmValidityChecker(arm)))
+        lo_l, hi_l = workloads.sample_limits(arm.joint_limits)
+        prm = BatchedPRM(conn, lo_l, hi_l, k_nearest=10)
+        prm.build(100000, seed=0)
+        walls = []
+        for sd in (1, 2, 3):
+            torch.cuda.synchronize(dev); t0 = time.perf_counter(); rm = prm.build(100000, seed=sd); torch.cuda.synchronize(dev)
+            walls.append(time.perf_counter() - t0)
+        ms_knn = best_ms(lambda: knn_earlier(rm.nodes, 10), n=3, warm=1)
+        nodes_s = rm.nodes[:2048]
+        idx_g, ok_g = knn_earlier(nodes_s, 10)
+        xn = nodes_s.double().cpu().numpy()
+        d2 = ((xn[:, None, :] - xn[None, :, :]) ** 2).sum(-1)
+        d2[np.triu_indices(len(xn))] = np.inf
+        idx_o = np.argsort(d2, axis=1, kind="stable")[:, :10]
+        ig = idx_g.cpu().numpy()
+        knn_bad = 0
+        for r in range(10, len(xn)):
+            diff = set(ig[r].tolist()) ^ set(idx_o[r].tolist())
+            # a float32 / float64 tie at the k-th place is not a mismatch
+            kth = d2[r, idx_o[r, 9]]
+            knn_bad += int(any(abs(d2[r, j] - kth) > 1e-5 * max(kth, 1e-12) for j in diff))
+        ok_all &= knn_bad == 0
+        nx["prm_roadmap_build"] = {
+            "vertices": 100000, "k_nearest": 10, "build_ms": min(walls) * 1e3, "candidate_edges": int(rm.candidates), "edges": int(rm.edges.shape[0]),
+            "knn_ms": ms_knn, "knn_pairs_per_sec": 0.5 * 1e10 / ms_knn * 1e3,
+            "api": "BatchedPRM.build (reference planners/prm.py:19-47 + faiss IndexFlatL2): one host round trip for the final compaction",
+            "parity": {"knn_rows": len(xn) - 10, "neighbour_set_mismatches": knn_bad,
+                       "against": "NumPy float64 brute force over the earlier vertices (the reference's faiss index is exact L2 too)"}}
+        out["next_rows"] = nx
     ok = max_over_ranks(0.0 if ok_all else 1.0, dev) == 0.0
     return out, ok
 
