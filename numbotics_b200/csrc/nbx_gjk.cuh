@@ -114,6 +114,14 @@ struct GjkOut {
 #ifndef NBX_GJK_COUNT_ITER
 #define NBX_GJK_COUNT_ITER(it)
 #endif
+#ifndef NBX_EPA_COUNT_EXPANSION
+#define NBX_EPA_COUNT_EXPANSION(it)
+#endif
+// the EPA stops when the bracket [closest face, smallest support value seen] is this narrow
+#ifndef NBX_EPA_TOL_ABS
+#define NBX_EPA_TOL_ABS 1e-5f
+#define NBX_EPA_TOL_REL 5e-5f
+#endif
 
 template <int MAX_ITER>
 __device__ GjkOut gjk_distance(const ShapeW& A, const ShapeW& B, float stop_above, float stop_below,
@@ -463,7 +471,8 @@ __device__ __noinline__ EpaOut epa_penetration(const ShapeW& A, const ShapeW& B,
         // lands in the plane of its face (the slivers that come out of such an expansion have garbage normals).  Converged: the
         // CLOSEST face carries the normal and the witness points (an earlier face can own the smallest h by a hair while its
         // own plane is millimetres closer to the origin -- witnesses taken from it would not be points of the shapes)
-        if (h - fd <= 1e-5f + 5e-5f * fabsf(h)) { bf = F[f]; break; }
+        NBX_EPA_COUNT_EXPANSION(it)
+        if (h - fd <= NBX_EPA_TOL_ABS + NBX_EPA_TOL_REL * fabsf(h)) { bf = F[f]; break; }
         if (nv >= kEpaV) break;
         W[nv] = w; PA[nv] = a;
         int ne = 0, nvis = 0;
