@@ -481,7 +481,7 @@ def main():
                 "peak_source": peak_src,
                 "peak_note": "the denominator is the measured COPY bandwidth (half reads, half writes); this kernel's stream is 89 % "
                              "writes in 8 KB + 21 KB bulk stores per tile, which DRAM sustains slightly better, so frac can exceed 1. "
-                             "ncu: dram__bytes.sum 6.6 TB/s = 81 % of the 8.18 TB/s pin rate (profiles/r01_ncu_full_summary_final.csv)",
+                             "ncu: dram__bytes.sum 6.6 TB/s = 81 % of the 8.18 TB/s pin rate (profiles/r02_ncu_full_summary_fk.csv)",
                 "fp32_tflops": FLOPS_PER_CFG * B / (avg_launch_ms * 1e-3) / 1e12}
 
     # ---- CPU baseline (reference numba kernels / oracle port) + parity gates, rank 0, N = 1 only ------------------
@@ -607,7 +607,7 @@ def secondary_measurements(arm, q, dev, rank, world, clocks_mhz):
         "hit_fraction": float(hit_gpu.float().mean()),
         "workload": "BASELINE configs[2]: Kinova-7 + 3 cubes, self + env pairs, 2^22 configurations per GPU",
         "kernels": "in_collision_kernel<split> (tree walk + broad phase) + narrow_kernel (GJK over the candidate queue)",
-        "roofline": {"bound": "issue (fp32 pipe)", "ncu": recorded_traffic("in_collision_ncu"),
+        "roofline": {"bound": "issue / dependent-instruction latency (fp32 + shared-memory chains at 16 warps per SM)", "ncu": recorded_traffic("in_collision_ncu"),
                      "fp32_peak_tflops": fp32_peak,
                      "survey_convention": {"flops_per_config": flops, "n_prims": n_prims, "self_pairs": n_self, "env_pairs": n_env,
                                            "tflops": flops * rate / world / 1e12,
@@ -654,7 +654,7 @@ def secondary_measurements(arm, q, dev, rank, world, clocks_mhz):
                                             "first_invalid output; issued = every sample of every edge (what the kernel evaluates)"},
                                 "kernels": "edge_prepare + edge_offsets + edges_flat_kernel (persistent grid, dynamic 32-sample tiles over the flat "
                                            "(edge, sample) space) + narrow_kernel",
-                                "roofline": {"bound": "issue (fp32 pipe)", "ncu": recorded_traffic("edges_flat_ncu")},
+                                "roofline": {"bound": "issue / dependent-instruction latency (same phase 1 as in_collision)", "ncu": recorded_traffic("edges_flat_ncu")},
                                 "workload": "BASELINE configs[3]: 100k nodes x 10-NN = 1M edges, resolution 0.1, contiguous E/G slices"}
     En = int(hi - lo)
     sh, gh = torch.empty((En, DOF), dtype=torch.float32).pin_memory(), torch.empty((En, DOF), dtype=torch.float32).pin_memory()
