@@ -18,10 +18,14 @@ def scene(cuda):
     return arm, cubes, collision.SceneOracle(arm)
 
 
-def check_verdicts(hit, d, thr=0.0):
+def check_verdicts(hit, d, thr=0.0, max_excluded=0.005):
+    """Verdicts equal the oracle's outside the stated contact band; the band may exclude at most `max_excluded` of the
+    samples (measured: ~1e-4 of uniformly random configurations, ~2e-3 of the contact-rich ones)."""
     clear = np.abs(d - thr) > EPS
-    assert clear.mean() > 0.97
+    excluded = 1.0 - clear.mean()
+    assert excluded <= max_excluded, f"the contact band excludes {excluded:.2e} of the samples"
     assert np.array_equal(hit[clear], (d < thr)[clear])
+    return excluded
 
 
 @pytest.mark.parametrize("margin_model", ["bullet", "sharp"])
@@ -157,7 +161,7 @@ def test_mixed_primitives_and_tree_branches(cuda):
     d = so.min_distance(q.astype(np.float64))
     hit = arm.in_collision(q)
     assert 0.05 < hit.mean() < 0.95
-    check_verdicts(hit, d)
+    check_verdicts(hit, d, max_excluded=0.01)       # a scene built so that most samples touch something: 8e-3 are inside the band
     dist = arm.min_distance(q)
     assert np.abs(dist[d > 0] - d[d > 0]).max() < 1e-4
 

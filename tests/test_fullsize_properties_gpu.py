@@ -74,7 +74,7 @@ def test_edges_1M(scene, cuda):
     # an invalid edge's minimum is only known up to its first invalid sample on the device side; the oracle's edge minimum
     # decides which edges are inside the contact band
     clear = np.abs(md) > EPS
-    assert clear.mean() > 0.97
+    assert 1.0 - clear.mean() <= 0.005, f"the contact band excludes {1.0 - clear.mean():.2e} of the samples"
     assert np.array_equal(valid[idx].cpu().numpy()[clear], np.asarray(vo, bool)[clear])
 
 
