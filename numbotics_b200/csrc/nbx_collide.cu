@@ -163,7 +163,6 @@ constexpr int kWarps = 4;            // autonomous warps per CTA (they only shar
 constexpr int kWT = NBX_WARP_TILE;   // items per tile
 constexpr int kQCap = 48;            // materialised candidates per warp
 constexpr int kPendCap = 256;        // survivors of one tile awaiting materialisation
-constexpr int kEpaCap = 40;          // kDist: overlapping candidates awaiting the EPA (run as soon as more than 8 wait: <= 8 + 32)
 constexpr int kEW = 34;              // words per queue entry
 constexpr int kMaxRange = 256;       // units a warp owns (flags kept in shared memory until the range is done)
 constexpr uint32_t kEnvFlag = 0x80000000u;
@@ -180,8 +179,7 @@ struct WCtx {
     const float* base;        // 12 floats (kernel parameter)
     float* poses;             // [pose_floats][32]
     float* queue;             // kDist: [kEW][kQCap] in shared memory, word-major so that lanes = entries is conflict free
-    float* epa_q;             // kDist: [kEW][kEpaCap] candidates whose cores overlap, awaiting the EPA
-    int* nepa;                // kDist: how many (warp-uniform, in shared memory)
+    int unit0;                // kDist: global index of the first unit of the warp's range (queue entries carry global unit indices)
     uint32_t* pend;           // [kPendCap] survivor codes: env flag | pair << 8 | item lane
     unsigned long long* flag; // kDist: [kMaxRange] running minimum: (ordered key of the distance) << 32 | pair code
     int* item_fi;             // [32] item lane -> flag index (kDist: within the warp's range; kSplit: global unit index)
@@ -623,30 +621,13 @@ __device__ __forceinline__ void phase1(const WCtx& C, bool valid, QF qf, int n_o
     }
 }
 
-// kDist: the EPA on the overlapping candidates that have been set aside, lane = candidate.  Run inline behind the GJK of a
-// drain pass it had 1.2 of 32 lanes active (3 % of random configurations collide) and was two thirds of the distance
-// kernel's time (ncu, profiles/r02_min_distance_*): an EPA is ~30 k instructions, a GJK a few hundred.
-__device__ __noinline__ void run_epa(const WCtx& C) {
-    const int lane = threadIdx.x & 31;
-    int n = *C.nepa;
-    __syncwarp();
-    while (n > 0) {
-        const int take = min(n, 32);
-        if (lane < take) {
-            Cand K;
-            load_cand(C.epa_q, n - take + lane, K, kEpaCap);
-            const float d = -K.m - core_penetration(K.A, K.B).depth;
-            atomicMin(&C.flag[K.fi], dist_entry(d, K.pc));
-        }
-        n -= take;
-    }
-    __syncwarp();
-    if (lane == 0) *C.nepa = 0;
-    __syncwarp();
-}
-
-// kDist: GJK on the 32 newest queue entries (all lanes busy), or on what is left at the end of the range.  Candidates
-// whose cores overlap (or sit in the contact regime) are set aside for run_epa.
+// kDist: GJK on the 32 newest queue entries (all lanes busy), or on what is left at the end of the range.  Candidates whose
+// cores overlap (or sit in the contact regime) need the EPA, ~30 k instructions against a few hundred for a GJK and needed by
+// 3 % of random configurations: run inline it had 1.2 of 32 lanes active and was two thirds of this kernel's time (ncu,
+// profiles/r02_min_distance_*), most of it waiting for its 3.6 KB polytope in local memory -- this kernel's 190 KB of shared
+// memory per SM leave ~30 KB of L1.  Such candidates go to a GLOBAL queue instead (global unit index in the entry); epa_kernel
+// runs them, lane = candidate, with the whole L1 for its arrays, and lowers the per-unit minimum that this kernel leaves in
+// global memory at the end of the range.  What the queue cannot take is evaluated here.
 __device__ __forceinline__ void drain(const WCtx& C, int& qn, bool all) {
     const int lane = threadIdx.x & 31;
     while (qn >= 32 || (all && qn > 0)) {
@@ -665,15 +646,48 @@ __device__ __forceinline__ void drain(const WCtx& C, int& qn, bool all) {
         qn -= take;
         const unsigned m = __ballot_sync(0xffffffffu, need_epa);
         if (m != 0) {
-            const int base = *C.nepa;
-            if (need_epa) store_cand(C.epa_q, base + __popc(m & ((1u << lane) - 1u)), K, kEpaCap);
-            __syncwarp();
-            if (lane == 0) *C.nepa = base + __popc(m);
-            __syncwarp();
-            if (base + __popc(m) > kEpaCap - 32) run_epa(C);
+            int base = 0;
+            const int leader = __ffs(m) - 1;
+            if (lane == leader) base = atomicAdd(&C.gq_count[0], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (need_epa) {
+                const int pos = base + __popc(m & ((1u << lane) - 1u));
+                if (pos < C.gq_half) {
+                    const int local = K.fi;
+                    K.fi = local + C.unit0;
+                    store_cand(C.gq, pos, K, C.gq_half);
+                } else {
+                    atomicMin(&C.flag[K.fi], dist_entry(-K.m - core_penetration(K.A, K.B).depth, K.pc));
+                }
+            }
         }
         __syncwarp();
     }
+}
+
+// The EPA over the global queue of the distance query: persistent, few warps per SM (each warp's polytopes are ~115 KB of
+// L1 lines), lane = candidate.  Lowers the running minimum (distance key << 32 | pair code) of the candidate's unit.
+__global__ void __launch_bounds__(32)
+epa_kernel(const float* __restrict__ gq, const int* __restrict__ gq_count, int gq_half, unsigned long long* __restrict__ entries) {
+    const int n = min(gq_count[0], gq_half);
+    for (int i = blockIdx.x * 32 + threadIdx.x; i < n; i += gridDim.x * 32) {
+        Cand K;
+        load_cand(gq, i, K, gq_half);
+        const float d = -K.m - core_penetration(K.A, K.B).depth;
+        atomicMin(&entries[K.fi], dist_entry(d, K.pc));
+    }
+}
+
+// per-unit running minimum -> the caller's arrays
+__global__ void dist_finalize_kernel(const unsigned long long* __restrict__ entries, int64_t B, float thr, uint8_t* __restrict__ verdict,
+                                     float* __restrict__ min_dist, uint32_t* __restrict__ pair_code) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const unsigned long long e = entries[i];
+    const float d = entry_dist(e);
+    min_dist[i] = d;
+    verdict[i] = d < thr ? 1 : 0;
+    if (pair_code != nullptr) pair_code[i] = (uint32_t)e;
 }
 
 // Verdict queries: the capsule bound of a bounding-sphere survivor (self pair of two cylinders),
@@ -750,8 +764,7 @@ __device__ __forceinline__ void materialise(const WCtx& C, int& npend, int& qn) 
 // per-warp work area: pose scratch, queue, pending list, flags, item -> flag map, + `extra_floats` for the caller
 __host__ __device__ inline size_t warp_smem_bytes(int mode, int pose_floats, int extra_floats) {
     return align16(sizeof(float) * (size_t)kWT * (pose_floats > 0 ? pose_floats : 1)) +
-           (mode == kDist ? align16(sizeof(float) * (size_t)kEW * kQCap) + align16(sizeof(unsigned long long) * kMaxRange) +
-                                align16(sizeof(float) * (size_t)kEW * kEpaCap) + 16 : 0) +
+           (mode == kDist ? align16(sizeof(float) * (size_t)kEW * kQCap) + align16(sizeof(unsigned long long) * kMaxRange) : 0) +
            align16(sizeof(uint32_t) * kPendCap) + 2 * align16(sizeof(int) * kWT) + align16(sizeof(float) * (size_t)extra_floats);
 }
 
@@ -760,13 +773,9 @@ __device__ __forceinline__ unsigned char* carve_warp(WCtx& C, unsigned char* p, 
     C.poses = reinterpret_cast<float*>(p);      p += align16(sizeof(float) * (size_t)kWT * max(pose_floats, 1));
     C.queue = nullptr;
     C.flag = nullptr;
-    C.epa_q = nullptr;
-    C.nepa = nullptr;
     if (MODE == kDist) {
         C.queue = reinterpret_cast<float*>(p);  p += align16(sizeof(float) * (size_t)kEW * kQCap);
         C.flag = reinterpret_cast<unsigned long long*>(p);   p += align16(sizeof(unsigned long long) * kMaxRange);
-        C.epa_q = reinterpret_cast<float*>(p);  p += align16(sizeof(float) * (size_t)kEW * kEpaCap);
-        C.nepa = reinterpret_cast<int*>(p);     p += 16;
     }
     C.pend = reinterpret_cast<uint32_t*>(p);    p += align16(sizeof(uint32_t) * kPendCap);
     C.item_fi = reinterpret_cast<int*>(p);      p += align16(sizeof(int) * kWT);
@@ -782,6 +791,7 @@ struct SplitArgs {
     int gq_half;
     int gjk_iters;
     int* first_bad;           // edges only, nullable
+    unsigned long long* entries;   // distance query only: per-unit running minimum in global memory
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -830,10 +840,7 @@ in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict_
         if (MODE == kDist) C.flag[i] = dist_entry(FLT_MAX, 0xffffffffu);
         else verdict[range0 + i] = 0;
     }
-    if (MODE == kDist) {
-        if (lane == 0) *C.nepa = 0;
-        __syncwarp();
-    }
+    C.unit0 = (int)range0;
     int npend = 0, qn = 0;
 #pragma unroll 1
     for (int t0 = 0; t0 < rangeN; t0 += kWT) {
@@ -852,15 +859,10 @@ in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict_
     }
     if (MODE == kDist) {
         drain(C, qn, true);
-        run_epa(C);
         __syncwarp();
-        for (int i = lane; i < rangeN; i += 32) {
-            const unsigned long long e = C.flag[i];
-            const float d = entry_dist(e);
-            min_dist[range0 + i] = d;
-            verdict[range0 + i] = d < thr ? 1 : 0;
-            if (pair_code != nullptr) pair_code[range0 + i] = (uint32_t)e;
-        }
+        // the running minima of the range, for epa_kernel to lower and dist_finalize_kernel to unpack (min_dist is the
+        // caller's float array: the 64-bit entries live in the query's workspace, G.entries)
+        for (int i = lane; i < rangeN; i += 32) G.entries[range0 + i] = C.flag[i];
     }
 }
 
@@ -1515,7 +1517,7 @@ int units_per_warp(int64_t n_units, int sm_count, int warps_per_sm, int waves = 
 struct SplitWs {
     void* p = nullptr;
     cudaStream_t st = nullptr;
-    SplitArgs args{nullptr, nullptr, 0, kGjkIters, nullptr};
+    SplitArgs args{nullptr, nullptr, 0, kGjkIters, nullptr, nullptr};
     int alloc(int device, int64_t n_items, cudaStream_t stream, bool zero_counters = true) {
         st = stream;
         cudaMemPool_t pool = nullptr;
@@ -1569,10 +1571,30 @@ int launch_in_collision(const nbx_chain* ch, const nbx_scene* sc, const float* q
     const int upw = units_per_warp(B, ch->sm_count, mode == kDist ? 12 : 16);
     const int64_t grid = (B + (int64_t)kWarps * upw - 1) / ((int64_t)kWarps * upw);
     if (mode == kDist) {
+        // workspace of the distance query: [counters 256 B][running minimum per unit, 8 B][EPA queue, kEW words per entry]
+        cudaMemPool_t pool = nullptr;
+        if ((rc = nbx_workspace_pool(ch->device, &pool)) != NBX_OK) return rc;
+        const int64_t cap = std::max<int64_t>(4096, std::min<int64_t>((B / 4 + 31) & ~(int64_t)31, 1 << 20));   // ~4 % of random configurations collide
+        const size_t entries_bytes = (sizeof(unsigned long long) * (size_t)B + 255) & ~(size_t)255;
+        void* wsp = nullptr;
+        NBX_CUDA_OK(cudaMallocFromPoolAsync(&wsp, 256 + entries_bytes + sizeof(float) * (size_t)kEW * (size_t)cap, pool, stream));
+        NBX_CUDA_OK(cudaMemsetAsync(wsp, 0, 256, stream));
+        SplitArgs G{nullptr, nullptr, 0, kGjkIters, nullptr, nullptr};
+        G.gq_count = static_cast<int*>(wsp);
+        G.entries = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(wsp) + 256);
+        G.gq = reinterpret_cast<float*>(static_cast<unsigned char*>(wsp) + 256 + entries_bytes);
+        G.gq_half = (int)cap;
         NBX_SMEM_LIMIT((in_collision_kernel<kDist, false>), smem);
-        in_collision_kernel<kDist, false><<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, q, B, ch->dof, thr, verdict, min_dist, pair_code, upw, SplitArgs{nullptr, nullptr, 0, kGjkIters, nullptr});
+        in_collision_kernel<kDist, false><<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, q, B, ch->dof, thr, verdict, min_dist, pair_code, upw, G);
         nbx_count_launch();
-        NBX_CUDA_OK(cudaGetLastError());
+        static const int epa_cps_env = std::getenv("NBX_EPA_CTAS_PER_SM") ? std::atoi(std::getenv("NBX_EPA_CTAS_PER_SM")) : 0;   // tuning only
+        epa_kernel<<<(unsigned)(ch->sm_count * (epa_cps_env > 0 ? epa_cps_env : 16)), 32, 0, stream>>>(G.gq, G.gq_count, G.gq_half, G.entries);
+        nbx_count_launch();
+        dist_finalize_kernel<<<(unsigned)((B + 255) / 256), 256, 0, stream>>>(G.entries, B, thr, verdict, min_dist, pair_code);
+        nbx_count_launch();
+        const cudaError_t e = cudaGetLastError();
+        cudaFreeAsync(wsp, stream);
+        NBX_CUDA_OK(e);
         return NBX_OK;
     }
     SplitWs ws;
