@@ -159,3 +159,24 @@ def test_negative_threshold_edges_and_bisection(scene):
     near = out - (far - centre) / 2 ** 12
     d_near = so.min_distance(near.astype(np.float64))
     assert (d_out < -0.005 + 2e-4).all() and (d_near > -0.005 - 2e-4).all()
+
+
+def test_epa_queue_overflow_of_the_distance_query_changes_nothing(scene):
+    """The distance query hands overlapping candidates to `epa_kernel` through a global queue of B / 4 entries (at least 4096)
+    and evaluates in place what the queue cannot take.  On contact-rich configurations more than a quarter of the batch
+    overlaps: one call on the whole batch (queue overflows) must give, bit for bit, the distances and closest pairs of calls
+    on chunks small enough for the queue; and both agree with the float64 oracle."""
+    arm, so = scene
+    q = _dense(40000, seed=77)
+    d_all = arm.min_distance(q)
+    assert (d_all < -1e-3).mean() > 0.3                     # > 12 000 configurations with an overlapping pair against 10 000 slots
+    d_chunks = np.concatenate([arm.min_distance(q[i:i + 4000]) for i in range(0, len(q), 4000)])
+    assert np.array_equal(d_all, d_chunks)
+    c_all = arm.closest_to(q[:12000])
+    c_chunks = [arm.closest_to(q[i:i + 3000]) for i in range(0, 12000, 3000)]
+    assert np.array_equal(c_all.distance, np.concatenate([c.distance for c in c_chunks]))
+    assert np.array_equal(c_all.position_on_subject, np.concatenate([c.position_on_subject for c in c_chunks]))
+    ref = so.min_distance(q[:3000].astype(np.float64))
+    err = np.abs(d_all[:3000] - ref)
+    pen = ref < -1e-3
+    assert pen.sum() > 800 and err[pen].max() < 2e-4 and err[~pen].max() < 5e-4
