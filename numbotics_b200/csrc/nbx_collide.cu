@@ -161,10 +161,11 @@ __device__ __forceinline__ void unround(ShapeW& S, float margin) {
 // ---------------------------------------------------------------------------------------------
 constexpr int kWarps = 4;            // autonomous warps per CTA (they only share the staged scene)
 constexpr int kWT = NBX_WARP_TILE;   // items per tile
-constexpr int kQCap = 48;            // materialised candidates per warp
+constexpr int kQCap = 40;            // materialised candidates per warp (kDist; < 32 wait between passes, a pass adds what fits)
 constexpr int kPendCap = 256;        // survivors of one tile awaiting materialisation
 constexpr int kEW = 34;              // words per queue entry
-constexpr int kMaxRange = 256;       // units a warp owns (flags kept in shared memory until the range is done)
+constexpr int kMaxRange = 256;       // units a warp owns
+constexpr int kMaxRangeDist = 128;   // ... in a distance query, whose running minima stay in shared memory until the range is done
 constexpr uint32_t kEnvFlag = 0x80000000u;
 
 constexpr int kSplit = 0;            // verdict query, global queue + narrow kernel
@@ -764,7 +765,7 @@ __device__ __forceinline__ void materialise(const WCtx& C, int& npend, int& qn) 
 // per-warp work area: pose scratch, queue, pending list, flags, item -> flag map, + `extra_floats` for the caller
 __host__ __device__ inline size_t warp_smem_bytes(int mode, int pose_floats, int extra_floats) {
     return align16(sizeof(float) * (size_t)kWT * (pose_floats > 0 ? pose_floats : 1)) +
-           (mode == kDist ? align16(sizeof(float) * (size_t)kEW * kQCap) + align16(sizeof(unsigned long long) * kMaxRange) : 0) +
+           (mode == kDist ? align16(sizeof(float) * (size_t)kEW * kQCap) + align16(sizeof(unsigned long long) * kMaxRangeDist) : 0) +
            align16(sizeof(uint32_t) * kPendCap) + 2 * align16(sizeof(int) * kWT) + align16(sizeof(float) * (size_t)extra_floats);
 }
 
@@ -775,7 +776,7 @@ __device__ __forceinline__ unsigned char* carve_warp(WCtx& C, unsigned char* p, 
     C.flag = nullptr;
     if (MODE == kDist) {
         C.queue = reinterpret_cast<float*>(p);  p += align16(sizeof(float) * (size_t)kEW * kQCap);
-        C.flag = reinterpret_cast<unsigned long long*>(p);   p += align16(sizeof(unsigned long long) * kMaxRange);
+        C.flag = reinterpret_cast<unsigned long long*>(p);   p += align16(sizeof(unsigned long long) * kMaxRangeDist);
     }
     C.pend = reinterpret_cast<uint32_t*>(p);    p += align16(sizeof(uint32_t) * kPendCap);
     C.item_fi = reinterpret_cast<int*>(p);      p += align16(sizeof(int) * kWT);
@@ -798,7 +799,7 @@ struct SplitArgs {
 // in_collision.  MODE kSplit: broad kernel of the verdict query (verdict[b] = 0 here, the narrow kernel raises it);
 // MODE kDist: fused distance query (min_dist[b] and the verdict at the end of the warp's range).
 template <int MODE, bool FAST>
-__global__ void __launch_bounds__(kWarps * 32, MODE == kDist ? 1 : 4)
+__global__ void __launch_bounds__(kWarps * 32, MODE == kDist ? 3 : 4)
 in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ q, int64_t B, int dof, float thr,
                     uint8_t* __restrict__ verdict, float* __restrict__ min_dist, uint32_t* __restrict__ pair_code, int upw,
                     const SplitArgs G) {
@@ -1512,17 +1513,17 @@ int fill_scene_dev(const nbx_chain* ch, const nbx_scene* sc, const double* base_
 
 // units (configurations / edges) per warp: long ranges amortise the final partial drain, but the grid must keep
 // every SM busy for several waves
-int units_per_warp(int64_t n_units, int sm_count, int warps_per_sm, int waves = 6) {
+int units_per_warp(int64_t n_units, int sm_count, int warps_per_sm, int waves = 6, int max_range = kMaxRange) {
     static const int env = std::getenv("NBX_COLLIDE_UPW") ? std::atoi(std::getenv("NBX_COLLIDE_UPW")) : 0;   // tuning only
     const int64_t tiles = (n_units + kWT - 1) / kWT, resident = (int64_t)sm_count * warps_per_sm;
     int64_t u;
-    if (tiles <= resident * (kMaxRange / kWT))
+    if (tiles <= resident * (max_range / kWT))
         u = (tiles + resident - 1) / resident;            // small batch (a bisection round, a planner's query): ONE wave, every
                                                           // warp resident from the start instead of a ragged second wave
     else
         u = n_units / (resident * waves * kWT);
-    u = std::max<int64_t>(1, std::min<int64_t>(u, kMaxRange / kWT));
-    if (env > 0) u = std::min(env, kMaxRange / kWT);
+    u = std::max<int64_t>(1, std::min<int64_t>(u, max_range / kWT));
+    if (env > 0) u = std::min(env, max_range / kWT);
     return (int)u * kWT;
 }
 
@@ -1581,7 +1582,7 @@ int launch_in_collision(const nbx_chain* ch, const nbx_scene* sc, const float* q
     const int mode = min_dist != nullptr ? kDist : kSplit;
     const size_t smem = scene_smem_bytes(S.n_mov, S.n_prims, S.n_obs, S.n_self, S.n_env) + kWarps * warp_smem_bytes(mode, S.scratch_floats, kWT * ch->dof);
     NBX_REQUIRE(smem <= 220 * 1024, "scene too large for shared memory (%zu bytes)", smem);
-    const int upw = units_per_warp(B, ch->sm_count, mode == kDist ? 12 : 16);
+    const int upw = mode == kDist ? units_per_warp(B, ch->sm_count, 12, 6, kMaxRangeDist) : units_per_warp(B, ch->sm_count, 16);
     const int64_t grid = (B + (int64_t)kWarps * upw - 1) / ((int64_t)kWarps * upw);
     if (mode == kDist) {
         // workspace of the distance query: [counters 256 B][running minimum per unit, 8 B][EPA queue, kEW words per entry]
