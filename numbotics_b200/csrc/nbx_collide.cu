@@ -638,7 +638,7 @@ __device__ __forceinline__ void drain(const WCtx& C, int& qn, bool all) {
         if (lane < take) {
             load_cand(C.queue, qn - take + lane, K, kQCap);
             const float best = entry_dist(((volatile unsigned long long*)C.flag)[K.fi]);
-            const GjkOut g = gjk_distance<kGjkItersDist>(K.A, K.B, best + K.m, -FLT_MAX, 2e-5f, 4e-5f);     // as eval_cand<kDist>
+            const GjkOut g = gjk_distance<kGjkItersDist, true>(K.A, K.B, best + K.m, -FLT_MAX, 2e-5f, 4e-5f);     // as eval_cand<kDist>
             if (!g.pruned) {
                 need_epa = g.overlap || g.contact;
                 if (!need_epa) atomicMin(&C.flag[K.fi], dist_entry(g.d - K.m, K.pc));

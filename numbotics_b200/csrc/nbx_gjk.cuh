@@ -98,6 +98,10 @@ __device__ __forceinline__ V3 closest_tri(V3 a, V3 b, V3 c, int* mask) {
     return madd(madd(a, vb * inv, ab), vc * inv, ac);
 }
 
+// out-of-line copy for instantiations that care more about their instruction footprint than about a call (the fused
+// distance kernel: five inlined copies of closest_tri are ~750 instructions of a GJK loop that does not fit the L0 I-cache)
+__device__ __noinline__ V3 closest_tri_call(V3 a, V3 b, V3 c, int* mask) { return closest_tri(a, b, c, mask); }
+
 // Result of one GJK query on the cores.
 //   d    : distance estimate.  If `pruned` it is a LOWER bound that already exceeds stop_above;
 //          otherwise an UPPER bound (|v| of a point of the Minkowski difference) that is either
@@ -123,9 +127,13 @@ struct GjkOut {
 #define NBX_EPA_TOL_REL 5e-5f
 #endif
 
-template <int MAX_ITER>
+template <int MAX_ITER, bool COMPACT = false>
 __device__ GjkOut gjk_distance(const ShapeW& A, const ShapeW& B, float stop_above, float stop_below,
                                 float conv_abs = 1e-6f, float conv_rel = 1e-5f, int max_iter = MAX_ITER) {
+    auto ctri = [](V3 a, V3 b, V3 c, int* m) {
+        if constexpr (COMPACT) return closest_tri_call(a, b, c, m);
+        else return closest_tri(a, b, c, m);
+    };
     GjkOut out;
     out.lb = 0.f;
     out.overlap = false;
@@ -164,7 +172,7 @@ __device__ GjkOut gjk_distance(const ShapeW& A, const ShapeW& B, float stop_abov
             else { nv = madd(w, t / den, ab); s1 = w; n = 2; }
         } else if (n == 2) {
             int m;
-            nv = closest_tri(w, s0, s1, &m);
+            nv = ctri(w, s0, s1, &m);
             // compact: bit0 = w, bit1 = s0, bit2 = s1
             V3 q0 = s0, q1 = s1;
             int k = 0;
@@ -191,7 +199,7 @@ __device__ GjkOut gjk_distance(const ShapeW& A, const ShapeW& B, float stop_abov
                 if (degenerate || sp * sd < 0.f) {                                     \
                     outside_any = true;                                                \
                     int m3;                                                            \
-                    const V3 cp = closest_tri(P0, P1, P2, &m3);                        \
+                    const V3 cp = ctri(P0, P1, P2, &m3);                               \
                     const float dd = dot(cp, cp);                                      \
                     if (dd < best) {                                                   \
                         best = dd; bp = cp;                                            \
