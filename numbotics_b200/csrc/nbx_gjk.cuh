@@ -290,6 +290,14 @@ __device__ __forceinline__ void closest_tri_bary(V3 a, V3 b, V3 c, float* la, fl
     *lb = vb * inv; *lc = vc * inv; *la = 1.f - *lb - *lc;
 }
 
+// out-of-line copy for gjk_witness (never on a verdict path; its callers are instruction-fetch-bound: ncu no_instruction 2.2
+// stalls per issue in pair_distances_kernel): five inlined copies are ~500 instructions of its loop
+__device__ __noinline__ V3 closest_tri_bary_call(V3 a, V3 b, V3 c) {
+    float l0, l1, l2;
+    closest_tri_bary(a, b, c, &l0, &l1, &l2);
+    return mk(l0, l1, l2);
+}
+
 template <int MAX_ITER>
 __device__ GjkWit gjk_witness(const ShapeW& A, const ShapeW& B, bool generic_start = false) {
     GjkWit out;
@@ -333,7 +341,8 @@ __device__ GjkWit gjk_witness(const ShapeW& A, const ShapeW& B, bool generic_sta
             const float t = den > 0.f ? fminf(fmaxf(-dot(w[0], e) / den, 0.f), 1.f) : 0.f;
             lam[0] = 1.f - t; lam[1] = t;
         } else if (n == 3) {
-            closest_tri_bary(w[0], w[1], w[2], &lam[0], &lam[1], &lam[2]);
+            const V3 l = closest_tri_bary_call(w[0], w[1], w[2]);
+            lam[0] = l.x; lam[1] = l.y; lam[2] = l.z;
         } else {
             // tetrahedron: the closest of the faces the origin lies outside of; inside all four = overlap
             float bd = FLT_MAX;
@@ -346,8 +355,8 @@ __device__ GjkWit gjk_witness(const ShapeW& A, const ShapeW& B, bool generic_sta
                 const float flat = 4e-6f * (fabsf(w[I0].x) + fabsf(w[I0].y) + fabsf(w[I0].z) + 1e-3f); \
                 if (sd * sd <= flat * flat * dot(nrm, nrm) || sp * sd < 0.f) {                 \
                     outside_any = true;                                                        \
-                    float l0, l1, l2;                                                          \
-                    closest_tri_bary(w[I0], w[I1], w[I2], &l0, &l1, &l2);                      \
+                    const V3 l = closest_tri_bary_call(w[I0], w[I1], w[I2]);                   \
+                    const float l0 = l.x, l1 = l.y, l2 = l.z;                                  \
                     const V3 cp = madd(madd(l0 * w[I0], l1, w[I1]), l2, w[I2]);                \
                     const float dd = dot(cp, cp);                                              \
                     if (dd < bd) { bd = dd; lam[I0] = l0; lam[I1] = l1; lam[I2] = l2; lam[IO] = 0.f; } \
