@@ -60,11 +60,12 @@ class Roadmap:
         return path[::-1]
 
 
-def knn_earlier(nodes, k: int, chunk: int = 4096):
+def knn_earlier(nodes, k: int, chunk: int = 4096, return_dist2: bool = False):
     """For every vertex i > 0 its (up to) k nearest vertices among 0..i-1 (the reference's incremental kNN:
     `ApproximateNearestNeighborsIndex.k_nearest` before `add_point`, planners/prm.py:35-40), exact L2, one kernel launch
-    (`nbx_knn_f32`, causal mode).  Returns (idx (N,k) int64 sorted by distance, valid (N,k) bool).  `chunk` is ignored
-    (kept for the signature of the earlier torch implementation)."""
+    (`nbx_knn_f32`, causal mode).  Returns (idx (N,k) int64 sorted by distance, valid (N,k) bool) and, with
+    `return_dist2`, the squared distances (N,k) float32.  `chunk` is ignored (kept for the signature of the earlier torch
+    implementation)."""
     from ... import _cabi
     if not nodes.is_cuda:
         raise ValueError("knn_earlier needs a CUDA tensor: numbotics_b200 has no CPU path")
@@ -72,17 +73,40 @@ def knn_earlier(nodes, k: int, chunk: int = 4096):
     N, dof = x.shape
     idx = torch.empty((N, k), dtype=torch.long, device=x.device)
     ok = torch.empty((N, k), dtype=torch.uint8, device=x.device)
+    d2 = torch.empty((N, k), dtype=torch.float32, device=x.device) if return_dist2 else None
     lib = _cabi.load()
     with torch.cuda.device(x.device):
-        _cabi.check(lib.nbx_knn_f32(x.data_ptr(), N, x.data_ptr(), N, dof, int(k), 1, idx.data_ptr(), ok.data_ptr(), None,
+        _cabi.check(lib.nbx_knn_f32(x.data_ptr(), N, x.data_ptr(), N, dof, int(k), 1, idx.data_ptr(), ok.data_ptr(),
+                                    d2.data_ptr() if return_dist2 else None,
                                     x.device.index, torch.cuda.current_stream(x.device).cuda_stream))
+    if return_dist2:
+        return idx, ok.to(torch.bool), d2
     return idx, ok.to(torch.bool)
+
+
+def prm_star_radius(n_nodes, dimension: int, space_volume: float):
+    """`PRMStar.connection_radius` (reference planners/prm_star.py:20-26) for a graph of `n_nodes` vertices:
+    gamma * (ln n / n)^(1/d),  gamma = 2 (1 + 1/d)^(1/d) (V_ball / V_space)^(1/d).  `n_nodes` may be an array."""
+    import math
+    d = float(dimension)
+    v_ball = math.pi ** (d / 2.0) / math.gamma(d / 2.0 + 1.0)
+    gamma = 2.0 * (1.0 + 1.0 / d) ** (1.0 / d) * (v_ball / float(space_volume)) ** (1.0 / d)
+    n = np.asarray(n_nodes, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return gamma * (np.log(n) / n) ** (1.0 / d)
 
 
 class BatchedPRM:
     """Roadmap over an Arm's configuration space with DiscreteConnector edge semantics."""
 
-    def __init__(self, connector: DiscreteConnector, lower_bounds, upper_bounds, k_nearest: int = 10):
+    def __init__(self, connector: DiscreteConnector, lower_bounds, upper_bounds, k_nearest: int = 10, star: bool = False,
+                 reference_self_slot: bool = False):
+        """`star`: PRM* (reference planners/prm_star.py:29-57) -- of the k nearest earlier vertices only those closer than
+        `prm_star_radius(number of vertices at insertion, dimension, volume of the box)` are tried.
+        `reference_self_slot`: the reference adds the new vertex to its index BEFORE it asks for the k nearest
+        (graph.py:53-57, then prm.py:35-37 / prm_star.py:47-50), so one of the k answers is the vertex itself and
+        `connect` rejects it (zero distance, connectors.py:64-65): effectively k - 1 earlier neighbours.  True reproduces
+        that; the default keeps k real neighbours."""
         chk = connector._params.validity_checker
         if not isinstance(chk, ArmValidityChecker):
             raise ValueError("BatchedPRM needs a DiscreteConnector whose validity checker is an ArmValidityChecker")
@@ -93,6 +117,10 @@ class BatchedPRM:
         if self.lower.shape != self.upper.shape or self.lower.ndim != 1:
             raise ValueError("Lower and upper bounds must be 1D arrays of the same shape")
         self.k = int(k_nearest)
+        self.star = bool(star)
+        self.k_eff = self.k - 1 if reference_self_slot else self.k
+        if self.k_eff < 1:
+            raise ValueError("k_nearest leaves no neighbour to connect to")
 
     def build(self, n_samples: int, start=None, goals=(), seed: int = 0, nodes=None) -> Roadmap:
         """Vertices = [start] + goals + uniform samples (or the given `nodes`); edges as described above."""
@@ -111,16 +139,25 @@ class BatchedPRM:
             nodes = torch.as_tensor(nodes, dtype=torch.float32, device=dev).contiguous()
         N = nodes.shape[0]
         node_valid = ~self.arm.in_collision(nodes, self.connector._params.validity_checker.threshold)
-        idx, ok = knn_earlier(nodes, self.k)
+        k = self.k_eff
+        if self.star:
+            idx, ok, d2 = knn_earlier(nodes, k, return_dist2=True)
+            # vertex i is inserted into a graph that then has i + 1 vertices (prm_star.py:44-47: add_vertex, then the radius)
+            radius = prm_star_radius(np.arange(1, N + 1), nodes.shape[1], float(np.prod(self.upper - self.lower)))
+            radius[0] = 0.0                                  # ln 1 = 0: the first vertex has no neighbours anyway
+            r = torch.as_tensor(radius, dtype=torch.float32, device=dev)
+            ok = ok & (d2.sqrt() < r[:, None])               # strict, graph.py:169
+        else:
+            idx, ok = knn_earlier(nodes, k)
         # every (vertex, neighbour slot) goes through the edge kernel -- the few empty slots of the first k vertices are
         # masked afterwards -- so that the only host round trip of the build is the final compaction of the edge list
         u = idx.reshape(-1)
-        v = torch.arange(N, device=dev).repeat_interleave(self.k)
+        v = torch.arange(N, device=dev).repeat_interleave(k)
         okf = ok.reshape(-1)
         starts = nodes[u]                   # connect(neighbor.state, new_node.state)
         ends = nodes[v]
         valid = self.connector.connect_batch(starts, ends) & okf
         edges = torch.stack([u[valid], v[valid]], dim=1)
         weights = (nodes[edges[:, 0]] - nodes[edges[:, 1]]).norm(dim=1)
-        n_candidates = int(min(N, self.k + 1) * (min(N, self.k + 1) - 1) // 2 + max(0, N - self.k - 1) * self.k)
+        n_candidates = int(okf.sum()) if self.star else int(min(N, k + 1) * (min(N, k + 1) - 1) // 2 + max(0, N - k - 1) * k)
         return Roadmap(nodes=nodes, edges=edges, weights=weights, candidates=n_candidates, node_valid=node_valid)

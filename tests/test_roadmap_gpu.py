@@ -96,3 +96,49 @@ def test_roadmap_equals_sequential_prm_loop(cuda):
         assert (min(a, b), max(a, b)) in got
     G = rm.to_networkx()
     assert G.number_of_nodes() == 302 and G.number_of_edges() == len(got)
+
+
+def test_prm_star_and_the_reference_self_slot(cuda):
+    """PRM* (reference planners/prm_star.py:20-57): of the k nearest earlier vertices only those strictly inside the
+    connection radius of the graph at insertion time are tried; and `reference_self_slot`: the reference's index already
+    holds the new vertex when it is queried, so k answers are k - 1 earlier vertices plus the vertex itself, which
+    `connect` rejects."""
+    import scipy.special
+    from numbotics_b200.planning.sampling_based.roadmap import prm_star_radius
+    arm, cubes = workloads.prm_scene(device=0)
+    so = collision.SceneOracle(arm)
+    conn = DiscreteConnector(ConnectorParams(resolution=0.1, max_distance=np.pi, validity_checker=ArmValidityChecker(arm)))
+    # a small box around a free configuration, so that the PRM* radius (which shrinks like (ln n / n)^(1/7)) finds neighbours
+    centre = np.array([0.3, 0.6, -0.2, 1.2, 0.1, 0.8, 0.0])
+    lo, hi = centre - 0.25, centre + 0.25
+    # the radius formula itself, against the reference's expression (prm_star.py:20-26)
+    dim, k, V = 7.0, 123.0, float(np.prod(hi - lo))
+    v_ball = (np.pi ** (dim / 2.0)) / scipy.special.gamma((dim / 2.0) + 1.0)
+    gamma = 2.0 * (1.0 + (1.0 / dim)) ** (1.0 / dim) * (v_ball / V) ** (1.0 / dim)
+    assert abs(prm_star_radius(123, 7, V) - gamma * (np.log(k) / k) ** (1 / dim)) < 1e-15
+    for star, self_slot in ((True, False), (False, True), (True, True)):
+        prm = BatchedPRM(conn, lo, hi, k_nearest=5, star=star, reference_self_slot=self_slot)
+        rm = prm.build(250, seed=11)
+        nodes = rm.nodes.cpu().numpy().astype(np.float64)
+        k_eff = 4 if self_slot else 5
+        want, borderline, tried = set(), set(), 0
+        for i in range(1, nodes.shape[0]):
+            d = np.linalg.norm(nodes[:i] - nodes[i], axis=1)
+            radius = prm_star_radius(i + 1, 7, V) if star else np.inf
+            for j in np.argsort(d, kind="stable")[: min(k_eff, i)]:
+                if abs(d[j] - radius) < 1e-6 * max(radius, 1e-9) if star else False:
+                    borderline.add((int(j), i))               # float32 distance against a float64 radius
+                    continue
+                if not d[j] < radius:
+                    continue
+                tried += 1
+                v, _, md = so.edges_valid(nodes[j][None], nodes[i][None], 0.1, return_detail=True)
+                if abs(md[0]) <= 1e-4:
+                    borderline.add((int(j), i))
+                elif v[0]:
+                    want.add((int(j), i))
+        got = {tuple(e) for e in rm.edges.cpu().numpy().tolist()}
+        assert got - borderline == want - borderline, (star, self_slot)
+        assert len(want) > 50
+        if star:
+            assert abs(rm.candidates - tried) <= len(borderline)
