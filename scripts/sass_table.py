@@ -47,5 +47,7 @@ print(f"{'kernel':70s} {'instrs':>7s} " + " ".join(f"{c:>6s}" for c in COLS))
 for name, cnt, n in sorted(rows, key=lambda r: short(r[0])):
     if keep(name):
         print(f"{short(name)[:70]:70s} {n:7d} " + " ".join(f"{cnt[c]:6d}" for c in COLS))
-tensor = len(re.findall(r"UTC[A-Z]*MMA|TCGEN|UTMA", sass))
-print(f"\n# tensor-core / TMEM mnemonics found in the whole library: {tensor}")
+tensor = len(re.findall(r"UTC[A-Z]*MMA|\bLDTM\b|\bSTTM\b|\b[HIQ]MMA\b", sass))
+flush = len(re.findall(r"UTMACMDFLUSH", sass))
+print(f"\n# tensor-core / TMEM mnemonics (UTC*MMA, LDTM, STTM, HMMA / IMMA / QMMA) found in the whole library: {tensor}")
+print(f"# UTMACMDFLUSH (cp.async.bulk.commit_group, the bulk stores' group commit): {flush}")
