@@ -78,3 +78,17 @@ def test_generic_callback_path_is_sequential_with_early_exit():
     assert len(calls) == 11
     with pytest.raises(ValueError, match="ArmValidityChecker"):
         conn.connect_batch(np.zeros((2, 2)), np.ones((2, 2)))
+
+
+def test_prm_star_radius_is_the_reference_expression():
+    """`PRMStar.connection_radius` (reference planners/prm_star.py:20-26), scalar and vectorised; ln 1 = 0 gives radius 0."""
+    import scipy.special
+    from numbotics_b200.planning.sampling_based.roadmap import prm_star_radius
+    for dim, n, V in ((7, 302, (2 * np.pi) ** 7), (3, 10, 8.0), (2, 2, 1.0)):
+        d, k = float(dim), float(n)
+        v_ball = (np.pi ** (d / 2.0)) / scipy.special.gamma((d / 2.0) + 1.0)
+        gamma = 2.0 * (1.0 + (1.0 / d)) ** (1.0 / d) * (v_ball / V) ** (1.0 / d)
+        want = gamma * (np.log(k) / k) ** (1 / d)
+        assert abs(prm_star_radius(n, dim, V) - want) <= 1e-15 * max(want, 1.0)
+    r = prm_star_radius(np.arange(1, 6), 7, 1.0)
+    assert r.shape == (5,) and r[0] == 0.0 and np.all(np.diff(r[2:]) < 0) and r[1] > 0      # ln n / n peaks at n = e
