@@ -182,7 +182,7 @@ struct WCtx {
     float* queue;             // kDist: [kEW][kQCap] in shared memory, word-major so that lanes = entries is conflict free
     int unit0;                // kDist: global index of the first unit of the warp's range (queue entries carry global unit indices)
     uint32_t* pend;           // [kPendCap] survivor codes: env flag | pair << 8 | item lane
-    unsigned long long* flag; // kDist: [kMaxRange] running minimum: (ordered key of the distance) << 32 | pair code
+    unsigned long long* flag; // kDist: [kMaxRangeDist] running minimum: (ordered key of the distance) << 32 | pair code
     int* item_fi;             // [32] item lane -> flag index (kDist: within the warp's range; kSplit: global unit index)
     int* item_aux;            // [32] edges only (else nullptr): the item's sample index on its edge, carried in the entry's pair-code word
     int* first_bad;           // edges only, nullable: per edge the smallest colliding sample index (atomicMin by the narrow phase)
