@@ -1918,17 +1918,23 @@ int nbx_edges_valid_host_f32(const nbx_chain* chain, const nbx_scene* scene, con
     NBX_REQUIRE(starts != nullptr && goals != nullptr && valid != nullptr, "starts / goals / valid is NULL");
     NBX_CUDA_OK(cudaSetDevice(chain->device));
     const int dof = chain->dof;
-    const int64_t chunk = host_chunk(E, (int64_t)1 << 17);
-    const size_t qb = (sizeof(float) * (size_t)chunk * dof + 255) & ~(size_t)255;
+    // Chunks GROW: an edge costs the kernels ~1.5 ns and the link ~1.0 ns (56 bytes at ~55 GB/s), so only the first upload is
+    // exposed and every further chunk adds the query's fixed cost (~0.1 ms: preparation launches, narrow phase, launch gaps).
+    // First chunk small, each next one 2.5 x the last -- what uploads while its predecessor is being validated; 10^6 edges
+    // are 4 chunks (62 k, 156 k, 390 k, the rest) instead of 8 equal ones.  NBX_HOST_CHUNK forces equal chunks (tuning).
+    static const int64_t chunk_env = std::getenv("NBX_HOST_CHUNK") ? std::atoll(std::getenv("NBX_HOST_CHUNK")) : 0;
     HostLanes hl(chain->device);
     int rc = hl.open();
     if (rc != NBX_OK) return rc;
     int lane = 0;
-    for (int64_t off = 0; off < E && rc == NBX_OK; off += chunk, lane ^= 1) {
-        const int64_t n = std::min(chunk, E - off);
+    int64_t chunk = chunk_env > 0 ? chunk_env : std::min<int64_t>(std::max<int64_t>((int64_t)1 << 15, ((E / 16) + 127) & ~(int64_t)127), (int64_t)1 << 21);
+    for (int64_t off = 0; off < E && rc == NBX_OK; lane ^= 1) {
+        int64_t n = std::min(chunk, E - off);
+        if (E - off - n < n / 2) n = E - off;                 // no stub at the end: fold it into this chunk
         cudaStream_t st = hl.st[lane];
+        const size_t qb = (sizeof(float) * (size_t)n * dof + 255) & ~(size_t)255;
         void* p = nullptr;
-        NBX_CUDA_OK(cudaMallocFromPoolAsync(&p, 2 * qb + (size_t)chunk, hl.pool, st));
+        NBX_CUDA_OK(cudaMallocFromPoolAsync(&p, 2 * qb + (size_t)n, hl.pool, st));
         float* ds = static_cast<float*>(p);
         float* dg = reinterpret_cast<float*>(static_cast<unsigned char*>(p) + qb);
         uint8_t* dv = static_cast<unsigned char*>(p) + 2 * qb;
@@ -1941,6 +1947,8 @@ int nbx_edges_valid_host_f32(const nbx_chain* chain, const nbx_scene* scene, con
         }
         cudaFreeAsync(p, st);
         if (e != cudaSuccess) { nbx_set_error("cudaMemcpyAsync failed: %s", cudaGetErrorString(e)); rc = NBX_ERR_CUDA; }
+        off += n;
+        if (chunk_env <= 0) chunk = std::min<int64_t>((chunk * 5 / 2 + 127) & ~(int64_t)127, (int64_t)1 << 21);   // staging stays bounded
     }
     return hl.finish(rc);
 }
