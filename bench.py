@@ -723,6 +723,7 @@ def secondary_measurements(arm, q, dev, rank, world, clocks_mhz):
             "sample_count_mismatches": cnt_bad, "useful_count_mismatches_outside_band": useful_bad,
             "against": "oracle/nbx_oracle.c, sequential connectors.py:57-100 semantics, on the same edges (an edge is in the band when its "
                        "smallest sample distance is within band_m of the threshold)"}
+    s_cont, g_cont = s_all[:100000].clone(), g_all[:100000].clone()      # for the continuous-edge row below
     del s_all, g_all, s, g, nodes
 
     # ---- float64 path (the drop-in caller's default dtype): device-resident and through host buffers ---------------
@@ -887,6 +888,31 @@ def secondary_measurements(arm, q, dev, rank, world, clocks_mhz):
             "api": "BatchedPRM.build (reference planners/prm.py:19-47 + faiss IndexFlatL2): one host round trip for the final compaction",
             "parity": {"knn_rows": len(xn) - 10, "neighbour_set_mismatches": knn_bad,
                        "against": "NumPy float64 brute force over the earlier vertices (the reference's faiss index is exact L2 too)"}}
+        # ContinuousConnector (reference connectors.py:108-185) batched: 10^5 of the PRM edges, every grid segment decided
+        from oracle import continuous as _ocont
+        Ec = 100000
+        sc_, gc_ = s_cont[:Ec].contiguous(), g_cont[:Ec].contiguous()
+        clear_g, det_c = arm.edges_clear(sc_, gc_, 0.1, return_detail=True)
+        ms_c = best_ms(lambda: arm.edges_clear(sc_, gc_, 0.1), n=3, warm=1)
+        n_c = 192
+        pick = torch.linspace(0, Ec - 1, n_c, device=dev).long()
+        s_np, g_np = sc_[pick].double().cpu().numpy(), gc_[pick].double().cpu().numpy()
+        c_star = np.array([_ocont.min_clearance(so, a_, b_, 0.1, per_segment=12)[0] for a_, b_ in zip(s_np, g_np)])
+        band_c = 3e-4
+        decided = np.abs(c_star) > band_c
+        cg = clear_g[pick].cpu().numpy()
+        bad_c = int(np.sum(cg[decided] != (c_star[decided] > 0.0)))
+        ok_all &= bad_c == 0
+        nx["continuous_edges_per_sec"] = {
+            "value": Ec / ms_c * 1e3, "best_ms": ms_c, "edges": Ec, "resolution": 0.1, "clear_fraction": float(clear_g.float().mean()),
+            "distance_evaluations": det_c["distance_evaluations"], "grid_samples": det_c["grid_samples"], "levels": det_c["levels"],
+            "unresolved_segments": det_c["unresolved_segments"],
+            "api": "Arm.edges_clear / ContinuousConnector.connect_batch: signed minimum distances at the grid samples of all edges in one "
+                   "launch of the fused distance query, segments certified by the edge's bound on the clearance's rate of change, "
+                   "the rest halved level by level (one launch per level)",
+            "parity": {"rows": n_c, "band_m": band_c, "mismatches_outside_band": bad_c, "in_band_fraction": float(1.0 - decided.mean()),
+                       "against": "oracle/continuous.py: float64 clearance sampled 12 times inside every grid segment + bounded Brent polish "
+                                  "(an exact solver's answer to the reference's per-segment SLSQP feasibility problem), parity UNPINNED against Bullet"}}
         out["next_rows"] = nx
     ok = max_over_ranks(0.0 if ok_all else 1.0, dev) == 0.0
     return out, ok

@@ -22,8 +22,13 @@ What changes is *where* the samples are evaluated:
   on the host exactly like the reference, validity is one batched `in_collision` call.
 * any other callable -> the reference's sequential loop over the user's callback.
 
-`ContinuousConnector` (scalar SLSQP over a signed distance) is out of scope
-(SURVEY.md section 2 row 8).
+* `ContinuousConnector.connect / steer / is_valid`  :108-185  -- the checker returns a signed clearance
+  (<= 0 = invalid) and an edge is rejected when SOME point of a grid segment is invalid.  The reference asks one
+  SLSQP solve per segment for such a point (`minimize t s.t. checker(trajectory(t)) <= 0`, success -> None).
+  With an `ArmClearanceChecker`, the default trajectory and the default distance the whole edge set is decided on the
+  GPU instead (`Arm.edges_clear`: signed minimum distances at the grid samples of all edges in one launch, segments
+  certified free by the edge's bound on the clearance's rate of change, the others halved level by level);
+  any other callable runs the reference's SLSQP loop statement for statement.
 """
 from abc import ABC, abstractmethod
 from dataclasses import dataclass
@@ -54,6 +59,20 @@ class ArmValidityChecker:
         if isinstance(hit, bool):
             return not hit
         return ~hit
+
+
+class ArmClearanceChecker:
+    """`q -> arm.min_distance(q) - threshold`: the signed clearance a `ContinuousConnector` expects from its
+    validity checker (reference connectors.py:131-134 constrains it to `<= 0`, `is_valid` is `> 0`, :184-185);
+    negative values are penetration depths.  Accepts one configuration (-> float) or a batch."""
+
+    def __init__(self, arm, threshold: float = 0.0):
+        self.arm = arm
+        self.threshold = float(threshold)
+
+    def __call__(self, q):
+        d = self.arm.min_distance(q) - self.threshold
+        return float(d) if getattr(d, "ndim", 1) == 0 else d
 
 
 @dataclass(frozen=True)
@@ -179,3 +198,67 @@ class DiscreteConnector(Connector):
                 t_f = np.minimum(self._params.max_distance / dist, 1.0)
             ends = (1.0 - t_f)[..., None] * s + t_f[..., None] * g
         return (valid, ends, out[1]) if return_samples else (valid, ends)
+
+
+class ContinuousConnector(Connector):
+    """Reference connectors.py:108-185.  `connect` / `steer` keep the reference's signatures and return values
+    (`None`, `copy(goal)`, `copy(trajectory(T_f))`); `connect_batch` / `steer_batch` decide E edges at once."""
+
+    def __init__(self, params: ConnectorParams):
+        self._params = params
+
+    def _fused(self, distance_func) -> bool:
+        p = self._params
+        return (isinstance(p.validity_checker, ArmClearanceChecker)
+                and p.trajectory_func is _default_trajectory and distance_func is _l2)
+
+    def _edge(self, start, goal, distance_func, steer: bool):
+        p = self._params
+        distance = distance_func(start, goal)
+        if distance <= np.finfo(np.float32).eps:
+            return None
+        t_f = 1.0
+        if steer and distance > p.max_distance:
+            t_f = p.max_distance / distance
+        trajectory = p.trajectory_func(start, goal)
+        chk = p.validity_checker
+        if self._fused(distance_func):
+            ok = chk.arm.edges_clear(np.asarray(start)[None], np.asarray(goal)[None], p.resolution,
+                                     p.max_distance if steer else None, chk.threshold)
+            if not bool(ok[0]):
+                return None
+        else:
+            from scipy.optimize import NonlinearConstraint, minimize
+            T = sample_times(distance, p.resolution, t_f)
+            for t0, t1 in zip(T[:-1], T[1:]):
+                constraint = NonlinearConstraint(lambda t: chk(trajectory(t[0])), lb=-np.inf, ub=0.0)
+                result = minimize(lambda t: t[0], x0=np.array([(t0 + t1) / 2.0]), bounds=[(t0, t1)],
+                                  method="SLSQP", constraints=[constraint])
+                if result.success:            # a point of the segment with clearance <= 0 exists
+                    return None
+        return np.copy(goal) if not steer else np.copy(trajectory(t_f))
+
+    def connect(self, start: np.ndarray, goal: np.ndarray, distance_func: Callable = _l2):
+        return self._edge(start, goal, distance_func, steer=False)
+
+    def steer(self, start: np.ndarray, goal: np.ndarray, distance_func: Callable = _l2):
+        return self._edge(start, goal, distance_func, steer=True)
+
+    def is_valid(self, state: np.ndarray):
+        return self._params.validity_checker(state) > 0.0
+
+    def _require_fused(self):
+        if not self._fused(_l2):
+            raise ValueError("batched continuous edge validation needs an ArmClearanceChecker, the default linear "
+                             "trajectory and the default L2 distance")
+        return self._params.validity_checker
+
+    def connect_batch(self, starts, goals, return_detail: bool = False):
+        """valid[e] == (connect(starts[e], goals[e]) is not None) for a solver that never misses a feasible point."""
+        chk = self._require_fused()
+        return chk.arm.edges_clear(starts, goals, self._params.resolution, None, chk.threshold, return_detail=return_detail)
+
+    def steer_batch(self, starts, goals, return_detail: bool = False):
+        chk = self._require_fused()
+        return chk.arm.edges_clear(starts, goals, self._params.resolution, self._params.max_distance, chk.threshold,
+                                   return_detail=return_detail)

@@ -187,6 +187,60 @@ def primitive_reach(chain_arrays: dict, joint_limits, from_first_joint: bool = F
     return out
 
 
+def lever_arms(chain_arrays: dict) -> np.ndarray:
+    """`rho[p, c]`: upper bound, over every configuration, on the speed of ANY point of link primitive `p` per unit rate
+    of q column `c` (0 when the joint of column `c` is not on the path from the root to the primitive).
+
+    Revolute joint: a point turns about an axis through the joint's origin, so its speed is at most its distance from
+    that origin <= sum of the translation norms of the link offsets between the joint and the primitive's frame + the
+    frame's trailing fixed run + the primitive's own offset + its bounding radius (rotations preserve norms).
+    Prismatic joint: |axis|.  A prismatic joint BETWEEN a revolute joint and the primitive makes that lever arm
+    unbounded (inf).  This is what turns clearances at two samples of a motion into a bound for the motion between them
+    (`Arm.edges_clear`, the batched form of reference connectors.py:108-185)."""
+    A = chain_arrays
+    n_mov = len(A["mov_type"])
+    off = np.asarray(A["mov_offset"]).reshape(n_mov, 12)
+    axis = np.asarray(A["mov_axis"]).reshape(n_mov, 3)
+    tail = np.asarray(A["frame_tail"]).reshape(-1, 12)
+    poff = np.asarray(A["prim_offset"]).reshape(-1, 12)
+    dims = np.asarray(A["prim_dims"]).reshape(-1, 3)
+    n_prims = len(A["prim_type"])
+    rho = np.zeros((n_prims, int(A["dof"])))
+    for p in range(n_prims):
+        f = int(A["prim_frame"][p])
+        t = int(A["prim_type"][p])
+        brad = dims[p, 0] if t == _cabi.NBX_PRIM_SPHERE else (np.linalg.norm(dims[p]) if t == _cabi.NBX_PRIM_BOX else np.hypot(dims[p, 0], dims[p, 1]))
+        arm = np.linalg.norm(tail[f, [3, 7, 11]]) + np.linalg.norm(poff[p, [3, 7, 11]]) + brad      # from the last movable joint's origin
+        j = int(A["frame_mov"][f])
+        while j >= 0:
+            c = int(A["mov_qidx"][j])
+            if int(A["mov_type"][j]) == _cabi.NBX_JOINT_PRISMATIC:
+                rho[p, c] = np.linalg.norm(axis[j])
+                arm = np.inf                                  # the slider's travel is not bounded (q is never clamped)
+            else:
+                rho[p, c] = arm
+            arm = arm + np.linalg.norm(off[j, [3, 7, 11]])
+            j = int(A["mov_parent"][j])
+    return rho
+
+
+def clearance_rate_rows(chain_arrays: dict, scene_arrays: dict) -> np.ndarray:
+    """Rows `M[r, c]` such that `|d(q') - d(q)| <= max_r sum_c M[r, c] |q'_c - q_c|` for the minimum distance `d` over the
+    scene's allowed pairs.  An obstacle pair changes at most as fast as the primitive's points move (`lever_arms`); a
+    self pair only through the joints that move ONE of its two links -- a joint above both moves them rigidly together."""
+    rho = lever_arms(chain_arrays)
+    rows = []
+    for a in sorted({int(a) for a, _ in np.asarray(scene_arrays["env_pairs"]).reshape(-1, 2)}):
+        rows.append(rho[a])
+    for a, b in np.asarray(scene_arrays["self_pairs"]).reshape(-1, 2):
+        ra, rb = rho[int(a)], rho[int(b)]
+        both = (ra > 0) & (rb > 0)
+        rows.append(np.where(both, 0.0, ra + rb))
+    if not rows:
+        return np.zeros((0, rho.shape[1]))
+    return np.unique(np.asarray(rows), axis=0)
+
+
 def obstacle_gap_from(origin_pose, obj) -> float:
     """Lower bound on the distance from the origin of `origin_pose` (4x4, world) to the obstacle."""
     cs = obj._collision_shape

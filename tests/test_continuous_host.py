@@ -1,0 +1,91 @@
+"""Host side of the continuous edge check (reference connectors.py:108-185): the bound on the clearance's rate of change
+that `Arm.edges_clear` certifies segments with, held against the float64 oracle; `ContinuousConnector` over an arbitrary
+scalar checker (the reference's SLSQP loop) on a case with a closed form."""
+import numpy as np
+import pytest
+
+from numbotics_b200 import workloads
+from numbotics_b200.robots import descriptor
+from numbotics_b200.planning.sampling_based import ConnectorParams, ContinuousConnector, DiscreteConnector
+from oracle import collision, continuous
+
+
+@pytest.fixture(scope="module")
+def scene():
+    arm, cubes = workloads.prm_scene(device=None)
+    arm._test_keepalive = cubes
+    return arm, collision.SceneOracle(arm)
+
+
+def test_lever_arms_bound_the_speed_of_primitive_centres(scene):
+    arm, so = scene
+    rho = descriptor.lever_arms(arm._arrays)
+    assert rho.shape == (len(arm._arrays["prim_type"]), arm.dof) and np.all(np.isfinite(rho))
+    prim = [arm._arrays["prim_of_link"][l] for l in so.links]
+    q = workloads.random_configs_np(arm, 64, seed=5)
+    h = 1e-6
+    P0 = so.link_poses(q)[:, :, [3, 7, 11]]
+    worst = 0.0
+    for c in range(arm.dof):
+        dq = np.zeros(arm.dof); dq[c] = h
+        speed = np.linalg.norm(so.link_poses(q + dq)[:, :, [3, 7, 11]] - P0, axis=2) / h        # (n, links)
+        bound = rho[prim, c][None]
+        assert np.all(speed <= bound + 1e-6), (c, float((speed - bound).max()))
+        worst = max(worst, float((speed / np.maximum(bound, 1e-12)).max()))
+    assert worst > 0.3            # not vacuous: some centre moves at a good fraction of its bound
+
+
+def test_clearance_rate_rows_bound_the_minimum_distance(scene):
+    arm, so = scene
+    M = descriptor.clearance_rate_rows(arm._arrays, arm.scene_arrays(None))
+    assert M.shape[1] == arm.dof and M.shape[0] >= 2
+    # a self pair is not charged for the joints above both of its links: some row has zeros in its first columns
+    assert np.any((M[:, 0] == 0.0) & (M.sum(axis=1) > 0))
+    rng = np.random.default_rng(11)
+    q = workloads.random_configs_np(arm, 3000, seed=6)
+    for scale in (1e-3, 0.05, 0.3):
+        dq = rng.normal(size=q.shape) * scale
+        d0, d1 = so.min_distance(q), so.min_distance(q + dq)
+        bound = (np.abs(dq) @ M.T).max(axis=1)
+        slack = bound - np.abs(d1 - d0)
+        assert slack.min() > -1e-9, (scale, float(slack.min()))
+    # ... and is not vacuous: for small steps the change reaches a fair share of the bound somewhere
+    dq = rng.normal(size=q.shape) * 1e-3
+    ratio = np.abs(so.min_distance(q + dq) - so.min_distance(q)) / (np.abs(dq) @ M.T).max(axis=1)
+    assert ratio.max() > 0.2
+
+
+def _disc_checker(centre, radius):
+    return lambda x: float(np.linalg.norm(np.asarray(x) - centre) - radius)
+
+
+def test_continuous_connector_slsqp_path_on_a_disc():
+    """A point in the plane and a disc: clearance |x - c| - r.  With a coarse grid the samples of a chord through the
+    disc can all be free -- DiscreteConnector accepts the edge, ContinuousConnector (reference :126-145) does not."""
+    centre, radius = np.array([0.5, 0.0]), 0.2
+    chk = _disc_checker(centre, radius)
+    params = ConnectorParams(resolution=0.9, max_distance=0.5, validity_checker=chk)
+    cont = ContinuousConnector(params)
+    disc = DiscreteConnector(ConnectorParams(resolution=0.9, max_distance=0.5, validity_checker=lambda x: chk(x) > 0.0))
+    a, b = np.array([0.0, 0.0]), np.array([1.0, 0.0])          # straight through the disc, samples at t = 0, 0.9, 1 are free
+    assert disc.connect(a, b) is not None
+    assert cont.connect(a, b) is None
+    assert continuous.connect_slsqp(chk, a, b, 0.9) is False
+    a2, b2 = np.array([0.0, 0.5]), np.array([1.0, 0.5])        # passes 0.3 above the disc
+    out = cont.connect(a2, b2)
+    assert out is not None and np.array_equal(out, b2) and out is not b2
+    assert continuous.connect_slsqp(chk, a2, b2, 0.9) is True
+    # steer stops at max_distance: the first 0.25 of the way is free even on the chord through the disc
+    short = ContinuousConnector(ConnectorParams(resolution=0.5, max_distance=0.25, validity_checker=chk))
+    out = short.steer(a, b)
+    assert out is not None and np.allclose(out, [0.25, 0.0])
+    assert cont.steer(a, b) is None                             # 0.5 of the way reaches the disc's rim region: |0.5 - 0.5| - 0.2 < 0
+    # degenerate edge and is_valid
+    assert cont.connect(a, a.copy()) is None
+    assert cont.is_valid(a) and not cont.is_valid(centre)
+
+
+def test_batched_form_needs_the_arm_checker():
+    cont = ContinuousConnector(ConnectorParams(validity_checker=_disc_checker(np.zeros(2), 0.1)))
+    with pytest.raises(ValueError, match="ArmClearanceChecker"):
+        cont.connect_batch(np.zeros((2, 2)), np.ones((2, 2)))
