@@ -70,6 +70,16 @@ __device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// Programmatic dependent launch (sm_90+): the kernels of one verdict query -- and the 46 of a bisection -- follow each other
+// on a stream.  Each one lets its successor be SCHEDULED as soon as all of its own CTAs have started
+// (`griddepcontrol.launch_dependents`), and waits for its predecessor's completion and memory flush
+// (`griddepcontrol.wait`) only after the part of its prologue that touches nothing a predecessor writes (staging the static
+// scene, carving shared memory): launch latency, CTA start-up and scene staging overlap the predecessor's tail.  Both
+// instructions are no-ops in a kernel launched without the attribute.  Rule kept by every kernel below: no global read of
+// query data and no global write before pdl_wait().
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void copy_words(void* dst, const void* src, size_t bytes) {
     const int n = (int)(bytes / 4);
     const int* s = static_cast<const int*>(src);
@@ -833,6 +843,8 @@ in_collision_kernel(const __grid_constant__ SceneDev S, const float* __restrict_
         }
         cp_async_commit();
     };
+    pdl_launch_dependents();
+    pdl_wait();                                          // q may be the predecessor's output (bisection midpoints)
     if (rangeN > 0) request_q(0);                        // travels together with the scene
     stage_wait();
     __syncthreads();                                     // the staged scene is the only thing the warps share
@@ -894,6 +906,8 @@ edge_prepare_kernel(const float* __restrict__ starts, const float* __restrict__ 
                     double max_distance, uint8_t* __restrict__ valid, int32_t* __restrict__ n_samples, int* __restrict__ first_bad,
                     EdgeMeta* __restrict__ meta, long long* __restrict__ offs /* [E + 1]: offs[e + 1] = count */,
                     long long* __restrict__ block_sums, int* __restrict__ gq_count, int* __restrict__ tile_counter) {
+    pdl_launch_dependents();
+    pdl_wait();                                            // the counters may still be read by the previous query's narrow kernel
     const int64_t e = (int64_t)blockIdx.x * kPrepBlock + threadIdx.x;
     if (e == 0) { gq_count[0] = 0; gq_count[1] = 0; *tile_counter = 0; }     // no memset node in front of the query
     int cnt = 0;
@@ -955,6 +969,8 @@ edge_offsets_kernel(long long* __restrict__ offs, int64_t E, const long long* __
                     long long warps, int* __restrict__ draw_edge) {
     __shared__ long long red[2][kPrepBlock / 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    pdl_launch_dependents();
+    pdl_wait();
     long long below = 0, all = 0;
     for (int i = threadIdx.x; i < n_blocks; i += kPrepBlock) {
         const long long v = __ldg(block_sums + i);
@@ -1035,6 +1051,8 @@ edges_flat_kernel(const __grid_constant__ SceneDev S, const float* __restrict__ 
     C.gq = G.gq; C.gq_count = G.gq_count; C.gq_half = G.gq_half;
     C.gflag = valid; C.hit_value = 0; C.gjk_iters = G.gjk_iters;
     C.first_bad = G.first_bad;
+    pdl_launch_dependents();
+    pdl_wait();                                            // offsets, draw table, counters: the preparation kernels' output
     stage_wait();
     __syncthreads();
 
@@ -1152,6 +1170,8 @@ narrow_kernel(const float* __restrict__ gq, const int* __restrict__ gq_count, in
     C.gflag = gflag;
     C.hit_value = hit_value;
     C.gjk_iters = gjk_iters;
+    pdl_launch_dependents();
+    pdl_wait();
     const int n_env = min(gq_count[0], gq_half), n_self = min(gq_count[1], gq_half);
     const int stride = gridDim.x * blockDim.x;
     const int first = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1467,8 +1487,10 @@ template <typename T>
 __global__ void bisect_step_kernel(double* __restrict__ lo, double* __restrict__ hi, const T* __restrict__ inside, int64_t inside_stride,
                                    const T* __restrict__ outside, const uint8_t* __restrict__ verdict, float* __restrict__ mid32,
                                    T* __restrict__ out, int64_t B, int dof, int round, int last, int* __restrict__ gq_count) {
+    pdl_launch_dependents();
+    pdl_wait();                                            // the previous round's narrow kernel is done and its verdicts visible
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) { gq_count[0] = 0; gq_count[1] = 0; }      // the previous round's narrow kernel is done (stream order)
+    if (i == 0) { gq_count[0] = 0; gq_count[1] = 0; }
     if (i >= B * dof) return;
     const int64_t b = i / dof;
     double l, h;
@@ -1483,6 +1505,24 @@ __global__ void bisect_step_kernel(double* __restrict__ lo, double* __restrict__
     if (last) { out[i] = (T)h; return; }
     lo[i] = l; hi[i] = h;
     mid32[i] = (float)((l + h) / 2.0);
+}
+
+// Launch with programmatic stream serialization (see pdl_wait above): the kernel may be scheduled while its predecessor on
+// the stream is still draining.  NBX_NO_PDL=1 turns the attribute off (A/B measurements).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, Args&&... args) {
+    static const bool off = std::getenv("NBX_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = off ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1558,9 +1598,9 @@ int launch_narrow(const nbx_chain* ch, const SplitArgs& G, float thr, uint8_t* g
     static const int per_sm_env = std::getenv("NBX_NARROW_CTAS_PER_SM") ? std::atoi(std::getenv("NBX_NARROW_CTAS_PER_SM")) : 0;   // tuning only
     const unsigned grid = (unsigned)(ch->sm_count * (per_sm_env > 0 ? per_sm_env : 10));      // 5 CTAs of 89 registers are resident per SM: two even waves
     if (thr < 0.f)
-        narrow_kernel<kSplitNeg><<<grid, 128, 0, stream>>>(G.gq, G.gq_count, G.gq_half, thr, gflag, hit_value, G.gjk_iters, G.first_bad);
+        NBX_CUDA_OK(launch_pdl(narrow_kernel<kSplitNeg>, grid, 128, 0, stream, G.gq, G.gq_count, G.gq_half, thr, gflag, hit_value, G.gjk_iters, G.first_bad));
     else
-        narrow_kernel<kSplit><<<grid, 128, 0, stream>>>(G.gq, G.gq_count, G.gq_half, thr, gflag, hit_value, G.gjk_iters, G.first_bad);
+        NBX_CUDA_OK(launch_pdl(narrow_kernel<kSplit>, grid, 128, 0, stream, G.gq, G.gq_count, G.gq_half, thr, gflag, hit_value, G.gjk_iters, G.first_bad));
     nbx_count_launch();
     NBX_CUDA_OK(cudaGetLastError());
     return NBX_OK;
@@ -1617,7 +1657,7 @@ int launch_in_collision(const nbx_chain* ch, const nbx_scene* sc, const float* q
     auto kern = thr < 0.f ? (ch->fast_walk ? in_collision_kernel<kSplitNeg, true> : in_collision_kernel<kSplitNeg, false>)
                           : (ch->fast_walk ? in_collision_kernel<kSplit, true> : in_collision_kernel<kSplit, false>);
     NBX_SMEM_LIMIT(kern, smem);
-    kern<<<(unsigned)grid, kWarps * 32, smem, stream>>>(S, q, B, ch->dof, thr, verdict, nullptr, nullptr, upw, G);
+    NBX_CUDA_OK(launch_pdl(kern, (unsigned)grid, kWarps * 32, smem, stream, S, q, B, ch->dof, thr, verdict, (float*)nullptr, (uint32_t*)nullptr, upw, G));
     nbx_count_launch();
     NBX_CUDA_OK(cudaGetLastError());
     return launch_narrow(ch, G, thr, verdict, 1, stream);
@@ -1665,15 +1705,17 @@ int launch_edges(const nbx_chain* ch, const nbx_scene* sc, const float* starts, 
     int* draws = reinterpret_cast<int*>(w + b_offs + b_meta + b_sums);
     int* counter = reinterpret_cast<int*>(w + b_offs + b_meta + b_sums + b_draws);
     const int grid_main = edges_grid(ch);
-    edge_prepare_kernel<<<(unsigned)n_blocks, kPrepBlock, 0, stream>>>(starts, goals, E, dof, resolution, max_distance, valid, n_samples,
-                                                                        first_invalid, meta, offs, sums, ws.args.gq_count, counter);
-    edge_offsets_kernel<<<(unsigned)n_blocks, kPrepBlock, 0, stream>>>(offs, E, sums, n_blocks, (long long)grid_main * kWarps, draws);
+    NBX_CUDA_OK(launch_pdl(edge_prepare_kernel, (unsigned)n_blocks, kPrepBlock, 0, stream, starts, goals, E, dof, resolution, max_distance,
+                           valid, n_samples, first_invalid, meta, offs, sums, ws.args.gq_count, counter));
+    NBX_CUDA_OK(launch_pdl(edge_offsets_kernel, (unsigned)n_blocks, kPrepBlock, 0, stream, offs, E, (const long long*)sums, n_blocks,
+                           (long long)grid_main * kWarps, draws));
     nbx_count_launch(2);
     NBX_CUDA_OK(cudaGetLastError());
     auto kern = thr < 0.f ? (ch->fast_walk ? edges_flat_kernel<true, kSplitNeg> : edges_flat_kernel<false, kSplitNeg>)
                           : (ch->fast_walk ? edges_flat_kernel<true, kSplit> : edges_flat_kernel<false, kSplit>);
     NBX_SMEM_LIMIT(kern, smem);
-    kern<<<(unsigned)grid_main, kWarps * 32, smem, stream>>>(S, starts, goals, E, dof, thr, valid, meta, offs, counter, draws, ws.args);
+    NBX_CUDA_OK(launch_pdl(kern, (unsigned)grid_main, kWarps * 32, smem, stream, S, starts, goals, E, dof, thr, valid, (const EdgeMeta*)meta,
+                           (const long long*)offs, counter, (const int*)draws, ws.args));
     nbx_count_launch();
     NBX_CUDA_OK(cudaGetLastError());
     return launch_narrow(ch, ws.args, thr, valid, 0, stream);
@@ -1777,7 +1819,8 @@ int launch_bisect(const nbx_chain* ch, const nbx_scene* sc, const T* inside, int
     if ((rc = ws.alloc(ch->device, 4 * B, stream)) != NBX_OK) return rc;
     for (int r = 0; r <= n_bisections; ++r) {
         const int last = r == n_bisections;
-        bisect_step_kernel<T><<<grid, 256, 0, stream>>>(lo, hi, inside, inside_stride, outside, verdict, mid, out, B, dof, r, last, ws.args.gq_count);
+        NBX_CUDA_OK(launch_pdl(bisect_step_kernel<T>, grid, 256, 0, stream, lo, hi, inside, inside_stride, outside, (const uint8_t*)verdict, mid, out,
+                               B, dof, r, last, ws.args.gq_count));
         nbx_count_launch();
         NBX_CUDA_OK(cudaGetLastError());
         if (last) break;
