@@ -28,6 +28,7 @@
 #include <float.h>
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 namespace {
 
@@ -165,35 +166,50 @@ knn_kernel(const float* __restrict__ packed, int64_t n_refs, const float* __rest
             cnt = 0;
             thr = filter_thr(worst);
         };
-        for (int rb = 0; rb < nt; rb += 4 * kKnnSlices) {       // warp-uniform trip count (the votes below need every lane)
+        // `check`: some lane's limit is below the tile's end, or the tile ends inside a trip (the diagonal tiles of the causal
+        // mode, the last tile, the last, ragged query block); everywhere else the limit test is compiled out of the loop
+        auto scan = [&](auto check) {
+            constexpr bool CHECK = decltype(check)::value;
+            constexpr bool CLAMP = (kKnnTile % (4 * kKnnSlices)) != 0;     // a trip may run past the END of the tile buffer
+            int* const pp0 = &pend[0][threadIdx.x];
+            int* pp = pp0;                                                  // next free pending slot (cnt is 0 here)
+            for (int rb = 0; rb < nt; rb += 4 * kKnnSlices) {               // warp-uniform trip count (the votes need every lane)
+                const float* tp = tile + (rb + slice) * D;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int r = rb + u * kKnnSlices + slice;
-                const float4* t4 = reinterpret_cast<const float4*>(tile + min(r, kKnnTile - 1) * D);
-                bool pass;
-                if (FILTER) {
-                    float sa = 0.f, sb = 0.f;      // two partial sums: half the dependent FFMA chain
+                for (int u = 0; u < 4; ++u) {
+                    const int r = rb + u * kKnnSlices + slice;              // beyond nt (CHECK only): stale data, never noted (r < lim <= nt)
+                    const float4* t4 = reinterpret_cast<const float4*>(CLAMP ? tile + min(r, kKnnTile - 1) * D : tp + u * kKnnSlices * D);
+                    bool pass;
+                    if (FILTER) {
+                        float sa = 0.f, sb = 0.f;      // two partial sums: half the dependent FFMA chain
 #pragma unroll
-                    for (int d = 0; d < D / 4; ++d) {
-                        const float4 c = t4[d];
-                        sa = fmaf(fv[4 * d], c.x, sa); sb = fmaf(fv[4 * d + 1], c.y, sb);
-                        sa = fmaf(fv[4 * d + 2], c.z, sa); sb = fmaf(fv[4 * d + 3], c.w, sb);
+                        for (int d = 0; d < D / 4; ++d) {
+                            const float4 c = t4[d];
+                            sa = fmaf(fv[4 * d], c.x, sa); sb = fmaf(fv[4 * d + 1], c.y, sb);
+                            sa = fmaf(fv[4 * d + 2], c.z, sa); sb = fmaf(fv[4 * d + 3], c.w, sb);
+                        }
+                        pass = sa + sb > thr;
+                    } else {
+                        float da = 0.f, db = 0.f;
+#pragma unroll
+                        for (int d = 0; d < D / 4; ++d) {
+                            const float4 c = t4[d];
+                            const float e0 = qv[4 * d] - c.x, e1 = qv[4 * d + 1] - c.y, e2 = qv[4 * d + 2] - c.z, e3 = qv[4 * d + 3] - c.w;
+                            da = fmaf(e0, e0, da); db = fmaf(e1, e1, db); da = fmaf(e2, e2, da); db = fmaf(e3, e3, db);
+                        }
+                        pass = da + db < worst;
                     }
-                    pass = sa + sb > thr;
-                } else {
-                    float da = 0.f, db = 0.f;
-#pragma unroll
-                    for (int d = 0; d < D / 4; ++d) {
-                        const float4 c = t4[d];
-                        const float e0 = qv[4 * d] - c.x, e1 = qv[4 * d + 1] - c.y, e2 = qv[4 * d + 2] - c.z, e3 = qv[4 * d + 3] - c.w;
-                        da = fmaf(e0, e0, da); db = fmaf(e1, e1, db); da = fmaf(e2, e2, da); db = fmaf(e3, e3, db);
-                    }
-                    pass = da + db < worst;
+                    if (pass && (!CHECK || r < lim)) { *pp = r; pp += kKnnThreads; }
                 }
-                if (pass && r < lim) { pend[cnt][threadIdx.x] = r; ++cnt; }
+                if (__any_sync(0xffffffffu, pp > pp0 + (kKnnPend - 4) * kKnnThreads)) {
+                    cnt = (int)(pp - pp0) / kKnnThreads;
+                    drain();
+                    pp = pp0;
+                }
             }
-            if (__any_sync(0xffffffffu, cnt > kKnnPend - 4)) drain();
-        }
+            cnt = (int)(pp - pp0) / kKnnThreads;
+        };
+        if (__all_sync(0xffffffffu, lim == nt) && nt % (4 * kKnnSlices) == 0) scan(std::false_type{}); else scan(std::true_type{});
         if (__any_sync(0xffffffffu, cnt > 0)) drain();
         // every few tiles the slices agree on the k-th best distance of the union of their lists; after the last tile the
         // lists go to shared memory for the final merge
