@@ -5,14 +5,16 @@
 // numbotics/planning/sampling_based/planners/prm.py:35-40: every new vertex asks for its k nearest EARLIER vertices.
 //
 // A CTA of four warps serves 32 queries: lane = query, warp = SLICE -- the four warps scan interleaved quarters of every
-// reference tile for the same queries, each keeping its own k best (distance, index) pairs sorted in registers, and after
-// every tile the slices agree on the exact k-th best distance of the union of their lists (a four-way merge of the sorted
-// lists through shared memory: ~12 k instructions per tile against ~2 500 for the tile's pairs), so a slice prunes with
-// the bound a single scanner would have had at that tile boundary.  (The first version gave a query one thread for the
-// whole scan: the roadmap's 3 125 warps each walked 10^5 references in sequence -- 10 warps per SM on average, every
-// instruction waiting on its predecessor: ncu issue 0.60, `wait` 1.26 stalls per issue.  Slices cut that critical path by
-// four and double the resident warps.)  The reference points stream through shared memory in tiles that all lanes read
-// at the same address (broadcast).
+// reference tile for the same queries, each keeping its own k best (distance, index) pairs sorted in registers, and every
+// few tiles the slices agree on the exact k-th best distance of the union of their lists (a four-way merge of the sorted
+// lists through shared memory: ~12 k instructions against ~5 000 for the pairs in between), so a slice prunes with the
+// bound a single scanner would have had at that point.  (The first version gave a query one thread for the whole scan:
+// the roadmap's 3 125 warps each walked 10^5 references in sequence -- 10 warps per SM on average, every instruction
+// waiting on its predecessor: ncu issue 0.60, `wait` 1.26 stalls per issue.  Slices cut that critical path by four and
+// double the resident warps.)  The reference points are packed once (knn_pack_kernel) and stream through shared memory in
+// tiles fetched by 16-byte cp.async, the next tile in flight while the current one is scanned; all lanes read a reference at
+// the same address (broadcast).  A reference that passes the test against the bound is only noted in a per-lane pending
+// list; the lists are drained -- exact distance, exact test, insertion -- by all lanes together (see the scan loop).
 //
 // Per pair, when the points have a spare component (dof < D, e.g. the 7-DoF arm in 8 floats): the tile stores
 // -(1 - 1.6e-5) |b|^2 / 2 in the spare slot and the query 1, so ONE 8-term FFMA chain gives  a.b - |b|^2 / 2 (+ 8e-6 |b|^2)
