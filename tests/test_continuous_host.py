@@ -89,3 +89,44 @@ def test_batched_form_needs_the_arm_checker():
     cont = ContinuousConnector(ConnectorParams(validity_checker=_disc_checker(np.zeros(2), 0.1)))
     with pytest.raises(ValueError, match="ArmClearanceChecker"):
         cont.connect_batch(np.zeros((2, 2)), np.ones((2, 2)))
+
+
+class _FakeArm:
+    """Records what the connector asks of the arm (the device path itself is tests/test_continuous_gpu.py)."""
+
+    def __init__(self, verdict):
+        self.verdict = verdict
+        self.calls = []
+
+    def edges_clear(self, starts, goals, resolution, max_distance=None, threshold=0.0, max_depth=12, return_detail=False):
+        self.calls.append((np.asarray(starts).shape, resolution, max_distance, threshold, return_detail))
+        return np.full(np.asarray(starts).shape[:-1], self.verdict)
+
+    def min_distance(self, q):
+        q = np.asarray(q)
+        return np.float32(0.25) if q.ndim == 1 else np.full(q.shape[:-1], 0.25, np.float32)
+
+
+def test_arm_checker_routes_to_the_batched_query():
+    from numbotics_b200.planning.sampling_based import ArmClearanceChecker
+    arm = _FakeArm(True)
+    chk = ArmClearanceChecker(arm, threshold=0.05)
+    cont = ContinuousConnector(ConnectorParams(resolution=0.1, max_distance=0.5, validity_checker=chk))
+    a, b = np.zeros(7), np.full(7, 0.4)
+    out = cont.connect(a, b)
+    assert np.array_equal(out, b) and out is not b
+    assert arm.calls[-1] == ((1, 7), 0.1, None, 0.05, False)             # connect: no max_distance
+    out = cont.steer(a, b)                                               # |b - a| = 1.058 > 0.5: stops at T_f = 0.5 / 1.058
+    assert arm.calls[-1] == ((1, 7), 0.1, 0.5, 0.05, False)
+    assert np.allclose(out, b * (0.5 / np.linalg.norm(b)))
+    assert cont.connect_batch(np.zeros((3, 7)), np.ones((3, 7))).shape == (3,)
+    assert arm.calls[-1][0] == (3, 7)
+    # the checker itself: clearance = distance - threshold, float for one configuration
+    assert isinstance(chk(a), float) and abs(chk(a) - 0.2) < 1e-6 and chk(np.zeros((4, 7))).shape == (4,)
+    assert cont.is_valid(a)
+    # an invalid verdict -> None; a custom distance function leaves the fused path (SLSQP over the checker instead)
+    arm.verdict = False
+    assert cont.connect(a, b) is None and cont.steer(a, b) is None
+    n_calls = len(arm.calls)
+    out = cont.connect(a, b, distance_func=lambda x, y: float(np.abs(x - y).max()))
+    assert len(arm.calls) == n_calls and out is not None                 # clearance 0.2 everywhere: no feasible point
