@@ -69,7 +69,7 @@ __global__ void knn_pack_kernel(const float* __restrict__ refs, int64_t n, int d
 template <int D, int K, bool FILTER>
 __global__ void __launch_bounds__(kKnnThreads)
 knn_kernel(const float* __restrict__ packed, int64_t n_refs, const float* __restrict__ queries, int64_t n_q, int dof, int k,
-           int causal, int64_t* __restrict__ idx_out, uint8_t* __restrict__ valid_out, float* __restrict__ d2_out) {
+           int causal, int64_t* __restrict__ idx_out, uint8_t* __restrict__ valid_out, float* __restrict__ d2_out, int share) {
     constexpr int kTileFloats = K <= 16 ? 3072 : 1536;       // two tiles + the lists + the pending lists fit the 48 KB of static shared memory
     constexpr int kKnnTile = kTileFloats / D;                // 384 points at D = 8
     __shared__ __align__(16) float tiles[2][kTileFloats];
@@ -216,7 +216,7 @@ knn_kernel(const float* __restrict__ packed, int64_t n_refs, const float* __rest
         // every few tiles the slices agree on the k-th best distance of the union of their lists; after the last tile the
         // lists go to shared memory for the final merge
         const bool last = r0 + kKnnTile >= r_end;
-        if (!last && (it % kKnnShare) != kKnnShare - 1) continue;
+        if (!last && (it % share) != share - 1) continue;
 #pragma unroll
         for (int s = 0; s < K; ++s) { ld[slice][s][lane] = bd[s]; li[slice][s][lane] = bi[s]; }
         __syncthreads();
@@ -279,6 +279,8 @@ int launch_knn_d(const float* refs, int64_t n_refs, const float* queries, int64_
     NBX_REQUIRE(grid <= 0x7fffffffLL, "too many queries for one launch");
     static const bool no_filter = std::getenv("NBX_KNN_NO_FILTER") != nullptr;      // A/B measurements and tests only
     const bool filter = dof < D && !no_filter;
+    static const int share_env = std::getenv("NBX_KNN_SHARE") ? std::atoi(std::getenv("NBX_KNN_SHARE")) : 0;   // tuning only
+    const int share = share_env > 0 ? share_env : kKnnShare;
     // packed copy of the reference points (stream-ordered workspace, freed after the scan)
     cudaMemPool_t pool = nullptr;
     int rc = nbx_workspace_pool(device, &pool);
@@ -293,7 +295,7 @@ int launch_knn_d(const float* refs, int64_t n_refs, const float* queries, int64_
         else knn_pack_kernel<D, false><<<pg, 256, 0, stream>>>(refs, n_refs, dof, packed);
         nbx_count_launch();
     }
-#define NBX_KNN_LAUNCH(KK, FF) knn_kernel<D, KK, FF><<<(unsigned)grid, kKnnThreads, 0, stream>>>(packed, n_refs, queries, n_q, dof, k, causal, idx, valid, d2)
+#define NBX_KNN_LAUNCH(KK, FF) knn_kernel<D, KK, FF><<<(unsigned)grid, kKnnThreads, 0, stream>>>(packed, n_refs, queries, n_q, dof, k, causal, idx, valid, d2, share)
     if (k <= 16) { if (filter) NBX_KNN_LAUNCH(16, true); else NBX_KNN_LAUNCH(16, false); }
     else         { if (filter) NBX_KNN_LAUNCH(32, true); else NBX_KNN_LAUNCH(32, false); }
 #undef NBX_KNN_LAUNCH
