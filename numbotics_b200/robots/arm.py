@@ -937,56 +937,12 @@ class Arm:
                                                      vd.data_ptr(), out.data_ptr(), stream))
             return out.double() - float(threshold)
 
+        from ..planning.sampling_based.continuous import decide_edges
         with torch.cuda.device(dev_index):
-            delta = gd - sd
-            dist = delta.norm(dim=1)
-            alive = dist > float(np.finfo(np.float32).eps)              # connectors.py:117-118
-            step = float(resolution) / torch.where(alive, dist, torch.ones_like(dist))
-            tf = torch.ones_like(dist)
-            if max_distance is not None:
-                tf = torch.where(dist > float(max_distance), float(max_distance) / torch.where(alive, dist, torch.ones_like(dist)), tf)
-            n_seg = torch.where(alive, torch.ceil(tf / step), torch.zeros_like(dist)).long()     # numpy.arange length rule
-            n_pts = torch.where(alive, n_seg + 1, torch.zeros_like(n_seg))
-            total = int(n_pts.sum())
-            if total > (1 << 28):
-                raise ValueError("too many samples for one call (%d): validate the edges in chunks" % total)
-            rate = (delta.abs() @ torch.as_tensor(M, dtype=torch.float64, device=dev).T).amax(dim=1) if M.shape[0] else torch.zeros_like(dist)
-
-            ids = torch.arange(E, device=dev)
-            edge = torch.repeat_interleave(ids, n_pts, output_size=total)
-            first = torch.cumsum(n_pts, 0) - n_pts
-            k = torch.arange(total, device=dev) - first[edge]
-            t = torch.where(k == n_seg[edge], tf[edge], k.double() * step[edge])
-            c = clearance(edge, t)
-            evals = total
-            clear = alive.clone()
-            cmin = torch.full((E,), float("inf"), dtype=torch.float64, device=dev)
-            cmin.scatter_reduce_(0, edge, c, "amin")
-            clear &= ~(cmin <= 0.0)
-            # segments: sample i -> i + 1 inside one edge.  One compaction (= one host round trip) per level.
-            ia = torch.nonzero(k < n_seg[edge]).flatten()
-            se, ta, tb, ca, cb = edge[ia], t[ia], t[ia + 1], c[ia], c[ia + 1]
-            levels, unresolved = 0, 0
-            while True:
-                keep = torch.nonzero(clear[se] & ~((ca + cb - rate[se] * (tb - ta)) * 0.5 > 0.0)).flatten()
-                if keep.numel() == 0:
-                    break
-                if levels == max_depth:
-                    unresolved = int(keep.numel())
-                    break
-                se, ta, tb, ca, cb = se[keep], ta[keep], tb[keep], ca[keep], cb[keep]
-                levels += 1
-                tm = 0.5 * (ta + tb)
-                cm = clearance(se, tm)
-                evals += int(se.numel())
-                cmin.scatter_reduce_(0, se, cm, "amin")
-                clear &= ~(cmin <= 0.0)
-                se = torch.cat([se, se])
-                ta, tb = torch.cat([ta, tm]), torch.cat([tm, tb])
-                ca, cb = torch.cat([ca, cm]), torch.cat([cm, cb])
+            clear, det = decide_edges(sd, gd, resolution, max_distance, M, clearance, max_depth)
         del base_keep
         conv = (lambda x: x.to(starts.device).reshape(shape)) if in_torch else (lambda x: x.cpu().numpy().reshape(shape))
         if not return_detail:
             return conv(clear)
-        return conv(clear), {"distance_evaluations": evals, "grid_samples": total, "levels": levels,
-                             "unresolved_segments": unresolved, "min_clearance": conv(cmin), "rate_bound": conv(rate)}
+        det["min_clearance"], det["rate_bound"] = conv(det["min_clearance"]), conv(det["rate_bound"])
+        return conv(clear), det

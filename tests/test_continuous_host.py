@@ -130,3 +130,44 @@ def test_arm_checker_routes_to_the_batched_query():
     n_calls = len(arm.calls)
     out = cont.connect(a, b, distance_func=lambda x, y: float(np.abs(x - y).max()))
     assert len(arm.calls) == n_calls and out is not None                 # clearance 0.2 everywhere: no feasible point
+
+
+def test_decision_procedure_on_the_cpu_against_the_dense_oracle(scene):
+    """`decide_edges` (the host logic of Arm.edges_clear) with the float64 oracle as its clearance: verdicts equal the
+    densely sampled, polished minimum clearance outside a small band, every segment resolved, few evaluations."""
+    import torch
+    from numbotics_b200.planning.sampling_based.continuous import decide_edges
+    arm, so = scene
+    rng = np.random.default_rng(21)
+    nodes = workloads.random_configs_np(arm, 1500, seed=8)
+    pick = rng.choice(1500, 90, replace=False)
+    d2 = ((nodes[None] - nodes[pick][:, None]) ** 2).sum(-1)
+    near = np.argsort(d2, axis=1)[np.arange(90), 1 + rng.integers(0, 10, 90)]
+    starts = np.concatenate([nodes[pick], nodes[:30], nodes[:2]])                  # kNN edges, long edges, two degenerate ones
+    goals = np.concatenate([nodes[near], nodes[700:730], nodes[:2]])
+    M = descriptor.clearance_rate_rows(arm._arrays, arm.scene_arrays(None))
+    S, G = torch.from_numpy(starts), torch.from_numpy(goals)
+    calls = []
+
+    def clearance(edge, t):
+        calls.append(int(edge.numel()))
+        e, tt = edge.numpy(), t.numpy()
+        q = starts[e] + tt[:, None] * (goals[e] - starts[e])
+        return torch.from_numpy(so.min_distance(q) if len(e) else np.zeros(0))
+
+    for resolution, md in ((0.1, None), (0.9, None), (0.1, 0.7)):
+        calls.clear()
+        clear, det = decide_edges(S, G, resolution, md, M, clearance)
+        clear = clear.numpy()
+        assert not clear[-2:].any()                                              # shorter than float32 eps -> None
+        c_star = np.array([continuous.min_clearance(so, a, b, resolution, md, per_segment=12)[0]
+                           for a, b in zip(starts[:-2], goals[:-2])])
+        decided = np.abs(c_star) > 1e-5          # same float64 clearance on both sides: only the oracle's own sampling is in the band
+        assert decided.mean() > 0.98
+        assert np.array_equal(clear[:-2][decided], c_star[decided] > 0.0), (resolution, md)
+        assert det["unresolved_segments"] == 0 and det["levels"] <= 12
+        assert det["distance_evaluations"] == sum(calls) and calls[0] == det["grid_samples"]
+        # a fine grid needs little refinement; a grid nine times coarser about three more halvings per segment
+        assert det["distance_evaluations"] < (5 if resolution == 0.1 else 16) * det["grid_samples"]
+        assert np.all(det["min_clearance"].numpy()[:-2] >= c_star - 1e-5)
+        assert 0 < (~clear[:-2]).sum() < len(c_star)
