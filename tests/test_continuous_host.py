@@ -171,3 +171,49 @@ def test_decision_procedure_on_the_cpu_against_the_dense_oracle(scene):
         assert det["distance_evaluations"] < (5 if resolution == 0.1 else 16) * det["grid_samples"]
         assert np.all(det["min_clearance"].numpy()[:-2] >= c_star - 1e-5)
         assert 0 < (~clear[:-2]).sum() < len(c_star)
+
+
+def _tree_arm():
+    """base -(rev z)-> a -(rev y)-> b -(prismatic x)-> c, and a second branch a -(rev x)-> d: spheres on a, b, c, d."""
+    import networkx as nx
+    from numbotics_b200.math import trans_mat
+    from numbotics_b200.physics import GraphChain, Joint, Constraint, BasicLink, Shape
+    from numbotics_b200.robots import Arm
+    w = workloads.fresh_world("lever_tree")
+    G = nx.DiGraph()
+    for n in ("base", "a", "b", "c", "d"):
+        G.add_node(n, link=BasicLink(1.0, np.eye(4), Shape.SPHERE, radius=0.05, name=n))
+    J = lambda off, ax, t, name: Joint(trans_mat(pos=np.array(off)), np.array(ax, float), t, name=name, lower_limit=-1.0, upper_limit=1.0)
+    G.add_edge("base", "a", joint=J([0.0, 0.0, 0.3], [0, 0, 1], Constraint.REVOLUTE, "j_a"))
+    G.add_edge("a", "b", joint=J([0.4, 0.0, 0.0], [0, 1, 0], Constraint.REVOLUTE, "j_b"))
+    G.add_edge("b", "c", joint=J([0.2, 0.0, 0.0], [1, 0, 0], Constraint.PRISMATIC, "j_c"))
+    G.add_edge("a", "d", joint=J([0.0, 0.5, 0.0], [1, 0, 0], Constraint.REVOLUTE, "j_d"))
+    return Arm(GraphChain(G, world_name=w.name))
+
+
+def test_lever_arms_of_a_tree_with_a_slider():
+    arm = _tree_arm()
+    A = arm._arrays
+    rho = descriptor.lever_arms(A)
+    prim = {l.name.split(":")[-1]: p for l, p in A["prim_of_link"].items()}          # names are world:chain:link
+    col = {name: int(arm._chain._joint_to_index[j]) for j in arm._chain._joints for name in [j.name] if j.type.name != "FIXED"}
+    r = 0.05
+    # a sits on its own joint: only its radius turns about j_a; nothing else moves it
+    assert np.isclose(rho[prim["a"], col["j_a"]], r) and rho[prim["a"]].sum() == rho[prim["a"], col["j_a"]]
+    # b: 0.4 from j_a's origin, on j_b's origin
+    assert np.isclose(rho[prim["b"], col["j_a"]], 0.4 + r) and np.isclose(rho[prim["b"], col["j_b"]], r)
+    assert rho[prim["b"], col["j_d"]] == 0.0 and rho[prim["b"], col["j_c"]] == 0.0
+    # c rides the slider: unit speed along it, and an unbounded lever arm about every revolute joint above it
+    assert np.isclose(rho[prim["c"], col["j_c"]], 1.0)
+    assert np.isinf(rho[prim["c"], col["j_b"]]) and np.isinf(rho[prim["c"], col["j_a"]])
+    # d hangs off a on the other branch
+    assert np.isclose(rho[prim["d"], col["j_a"]], 0.5 + r) and np.isclose(rho[prim["d"], col["j_d"]], r)
+    assert rho[prim["d"], col["j_b"]] == 0.0 and rho[prim["base"]].sum() == 0.0
+    # rows: the pair (b, d) is not charged for j_a (above both), and is charged for j_b and j_d
+    pairs = np.array([[prim["b"], prim["d"]]], np.int32)
+    M = descriptor.clearance_rate_rows(A, {"env_pairs": np.zeros((0, 2), np.int32), "self_pairs": pairs})
+    assert M.shape == (1, arm.dof)
+    assert M[0, col["j_a"]] == 0.0 and np.isclose(M[0, col["j_b"]], r) and np.isclose(M[0, col["j_d"]], r) and M[0, col["j_c"]] == 0.0
+    # the slider makes (c, anything) unbounded: Arm.edges_clear refuses such scenes (NotImplementedError) instead of guessing
+    M = descriptor.clearance_rate_rows(A, {"env_pairs": np.array([[prim["c"], 0]], np.int32), "self_pairs": np.zeros((0, 2), np.int32)})
+    assert not np.all(np.isfinite(M))
