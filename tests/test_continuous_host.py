@@ -217,3 +217,25 @@ def test_lever_arms_of_a_tree_with_a_slider():
     # the slider makes (c, anything) unbounded: Arm.edges_clear refuses such scenes (NotImplementedError) instead of guessing
     M = descriptor.clearance_rate_rows(A, {"env_pairs": np.array([[prim["c"], 0]], np.int32), "self_pairs": np.zeros((0, 2), np.int32)})
     assert not np.all(np.isfinite(M))
+
+
+def test_reference_slsqp_loop_agrees_with_the_exact_decision(scene):
+    """The reference's own per-segment SLSQP search (connectors.py:126-145, restated in oracle/continuous.py and run with
+    scipy, its dependency) over the oracle's clearance, on the edges where it matters -- every invalid edge of a sample and
+    the valid ones that come closest to contact: same verdicts as the exact decision the batched path implements.
+    (On 80 + 80 random PRM edges at resolutions 0.1 and 0.9 the two agreed on all 160; that run takes minutes.)"""
+    arm, so = scene
+    rng = np.random.default_rng(5)
+    nodes = workloads.random_configs_np(arm, 2000, seed=4)
+    pick = rng.choice(2000, 80, replace=False)
+    d2 = ((nodes[None] - nodes[pick][:, None]) ** 2).sum(-1)
+    near = np.argsort(d2, axis=1)[np.arange(80), 1 + rng.integers(0, 10, 80)]
+    S, G = nodes[pick], nodes[near]
+    res = 0.3
+    c_star = np.array([continuous.min_clearance(so, a, b, res, per_segment=12)[0] for a, b in zip(S, G)])
+    invalid = np.nonzero(c_star < -1e-4)[0][:4]
+    tight = np.argsort(np.where(c_star > 1e-4, c_star, np.inf))[:4]
+    assert len(invalid) >= 2
+    chk = lambda q: float(so.min_distance(np.asarray(q)[None])[0])
+    for e in np.concatenate([invalid, tight]):
+        assert continuous.connect_slsqp(chk, S[e], G[e], res) == bool(c_star[e] > 0.0), (int(e), float(c_star[e]))
