@@ -903,7 +903,19 @@ def secondary_measurements(arm, q, dev, rank, world, clocks_mhz):
         cg = clear_g[pick].cpu().numpy()
         bad_c = int(np.sum(cg[decided] != (c_star[decided] > 0.0)))
         ok_all &= bad_c == 0
+        # the reference's own loop (connectors.py:126-145: one scipy SLSQP solve per grid segment) over the oracle's clearance,
+        # on two of the same edges and one host core: what the batched query replaces (reported, not gated)
+        try:
+            chk_o = lambda qq: float(so.min_distance(np.asarray(qq, dtype=np.float64)[None])[0])
+            t0 = time.perf_counter()
+            ref_v = [bool(_ocont.connect_slsqp(chk_o, s_np[i], g_np[i], 0.1)) for i in (0, 1)]
+            dt_ref = time.perf_counter() - t0
+            ref_loop = {"value": 2.0 / dt_ref, "unit": "edges/s", "cores": 1, "edges": 2, "kind": "the reference's SLSQP loop restated (oracle/continuous.py) over the restated clearance",
+                        "same_verdict_as_gpu": [ref_v[i] == bool(cg[i]) for i in (0, 1)]}
+        except Exception as exc:            # never lose the line over a reported-only figure
+            ref_loop = {"error": repr(exc)}
         nx["continuous_edges_per_sec"] = {
+            "cpu_reference_loop": ref_loop,
             "value": Ec / ms_c * 1e3, "best_ms": ms_c, "edges": Ec, "resolution": 0.1, "clear_fraction": float(clear_g.float().mean()),
             "distance_evaluations": det_c["distance_evaluations"], "grid_samples": det_c["grid_samples"], "levels": det_c["levels"],
             "unresolved_segments": det_c["unresolved_segments"],
