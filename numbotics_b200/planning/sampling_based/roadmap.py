@@ -62,7 +62,7 @@ class Roadmap:
 
 def knn_earlier(nodes, k: int, chunk: int = 4096, return_dist2: bool = False):
     """For every vertex i > 0 its (up to) k nearest vertices among 0..i-1 (the reference's incremental kNN:
-    `ApproximateNearestNeighborsIndex.k_nearest` before `add_point`, planners/prm.py:35-40), exact L2, one kernel launch
+    `ApproximateNearestNeighborsIndex.k_nearest` before `add_point`, planners/prm.py:35-40), exact L2, one C-ABI call
     (`nbx_knn_f32`, causal mode).  Returns (idx (N,k) int64 sorted by distance, valid (N,k) bool) and, with
     `return_dist2`, the squared distances (N,k) float32.  `chunk` is ignored (kept for the signature of the earlier torch
     implementation)."""
